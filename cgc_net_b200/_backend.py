@@ -1,0 +1,360 @@
+"""ctypes binding of ``libcgc_sm100.so`` (the C-ABI declared in ``include/cgc_sm100.h``).
+
+``get()`` returns the one backend the product path uses: ``CudaBackend``.  There is NO
+CPU / eager fallback -- if the shared library has not been built, or a tensor is not on a
+CUDA device, the call raises.  ``use_backend_for_testing`` exists only so ``tests/`` can
+substitute the per-operator CPU formulas of ``oracle/op_reference.py`` to check the autograd
+wiring of ``ops.py`` on a host without a GPU; nothing in the package calls it.
+
+Each method is a 1:1 wrapper of the ``extern "C"`` function of the same name
+(``cgc_<method>``): it extracts raw device pointers / leading dimensions from the torch
+tensors, passes the current CUDA stream, and raises ``CgcError`` on a non-zero return code.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libcgc_sm100.so')
+
+_c_i32, _c_i64, _c_f32, _c_vp, _c_int = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
+                                         ctypes.c_void_p, ctypes.c_int)
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+_SIGNATURES = {
+    'cgc_version': [],
+    'cgc_last_error': [],
+    'cgc_workspace_bytes': [],
+    'cgc_count_nodes': [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp],
+    'cgc_pad_nodes': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp],
+    'cgc_coo_to_csr_workspace': [_c_i64, _c_i64],
+    'cgc_coo_to_csr': [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_vp,
+                       _c_vp, _c_i64, _c_vp],
+    'cgc_row_inv_degree': [_c_vp, _c_i64, _c_vp, _c_vp],
+    'cgc_edge_renorm': [_c_vp, _c_vp, _c_i64, _c_f32, _c_vp, _c_vp, _c_vp],
+    'cgc_csr_transpose': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    'cgc_spmm': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64,
+                 _c_int, _c_vp],
+    'cgc_sage_gather_mean_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp,
+                                 _c_vp],
+    'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32,
+                              _c_vp, _c_i64, _c_vp],
+    'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
+                    _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp],
+    'cgc_scale_rows_bwd': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp],
+    'cgc_bn_stats': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp,
+                     _c_vp, _c_i64, _c_vp],
+    'cgc_bn_eval_stats': [_c_vp, _c_vp, _c_i32, _c_f32, _c_vp, _c_vp, _c_vp],
+    'cgc_bn_apply': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32,
+                     _c_vp, _c_i64, _c_vp],
+    'cgc_bn_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64,
+                   _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    'cgc_softmax_fwd': [_c_vp, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp],
+    'cgc_softmax_bwd': [_c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp],
+    'cgc_colmax_fwd': [_c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_vp],
+    'cgc_colmax_bwd': [_c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp],
+    'cgc_row_inv_clamped_sum': [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp],
+    'cgc_add_rs_grad': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp],
+    'cgc_dense_renorm_fwd': [_c_vp, _c_i32, _c_i32, _c_f32, _c_vp, _c_vp, _c_vp, _c_vp],
+    'cgc_dense_renorm_bwd': [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_f32, _c_vp, _c_vp, _c_vp],
+    'cgc_gemm': [_c_int, _c_int, _c_i32, _c_i32, _c_i32, _c_f32, _c_vp, _c_i64, _c_i64, _c_vp,
+                 _c_i64, _c_i64, _c_f32, _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp,
+                 _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
+    'cgc_colsum': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp],
+}
+_RESTYPES = {'cgc_last_error': ctypes.c_char_p, 'cgc_workspace_bytes': _c_i64,
+             'cgc_coo_to_csr_workspace': _c_i64}
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+
+class CgcError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the library and attach argtypes; raises if it is missing or a symbol is absent."""
+    if not os.path.isfile(path):
+        raise CgcError('%s not found: build it with `python -c "import __graft_entry__ as g; '
+                       'g.build()"` (or `make -C cgc_net_b200/csrc`). There is no CPU fallback.' % path)
+    lib = ctypes.CDLL(path)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError -> missing export
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, _c_int)
+    return lib
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CgcError('libcgc_sm100 needs CUDA tensors (got a %s tensor); no CPU fallback' % t.device)
+    if dtype is not None and t.dtype != dtype:
+        raise CgcError('expected %s, got %s' % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _mat(t):
+    """(pointer, leading dimension) of a 2-D fp32 tensor whose last dim is contiguous."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise CgcError('expected a row-major 2-D tensor, got shape %s strides %s'
+                       % (tuple(t.shape), t.stride()))
+    return _ptr(t, torch.float32), t.stride(0)
+
+
+def _mask(mask):
+    if mask is None:
+        return None, 0
+    return _ptr(mask.num_nodes, torch.int32), mask.nmax
+
+
+class CudaBackend(object):
+    name = 'libcgc_sm100'
+
+    def __init__(self, path=LIB_PATH):
+        self.lib = load_library(path)
+        self._work = {}
+        self.work_bytes = int(self.lib.cgc_workspace_bytes())
+        self.launches = 0           # C-ABI calls issued (bench.py reports it as gpu_launches)
+        self.gemm_precision = int(os.environ.get('CGC_GEMM_PRECISION', '-1'))
+
+    # -- helpers
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _workspace(self, device):
+        w = self._work.get(device)
+        if w is None:
+            w = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
+            self._work[device] = w
+        return w.data_ptr(), self.work_bytes
+
+    def _check(self, rc, name):
+        self.launches += 1
+        if rc != 0:
+            msg = self.lib.cgc_last_error()
+            raise CgcError('%s failed (%d): %s' % (name, rc, msg.decode() if msg else ''))
+
+    # -- graph construction
+    def count_nodes(self, batch, num_nodes):
+        num_nodes.zero_()
+        self._check(self.lib.cgc_count_nodes(_ptr(batch, torch.int64), batch.numel(), num_nodes.numel(),
+                                             _ptr(num_nodes, torch.int32), self._stream()), 'cgc_count_nodes')
+
+    def pad_nodes(self, x, batch, start, nmax, out):
+        self._check(self.lib.cgc_pad_nodes(_ptr(x, torch.float32), _ptr(batch, torch.int64),
+                                           _ptr(start, torch.int32), x.shape[0], x.shape[1], nmax,
+                                           out.shape[0] // max(nmax, 1), _ptr(out, torch.float32),
+                                           self._stream()), 'cgc_pad_nodes')
+
+    def coo_to_csr_workspace(self, cap, rows):
+        return int(self.lib.cgc_coo_to_csr_workspace(cap, rows))
+
+    def coo_to_csr(self, edge_index, batch, start, num_nodes, nmax, num_graphs, n_total,
+                   add_self_loops, rowptr, col, work):
+        self._check(self.lib.cgc_coo_to_csr(_ptr(edge_index, torch.int64), edge_index.shape[1],
+                                            _ptr(batch, torch.int64), _ptr(start, torch.int32), n_total,
+                                            num_graphs, nmax, int(add_self_loops),
+                                            _ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                            _ptr(work, torch.int32), work.numel(), self._stream()),
+                    'cgc_coo_to_csr')
+
+    def row_inv_degree(self, rowptr, rs):
+        self._check(self.lib.cgc_row_inv_degree(_ptr(rowptr, torch.int32), rs.numel(),
+                                                _ptr(rs, torch.float32), self._stream()), 'cgc_row_inv_degree')
+
+    def edge_renorm(self, rowptr, col, p, val, rs):
+        self._check(self.lib.cgc_edge_renorm(_ptr(rowptr, torch.int32), _ptr(col, torch.int32), rs.numel(),
+                                             float(p), _ptr(val, torch.float32), _ptr(rs, torch.float32),
+                                             self._stream()), 'cgc_edge_renorm')
+
+    def csr_transpose(self, rowptr, col, val, colptr, row, val_t, work):
+        self._check(self.lib.cgc_csr_transpose(_ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                               _ptr(val, torch.float32), rowptr.numel() - 1,
+                                               _ptr(colptr, torch.int32), _ptr(row, torch.int32),
+                                               _ptr(val_t, torch.float32), _ptr(work, torch.int32),
+                                               work.numel(), self._stream()), 'cgc_csr_transpose')
+
+    # -- sparse gather
+    def spmm(self, rowptr, col, val, x, src_scale, row_scale, out, accumulate):
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        self._check(self.lib.cgc_spmm(_ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                      _ptr(val, torch.float32), rowptr.numel() - 1, xp, ldx, x.shape[1],
+                                      _ptr(src_scale, torch.float32), _ptr(row_scale, torch.float32),
+                                      op, ldo, int(accumulate), self._stream()), 'cgc_spmm')
+
+    def sage_gather_mean_fwd(self, rowptr, col, val, row_scale, x, num_graphs, nmax, out):
+        if not (x.is_contiguous() and out.is_contiguous()):
+            raise CgcError('cgc_sage_gather_mean_fwd needs contiguous x / out')
+        self._check(self.lib.cgc_sage_gather_mean_fwd(_ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                                      _ptr(val, torch.float32),
+                                                      _ptr(row_scale, torch.float32),
+                                                      _ptr(x, torch.float32), num_graphs, nmax,
+                                                      x.shape[1], _ptr(out, torch.float32),
+                                                      self._stream()), 'cgc_sage_gather_mean_fwd')
+
+    # -- SAGE epilogue
+    def sage_epilogue_fwd(self, sa, w, b, mask, y):
+        sp, lds = _mat(sa)
+        yp, ldy = _mat(y)
+        nn, nmax = _mask(mask)
+        self._check(self.lib.cgc_sage_epilogue_fwd(sp, lds, _ptr(w.contiguous(), torch.float32),
+                                                   _ptr(b, torch.float32), nn, nmax, sa.shape[0],
+                                                   w.shape[0], w.shape[1], yp, ldy, self._stream()),
+                    'cgc_sage_epilogue_fwd')
+
+    def sage_dh(self, gy, sa, w, b, y, mask, dh):
+        gp, ldg = _mat(gy)
+        sp, lds = _mat(sa)
+        yp, ldy = _mat(y)
+        dp, ldd = _mat(dh)
+        nn, nmax = _mask(mask)
+        self._check(self.lib.cgc_sage_dh(gp, ldg, sp, lds, _ptr(w.contiguous(), torch.float32),
+                                         _ptr(b, torch.float32), yp, ldy, nn, nmax, sa.shape[0],
+                                         w.shape[0], w.shape[1], dp, ldd, self._stream()), 'cgc_sage_dh')
+
+    def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
+        for t in (dsa, sa, ga):
+            if not t.is_contiguous():
+                raise CgcError('cgc_scale_rows_bwd needs contiguous matrices')
+        self._check(self.lib.cgc_scale_rows_bwd(_ptr(dsa, torch.float32), _ptr(sa, torch.float32),
+                                                _ptr(rs, torch.float32), dsa.shape[0], dsa.shape[1],
+                                                _ptr(ga, torch.float32), _ptr(d_rs, torch.float32),
+                                                self._stream()), 'cgc_scale_rows_bwd')
+
+    # -- batch norm
+    def bn_stats(self, y, rmean, rvar, momentum, eps, mean, invstd):
+        yp, ldy = _mat(y)
+        wp, wb = self._workspace(y.device)
+        self._check(self.lib.cgc_bn_stats(yp, ldy, y.shape[0], y.shape[1], _ptr(rmean, torch.float32),
+                                          _ptr(rvar, torch.float32), float(momentum), float(eps),
+                                          _ptr(mean, torch.float32), _ptr(invstd, torch.float32), wp, wb,
+                                          self._stream()), 'cgc_bn_stats')
+
+    def bn_eval_stats(self, rmean, rvar, eps, mean, invstd):
+        self._check(self.lib.cgc_bn_eval_stats(_ptr(rmean, torch.float32), _ptr(rvar, torch.float32),
+                                               rmean.numel(), float(eps), _ptr(mean, torch.float32),
+                                               _ptr(invstd, torch.float32), self._stream()),
+                    'cgc_bn_eval_stats')
+
+    def bn_apply(self, y, mean, invstd, gamma, beta, mask, out):
+        yp, ldy = _mat(y)
+        op, ldo = _mat(out)
+        nn, nmax = _mask(mask)
+        self._check(self.lib.cgc_bn_apply(yp, ldy, _ptr(mean, torch.float32), _ptr(invstd, torch.float32),
+                                          _ptr(gamma, torch.float32), _ptr(beta, torch.float32), nn, nmax,
+                                          y.shape[0], y.shape[1], op, ldo, self._stream()), 'cgc_bn_apply')
+
+    def bn_bwd(self, gx, y, mean, invstd, gamma, mask, training, gy, d_gamma, d_beta):
+        gp, ldg = _mat(gx)
+        yp, ldy = _mat(y)
+        op, ldo = _mat(gy)
+        nn, nmax = _mask(mask)
+        wp, wb = self._workspace(y.device)
+        self._check(self.lib.cgc_bn_bwd(gp, ldg, yp, ldy, _ptr(mean, torch.float32),
+                                        _ptr(invstd, torch.float32), _ptr(gamma, torch.float32), nn, nmax,
+                                        y.shape[0], y.shape[1], int(training), op, ldo,
+                                        _ptr(d_gamma, torch.float32), _ptr(d_beta, torch.float32), wp, wb,
+                                        self._stream()), 'cgc_bn_bwd')
+
+    # -- softmax / readout
+    def softmax_fwd(self, z, mask, s, s_full, arg):
+        nn, nmax = _mask(mask)
+        self._check(self.lib.cgc_softmax_fwd(_ptr(z, torch.float32), z.shape[0], z.shape[1], nn, nmax,
+                                             _ptr(s, torch.float32), _ptr(s_full, torch.float32),
+                                             _ptr(arg, torch.int32), self._stream()), 'cgc_softmax_fwd')
+
+    def softmax_bwd(self, gs, s, gz):
+        self._check(self.lib.cgc_softmax_bwd(_ptr(gs, torch.float32), _ptr(s, torch.float32), s.shape[0],
+                                             s.shape[1], _ptr(gz, torch.float32), self._stream()),
+                    'cgc_softmax_bwd')
+
+    def colmax_fwd(self, x, b, n, out, arg):
+        self._check(self.lib.cgc_colmax_fwd(_ptr(x, torch.float32), b, n, x.shape[1],
+                                            _ptr(out, torch.float32), _ptr(arg, torch.int32),
+                                            self._stream()), 'cgc_colmax_fwd')
+
+    def colmax_bwd(self, g, arg, b, n, gx):
+        self._check(self.lib.cgc_colmax_bwd(_ptr(g, torch.float32), _ptr(arg, torch.int32), b, n,
+                                            g.shape[1], _ptr(gx, torch.float32), self._stream()),
+                    'cgc_colmax_bwd')
+
+    # -- dense adjacency helpers
+    def row_inv_clamped_sum(self, adj, rs, rsum):
+        adj = adj.contiguous()
+        self._check(self.lib.cgc_row_inv_clamped_sum(_ptr(adj, torch.float32), rs.numel(), adj.shape[-1],
+                                                     _ptr(rs, torch.float32), _ptr(rsum, torch.float32),
+                                                     self._stream()), 'cgc_row_inv_clamped_sum')
+
+    def add_rs_grad(self, d_adj, rsum, d_rs):
+        self._check(self.lib.cgc_add_rs_grad(_ptr(d_adj, torch.float32), _ptr(rsum, torch.float32),
+                                             _ptr(d_rs, torch.float32), rsum.numel(), d_adj.shape[-1],
+                                             self._stream()), 'cgc_add_rs_grad')
+
+    def dense_renorm_fwd(self, adj, p, mask, out, rho):
+        nn, _ = _mask(mask)
+        self._check(self.lib.cgc_dense_renorm_fwd(_ptr(adj, torch.float32), adj.shape[0], adj.shape[1],
+                                                  float(p), nn, _ptr(out, torch.float32),
+                                                  _ptr(rho, torch.float32), self._stream()),
+                    'cgc_dense_renorm_fwd')
+
+    def dense_renorm_bwd(self, g, out, rho, p, mask, g_adj):
+        nn, _ = _mask(mask)
+        self._check(self.lib.cgc_dense_renorm_bwd(_ptr(g, torch.float32), _ptr(out, torch.float32),
+                                                  _ptr(rho, torch.float32), g.shape[0], g.shape[1],
+                                                  float(p), nn, _ptr(g_adj, torch.float32),
+                                                  self._stream()), 'cgc_dense_renorm_bwd')
+
+    # -- dense contractions
+    def gemm(self, a, b, c, ta, tb, alpha=1.0, beta=0.0, bias=None, row_scale=None, rowmask=None,
+             precision=None):
+        def geom(t):
+            if t.dim() == 2:
+                if t.shape[1] > 1 and t.stride(1) != 1:
+                    raise CgcError('gemm operand must be row-major')
+                return 1, t.shape[0], t.shape[1], t.stride(0), 0
+            if t.dim() != 3 or (t.shape[2] > 1 and t.stride(2) != 1):
+                raise CgcError('gemm operand must be [batch, rows, cols] row-major')
+            return t.shape[0], t.shape[1], t.shape[2], t.stride(1), t.stride(0)
+        ba, ra, ca, lda, sa_ = geom(a)
+        bb, rb, cb, ldb, sb_ = geom(b)
+        bc, m, n, ldc, sc_ = geom(c)
+        k = ra if ta else ca
+        if (ca if ta else ra) != m or (rb if tb else cb) != n or (cb if tb else rb) != k \
+                or ba != bc or bb != bc:
+            raise CgcError('gemm shape mismatch: a%s b%s c%s ta=%s tb=%s'
+                           % (tuple(a.shape), tuple(b.shape), tuple(c.shape), ta, tb))
+        nn, nmax = _mask(rowmask)
+        wp, wb = self._workspace(c.device)
+        prec = self.gemm_precision if precision is None else precision
+        self._check(self.lib.cgc_gemm(int(ta), int(tb), m, n, k, float(alpha),
+                                      _ptr(a, torch.float32), lda, sa_, _ptr(b, torch.float32), ldb, sb_,
+                                      float(beta), _ptr(c, torch.float32), ldc, sc_, bc,
+                                      _ptr(bias, torch.float32), _ptr(row_scale, torch.float32), nn, nmax,
+                                      prec, wp, wb, self._stream()), 'cgc_gemm')
+
+    def colsum(self, x, mask, out):
+        xp, ldx = _mat(x)
+        nn, nmax = _mask(mask)
+        wp, wb = self._workspace(x.device)
+        self._check(self.lib.cgc_colsum(xp, ldx, x.shape[0], x.shape[1], nn, nmax,
+                                        _ptr(out, torch.float32), wp, wb, self._stream()), 'cgc_colsum')
+
+
+_active = None
+
+
+def get():
+    """The backend of the product path: ``CudaBackend`` (raises if the library is missing)."""
+    global _active
+    if _active is None:
+        _active = CudaBackend()
+    return _active
+
+
+def use_backend_for_testing(backend):
+    """TESTS ONLY: substitute the backend (``None`` restores the CUDA library)."""
+    global _active
+    _active = backend

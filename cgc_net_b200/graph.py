@@ -1,0 +1,125 @@
+"""Host-side graph containers and the synthetic cell-graph generator.
+
+The reference feeds ``SoftPoolingGcnEncoder.forward`` either a PyG ``Batch`` (attributes
+``x``, ``edge_index``, ``batch``, ``y``; ``model/network.py:237-243``) or a dense tuple
+(``network.py:254-256``).  ``Data`` / ``Batch`` below are the minimal attribute bags that
+carry the same fields (``Batch.from_data_list`` follows PyG 1.2.1 ``data/batch.py``:
+tensors concatenated along dim 0, ``edge_index`` along dim 1 with a running node offset,
+``batch`` = graph id per node, sorted).  They additionally carry HOST-side metadata
+(``num_graphs``, ``num_nodes_list``) so the CUDA path needs no device->host sync to size
+its buffers (the reference pays two ``.item()`` syncs, ``model/utils.py:17,21``).
+
+Synthetic inputs follow SURVEY.md section 8(d): nodes uniformly placed in a square,
+k-nearest-neighbour edges including the self loop, ``x ~ N(0, 1)`` (the reference
+z-scores its features, ``dataflow/data.py:353``), labels ``U{0,1,2}``.
+"""
+import torch
+
+
+class Data(object):
+    """One cell graph: ``x [N,F]``, ``edge_index [2,E]`` (int64), ``y [1]``, optional ``pos``."""
+
+    def __init__(self, x=None, edge_index=None, y=None, pos=None, patch_idx=None):
+        self.x, self.edge_index, self.y, self.pos, self.patch_idx = x, edge_index, y, pos, patch_idx
+
+    @property
+    def num_nodes(self):
+        return self.x.shape[0]
+
+
+class Batch(object):
+    """Concatenation of ``Data`` objects (PyG ``Batch`` fields used by network.py:239-240)."""
+
+    def __init__(self, x, edge_index, batch, y=None, num_nodes_list=None):
+        self.x, self.edge_index, self.batch, self.y = x, edge_index, batch, y
+        self.num_nodes_list = None if num_nodes_list is None else [int(n) for n in num_nodes_list]
+
+    @property
+    def num_graphs(self):
+        if self.num_nodes_list is not None:
+            return len(self.num_nodes_list)
+        return int(self.batch[-1]) + 1
+
+    @staticmethod
+    def from_data_list(data_list):
+        xs, eis, bs, ys, counts = [], [], [], [], []
+        offset = 0
+        for g, d in enumerate(data_list):
+            n = d.x.shape[0]
+            xs.append(d.x)
+            eis.append(d.edge_index + offset)
+            bs.append(torch.full((n,), g, dtype=torch.long))
+            if d.y is not None:
+                ys.append(d.y.view(-1))
+            counts.append(n)
+            offset += n
+        y = torch.cat(ys) if ys else None
+        return Batch(torch.cat(xs), torch.cat(eis, dim=1), torch.cat(bs), y, counts)
+
+    def _map(self, fn):
+        y = None if self.y is None else fn(self.y)
+        return Batch(fn(self.x), fn(self.edge_index), fn(self.batch), y, self.num_nodes_list)
+
+    def to(self, device, non_blocking=False):
+        return self._map(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self):
+        return self._map(lambda t: t.pin_memory())
+
+    def nbytes(self):
+        ts = [self.x, self.edge_index, self.batch] + ([] if self.y is None else [self.y])
+        return sum(t.numel() * t.element_size() for t in ts)
+
+
+def knn_edges(pos, k, row_is_centre=True):
+    """k nearest neighbours INCLUDING the node itself, as a COO ``edge_index [2, N*k]``.
+
+    ``row_is_centre=True``: ``edge_index[0]`` = centre, ``edge_index[1]`` = its k nearest, so
+    every adjacency ROW has exactly ``k`` non-zeros (the fixed-degree roofline variant of
+    SURVEY 8(d)).  ``False`` mimics ``radius_graph`` (``dataflow/data.py:348``):
+    ``edge_index[0]`` = neighbour, ``edge_index[1]`` = centre (column degree fixed, row degree varies).
+    """
+    n = pos.shape[0]
+    k = min(k, n)
+    d = torch.cdist(pos, pos)
+    d.fill_diagonal_(-1.0)                       # self first
+    nbr = d.topk(k, dim=1, largest=False).indices   # [N, k]
+    centre = torch.arange(n).view(-1, 1).expand(n, k)
+    if row_is_centre:
+        return torch.stack([centre.reshape(-1), nbr.reshape(-1)])
+    return torch.stack([nbr.reshape(-1), centre.reshape(-1)])
+
+
+def synthetic_cell_graph(num_nodes, degree, feat_dim=16, seed=0, row_is_centre=True, num_classes=3):
+    """One synthetic cell graph; generator seeded with ``1000 + seed``."""
+    g = torch.Generator().manual_seed(1000 + int(seed))
+    pos = torch.rand(num_nodes, 2, generator=g) * 1000.0
+    x = torch.randn(num_nodes, feat_dim, generator=g)
+    y = torch.randint(0, num_classes, (1,), generator=g)
+    return Data(x=x, edge_index=knn_edges(pos, degree, row_is_centre), y=y, pos=pos)
+
+
+def synthetic_batch(num_graphs, num_nodes=1800, degree=8, feat_dim=16, seed=0, row_is_centre=True,
+                    ragged=None):
+    """Batch of synthetic graphs.  ``ragged=(nmin, nmax, dmin, dmax)`` draws size and degree
+    per graph (BASELINE config #5: 500-3000 nodes, degree 5-12)."""
+    g = torch.Generator().manual_seed(77 + int(seed))
+    graphs = []
+    for i in range(num_graphs):
+        n, k = num_nodes, degree
+        if ragged is not None:
+            n = int(torch.randint(ragged[0], ragged[1] + 1, (1,), generator=g))
+            k = int(torch.randint(ragged[2], ragged[3] + 1, (1,), generator=g))
+        graphs.append(synthetic_cell_graph(n, k, feat_dim, seed * 100003 + i, row_is_centre))
+    return graphs
+
+
+def split_by_node_count(data_list, world_size):
+    """Contiguous split with ~equal cumulative node count per rank -- PyG 1.2.1
+    ``DataParallel.scatter`` (``nn/data_parallel.py``; call site train.py:280,285):
+    ``device_id = floor(R * midpoint_cumsum / total)``."""
+    counts = torch.tensor([d.num_nodes for d in data_list], dtype=torch.float64)
+    cum = counts.cumsum(0)
+    mid = (cum - counts / 2.0) * world_size / cum[-1]
+    dev = mid.floor().long().clamp_(max=world_size - 1)
+    return [[d for d, r in zip(data_list, dev.tolist()) if r == rank] for rank in range(world_size)]

@@ -1,0 +1,220 @@
+"""Drop-in ``SoftPoolingGcnEncoder`` for CGC-Net's ``model/network.py`` on B200.
+
+Same public surface as the reference:
+
+* constructor signature of ``SoftPoolingGcnEncoder`` (``model/network.py:128-131``; built at
+  ``train.py:254-261``) and of ``GNN_Module`` (``network.py:58-59``);
+* ``forward(data)`` -> ``(logits, loss)`` in training mode, ``logits`` in eval mode
+  (``network.py:288-291``), for both input formats (PyG-style batch with ``x / edge_index /
+  batch / y`` when ``load_data_sparse``; dense tuple ``(x, adj, num_nodes[, label])`` otherwise,
+  ``network.py:251-256``);
+* parameter / buffer names and shapes (``GCN_embed_1.gcn1.weight [in,out]``,
+  ``...bn1.running_mean``, ``GCN_pool_1.lin.weight``, ``pred_model.0.weight`` ...), so reference
+  checkpoints load with ``load_state_dict`` (``train.py:274``, ``common/utils.py:88-94``);
+* ``assign_matrix`` (softmax ``S`` per pooling stage, detached) when ``collect_assign``
+  (``network.py:141,201-202``, read at ``train.py:71``).
+
+What differs is the execution: every graph operator runs as a hand-written sm_100a kernel
+behind the C-ABI of ``include/cgc_sm100.h`` (see ``ops.py``); the stage-1 adjacency stays
+sparse (CSR/CSC) instead of a dense ``[B, Nmax, Nmax]`` tensor.  The MLP head, cross-entropy,
+dropout and the optimiser remain stock torch modules ("not behind the boundary").
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+EPS = 1e-15
+
+
+class DenseSAGEConv(nn.Module):
+    """Parameter holder with PyG 1.2.1 ``DenseSAGEConv`` names, shapes and init
+    (``weight [in, out]`` and ``bias [out]`` both ``U(-1/sqrt(in), 1/sqrt(in))``; one weight, no
+    root weight).  The arithmetic runs inside ``ops.GnnModuleFunction``."""
+
+    def __init__(self, in_channels, out_channels, normalize=True, bias=True):
+        super(DenseSAGEConv, self).__init__()
+        assert normalize, 'the reference always builds DenseSAGEConv(normalize=True) (network.py:95)'
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.in_channels)
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                self.bias.uniform_(-bound, bound)
+
+
+class GNN_Module(nn.Module):
+    """Three SAGE conv -> ReLU -> BatchNorm1d blocks, concat, optional Linear (network.py:57-125)."""
+
+    def __init__(self, input_dim, hidden_dim, embedding_dim, bias, bn, add_loop, lin=True,
+                 gcn_name='SAGE', sync=False, activation='relu', jk=False):
+        super(GNN_Module, self).__init__()
+        if gcn_name != 'SAGE':
+            raise NotImplementedError('gcn_name=%r: only the SAGE path (network.py:94-95) is built; '
+                                      'DenseGINConv is a SURVEY 8(f) "next" row' % (gcn_name,))
+        if activation != 'relu':
+            raise NotImplementedError('activation=%r: only relu has a CUDA epilogue' % (activation,))
+        if add_loop:
+            raise NotImplementedError('add_loop=True is never used by the reference '
+                                      '(network.py:144,148,157,161,164)')
+        self.jk = jk
+        self.add_loop = add_loop
+        self.gcn1 = DenseSAGEConv(input_dim, hidden_dim, normalize=True, bias=bias)
+        self.gcn2 = DenseSAGEConv(hidden_dim, hidden_dim, normalize=True, bias=bias)
+        self.gcn3 = DenseSAGEConv(hidden_dim, embedding_dim, normalize=True, bias=bias)
+        self.has_bn = bool(bn)
+        if bn:
+            self.bn1 = nn.BatchNorm1d(hidden_dim)
+            self.bn2 = nn.BatchNorm1d(hidden_dim)
+            self.bn3 = nn.BatchNorm1d(embedding_dim)
+        if lin is True:
+            self.lin = nn.Linear(2 * hidden_dim + embedding_dim, embedding_dim)
+        else:
+            self.lin = None
+
+    def forward(self, x, adj, mask=None, graph=None, num_graphs=None, nmax=None, scale=None):
+        """``x [M, Cin]`` in the padded node layout.  Either ``graph`` (``ops.SparseGraph``,
+        stage 1) or a dense ``adj [B, N, N]`` with ``scale = ops.dense_row_scale(adj)``."""
+        params, buffers = [], []
+        for k in (1, 2, 3):
+            conv = getattr(self, 'gcn%d' % k)
+            params += [conv.weight, conv.bias]
+            if self.has_bn:
+                bn = getattr(self, 'bn%d' % k)
+                params += [bn.weight, bn.bias]
+                buffers.append((bn.running_mean, bn.running_var))
+                if self.training:
+                    bn.num_batches_tracked += 1
+            else:
+                params += [None, None]
+        params += [self.lin.weight, self.lin.bias] if self.lin is not None else [None, None]
+        if graph is not None:
+            cfg = ops.GnnConfig(graph=graph, num_graphs=graph.num_graphs, nmax=graph.nmax,
+                                mask=graph.mask, training=self.training, has_bn=self.has_bn,
+                                has_lin=self.lin is not None, bn_buffers=buffers)
+            return ops.GnnModuleFunction.apply(cfg, x, None, graph.rs, None, *params)
+        rs, rsum = scale
+        cfg = ops.GnnConfig(graph=None, num_graphs=num_graphs, nmax=nmax, mask=mask,
+                            training=self.training, has_bn=self.has_bn,
+                            has_lin=self.lin is not None, bn_buffers=buffers)
+        return ops.GnnModuleFunction.apply(cfg, x, adj, rs, rsum, *params)
+
+
+class SoftPoolingGcnEncoder(nn.Module):
+    """CGC-Net's 3-stage DiffPool encoder (network.py:127-291) on hand-written sm_100a kernels."""
+
+    def __init__(self, max_num_nodes, input_dim, hidden_dim, embedding_dim, bias, bn, assign_hidden_dim,
+                 label_dim, assign_ratio=0.25, pred_hidden_dims=[50], concat=True, gcn_name='SAGE',
+                 collect_assign=False, load_data_sparse=False, norm_adj=False,
+                 activation='relu', drop_out=0., jk=False):
+        super(SoftPoolingGcnEncoder, self).__init__()
+        if jk:
+            raise NotImplementedError('jk=True (DenseJK, network.py:11-55) is a SURVEY 8(f) "next" row')
+        self.jk = jk
+        self.drop_out = drop_out
+        self.norm_adj = norm_adj
+        self.load_data_sparse = load_data_sparse
+        self.collect_assign = collect_assign
+        self.assign_matrix = []
+        self.assign_index = []          # argmax(S) per pooling stage (cluster id per node)
+        assign_dim = int(max_num_nodes * assign_ratio)
+        kw = dict(gcn_name=gcn_name, activation=activation, jk=jk)
+        self.GCN_embed_1 = GNN_Module(input_dim, hidden_dim, embedding_dim, bias, bn,
+                                      add_loop=False, lin=False, **kw)
+        self.GCN_pool_1 = GNN_Module(input_dim, assign_hidden_dim, assign_dim, bias, bn,
+                                     add_loop=False, **kw)
+        if concat and not jk:
+            input_dim = hidden_dim * 2 + embedding_dim
+        else:
+            input_dim = embedding_dim
+        assign_dim = int(assign_dim * assign_ratio)
+        self.GCN_embed_2 = GNN_Module(input_dim, hidden_dim, embedding_dim, bias, bn,
+                                      add_loop=False, lin=False, **kw)
+        self.GCN_pool_2 = GNN_Module(input_dim, assign_hidden_dim, assign_dim, bias, bn,
+                                     add_loop=False, **kw)
+        self.GCN_embed_3 = GNN_Module(input_dim, hidden_dim, embedding_dim, bias, bn,
+                                      add_loop=False, lin=False, **kw)
+        pred_input = input_dim * 3
+        self.pred_model = self.build_readout_module(pred_input, pred_hidden_dims, label_dim, activation)
+
+    def build_readout_module(self, pred_input_dim, pred_hidden_dims, label_dim, activation):
+        """MLP head; stays a stock torch module (network.py:220-234)."""
+        if len(pred_hidden_dims) == 0:
+            return nn.Linear(pred_input_dim, label_dim)
+        layers = []
+        for pred_dim in pred_hidden_dims:
+            layers.append(nn.Linear(pred_input_dim, pred_dim))
+            layers.append(nn.ReLU(inplace=True))
+            pred_input_dim = pred_dim
+            if self.drop_out > 0:
+                layers.append(nn.Dropout(self.drop_out))
+        layers.append(nn.Linear(pred_dim, label_dim))
+        return nn.Sequential(*layers)
+
+    # ------------------------------------------------------------------ input handling
+    def _sparse_input(self, data):
+        """network.py:237-243 without the dense adjacency."""
+        counts = getattr(data, 'num_nodes_list', None)
+        xp, graph = ops.build_sparse_graph(data.x, data.edge_index, data.batch, counts, self.norm_adj)
+        return xp, graph, data.y
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, data):
+        self.assign_matrix = []
+        self.assign_index = []
+        readouts = []
+        label = None
+        if self.load_data_sparse:
+            x, graph, label = self._sparse_input(data)
+            b, n, mask = graph.num_graphs, graph.nmax, graph.mask
+            adj = scale = None
+        else:
+            x3, adj, counts = data[0], data[1], data[2]
+            if self.training:
+                label = data[3]
+            b, n = adj.shape[0], adj.shape[1]
+            graph = None
+            num_nodes = torch.as_tensor(counts).to(device=x3.device, dtype=torch.int32)
+            mask = ops.RowMask(num_nodes, n)
+            x = x3.reshape(b * n, -1).contiguous().float()
+            adj = adj.contiguous().float()
+            if self.norm_adj:
+                adj = ops.DenseRenormFunction.apply(adj, ops.RENORM_P, mask)
+            scale = ops.dense_row_scale(adj)
+
+        for stage in (1, 2, 3):
+            embed = getattr(self, 'GCN_embed_%d' % stage)
+            feat = embed(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
+            pooled, _ = ops.ColMaxFunction.apply(feat, b, n)
+            readouts.append(pooled)
+            if stage == 3:
+                break
+            pool = getattr(self, 'GCN_pool_%d' % stage)
+            assign = pool(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
+            cfg = ops.GnnConfig(graph=graph, num_graphs=b, nmax=n, mask=mask)
+            xp, ap, s_full, arg = ops.DiffPoolFunction.apply(cfg, assign, feat, adj, self.collect_assign)
+            if self.collect_assign:
+                self.assign_matrix.append(s_full.view(b, n, -1))
+                self.assign_index.append(arg.view(b, n))
+            n = xp.shape[1]
+            x = xp.reshape(b * n, -1)
+            adj, graph, mask = ap, None, None
+            if self.norm_adj:
+                adj = ops.DenseRenormFunction.apply(adj, ops.RENORM_P, None)
+            scale = ops.dense_row_scale(adj)
+
+        output = self.pred_model(torch.cat(readouts, 1))
+        if self.training:
+            return output, F.cross_entropy(output, label)
+        return output

@@ -1,0 +1,395 @@
+"""Autograd boundary of the CUDA hot path.
+
+Every numerical step here is ONE call into ``libcgc_sm100.so`` through ``_backend`` (the
+C-ABI of ``include/cgc_sm100.h``); torch only allocates buffers and chains the
+``torch.autograd.Function``s.  There is no CPU or eager fallback: ``_backend.get()``
+raises if the library is missing.
+
+Node features live in the PADDED node layout ``[B * Nmax, C]`` (row ``b * Nmax + i`` is
+node ``i`` of graph ``b``): the reference normalises BatchNorm over all ``B * Nmax`` rows
+and max-pools over all ``Nmax`` rows (``model/network.py:101-107,264``), so padded rows are
+part of the arithmetic.  The stage-1 adjacency never becomes dense: it is a CSR (forward)
+plus CSC (backward) pair over the padded rows with int32 indices.
+
+Mapping to the reference:
+
+* ``GnnModuleFunction``   = ``GNN_Module.forward`` (network.py:109-125) with PyG 1.2.1
+  ``DenseSAGEConv.forward`` inlined (gather / mean / W / bias / L2-normalise / mask),
+  ReLU, training-mode ``BatchNorm1d``, concat, optional ``lin``.
+* ``DiffPoolFunction``    = ``_diff_pool`` (network.py:194-208).
+* ``ColMaxFunction``      = ``torch.max(embed_feature, dim=1)`` (network.py:264,275,284).
+* ``DenseRenormFunction`` = ``_re_norm_adj`` on a dense soft adjacency (network.py:183-191).
+* ``build_sparse_graph``  = ``_sparse_to_dense_input`` (network.py:237-243) +
+  ``construct_mask`` (:172-180) + stage-1 ``_re_norm_adj`` folded into edge weights.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _backend
+
+RENORM_P = 0.4       # model/network.py:260,271,280
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+class RowMask(object):
+    """Validity of padded rows: row ``r`` is real iff ``r % nmax < num_nodes[r // nmax]``."""
+
+    def __init__(self, num_nodes, nmax):
+        self.num_nodes, self.nmax = num_nodes, int(nmax)
+
+
+class SparseGraph(object):
+    """Stage-1 adjacency over padded rows: CSR for ``A x``, CSC for ``A^T g``.
+
+    ``val`` / ``val_t`` are the pooling-adjacency weights (``None`` = binary 0/1 adjacency;
+    with ``norm_adj`` the ``_re_norm_adj`` values).  ``rs[i] = 1 / max(rowsum_i, 1)`` is the
+    mean normaliser of DenseSAGEConv (``adj.sum(-1).clamp(min=1)``).
+    """
+
+    def __init__(self):
+        self.num_graphs = self.nmax = self.rows = 0
+        self.num_nodes = None
+        self.rowptr = self.col = self.val = None
+        self.colptr = self.row = self.val_t = None
+        self.rs = None
+        self.mask = None
+
+
+def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False):
+    """COO ``edge_index`` + sorted ``batch`` -> (padded ``x``, ``SparseGraph``).
+
+    Replaces ``to_dense_adj`` (model/utils.py:3-37: ``adj[b, src, dst] = 1``, duplicates
+    collapse) and ``to_dense_batch`` without materialising ``[B, Nmax, Nmax]``.
+    """
+    be = _backend.get()
+    dev = x.device
+    n_total = x.shape[0]
+    if num_nodes_list is not None:
+        num_graphs, nmax = len(num_nodes_list), int(max(num_nodes_list))
+        num_nodes = torch.tensor(num_nodes_list, dtype=torch.int32).to(dev, non_blocking=True)
+    else:                                   # same host syncs as model/utils.py:17,21
+        num_graphs = int(batch[-1].item()) + 1
+        num_nodes = torch.zeros(num_graphs, dtype=torch.int32, device=dev)
+        be.count_nodes(batch, num_nodes)
+        nmax = int(num_nodes.max().item())
+    start = torch.zeros(num_graphs + 1, dtype=torch.int32, device=dev)
+    start[1:] = torch.cumsum(num_nodes, 0)
+    g = SparseGraph()
+    g.num_graphs, g.nmax, g.rows = num_graphs, nmax, num_graphs * nmax
+    g.num_nodes = num_nodes
+    g.mask = RowMask(num_nodes, nmax)
+    rows = g.rows
+    xp = _f32(rows, x.shape[1], device=dev)
+    be.pad_nodes(x.contiguous(), batch, start, nmax, xp)
+
+    n_edges = edge_index.shape[1]
+    cap = n_edges + (n_total if norm_adj else 0)     # renorm forces the diagonal (network.py:188)
+    g.rowptr = torch.empty(rows + 1, dtype=torch.int32, device=dev)
+    g.col = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    work = torch.empty(be.coo_to_csr_workspace(cap, rows), dtype=torch.int32, device=dev)
+    be.coo_to_csr(edge_index.contiguous(), batch, start, num_nodes, nmax, num_graphs, n_total,
+                  bool(norm_adj), g.rowptr, g.col, work)
+    g.rs = _f32(rows, device=dev)
+    if norm_adj:
+        g.val = _f32(max(cap, 1), device=dev)
+        be.edge_renorm(g.rowptr, g.col, RENORM_P, g.val, g.rs)
+    else:
+        be.row_inv_degree(g.rowptr, g.rs)
+    g.colptr = torch.empty(rows + 1, dtype=torch.int32, device=dev)
+    g.row = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    g.val_t = _f32(max(cap, 1), device=dev) if norm_adj else None
+    be.csr_transpose(g.rowptr, g.col, g.val, g.colptr, g.row, g.val_t, work)
+    return xp, g
+
+
+# ----------------------------------------------------------------------------- GNN module
+class GnnConfig(object):
+    """Static description of one ``GNN_Module`` call (not a tensor; passed through autograd)."""
+
+    def __init__(self, graph=None, num_graphs=0, nmax=0, mask=None, training=True, has_bn=True,
+                 has_lin=False, bn_buffers=None, need_adj_grad=False):
+        self.graph = graph              # SparseGraph, or None when the adjacency is dense
+        self.num_graphs, self.nmax = num_graphs, nmax
+        self.mask = mask                # RowMask or None
+        self.training, self.has_bn, self.has_lin = training, has_bn, has_lin
+        self.bn_buffers = bn_buffers    # [(running_mean, running_var)] * 3 (updated in place)
+        self.need_adj_grad = need_adj_grad
+
+
+def _agg(be, cfg, adj, rs, x_prev, out):
+    """Mean-aggregated neighbours ``sa = rs * (A x)`` (DenseSAGEConv: matmul(adj, x) / deg)."""
+    if cfg.graph is not None:
+        g = cfg.graph
+        be.spmm(g.rowptr, g.col, g.val, x_prev, None, rs, out, False)
+    else:
+        b, n = cfg.num_graphs, cfg.nmax
+        be.gemm(adj, _as3d(x_prev, b, n), out.view(b, n, -1), False, False, row_scale=rs)
+
+
+def _agg_t(be, cfg, adj, g_a, src_scale, out, accumulate):
+    """``A^T (src_scale * g)`` into ``out`` (``+=`` when ``accumulate``)."""
+    if cfg.graph is not None:
+        g = cfg.graph
+        be.spmm(g.colptr, g.row, g.val_t, g_a, src_scale, None, out, accumulate)
+    else:
+        b, n = cfg.num_graphs, cfg.nmax
+        be.gemm(adj, g_a.view(b, n, -1), _as3d(out, b, n), True, False,
+                beta=1.0 if accumulate else 0.0)
+
+
+def _as3d(t, b, n):
+    """View a (possibly column-sliced) ``[b*n, c]`` matrix as ``[b, n, c]`` without copying."""
+    return t.as_strided((b, n, t.shape[1]), (n * t.stride(0), t.stride(0), 1), t.storage_offset())
+
+
+class GnnModuleFunction(Function):
+    """``GNN_Module.forward`` (network.py:109-125), forward and hand-written backward.
+
+    Inputs: ``x0 [M, Cin]``; ``adj`` = dense ``[B, N, N]`` adjacency or ``None`` (sparse stage 1);
+    ``rs [M]`` mean normaliser and (dense only) ``rsum [M]`` the raw row sums; then per conv
+    layer ``weight [Cin, Cout]``, ``bias``, ``bn.weight``, ``bn.bias``; finally
+    ``lin.weight [E, Ctot]``, ``lin.bias`` (or ``None``s).
+    Output: ``[M, Ctot]`` concat (``lin=False``) or ``[M, E]``.
+    """
+
+    @staticmethod
+    def forward(ctx, cfg, x0, adj, rs, rsum, *params):
+        be = _backend.get()
+        dev = x0.device
+        m = x0.shape[0]
+        conv = [params[4 * k: 4 * k + 4] for k in range(3)]
+        w_lin, b_lin = params[12], params[13]
+        couts = [c[0].shape[1] for c in conv]
+        ctot = sum(couts)
+        cat = _f32(m, ctot, device=dev)
+        saved = []
+        x_prev, off = x0, 0
+        for k in range(3):
+            w, b, gamma, beta = conv[k]
+            a = _f32(m, w.shape[0], device=dev)          # sa = rs * (A x)
+            _agg(be, cfg, adj, rs, x_prev, a)
+            y = _f32(m, couts[k], device=dev)
+            be.sage_epilogue_fwd(a, w, b, cfg.mask, y)
+            dst = cat[:, off: off + couts[k]]
+            mean = invstd = None
+            if cfg.has_bn:
+                mean = _f32(couts[k], device=dev)
+                invstd = _f32(couts[k], device=dev)
+                rmean, rvar = cfg.bn_buffers[k]
+                if cfg.training:
+                    be.bn_stats(y, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
+                else:
+                    be.bn_eval_stats(rmean, rvar, BN_EPS, mean, invstd)
+            be.bn_apply(y, mean, invstd, gamma if cfg.has_bn else None,
+                        beta if cfg.has_bn else None, cfg.mask, dst)
+            saved += [a, y, mean, invstd]
+            x_prev, off = dst, off + couts[k]
+        if cfg.has_lin:
+            out = _f32(m, w_lin.shape[0], device=dev)
+            be.gemm(cat, w_lin, out, False, True, bias=b_lin, rowmask=cfg.mask)
+        else:
+            out = cat
+        ctx.cfg, ctx.couts = cfg, couts
+        ctx.save_for_backward(x0, adj, rs, rsum, cat, *saved, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        be = _backend.get()
+        cfg, couts = ctx.cfg, ctx.couts
+        t = ctx.saved_tensors
+        x0, adj, rs, rsum, cat = t[0:5]
+        saved, params = t[5:17], t[17:]
+        conv = [params[4 * k: 4 * k + 4] for k in range(3)]
+        w_lin, b_lin = params[12], params[13]
+        dev = g_out.device
+        m = cat.shape[0]
+        g_out = g_out.contiguous()
+        grads = [None] * 14
+        if cfg.has_lin:
+            d_wl = torch.empty_like(w_lin)
+            be.gemm(g_out, cat, d_wl, True, False)            # dY^T X (K = M; padded rows of X are 0)
+            grads[12] = d_wl
+            if b_lin is not None:
+                d_bl = torch.empty_like(b_lin)
+                be.colsum(g_out, cfg.mask, d_bl)
+                grads[13] = d_bl
+            g_cat = _f32(m, cat.shape[1], device=dev)
+            be.gemm(g_out, w_lin, g_cat, False, False, rowmask=cfg.mask)   # (dY * mask) W
+        else:
+            g_cat = g_out.clone()                              # accumulated into below
+        dense = cfg.graph is None
+        want_adj = dense and ctx.needs_input_grad[2]
+        d_adj = torch.empty_like(adj) if want_adj else None
+        d_rs = torch.zeros_like(rs) if dense else None
+        g_x0 = None
+        offs = [0, couts[0], couts[0] + couts[1]]
+        for k in (2, 1, 0):
+            w, b, gamma, beta = conv[k]
+            a, y, mean, invstd = saved[4 * k: 4 * k + 4]
+            gx = g_cat[:, offs[k]: offs[k] + couts[k]]
+            gy = _f32(m, couts[k], device=dev)
+            if cfg.has_bn:
+                d_gamma, d_beta = torch.empty_like(gamma), torch.empty_like(beta)
+                be.bn_bwd(gx, y, mean, invstd, gamma, cfg.mask, cfg.training, gy, d_gamma, d_beta)
+                grads[4 * k + 2], grads[4 * k + 3] = d_gamma, d_beta
+            else:
+                be.bn_apply(gx, None, None, None, None, cfg.mask, gy)     # gy = gx * mask
+            be.sage_dh(gy, a, w, b, y, cfg.mask, gy)            # gy <- dh = dL/d(sa W + b), in place
+            d_w = torch.empty_like(w)
+            be.gemm(a, gy, d_w, True, False)                    # dW = sa^T dh   (K = M)
+            grads[4 * k] = d_w
+            if b is not None:
+                d_b = torch.empty_like(b)
+                be.colsum(gy, None, d_b)
+                grads[4 * k + 1] = d_b
+            dsa = _f32(m, w.shape[0], device=dev)
+            be.gemm(gy, w, dsa, False, True)                    # dsa = dh W^T
+            x_prev = x0 if k == 0 else cat[:, offs[k - 1]: offs[k - 1] + couts[k - 1]]
+            if dense:
+                ga = _f32(m, w.shape[0], device=dev)
+                be.scale_rows_bwd(dsa, a, rs, ga, d_rs)         # ga = rs*dsa ; d_rs += dsa.sa/rs
+                src_scale = None
+            else:
+                ga, src_scale = dsa, rs                         # rs applied inside the CSC gather
+            if want_adj:
+                b_, n_ = cfg.num_graphs, cfg.nmax
+                be.gemm(ga.view(b_, n_, -1), _as3d(x_prev, b_, n_), d_adj, False, True,
+                        beta=0.0 if k == 2 else 1.0)           # dA += gA x^T
+            if k > 0:
+                _agg_t(be, cfg, adj, ga, src_scale,
+                       g_cat[:, offs[k - 1]: offs[k - 1] + couts[k - 1]], True)
+            elif ctx.needs_input_grad[1]:
+                g_x0 = _f32(m, x0.shape[1], device=dev)
+                _agg_t(be, cfg, adj, ga, src_scale, g_x0, False)
+        if want_adj:
+            # rs_i = 1 / clamp(rsum_i, 1)  ->  dA_ij += -[rsum_i >= 1] d_rs_i / rsum_i^2   (all j)
+            be.add_rs_grad(d_adj, rsum, d_rs)
+        return (None, g_x0, d_adj, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------- diff-pool
+class DiffPoolFunction(Function):
+    """``_diff_pool`` (network.py:194-208): ``S = softmax(Z) * mask``; ``X' = S^T X``; ``A' = S^T (A S)``.
+
+    Returns ``(X' [B,C,F], A' [B,C,C], S_full or None, argmax or None)``; the last two are the
+    un-masked softmax (``collect_assign``, network.py:201-202) and the cluster index per node.
+    """
+
+    @staticmethod
+    def forward(ctx, cfg, z, x, adj, collect):
+        be = _backend.get()
+        dev = z.device
+        m, c = z.shape
+        b, n = cfg.num_graphs, cfg.nmax
+        s = _f32(m, c, device=dev)
+        s_full = _f32(m, c, device=dev) if collect else None
+        arg = torch.empty(m, dtype=torch.int32, device=dev) if collect else None
+        be.softmax_fwd(z.contiguous(), cfg.mask, s, s_full, arg)
+        x = x.contiguous()
+        xp = _f32(b, c, x.shape[1], device=dev)
+        be.gemm(s.view(b, n, c), x.view(b, n, -1), xp, True, False)
+        p = _f32(m, c, device=dev)
+        if cfg.graph is not None:
+            g = cfg.graph
+            be.spmm(g.rowptr, g.col, g.val, s, None, None, p, False)
+        else:
+            be.gemm(adj, s.view(b, n, c), p.view(b, n, c), False, False)
+        ap = _f32(b, c, c, device=dev)
+        be.gemm(s.view(b, n, c), p.view(b, n, c), ap, True, False)
+        ctx.cfg, ctx.s, ctx.p, ctx.x, ctx.adj = cfg, s, p, x, adj
+        ctx.want_adj = adj is not None and ctx.needs_input_grad[3]
+        outs = (xp, ap, s_full, arg)
+        ctx.mark_non_differentiable(*[t for t in (s_full, arg) if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_xp, g_ap, _gs_full, _garg):
+        be = _backend.get()
+        cfg, s, p, x, adj = ctx.cfg, ctx.s, ctx.p, ctx.x, ctx.adj
+        dev = s.device
+        m, c = s.shape
+        b, n = cfg.num_graphs, cfg.nmax
+        g_ap = g_ap.contiguous() if g_ap is not None else torch.zeros(b, c, c, device=dev)
+        g_xp = g_xp.contiguous() if g_xp is not None else torch.zeros(b, c, x.shape[1], device=dev)
+        g_s = _f32(m, c, device=dev)
+        be.gemm(p.view(b, n, c), g_ap, g_s.view(b, n, c), False, True)                 # P gA'^T
+        be.gemm(x.view(b, n, -1), g_xp, g_s.view(b, n, c), False, True, beta=1.0)      # + X gX'^T
+        g_p = _f32(m, c, device=dev)
+        be.gemm(s.view(b, n, c), g_ap, g_p.view(b, n, c), False, False)                # S gA'
+        g_adj = None
+        if cfg.graph is not None:
+            g = cfg.graph
+            be.spmm(g.colptr, g.row, g.val_t, g_p, None, None, g_s, True)                          # + A^T gP
+        else:
+            be.gemm(adj, g_p.view(b, n, c), g_s.view(b, n, c), True, False, beta=1.0)
+            if ctx.want_adj:
+                g_adj = torch.empty_like(adj)
+                be.gemm(g_p.view(b, n, c), s.view(b, n, c), g_adj, False, True)        # gP S^T
+        g_x = _f32(m, x.shape[1], device=dev)
+        be.gemm(s.view(b, n, c), g_xp, g_x.view(b, n, -1), False, False)               # S gX'
+        g_z = _f32(m, c, device=dev)
+        be.softmax_bwd(g_s, s, g_z)
+        return None, g_z, g_x, g_adj, None
+
+
+# ----------------------------------------------------------------------------- readout
+class ColMaxFunction(Function):
+    """Per-graph channel max over ALL ``Nmax`` rows, padded zero rows included (network.py:264)."""
+
+    @staticmethod
+    def forward(ctx, x, num_graphs, nmax):
+        be = _backend.get()
+        x = x.contiguous()
+        out = _f32(num_graphs, x.shape[1], device=x.device)
+        arg = torch.empty(num_graphs, x.shape[1], dtype=torch.int32, device=x.device)
+        be.colmax_fwd(x, num_graphs, nmax, out, arg)
+        ctx.arg, ctx.dims = arg, (num_graphs, nmax, x.shape[1])
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, g, _garg):
+        be = _backend.get()
+        b, n, c = ctx.dims
+        gx = torch.zeros(b * n, c, dtype=torch.float32, device=g.device)
+        be.colmax_bwd(g.contiguous(), ctx.arg, b, n, gx)
+        return gx, None, None
+
+
+# ----------------------------------------------------------------------------- dense re-norm
+class DenseRenormFunction(Function):
+    """``_re_norm_adj(adj, p, mask)`` on a dense adjacency (network.py:183-191)."""
+
+    @staticmethod
+    def forward(ctx, adj, p, mask):
+        be = _backend.get()
+        adj = adj.contiguous()
+        out = torch.empty_like(adj)
+        rho = _f32(adj.shape[0] * adj.shape[1], device=adj.device)   # off-diagonal row sums + EPS
+        be.dense_renorm_fwd(adj, p, mask, out, rho)
+        ctx.p, ctx.mask, ctx.out, ctx.rho = p, mask, out, rho
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        be = _backend.get()
+        g_adj = torch.empty_like(ctx.out)
+        be.dense_renorm_bwd(g.contiguous(), ctx.out, ctx.rho, ctx.p, ctx.mask, g_adj)
+        return g_adj, None, None
+
+
+def dense_row_scale(adj):
+    """``rsum = adj.sum(-1)`` and ``rs = 1 / clamp(rsum, min=1)`` of DenseSAGEConv on a dense
+    adjacency.  Not an autograd node: its gradient w.r.t. ``adj`` is folded into
+    ``GnnModuleFunction.backward`` (``add_rs_grad``)."""
+    be = _backend.get()
+    rows = adj.shape[0] * adj.shape[1]
+    rs, rsum = _f32(rows, device=adj.device), _f32(rows, device=adj.device)
+    be.row_inv_clamped_sum(adj.detach(), rs, rsum)
+    return rs, rsum

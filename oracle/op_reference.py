@@ -1,0 +1,263 @@
+"""Per-operator CPU formulas for every C-ABI entry point.  TEST INFRASTRUCTURE.
+
+``TorchBackend`` exposes the same method names and argument order as
+``cgc_net_b200._backend.CudaBackend`` (one method per ``extern "C"`` function of
+``include/cgc_sm100.h``) and computes each operator -- forward AND the hand-derived backward
+ -- with plain torch ops on the tensors it is given, writing results
+into the caller-allocated outputs exactly like the library does.
+
+Used two ways, both from ``tests/`` only:
+* injected with ``_backend.use_backend_for_testing`` so the autograd wiring in
+  ``cgc_net_b200/ops.py`` can be checked against the dense oracle on a CPU-only host;
+* as the op-level checker for each CUDA kernel in the ``-m gpu`` tests.
+
+It is never reachable from the product path.
+"""
+import torch
+
+L2_EPS = 1e-12          # F.normalize eps (torch 1.1 semantics)
+RENORM_EPS = 1e-15      # model/network.py:8
+
+
+def _valid_rows(mask, rows, device):
+    """[rows] bool: row r is a real node (``r % nmax < num_nodes[r // nmax]``)."""
+    if mask is None:
+        return torch.ones(rows, dtype=torch.bool, device=device)
+    r = torch.arange(rows, device=device)
+    return (r % mask.nmax) < mask.num_nodes.to(device).long()[r // mask.nmax]
+
+
+class TorchBackend(object):
+    name = 'torch-op-reference'
+
+    # ---------------------------------------------------------------- graph construction
+    def count_nodes(self, batch, num_nodes):
+        num_nodes.zero_()
+        num_nodes.index_add_(0, batch, torch.ones_like(batch, dtype=torch.int32))
+
+    def pad_nodes(self, x, batch, start, nmax, out):
+        out.zero_()
+        slot = torch.arange(batch.numel(), device=x.device) - start.long()[batch] + batch * nmax
+        out[slot] = x
+
+    def coo_to_csr_workspace(self, cap, rows):
+        return 1
+
+    def coo_to_csr(self, edge_index, batch, start, num_nodes, nmax, num_graphs, n_total,
+                   add_self_loops, rowptr, col, work):
+        # adj[batch[src], src - cum[batch[src]], dst - cum[batch[dst]]] = 1  (model/utils.py:29-33)
+        src, dst = edge_index[0], edge_index[1]
+        st = start.long()
+        g = batch[src]
+        r = g * nmax + (src - st[g])
+        c = g * nmax + (dst - st[batch[dst]])
+        if add_self_loops:
+            node = torch.arange(n_total, device=src.device)
+            d = batch * nmax + (node - st[batch])
+            r, c = torch.cat([r, d]), torch.cat([c, d])
+        rows = num_graphs * nmax
+        key = torch.unique(r * rows + c)               # sorted, duplicates collapsed
+        rr, cc = key // rows, key % rows
+        counts = torch.zeros(rows, dtype=torch.long, device=src.device).index_add_(
+            0, rr, torch.ones_like(rr))
+        rowptr[0] = 0
+        rowptr[1:] = counts.cumsum(0).to(torch.int32)
+        col[:cc.numel()] = cc.to(torch.int32)
+
+    def row_inv_degree(self, rowptr, rs):
+        deg = (rowptr[1:] - rowptr[:-1]).float()
+        rs.copy_(1.0 / deg.clamp(min=1))
+
+    def edge_renorm(self, rowptr, col, p, val, rs):
+        # _re_norm_adj (network.py:183-191) on the stored entries: diag := p,
+        # off-diag := 1 / (offdiag_degree + EPS) * (1 - p);  rs = 1 / clamp(rowsum, 1)
+        rows = rowptr.numel() - 1
+        nnz = int(rowptr[-1])
+        deg = (rowptr[1:] - rowptr[:-1]).long()
+        row_of = torch.repeat_interleave(torch.arange(rows, device=col.device), deg)
+        c = col[:nnz].long()
+        is_diag = c == row_of
+        off = torch.zeros(rows, device=col.device).index_add_(0, row_of, (~is_diag).float())
+        v = torch.where(is_diag, torch.full_like(off[row_of], p),
+                        (1.0 / (off[row_of] + RENORM_EPS)) * (1 - p))
+        val[:nnz] = v
+        rsum = torch.zeros(rows, device=col.device).index_add_(0, row_of, v)
+        rs.copy_(1.0 / rsum.clamp(min=1))
+
+    def csr_transpose(self, rowptr, col, val, colptr, row, val_t, work):
+        rows = rowptr.numel() - 1
+        nnz = int(rowptr[-1])
+        deg = (rowptr[1:] - rowptr[:-1]).long()
+        row_of = torch.repeat_interleave(torch.arange(rows, device=col.device), deg)
+        c = col[:nnz].long()
+        order = torch.argsort(c * rows + row_of)
+        counts = torch.zeros(rows, dtype=torch.long, device=col.device).index_add_(
+            0, c, torch.ones_like(c))
+        colptr[0] = 0
+        colptr[1:] = counts.cumsum(0).to(torch.int32)
+        row[:nnz] = row_of[order].to(torch.int32)
+        if val is not None:
+            val_t[:nnz] = val[:nnz][order]
+
+    # ---------------------------------------------------------------- sparse gather
+    def spmm(self, rowptr, col, val, x, src_scale, row_scale, out, accumulate):
+        rows = rowptr.numel() - 1
+        nnz = int(rowptr[-1])
+        deg = (rowptr[1:] - rowptr[:-1]).long()
+        row_of = torch.repeat_interleave(torch.arange(rows, device=col.device), deg)
+        c = col[:nnz].long()
+        src = x[c]
+        if src_scale is not None:
+            src = src * src_scale[c][:, None]
+        if val is not None:
+            src = src * val[:nnz, None]
+        res = torch.zeros(rows, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, row_of, src)
+        if row_scale is not None:
+            res = res * row_scale[:, None]
+        if accumulate:
+            out += res
+        else:
+            out.copy_(res)
+
+    def sage_gather_mean_fwd(self, rowptr, col, val, row_scale, x, num_graphs, nmax, out):
+        if val is None and row_scale is None:
+            deg = (rowptr[1:] - rowptr[:-1]).float()
+            row_scale = 1.0 / deg.clamp(min=1)
+        self.spmm(rowptr, col, val, x, None, row_scale, out, False)
+
+    # ---------------------------------------------------------------- SAGE epilogue
+    def _epilogue(self, sa, w, b, mask):
+        h = sa @ w
+        if b is not None:
+            h = h + b
+        nrm = h.norm(dim=1, keepdim=True)
+        inv = 1.0 / nrm.clamp(min=L2_EPS)
+        valid = _valid_rows(mask, sa.shape[0], sa.device)[:, None].float()
+        return h, nrm, inv, valid
+
+    def sage_epilogue_fwd(self, sa, w, b, mask, y):
+        h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
+        y.copy_(torch.relu(h * inv * valid))
+
+    def sage_dh(self, gy, sa, w, b, y, mask, dh):
+        h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
+        hn = h * inv
+        gm = gy * (y > 0).float() * valid                # ReLU (output sign) and row mask
+        dot = (gm * hn).sum(1, keepdim=True)
+        # y = h / max(|h|, eps): d/dh = (g - hn (hn . g)) / |h|   when |h| >= eps, g / eps otherwise
+        dh.copy_(torch.where(nrm >= L2_EPS, (gm - hn * dot) * inv, gm * inv))
+
+    def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
+        ga.copy_(dsa * rs[:, None])
+        d_rs += (dsa * sa).sum(1) / rs
+
+    # ---------------------------------------------------------------- batch norm
+    def bn_stats(self, y, rmean, rvar, momentum, eps, mean, invstd):
+        m = y.shape[0]
+        mu = y.mean(0)
+        var = y.var(0, unbiased=False)
+        mean.copy_(mu)
+        invstd.copy_(torch.rsqrt(var + eps))
+        rmean.mul_(1 - momentum).add_(momentum * mu)
+        rvar.mul_(1 - momentum).add_(momentum * var * (m / max(m - 1, 1)))
+
+    def bn_eval_stats(self, rmean, rvar, eps, mean, invstd):
+        mean.copy_(rmean)
+        invstd.copy_(torch.rsqrt(rvar + eps))
+
+    def bn_apply(self, y, mean, invstd, gamma, beta, mask, out):
+        valid = _valid_rows(mask, y.shape[0], y.device)[:, None].float()
+        if mean is None:
+            out.copy_(y * valid)
+        else:
+            out.copy_(((y - mean) * invstd * gamma + beta) * valid)
+
+    def bn_bwd(self, gx, y, mean, invstd, gamma, mask, training, gy, d_gamma, d_beta):
+        m = y.shape[0]
+        valid = _valid_rows(mask, m, y.device)[:, None].float()
+        g = gx * valid
+        xhat = (y - mean) * invstd
+        dg, db = (g * xhat).sum(0), g.sum(0)
+        d_gamma.copy_(dg)
+        d_beta.copy_(db)
+        if training:
+            gy.copy_(gamma * invstd * (g - db / m - xhat * dg / m))
+        else:
+            gy.copy_(gamma * invstd * g)
+
+    # ---------------------------------------------------------------- softmax / readout
+    def softmax_fwd(self, z, mask, s, s_full, arg):
+        p = torch.softmax(z, dim=1)
+        valid = _valid_rows(mask, z.shape[0], z.device)[:, None].float()
+        s.copy_(p * valid)
+        if s_full is not None:
+            s_full.copy_(p)
+        if arg is not None:
+            arg.copy_(z.argmax(dim=1).to(torch.int32))
+
+    def softmax_bwd(self, gs, s, gz):
+        gz.copy_(s * (gs - (gs * s).sum(1, keepdim=True)))
+
+    def colmax_fwd(self, x, b, n, out, arg):
+        v, i = x.view(b, n, -1).max(dim=1)
+        out.copy_(v)
+        arg.copy_(i.to(torch.int32))
+
+    def colmax_bwd(self, g, arg, b, n, gx):
+        gx.view(b, n, -1).scatter_add_(1, arg.long().unsqueeze(1), g.unsqueeze(1))
+
+    # ---------------------------------------------------------------- dense adjacency helpers
+    def row_inv_clamped_sum(self, adj, rs, rsum):
+        r = adj.sum(-1).reshape(-1)
+        rsum.copy_(r)
+        rs.copy_(1.0 / r.clamp(min=1))
+
+    def add_rs_grad(self, d_adj, rsum, d_rs):
+        v = torch.where(rsum >= 1, -d_rs / (rsum * rsum), torch.zeros_like(rsum))
+        d_adj += v.view(d_adj.shape[0], d_adj.shape[1], 1)
+
+    def dense_renorm_fwd(self, adj, p, mask, out, rho):
+        b, n, _ = adj.shape
+        eye = torch.eye(n, dtype=torch.bool, device=adj.device)
+        a0 = adj.masked_fill(eye, 0.0)
+        r = a0.sum(-1, keepdim=True) + RENORM_EPS
+        o = a0 / r * (1 - p)
+        o = o.masked_fill(eye, p)
+        valid = _valid_rows(mask, b * n, adj.device).view(b, n, 1).float()
+        out.copy_(o * valid)
+        rho.copy_(r.reshape(-1))
+
+    def dense_renorm_bwd(self, g, out, rho, p, mask, g_adj):
+        # N_ij = (1-p) A_ij / rho_i (i != j); diag constant.  dA_ij = (1-p)/rho_i (g_ij - sum_k g_ik N_ik/(1-p))
+        b, n, _ = g.shape
+        eye = torch.eye(n, dtype=torch.bool, device=g.device)
+        valid = _valid_rows(mask, b * n, g.device).view(b, n, 1).float()
+        gm = (g * valid).masked_fill(eye, 0.0)
+        nn_ = out.masked_fill(eye, 0.0)              # masked rows are already 0
+        # for masked-out rows `out` is 0 but the un-masked N is needed only where gm != 0 (valid rows)
+        dot = (gm * nn_).sum(-1, keepdim=True) / (1 - p)
+        ga = (1 - p) / rho.view(b, n, 1) * (gm - dot)
+        g_adj.copy_(ga.masked_fill(eye, 0.0))
+
+    # ---------------------------------------------------------------- dense contractions
+    def gemm(self, a, b, c, ta, tb, alpha=1.0, beta=0.0, bias=None, row_scale=None, rowmask=None,
+             precision=-1):
+        aa = a.transpose(-1, -2) if ta else a
+        bb = b.transpose(-1, -2) if tb else b
+        r = alpha * (aa @ bb)
+        if bias is not None:
+            r = r + bias
+        if row_scale is not None:
+            r = r * row_scale.view(*r.shape[:-1], 1)
+        if rowmask is not None:
+            rows = r.shape[-2] if r.dim() == 2 else r.shape[0] * r.shape[1]
+            valid = _valid_rows(rowmask, rows, r.device).float()
+            r = r * valid.view(*r.shape[:-1], 1)
+        if beta != 0.0:
+            c.mul_(beta).add_(r)
+        else:
+            c.copy_(r)
+
+    def colsum(self, x, mask, out):
+        valid = _valid_rows(mask, x.shape[0], x.device)[:, None].float()
+        out.copy_((x * valid).sum(0))
