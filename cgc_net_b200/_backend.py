@@ -20,19 +20,21 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libcgc_sm100.so')
 
 _c_i32, _c_i64, _c_f32, _c_vp, _c_int = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
                                          ctypes.c_void_p, ctypes.c_int)
+_c_f64 = ctypes.c_double
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
     'cgc_version': [],
     'cgc_last_error': [],
     'cgc_workspace_bytes': [],
+    'cgc_launch_count': [],
     'cgc_count_nodes': [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp],
     'cgc_pad_nodes': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp],
     'cgc_coo_to_csr_workspace': [_c_i64, _c_i64],
     'cgc_coo_to_csr': [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_vp,
                        _c_vp, _c_i64, _c_vp],
     'cgc_row_inv_degree': [_c_vp, _c_i64, _c_vp, _c_vp],
-    'cgc_edge_renorm': [_c_vp, _c_vp, _c_i64, _c_f32, _c_vp, _c_vp, _c_vp],
+    'cgc_edge_renorm': [_c_vp, _c_vp, _c_i64, _c_f64, _c_vp, _c_vp, _c_vp],
     'cgc_csr_transpose': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_spmm': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64,
                  _c_int, _c_vp],
@@ -56,14 +58,14 @@ _SIGNATURES = {
     'cgc_colmax_bwd': [_c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp],
     'cgc_row_inv_clamped_sum': [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp],
     'cgc_add_rs_grad': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp],
-    'cgc_dense_renorm_fwd': [_c_vp, _c_i32, _c_i32, _c_f32, _c_vp, _c_vp, _c_vp, _c_vp],
-    'cgc_dense_renorm_bwd': [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_f32, _c_vp, _c_vp, _c_vp],
+    'cgc_dense_renorm_fwd': [_c_vp, _c_i32, _c_i32, _c_f64, _c_vp, _c_vp, _c_vp, _c_vp],
+    'cgc_dense_renorm_bwd': [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_f64, _c_vp, _c_vp, _c_vp],
     'cgc_gemm': [_c_int, _c_int, _c_i32, _c_i32, _c_i32, _c_f32, _c_vp, _c_i64, _c_i64, _c_vp,
                  _c_i64, _c_i64, _c_f32, _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp,
                  _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_colsum': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp],
 }
-_RESTYPES = {'cgc_last_error': ctypes.c_char_p, 'cgc_workspace_bytes': _c_i64,
+_RESTYPES = {'cgc_last_error': ctypes.c_char_p, 'cgc_workspace_bytes': _c_i64, 'cgc_launch_count': _c_i64,
              'cgc_coo_to_csr_workspace': _c_i64}
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
@@ -118,6 +120,10 @@ class CudaBackend(object):
         self.work_bytes = int(self.lib.cgc_workspace_bytes())
         self.launches = 0           # C-ABI calls issued (bench.py reports it as gpu_launches)
         self.gemm_precision = int(os.environ.get('CGC_GEMM_PRECISION', '-1'))
+
+    def kernel_launches(self):
+        """CUDA kernels launched by the library so far (process-wide)."""
+        return int(self.lib.cgc_launch_count())
 
     # -- helpers
     def _stream(self):

@@ -1,0 +1,308 @@
+// Column-wise operators: BatchNorm1d over all padded rows (reference GNN_Module.bn,
+// model/network.py:101-107), bias gradients (column sums) and the max read-out (network.py:264).
+// Column reductions are two-phase and deterministic: per-CTA partials in the workspace, then a
+// fixed-order finalize in double precision.
+#include "common.cuh"
+
+namespace cgc {
+
+constexpr int kRedX = 32, kRedY = 8;
+enum { RED_STATS = 0, RED_BN_BWD = 1, RED_COLSUM = 2 };
+
+// partial[(rb * 2 + which) * c + col]
+template <int MODE>
+__global__ void __launch_bounds__(kRedX* kRedY)
+k_colreduce(const float* __restrict__ a, int64_t lda, const float* __restrict__ y, int64_t ldy,
+            const float* __restrict__ mean, const float* __restrict__ invstd,
+            const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c, int64_t rows_per_block,
+            float* __restrict__ partial) {
+  __shared__ float s1[kRedY][kRedX], s2[kRedY][kRedX];
+  const int col = blockIdx.x * kRedX + threadIdx.x;
+  const int64_t rb = blockIdx.y;
+  const int64_t r_begin = rb * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  float acc1 = 0.f, acc2 = 0.f;
+  if (col < c) {
+    float mu = 0.f, is = 1.f;
+    if (MODE == RED_BN_BWD) { mu = mean[col]; is = invstd[col]; }
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += kRedY) {
+      if (MODE == RED_STATS) {
+        float v = __ldg(a + r * lda + col);
+        acc1 += v;
+        acc2 = fmaf(v, v, acc2);
+      } else {
+        if (!row_valid(num_nodes, nmax, r)) continue;
+        float g = __ldg(a + r * lda + col);
+        acc1 += g;
+        if (MODE == RED_BN_BWD) acc2 = fmaf(g, (__ldg(y + r * ldy + col) - mu) * is, acc2);
+      }
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = acc1;
+  s2[threadIdx.y][threadIdx.x] = acc2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < c) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRedY; ++i) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+    partial[(rb * 2 + 0) * c + col] = t1;
+    partial[(rb * 2 + 1) * c + col] = t2;
+  }
+}
+
+__global__ void k_bn_finalize(const float* __restrict__ partial, int nrb, int c, int64_t rows,
+                              float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                              float eps, float* __restrict__ mean, float* __restrict__ invstd) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= c) return;
+  double t1 = 0.0, t2 = 0.0;
+  for (int rb = 0; rb < nrb; ++rb) {
+    t1 += (double)partial[(rb * 2 + 0) * (int64_t)c + col];
+    t2 += (double)partial[(rb * 2 + 1) * (int64_t)c + col];
+  }
+  double mu = t1 / (double)rows;
+  double var = t2 / (double)rows - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[col] = (float)mu;
+  invstd[col] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)mu;
+  if (running_var) {
+    double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_var[col] = (1.0f - momentum) * running_var[col] + momentum * (float)unbiased;
+  }
+}
+
+// out1[col] = sum partial[., 0, col]; out2[col] = sum partial[., 1, col]   (out2 nullable)
+__global__ void k_sum_finalize(const float* __restrict__ partial, int nrb, int c, float* __restrict__ out1,
+                               float* __restrict__ out2) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= c) return;
+  double t1 = 0.0, t2 = 0.0;
+  for (int rb = 0; rb < nrb; ++rb) {
+    t1 += (double)partial[(rb * 2 + 0) * (int64_t)c + col];
+    t2 += (double)partial[(rb * 2 + 1) * (int64_t)c + col];
+  }
+  out1[col] = (float)t1;
+  if (out2) out2[col] = (float)t2;
+}
+
+__global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __restrict__ rv, int c, float eps,
+                                float* __restrict__ mean, float* __restrict__ invstd) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= c) return;
+  mean[col] = rm[col];
+  invstd[col] = 1.0f / sqrtf(rv[col] + eps);
+}
+
+// out = mask * ((y - mean) * invstd * gamma + beta)      (mean == nullptr: out = mask * y)
+__global__ void __launch_bounds__(256)
+k_bn_apply(const float* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+           const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+           const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c, float* __restrict__ out,
+           int64_t ldo) {
+  const int64_t total = rows * c;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / c;
+    const int col = (int)(idx - r * c);
+    float v = 0.f;
+    if (row_valid(num_nodes, nmax, r)) {
+      v = y[r * ldy + col];
+      if (mean != nullptr) v = (v - mean[col]) * invstd[col] * gamma[col] + beta[col];
+    }
+    out[r * ldo + col] = v;
+  }
+}
+
+// gy = gamma*invstd*(g - d_beta/rows - xhat*d_gamma/rows)   (training) | gamma*invstd*g   (eval)
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const float* __restrict__ gx, int64_t ldgx, const float* __restrict__ y, int64_t ldy,
+               const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+               const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
+               const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c, int training,
+               float* __restrict__ gy, int64_t ldgy) {
+  const int64_t total = rows * c;
+  const float inv_rows = 1.0f / (float)rows;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / c;
+    const int col = (int)(idx - r * c);
+    const float g = row_valid(num_nodes, nmax, r) ? gx[r * ldgx + col] : 0.f;
+    const float is = invstd[col];
+    float v;
+    if (training) {
+      const float xhat = (y[r * ldy + col] - mean[col]) * is;
+      v = gamma[col] * is * (g - d_beta[col] * inv_rows - xhat * d_gamma[col] * inv_rows);
+    } else {
+      v = gamma[col] * is * g;
+    }
+    gy[r * ldgy + col] = v;
+  }
+}
+
+// torch.max(x.view(B, nmax, c), dim=1): first maximal row wins ties
+__global__ void __launch_bounds__(kRedX* kRedY)
+k_colmax_fwd(const float* __restrict__ x, int nmax, int c, float* __restrict__ out, int32_t* __restrict__ arg) {
+  __shared__ float sv[kRedY][kRedX];
+  __shared__ int si[kRedY][kRedX];
+  const int col = blockIdx.x * kRedX + threadIdx.x;
+  const int g = blockIdx.y;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  if (col < c) {
+    const float* base = x + (int64_t)g * nmax * c + col;
+    for (int r = threadIdx.y; r < nmax; r += kRedY) {
+      float v = __ldg(base + (int64_t)r * c);
+      if (v > best) { best = v; bi = r; }
+    }
+  }
+  sv[threadIdx.y][threadIdx.x] = best;
+  si[threadIdx.y][threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < c) {
+#pragma unroll
+    for (int i = 1; i < kRedY; ++i) {
+      float v = sv[i][threadIdx.x];
+      int ii = si[i][threadIdx.x];
+      if (v > best || (v == best && ii < bi)) { best = v; bi = ii; }
+    }
+    out[(int64_t)g * c + col] = best;
+    arg[(int64_t)g * c + col] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+__global__ void k_colmax_bwd(const float* __restrict__ g, const int32_t* __restrict__ arg, int num_graphs,
+                             int nmax, int c, float* __restrict__ gx) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)num_graphs * c) return;
+  int64_t gi = idx / c;
+  int col = (int)(idx - gi * c);
+  gx[(gi * nmax + arg[idx]) * c + col] += g[idx];
+}
+
+// ---------------------------------------------------------------------------------------------
+static void reduce_geometry(int64_t rows, int c, int& nrb, int64_t& rows_per_block, dim3& grid) {
+  int colblocks = (int)ceil_div(c, kRedX);
+  int64_t want = ceil_div((int64_t)kNumSMs * 8, colblocks);
+  int64_t max_by_rows = ceil_div(rows, kRedY * 4);      // at least ~4 rows per thread
+  if (want > max_by_rows) want = max_by_rows;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  rows_per_block = ceil_div(rows, want);
+  nrb = (int)ceil_div(rows, rows_per_block);
+  grid = dim3((unsigned)colblocks, (unsigned)nrb);
+}
+
+}  // namespace cgc
+
+using namespace cgc;
+
+extern "C" int cgc_bn_stats(const float* y, int64_t ldy, int64_t rows, int32_t c, float* running_mean,
+                            float* running_var, float momentum, float eps, float* mean, float* invstd,
+                            void* work, int64_t work_bytes, void* stream) {
+  CGC_REQUIRE(y && mean && invstd && work && rows > 0 && c > 0 && ldy >= c, CGC_ERR_ARG, "cgc_bn_stats: bad args");
+  int nrb;
+  int64_t rpb;
+  dim3 grid;
+  reduce_geometry(rows, c, nrb, rpb, grid);
+  CGC_REQUIRE((int64_t)nrb * 2 * c * 4 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_bn_stats: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(work);
+  k_colreduce<RED_STATS><<<grid, dim3(kRedX, kRedY), 0, st>>>(y, ldy, nullptr, 0, nullptr, nullptr, nullptr, 0, rows,
+                                                              c, rpb, partial);
+  CGC_CHECK_LAUNCH("k_colreduce<stats>");
+  k_bn_finalize<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nrb, c, rows, running_mean, running_var,
+                                                            momentum, eps, mean, invstd);
+  CGC_CHECK_LAUNCH("k_bn_finalize");
+  return 0;
+}
+
+extern "C" int cgc_bn_eval_stats(const float* running_mean, const float* running_var, int32_t c, float eps,
+                                 float* mean, float* invstd, void* stream) {
+  CGC_REQUIRE(running_mean && running_var && mean && invstd && c > 0, CGC_ERR_ARG, "cgc_bn_eval_stats: bad args");
+  k_bn_eval_stats<<<(unsigned)ceil_div(c, 128), 128, 0, as_stream(stream)>>>(running_mean, running_var, c, eps,
+                                                                             mean, invstd);
+  CGC_CHECK_LAUNCH("k_bn_eval_stats");
+  return 0;
+}
+
+static unsigned elementwise_grid(int64_t total) {
+  int64_t blocks = ceil_div(total, 256);
+  int64_t cap = (int64_t)kNumSMs * 32;
+  return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+extern "C" int cgc_bn_apply(const float* y, int64_t ldy, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, const int32_t* num_nodes, int32_t nmax,
+                            int64_t rows, int32_t c, float* out, int64_t ldo, void* stream) {
+  CGC_REQUIRE(y && out && rows > 0 && c > 0 && ldy >= c && ldo >= c, CGC_ERR_ARG, "cgc_bn_apply: bad args");
+  CGC_REQUIRE(mean == nullptr || (invstd && gamma && beta), CGC_ERR_ARG, "cgc_bn_apply: incomplete BN params");
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_bn_apply: mask without nmax");
+  k_bn_apply<<<elementwise_grid(rows * c), 256, 0, as_stream(stream)>>>(y, ldy, mean, invstd, gamma, beta,
+                                                                        num_nodes, nmax, rows, c, out, ldo);
+  CGC_CHECK_LAUNCH("k_bn_apply");
+  return 0;
+}
+
+extern "C" int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ldy, const float* mean,
+                          const float* invstd, const float* gamma, const int32_t* num_nodes, int32_t nmax,
+                          int64_t rows, int32_t c, int training, float* gy, int64_t ldgy, float* d_gamma,
+                          float* d_beta, void* work, int64_t work_bytes, void* stream) {
+  CGC_REQUIRE(gx && y && mean && invstd && gamma && gy && d_gamma && d_beta && work && rows > 0 && c > 0,
+              CGC_ERR_ARG, "cgc_bn_bwd: bad args");
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_bn_bwd: mask without nmax");
+  int nrb;
+  int64_t rpb;
+  dim3 grid;
+  reduce_geometry(rows, c, nrb, rpb, grid);
+  CGC_REQUIRE((int64_t)nrb * 2 * c * 4 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_bn_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(work);
+  k_colreduce<RED_BN_BWD><<<grid, dim3(kRedX, kRedY), 0, st>>>(gx, ldgx, y, ldy, mean, invstd, num_nodes, nmax, rows,
+                                                               c, rpb, partial);
+  CGC_CHECK_LAUNCH("k_colreduce<bn_bwd>");
+  k_sum_finalize<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nrb, c, d_beta, d_gamma);
+  CGC_CHECK_LAUNCH("k_sum_finalize");
+  k_bn_bwd_apply<<<elementwise_grid(rows * c), 256, 0, st>>>(gx, ldgx, y, ldy, mean, invstd, gamma, d_gamma, d_beta,
+                                                             num_nodes, nmax, rows, c, training, gy, ldgy);
+  CGC_CHECK_LAUNCH("k_bn_bwd_apply");
+  return 0;
+}
+
+extern "C" int cgc_colsum(const float* x, int64_t ldx, int64_t rows, int32_t c, const int32_t* num_nodes,
+                          int32_t nmax, float* out, void* work, int64_t work_bytes, void* stream) {
+  CGC_REQUIRE(x && out && work && rows > 0 && c > 0 && ldx >= c, CGC_ERR_ARG, "cgc_colsum: bad args");
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_colsum: mask without nmax");
+  int nrb;
+  int64_t rpb;
+  dim3 grid;
+  reduce_geometry(rows, c, nrb, rpb, grid);
+  CGC_REQUIRE((int64_t)nrb * 2 * c * 4 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_colsum: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(work);
+  k_colreduce<RED_COLSUM><<<grid, dim3(kRedX, kRedY), 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, num_nodes, nmax,
+                                                               rows, c, rpb, partial);
+  CGC_CHECK_LAUNCH("k_colreduce<colsum>");
+  k_sum_finalize<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nrb, c, out, nullptr);
+  CGC_CHECK_LAUNCH("k_sum_finalize");
+  return 0;
+}
+
+extern "C" int cgc_colmax_fwd(const float* x, int32_t num_graphs, int32_t nmax, int32_t c, float* out,
+                              int32_t* arg, void* stream) {
+  CGC_REQUIRE(x && out && arg && num_graphs > 0 && nmax > 0 && c > 0, CGC_ERR_ARG, "cgc_colmax_fwd: bad args");
+  CGC_REQUIRE(num_graphs <= 65535, CGC_ERR_UNSUPPORTED, "cgc_colmax_fwd: more than 65535 graphs");
+  dim3 grid((unsigned)ceil_div(c, kRedX), (unsigned)num_graphs);
+  k_colmax_fwd<<<grid, dim3(kRedX, kRedY), 0, as_stream(stream)>>>(x, nmax, c, out, arg);
+  CGC_CHECK_LAUNCH("k_colmax_fwd");
+  return 0;
+}
+
+extern "C" int cgc_colmax_bwd(const float* g, const int32_t* arg, int32_t num_graphs, int32_t nmax, int32_t c,
+                              float* gx, void* stream) {
+  CGC_REQUIRE(g && arg && gx && num_graphs > 0 && nmax > 0 && c > 0, CGC_ERR_ARG, "cgc_colmax_bwd: bad args");
+  k_colmax_bwd<<<(unsigned)ceil_div((int64_t)num_graphs * c, 256), 256, 0, as_stream(stream)>>>(g, arg, num_graphs,
+                                                                                               nmax, c, gx);
+  CGC_CHECK_LAUNCH("k_colmax_bwd");
+  return 0;
+}

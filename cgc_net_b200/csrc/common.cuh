@@ -1,0 +1,74 @@
+// Shared helpers of libcgc_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cgc_sm100.h"
+
+namespace cgc {
+
+// thread-local error message returned by cgc_last_error()
+void set_error(const char* fmt, ...);
+// process-wide count of kernels this library has launched (cgc_launch_count())
+void count_launch();
+
+#define CGC_REQUIRE(cond, code, ...)      \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::cgc::set_error(__VA_ARGS__);      \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+// Check the launch of the kernel just enqueued (no synchronisation).
+#define CGC_CHECK_LAUNCH(name)                                                  \
+  do {                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                        \
+    if (e_ != cudaSuccess) {                                                    \
+      ::cgc::set_error("%s: %s", name, cudaGetErrorString(e_));                 \
+      return (int)e_;                                                           \
+    }                                                                           \
+    ::cgc::count_launch();                                                      \
+  } while (0)
+
+#define CGC_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      ::cgc::set_error("%s: %s", #call, cudaGetErrorString(e_));                \
+      return (int)e_;                                                           \
+    }                                                                           \
+  } while (0)
+
+constexpr int kNumSMs = 148;            // B200: 2 dies x 74 SMs
+constexpr float kL2NormEps = 1e-12f;    // F.normalize eps
+constexpr float kRenormEps = 1e-15f;    // model/network.py:8
+
+// Row mask in the padded node layout: row r is a real node iff r % nmax < num_nodes[r / nmax].
+__device__ __forceinline__ bool row_valid(const int32_t* __restrict__ num_nodes, int nmax, int64_t r) {
+  if (num_nodes == nullptr) return true;
+  int64_t g = r / nmax;
+  return (int)(r - g * nmax) < __ldg(num_nodes + g);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Scratch layout: every entry point that needs scratch uses the front of the shared buffer.
+constexpr int64_t kWorkspaceBytes = 256ll << 20;   // 256 MiB (split-K partials dominate)
+
+}  // namespace cgc

@@ -1,0 +1,476 @@
+// Row-wise operators of the SAGE layer and the diff-pool:
+//   cgc_sage_epilogue_fwd / cgc_sage_dh   (sa @ W + b, L2-normalise, mask, ReLU and its gradient)
+//   cgc_softmax_fwd / cgc_softmax_bwd     (cluster assignment, network.py:200-205)
+//   cgc_scale_rows_bwd, cgc_row_inv_clamped_sum, cgc_add_rs_grad, cgc_dense_renorm_fwd/bwd
+// Reference: PyG 1.2.1 DenseSAGEConv.forward (called at model/network.py:114-116), nn.ReLU(inplace)
+// (network.py:87), _diff_pool (:194-208), _re_norm_adj (:183-191).
+#include "common.cuh"
+
+namespace cgc {
+
+// =================================================================== narrow epilogue (cout <= 32)
+// one warp per row; lane c owns output column c.  W, b live in shared memory.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+k_epi_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
+             const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
+             float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
+             float* __restrict__ dh, int64_t lddh) {
+  extern __shared__ float s_w[];          // [cin][cout] then bias[cout]
+  float* s_b = s_w + cin * cout;
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* srow = sa + r * ldsa;
+    float a0 = lane < cin ? __ldg(srow + lane) : 0.f;
+    float a1 = (32 + lane) < cin ? __ldg(srow + 32 + lane) : 0.f;
+    float h = (lane < cout) ? s_b[lane] : 0.f;
+    const int c = lane < cout ? lane : 0;
+    for (int k = 0; k < cin; ++k) {
+      float a = (k < 32) ? __shfl_sync(0xffffffffu, a0, k) : __shfl_sync(0xffffffffu, a1, k - 32);
+      h = fmaf(a, s_w[k * cout + c], h);
+    }
+    if (lane >= cout) h = 0.f;
+    const float nrm = sqrtf(warp_sum(h * h));
+    const float inv = 1.0f / fmaxf(nrm, kL2NormEps);
+    const bool valid = row_valid(num_nodes, nmax, r);
+    if (!BWD) {
+      if (lane < cout) y[r * ldy + lane] = valid ? fmaxf(h * inv, 0.f) : 0.f;
+    } else {
+      float hn = h * inv;
+      float g = 0.f;
+      if (lane < cout && valid && __ldg(y + r * ldy + lane) > 0.f) g = gy[r * ldgy + lane];
+      const float dot = warp_sum(g * hn);
+      float d = (nrm >= kL2NormEps) ? (g - hn * dot) * inv : g * inv;
+      if (lane < cout) dh[r * lddh + lane] = d;
+    }
+  }
+}
+
+// =================================================================== wide epilogue (cout > 32)
+// CTA of 256 threads processes RT rows at a time; thread t owns columns t + 256*j (j < NC).
+constexpr int kEpiThreads = 256;
+constexpr int kEpiRows = 8;
+
+template <int NC, bool BWD>
+__global__ void __launch_bounds__(kEpiThreads)
+k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
+           const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
+           float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
+           float* __restrict__ dh, int64_t lddh) {
+  extern __shared__ float smem[];
+  float* s_w = smem;                                 // [cin][cout]
+  float* s_a = s_w + cin * cout;                     // [cin][kEpiRows]  (transposed row tile)
+  float* s_red = s_a + cin * kEpiRows;               // [8 warps][kEpiRows]
+  for (int i = threadIdx.x; i < cin * cout; i += kEpiThreads) s_w[i] = w[i];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  float bj[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    int c = t + kEpiThreads * j;
+    bj[j] = (bias && c < cout) ? bias[c] : 0.f;
+  }
+  const int64_t ntiles = (rows + kEpiRows - 1) / kEpiRows;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kEpiRows;
+    __syncthreads();                                 // previous tile done with s_a / s_red (and s_w loaded)
+    for (int i = t; i < cin * kEpiRows; i += kEpiThreads) {
+      int rr = i / cin, k = i - rr * cin;
+      s_a[k * kEpiRows + rr] = (r0 + rr < rows) ? __ldg(sa + (r0 + rr) * ldsa + k) : 0.f;
+    }
+    __syncthreads();
+    float acc[kEpiRows][NC];
+#pragma unroll
+    for (int rr = 0; rr < kEpiRows; ++rr)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[rr][j] = bj[j];
+    for (int k = 0; k < cin; ++k) {
+      float wv[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        int c = t + kEpiThreads * j;
+        wv[j] = (c < cout) ? s_w[k * cout + c] : 0.f;
+      }
+      const float4 a_lo = *reinterpret_cast<const float4*>(s_a + k * kEpiRows);
+      const float4 a_hi = *reinterpret_cast<const float4*>(s_a + k * kEpiRows + 4);
+      const float av[kEpiRows] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+#pragma unroll
+      for (int rr = 0; rr < kEpiRows; ++rr)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[rr][j] = fmaf(av[rr], wv[j], acc[rr][j]);
+    }
+    // row norms
+    float part[kEpiRows];
+#pragma unroll
+    for (int rr = 0; rr < kEpiRows; ++rr) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (t + kEpiThreads * j < cout) s = fmaf(acc[rr][j], acc[rr][j], s);
+      part[rr] = warp_sum(s);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < kEpiRows; ++rr) s_red[warp * kEpiRows + rr] = part[rr];
+    }
+    __syncthreads();
+    float nrm[kEpiRows], inv[kEpiRows];
+#pragma unroll
+    for (int rr = 0; rr < kEpiRows; ++rr) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kEpiThreads / 32; ++wv) s += s_red[wv * kEpiRows + rr];
+      nrm[rr] = sqrtf(s);
+      inv[rr] = 1.0f / fmaxf(nrm[rr], kL2NormEps);
+    }
+    if (!BWD) {
+#pragma unroll
+      for (int rr = 0; rr < kEpiRows; ++rr) {
+        const int64_t r = r0 + rr;
+        if (r >= rows) break;
+        const bool valid = row_valid(num_nodes, nmax, r);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          int c = t + kEpiThreads * j;
+          if (c < cout) y[r * ldy + c] = valid ? fmaxf(acc[rr][j] * inv[rr], 0.f) : 0.f;
+        }
+      }
+    } else {
+      // gm = gy * [y > 0] * mask ; dot_r = sum_c gm * hn
+      float gm[kEpiRows][NC];
+#pragma unroll
+      for (int rr = 0; rr < kEpiRows; ++rr) {
+        const int64_t r = r0 + rr;
+        const bool valid = (r < rows) && row_valid(num_nodes, nmax, r);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          int c = t + kEpiThreads * j;
+          float g = 0.f;
+          if (valid && c < cout && __ldg(y + r * ldy + c) > 0.f) g = gy[r * ldgy + c];
+          gm[rr][j] = g;
+          s = fmaf(g, acc[rr][j] * inv[rr], s);
+        }
+        part[rr] = warp_sum(s);
+      }
+      __syncthreads();                               // everyone has read s_red (norms)
+      if (lane == 0) {
+#pragma unroll
+        for (int rr = 0; rr < kEpiRows; ++rr) s_red[warp * kEpiRows + rr] = part[rr];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < kEpiRows; ++rr) {
+        const int64_t r = r0 + rr;
+        if (r >= rows) break;
+        float dot = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kEpiThreads / 32; ++wv) dot += s_red[wv * kEpiRows + rr];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          int c = t + kEpiThreads * j;
+          if (c < cout) {
+            float hn = acc[rr][j] * inv[rr];
+            float d = (nrm[rr] >= kL2NormEps) ? (gm[rr][j] - hn * dot) * inv[rr] : gm[rr][j] * inv[rr];
+            dh[r * lddh + c] = d;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool BWD>
+static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const float* b,
+                           const int32_t* num_nodes, int nmax, int64_t rows, int cin, int cout, float* y,
+                           int64_t ldy, const float* gy, int64_t ldgy, float* dh, int64_t lddh,
+                           cudaStream_t st) {
+  if (cout <= 32) {
+    CGC_REQUIRE(cin <= 64, CGC_ERR_UNSUPPORTED, "sage epilogue: cin=%d > 64", cin);
+    size_t smem = sizeof(float) * (size_t)(cin * cout + cout);
+    int64_t warps_needed = rows;
+    int64_t blocks = ceil_div(warps_needed, 8);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    k_epi_narrow<BWD><<<(unsigned)blocks, 256, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy,
+                                                           gy, ldgy, dh, lddh);
+    CGC_CHECK_LAUNCH("k_epi_narrow");
+    return 0;
+  }
+  const int nc = (int)ceil_div(cout, kEpiThreads);
+  CGC_REQUIRE(nc <= 5, CGC_ERR_UNSUPPORTED, "sage epilogue: cout=%d > 1280", cout);
+  size_t smem = sizeof(float) * (size_t)(cin * cout + cin * kEpiRows + (kEpiThreads / 32) * kEpiRows);
+  CGC_REQUIRE(smem <= 200 * 1024, CGC_ERR_UNSUPPORTED, "sage epilogue: W of %dx%d does not fit in shared memory",
+              cin, cout);
+  int64_t tiles = ceil_div(rows, kEpiRows);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int64_t blocks = tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm;
+#define CGC_EPI_CASE(N)                                                                                       \
+  case N: {                                                                                                   \
+    auto kern = k_epi_wide<N, BWD>;                                                                           \
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    kern<<<(unsigned)blocks, kEpiThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, \
+                                                      gy, ldgy, dh, lddh);                                    \
+  } break;
+  switch (nc) {
+    CGC_EPI_CASE(1)
+    CGC_EPI_CASE(2)
+    CGC_EPI_CASE(3)
+    CGC_EPI_CASE(4)
+    CGC_EPI_CASE(5)
+  }
+#undef CGC_EPI_CASE
+  CGC_CHECK_LAUNCH("k_epi_wide");
+  return 0;
+}
+
+// =================================================================== softmax over clusters
+// one warp per row, row cached in registers (NREG values per lane)
+template <int NREG>
+__global__ void __launch_bounds__(256)
+k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* __restrict__ num_nodes, int nmax,
+              float* __restrict__ s, float* __restrict__ s_full, int32_t* __restrict__ arg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float* zr = z + r * (int64_t)c;
+  float v[NREG];
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) {
+    int i = lane + 32 * j;
+    v[j] = (i < c) ? __ldg(zr + i) : -INFINITY;
+    if (v[j] > m) { m = v[j]; mi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, m, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) {
+    int i = lane + 32 * j;
+    v[j] = (i < c) ? expf(v[j] - m) : 0.f;
+    sum += v[j];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  const bool valid = row_valid(num_nodes, nmax, r);
+  float* sr = s + r * (int64_t)c;
+  float* fr = s_full ? s_full + r * (int64_t)c : nullptr;
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) {
+    int i = lane + 32 * j;
+    if (i < c) {
+      float p = v[j] * inv;
+      sr[i] = valid ? p : 0.f;
+      if (fr) fr[i] = p;
+    }
+  }
+  if (arg && lane == 0) arg[r] = mi;
+}
+
+__global__ void __launch_bounds__(256)
+k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t rows, int c,
+              float* __restrict__ gz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float* g = gs + r * (int64_t)c;
+  const float* p = s + r * (int64_t)c;
+  float dot = 0.f;
+  for (int i = lane; i < c; i += 32) dot = fmaf(__ldg(g + i), __ldg(p + i), dot);
+  dot = warp_sum(dot);
+  float* o = gz + r * (int64_t)c;
+  for (int i = lane; i < c; i += 32) o[i] = p[i] * (g[i] - dot);
+}
+
+// =================================================================== small row helpers
+__global__ void __launch_bounds__(256)
+k_scale_rows_bwd(const float* __restrict__ dsa, const float* __restrict__ sa, const float* __restrict__ rs,
+                 int64_t rows, int c, float* __restrict__ ga, float* __restrict__ d_rs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float sc = rs[r];
+  float dot = 0.f;
+  for (int i = lane; i < c; i += 32) {
+    float d = dsa[r * c + i];
+    dot = fmaf(d, sa[r * c + i], dot);
+    ga[r * c + i] = d * sc;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0 && d_rs) d_rs[r] += dot / sc;
+}
+
+__global__ void __launch_bounds__(256)
+k_row_inv_clamped_sum(const float* __restrict__ adj, int64_t rows, int n, float* __restrict__ rs,
+                      float* __restrict__ rsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float* a = adj + r * (int64_t)n;
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s += __ldg(a + i);
+  s = warp_sum(s);
+  if (lane == 0) {
+    rsum[r] = s;
+    rs[r] = 1.0f / fmaxf(s, 1.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_add_rs_grad(float* __restrict__ d_adj, const float* __restrict__ rsum, const float* __restrict__ d_rs,
+              int64_t rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float s = rsum[r];
+  if (!(s >= 1.0f)) return;
+  const float v = -d_rs[r] / (s * s);
+  float* a = d_adj + r * (int64_t)n;
+  for (int i = lane; i < n; i += 32) a[i] += v;
+}
+
+__global__ void __launch_bounds__(256)
+k_dense_renorm_fwd(const float* __restrict__ adj, int64_t rows, int n, float p, float omp,
+                   const int32_t* __restrict__ num_nodes, float* __restrict__ out, float* __restrict__ rho) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int diag = (int)(r % n);
+  const float* a = adj + r * (int64_t)n;
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s += (i == diag) ? 0.f : __ldg(a + i);
+  s = warp_sum(s) + kRenormEps;
+  const bool valid = row_valid(num_nodes, n, r);
+  float* o = out + r * (int64_t)n;
+  for (int i = lane; i < n; i += 32) {
+    float v = (i == diag) ? p : (a[i] / s) * omp;
+    o[i] = valid ? v : 0.f;
+  }
+  if (lane == 0) rho[r] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_dense_renorm_bwd(const float* __restrict__ g, const float* __restrict__ out, const float* __restrict__ rho,
+                   int64_t rows, int n, float omp, const int32_t* __restrict__ num_nodes,
+                   float* __restrict__ g_adj) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int diag = (int)(r % n);
+  const bool valid = row_valid(num_nodes, n, r);
+  const float* gr = g + r * (int64_t)n;
+  const float* nr = out + r * (int64_t)n;
+  float* o = g_adj + r * (int64_t)n;
+  if (!valid) {
+    for (int i = lane; i < n; i += 32) o[i] = 0.f;
+    return;
+  }
+  float dot = 0.f;
+  for (int i = lane; i < n; i += 32)
+    if (i != diag) dot = fmaf(__ldg(gr + i), __ldg(nr + i), dot);
+  dot = warp_sum(dot) / omp;
+  const float sc = omp / rho[r];
+  for (int i = lane; i < n; i += 32) o[i] = (i == diag) ? 0.f : sc * (gr[i] - dot);
+}
+
+}  // namespace cgc
+
+using namespace cgc;
+
+extern "C" int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w, const float* b,
+                                     const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
+                                     int32_t cout, float* y, int64_t ldy, void* stream) {
+  CGC_REQUIRE(sa && w && y && rows > 0 && cin > 0 && cout > 0 && ldsa >= cin && ldy >= cout, CGC_ERR_ARG,
+              "cgc_sage_epilogue_fwd: bad args");
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_epilogue_fwd: mask without nmax");
+  return launch_epilogue<false>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, nullptr, 0, nullptr, 0,
+                                as_stream(stream));
+}
+
+extern "C" int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,
+                           const float* b, const float* y, int64_t ldy, const int32_t* num_nodes, int32_t nmax,
+                           int64_t rows, int32_t cin, int32_t cout, float* dh, int64_t lddh, void* stream) {
+  CGC_REQUIRE(gy && sa && w && y && dh && rows > 0 && cin > 0 && cout > 0, CGC_ERR_ARG, "cgc_sage_dh: bad args");
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_dh: mask without nmax");
+  return launch_epilogue<true>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, const_cast<float*>(y), ldy, gy,
+                               ldgy, dh, lddh, as_stream(stream));
+}
+
+extern "C" int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows, int32_t c,
+                                  float* ga, float* d_rs, void* stream) {
+  CGC_REQUIRE(dsa && sa && rs && ga && rows > 0 && c > 0, CGC_ERR_ARG, "cgc_scale_rows_bwd: bad args");
+  k_scale_rows_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(dsa, sa, rs, rows, c, ga, d_rs);
+  CGC_CHECK_LAUNCH("k_scale_rows_bwd");
+  return 0;
+}
+
+extern "C" int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const int32_t* num_nodes, int32_t nmax,
+                               float* s, float* s_full, int32_t* arg, void* stream) {
+  CGC_REQUIRE(z && s && rows > 0 && c > 0, CGC_ERR_ARG, "cgc_softmax_fwd: bad args");
+  CGC_REQUIRE(c <= 32 * 40, CGC_ERR_UNSUPPORTED, "cgc_softmax_fwd: %d clusters > 1280", c);
+  cudaStream_t st = as_stream(stream);
+  unsigned grid = (unsigned)ceil_div(rows, 8);
+  if (c <= 128)
+    k_softmax_fwd<4><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, s_full, arg);
+  else if (c <= 512)
+    k_softmax_fwd<16><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, s_full, arg);
+  else
+    k_softmax_fwd<40><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, s_full, arg);
+  CGC_CHECK_LAUNCH("k_softmax_fwd");
+  return 0;
+}
+
+extern "C" int cgc_softmax_bwd(const float* gs, const float* s, int64_t rows, int32_t c, float* gz,
+                               void* stream) {
+  CGC_REQUIRE(gs && s && gz && rows > 0 && c > 0, CGC_ERR_ARG, "cgc_softmax_bwd: bad args");
+  k_softmax_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(gs, s, rows, c, gz);
+  CGC_CHECK_LAUNCH("k_softmax_bwd");
+  return 0;
+}
+
+extern "C" int cgc_row_inv_clamped_sum(const float* adj, int64_t rows, int32_t n, float* rs, float* rsum,
+                                       void* stream) {
+  CGC_REQUIRE(adj && rs && rsum && rows > 0 && n > 0, CGC_ERR_ARG, "cgc_row_inv_clamped_sum: bad args");
+  k_row_inv_clamped_sum<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(adj, rows, n, rs, rsum);
+  CGC_CHECK_LAUNCH("k_row_inv_clamped_sum");
+  return 0;
+}
+
+extern "C" int cgc_add_rs_grad(float* d_adj, const float* rsum, const float* d_rs, int64_t rows, int32_t n,
+                               void* stream) {
+  CGC_REQUIRE(d_adj && rsum && d_rs && rows > 0 && n > 0, CGC_ERR_ARG, "cgc_add_rs_grad: bad args");
+  k_add_rs_grad<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(d_adj, rsum, d_rs, rows, n);
+  CGC_CHECK_LAUNCH("k_add_rs_grad");
+  return 0;
+}
+
+extern "C" int cgc_dense_renorm_fwd(const float* adj, int32_t num_graphs, int32_t n, double p,
+                                    const int32_t* num_nodes, float* out, float* rho, void* stream) {
+  CGC_REQUIRE(adj && out && rho && num_graphs > 0 && n > 0, CGC_ERR_ARG, "cgc_dense_renorm_fwd: bad args");
+  int64_t rows = (int64_t)num_graphs * n;
+  k_dense_renorm_fwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(adj, rows, n, (float)p,
+                                                                                 (float)(1.0 - p), num_nodes, out, rho);
+  CGC_CHECK_LAUNCH("k_dense_renorm_fwd");
+  return 0;
+}
+
+extern "C" int cgc_dense_renorm_bwd(const float* g, const float* out, const float* rho, int32_t num_graphs,
+                                    int32_t n, double p, const int32_t* num_nodes, float* g_adj, void* stream) {
+  CGC_REQUIRE(g && out && rho && g_adj && num_graphs > 0 && n > 0, CGC_ERR_ARG, "cgc_dense_renorm_bwd: bad args");
+  int64_t rows = (int64_t)num_graphs * n;
+  k_dense_renorm_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(g, out, rho, rows, n,
+                                                                                 (float)(1.0 - p), num_nodes, g_adj);
+  CGC_CHECK_LAUNCH("k_dense_renorm_bwd");
+  return 0;
+}

@@ -1,0 +1,297 @@
+// Sparse neighbour gather over the padded-row CSR/CSC.
+//
+//   cgc_spmm                 generic: any feature width / leading dimension, gathers through L2.
+//   cgc_sage_gather_mean_fwd the SAGE roofline kernel: one graph's feature tile is staged in shared
+//                            memory with bulk async copies (TMA, cp.async.bulk + mbarrier), column
+//                            indices are staged with coalesced loads, neighbour rows are then read
+//                            from shared memory and rows are written back coalesced.
+//
+// Reference arithmetic: torch.matmul(adj, x) / adj.sum(-1).clamp(min=1) of PyG 1.2.1
+// DenseSAGEConv.forward (call sites model/network.py:114-116) and adj @ s of _diff_pool (:207).
+#include "common.cuh"
+
+namespace cgc {
+
+// ------------------------------------------------------------------ generic gather
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  using T = float4;
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void fma(T& a, float w, const T& v) {
+    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+  }
+  static __device__ __forceinline__ void store(float* p, T v, float s, bool acc) {
+    float4* q = reinterpret_cast<float4*>(p);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    if (acc) { float4 o = *q; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    *q = v;
+  }
+};
+template <>
+struct Vec<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void fma(T& a, float w, const T& v) { a = fmaf(w, v, a); }
+  static __device__ __forceinline__ void store(float* p, T v, float s, bool acc) {
+    v *= s;
+    if (acc) v += *p;
+    *p = v;
+  }
+};
+
+// L lanes cooperate on one row (L = power of two <= 32); each lane owns chunks sl, sl+L, ... of the
+// row, kept CH at a time in registers while the row's edges are streamed.
+template <int VEC, int CH>
+__global__ void __launch_bounds__(256) k_spmm(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                              const float* __restrict__ val, int64_t rows,
+                                              const float* __restrict__ x, int64_t ldx, int nchunks,
+                                              const float* __restrict__ src_scale,
+                                              const float* __restrict__ row_scale, float* __restrict__ out,
+                                              int64_t ldo, int accumulate, int L) {
+  using V = Vec<VEC>;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t r = t / L;
+  int sl = (int)(t - r * L);
+  if (r >= rows) return;
+  const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+  const float rsc = row_scale ? __ldg(row_scale + r) : 1.0f;
+  for (int c0 = sl; c0 < nchunks; c0 += L * CH) {
+    typename V::T acc[CH];
+#pragma unroll
+    for (int u = 0; u < CH; ++u) acc[u] = V::zero();
+#pragma unroll 4
+    for (int i = b; i < e; ++i) {
+      const int j = __ldg(col + i);
+      float w = val ? __ldg(val + i) : 1.0f;
+      if (src_scale) w *= __ldg(src_scale + j);
+      const float* xr = x + (int64_t)j * ldx;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        int c = c0 + u * L;
+        if (c < nchunks) V::fma(acc[u], w, V::load(xr + (int64_t)c * VEC));
+      }
+    }
+    float* orow = out + r * ldo;
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+      int c = c0 + u * L;
+      if (c < nchunks) V::store(orow + (int64_t)c * VEC, acc[u], rsc, accumulate != 0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ TMA-staged SAGE gather
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kGatherThreads = 512;
+constexpr int kGatherMaxRows = 1024;        // rows of one CTA (rowptr staging buffer)
+constexpr int kStageUnroll = 16;            // independent loads in flight per thread while staging
+constexpr uint32_t kBulkChunk = 32768;      // bytes per cp.async.bulk
+
+// coalesced, deeply unrolled global -> shared staging of n 4-byte words
+template <typename T>
+__device__ __forceinline__ void stage_words(T* __restrict__ dst, const T* __restrict__ src, int n) {
+  for (int base = 0; base < n; base += kStageUnroll * kGatherThreads) {
+    T tmp[kStageUnroll];
+#pragma unroll
+    for (int u = 0; u < kStageUnroll; ++u) {
+      int i = base + u * kGatherThreads + threadIdx.x;
+      if (i < n) tmp[u] = __ldg(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kStageUnroll; ++u) {
+      int i = base + u * kGatherThreads + threadIdx.x;
+      if (i < n) dst[i] = tmp[u];
+    }
+  }
+}
+
+// grid = num_graphs * parts.  CTA (g, p) owns rows [p*rpp, min((p+1)*rpp, nmax)) of graph g.
+// LPR lanes per row, each lane one float4 of the feature row.
+template <int LPR>
+__global__ void __launch_bounds__(kGatherThreads, 1)
+k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                   const float* __restrict__ row_scale, const float* __restrict__ x, int nmax, int feat,
+                   int parts, int rpp, int col_cap, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
+  const int r0 = p * rpp;
+  const int nrows = min(rpp, nmax - r0);
+  if (nrows <= 0) return;
+  const int64_t grow0 = (int64_t)g * nmax;           // first padded row of this graph
+  const uint32_t tile_bytes = (uint32_t)nmax * feat * 4u;
+
+  float* s_x = reinterpret_cast<float*>(smem_raw);
+  int* s_ptr = reinterpret_cast<int*>(smem_raw + tile_bytes);
+  int* s_col = s_ptr + (kGatherMaxRows + 4);
+  float* s_val = reinterpret_cast<float*>(s_col + col_cap);
+  __shared__ __align__(8) uint64_t bar;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, tile_bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + grow0 * feat);
+    for (uint32_t off = 0; off < tile_bytes; off += kBulkChunk) {
+      uint32_t n = min(kBulkChunk, tile_bytes - off);
+      bulk_g2s(smem_raw + off, src + off, n, &bar);
+    }
+  }
+  // while the tile is in flight: stage this CTA's rowptr slice and column indices
+  const int* gptr = rowptr + grow0 + r0;
+  stage_words(s_ptr, gptr, nrows + 1);
+  __syncthreads();
+  const int e0 = s_ptr[0];
+  const int nnz = s_ptr[nrows] - e0;
+  const bool staged = nnz <= col_cap;
+  if (staged) {
+    stage_words(s_col, col + e0, nnz);
+    if (val != nullptr) stage_words(s_val, val + e0, nnz);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const int sl = threadIdx.x % LPR;                  // float4 chunk of the row
+  const int grp = threadIdx.x / LPR;
+  constexpr int kGroups = kGatherThreads / LPR;
+  const bool lane_on = sl * 4 < feat;
+  const int base_col = (int)grow0;
+  for (int r = grp; r < nrows; r += kGroups) {
+    const int b = s_ptr[r] - e0, e = s_ptr[r + 1] - e0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_on) {
+#pragma unroll 4
+      for (int i = b; i < e; ++i) {
+        int j;
+        float w = 1.0f;
+        if (staged) {
+          j = s_col[i] - base_col;
+          if (val != nullptr) w = s_val[i];
+        } else {
+          j = __ldg(col + e0 + i) - base_col;
+          if (val != nullptr) w = __ldg(val + e0 + i);
+        }
+        const float4 v = *reinterpret_cast<const float4*>(s_x + (size_t)j * feat + sl * 4);
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+      float s;
+      if (row_scale != nullptr) s = __ldg(row_scale + grow0 + r0 + r);
+      else if (val == nullptr) s = 1.0f / fmaxf((float)(e - b), 1.0f);
+      else s = 1.0f;
+      acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s;
+      *reinterpret_cast<float4*>(out + (grow0 + r0 + r) * feat + sl * 4) = acc;
+    }
+  }
+}
+
+}  // namespace cgc
+
+using namespace cgc;
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+extern "C" int cgc_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t rows,
+                        const float* x, int64_t ldx, int32_t feat, const float* src_scale,
+                        const float* row_scale, float* out, int64_t ldo, int accumulate, void* stream) {
+  CGC_REQUIRE(rowptr && col && x && out && rows > 0 && feat > 0 && ldx >= feat && ldo >= feat, CGC_ERR_ARG,
+              "cgc_spmm: bad args");
+  cudaStream_t st = as_stream(stream);
+  const bool vec = (feat % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
+  if (vec) {
+    int nchunks = feat / 4;
+    int L = pow2_ceil(nchunks) > 32 ? 32 : pow2_ceil(nchunks);
+    int64_t threads = rows * L;
+    unsigned grid = (unsigned)ceil_div(threads, 256);
+    if (nchunks > L)
+      k_spmm<4, 4><<<grid, 256, 0, st>>>(rowptr, col, val, rows, x, ldx, nchunks, src_scale, row_scale, out, ldo,
+                                         accumulate, L);
+    else
+      k_spmm<4, 1><<<grid, 256, 0, st>>>(rowptr, col, val, rows, x, ldx, nchunks, src_scale, row_scale, out, ldo,
+                                         accumulate, L);
+  } else {
+    int L = pow2_ceil(feat) > 32 ? 32 : pow2_ceil(feat);
+    int64_t threads = rows * L;
+    unsigned grid = (unsigned)ceil_div(threads, 256);
+    if (feat > L)
+      k_spmm<1, 4><<<grid, 256, 0, st>>>(rowptr, col, val, rows, x, ldx, feat, src_scale, row_scale, out, ldo,
+                                         accumulate, L);
+    else
+      k_spmm<1, 1><<<grid, 256, 0, st>>>(rowptr, col, val, rows, x, ldx, feat, src_scale, row_scale, out, ldo,
+                                         accumulate, L);
+  }
+  CGC_CHECK_LAUNCH("k_spmm");
+  return 0;
+}
+
+extern "C" int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, const float* val,
+                                        const float* row_scale, const float* x, int32_t num_graphs,
+                                        int32_t nmax, int32_t feat, float* out, void* stream) {
+  CGC_REQUIRE(rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
+              "cgc_sage_gather_mean_fwd: bad args");
+  CGC_REQUIRE(feat % 4 == 0 && feat <= 32 && aligned16(x) && aligned16(out), CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_mean_fwd: feat must be a multiple of 4 and <= 32 (got %d), 16B-aligned x/out",
+              feat);
+  const int64_t tile_bytes = (int64_t)nmax * feat * 4;
+  const int64_t fixed = tile_bytes + (kGatherMaxRows + 4) * 4;
+  const int64_t budget = 220 * 1024;
+  CGC_REQUIRE(fixed + 4096 <= budget, CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_mean_fwd: feature tile of %lld B does not fit in shared memory",
+              (long long)tile_bytes);
+  int parts = kNumSMs / num_graphs;
+  if (parts < 1) parts = 1;
+  int min_parts = (int)ceil_div(nmax, kGatherMaxRows);
+  if (parts < min_parts) parts = min_parts;
+  int rpp = (int)ceil_div(nmax, parts);
+  int64_t cap = (budget - fixed) / (val ? 8 : 4);
+  if (cap > 16384) cap = 16384;
+  cap &= ~(int64_t)511;
+  size_t smem = (size_t)(fixed + cap * (val ? 8 : 4));
+  cudaStream_t st = as_stream(stream);
+  const int lpr = feat <= 16 ? 4 : 8;
+  auto kern = lpr == 4 ? k_sage_gather_tile<4> : k_sage_gather_tile<8>;
+  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<num_graphs * parts, kGatherThreads, smem, st>>>(rowptr, col, val, row_scale, x, nmax, feat, parts, rpp,
+                                                         (int)cap, out);
+  CGC_CHECK_LAUNCH("k_sage_gather_tile");
+  return 0;
+}

@@ -1,0 +1,61 @@
+"""Data parallelism for the hot path: one process per GPU, one gradient all-reduce per step.
+
+The reference uses single-process ``DataParallel`` (``train.py:276-287``): parameters are
+re-broadcast every iteration, per-replica mean losses are averaged (``train.py:179``) and
+gradients are reduced onto device 0.  Here every rank owns a replica; graphs are sharded by
+batch index (``graph.split_by_node_count`` mirrors PyG's node-balanced scatter), BatchNorm stays
+per-replica as in the reference, and the only collective is ONE ``all_reduce(sum)`` over a flat
+fp32 bucket holding every gradient (1 410 275 elements = 5.64 MB for the BASELINE model),
+followed by a scale of ``1 / world_size`` -- NCCL over NVLink/NVSwitch on B200, gloo in the CPU
+tests.  No data-path collective exists: graphs never interact across ranks.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBucket(object):
+    """All parameter gradients as views of one contiguous buffer."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        """Use instead of ``optimizer.zero_grad()`` (keeps the views alive)."""
+        self.flat.zero_()
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+    def all_reduce_mean(self, group=None):
+        """Sum over ranks, then 1/R: the mean of per-replica mean losses (train.py:179)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.mul_(1.0 / world)
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Once at start-up (the reference re-broadcasts every iteration inside DataParallel.replicate)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def shard_for_rank(data_list, rank, world_size, by_nodes=False):
+    """Contiguous shard of the list of graphs for ``rank``.  ``by_nodes`` = PyG's node-balanced split."""
+    if by_nodes:
+        from .graph import split_by_node_count
+        return split_by_node_count(data_list, world_size)[rank]
+    per = (len(data_list) + world_size - 1) // world_size
+    return data_list[rank * per: (rank + 1) * per]

@@ -35,30 +35,38 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CGC_API __attribute__((visibility("default")))
+#else
+#define CGC_API
+#endif
+
 #define CGC_OK 0
 #define CGC_ERR_ARG (-1)        /* invalid argument (size, alignment, null pointer)      */
 #define CGC_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are instantiated for  */
 #define CGC_ERR_WORKSPACE (-3)  /* workspace too small                                   */
 
-int cgc_version(void);
-const char* cgc_last_error(void);
+CGC_API int cgc_version(void);
+CGC_API const char* cgc_last_error(void);
 /* Bytes of scratch that is enough for every entry point below at any supported shape. */
-int64_t cgc_workspace_bytes(void);
+CGC_API int64_t cgc_workspace_bytes(void);
+/* Number of CUDA kernels this library has launched so far in the process (bench.py's gpu_launches). */
+CGC_API int64_t cgc_launch_count(void);
 
 /* ------------------------------------------------------------------ graph construction
  * Replaces to_dense_adj (model/utils.py:3-37) + to_dense_batch (network.py:242) +
  * construct_mask (network.py:172-180).  No dense [B, Nmax, Nmax] tensor is built. */
 
 /* num_nodes[g] = #{i : batch[i] == g}   (scatter_('add', ones, batch), model/utils.py:18-19) */
-int cgc_count_nodes(const int64_t* batch, int64_t n_total, int32_t num_graphs,
+CGC_API int cgc_count_nodes(const int64_t* batch, int64_t n_total, int32_t num_graphs,
                     int32_t* num_nodes, void* stream);
 
 /* out[batch[i] * nmax + (i - start[batch[i]]), :] = x[i, :], other rows 0   (to_dense_batch) */
-int cgc_pad_nodes(const float* x, const int64_t* batch, const int32_t* start, int64_t n_total,
+CGC_API int cgc_pad_nodes(const float* x, const int64_t* batch, const int32_t* start, int64_t n_total,
                   int32_t feat, int32_t nmax, int32_t num_graphs, float* out, void* stream);
 
 /* int32 elements of `work` needed by cgc_coo_to_csr / cgc_csr_transpose */
-int64_t cgc_coo_to_csr_workspace(int64_t edge_capacity, int64_t rows);
+CGC_API int64_t cgc_coo_to_csr_workspace(int64_t edge_capacity, int64_t rows);
 
 /* COO edge_index[2, n_edges] (int64, global node ids) -> CSR over the padded rows:
  * entry (r, c) with r = g*nmax + (src - start[g]), c = g*nmax + (dst - start[batch[dst]]),
@@ -66,21 +74,21 @@ int64_t cgc_coo_to_csr_workspace(int64_t edge_capacity, int64_t rows);
  * collapse; columns are sorted within a row.  add_self_loops != 0 forces the diagonal entry
  * of every real node (needed by the norm_adj edge weights, network.py:188).
  * rowptr[rows + 1], col[>= n_edges (+ n_total)].  The final nnz is rowptr[rows] (device). */
-int cgc_coo_to_csr(const int64_t* edge_index, int64_t n_edges, const int64_t* batch,
+CGC_API int cgc_coo_to_csr(const int64_t* edge_index, int64_t n_edges, const int64_t* batch,
                    const int32_t* start, int64_t n_total, int32_t num_graphs, int32_t nmax,
                    int add_self_loops, int32_t* rowptr, int32_t* col, int32_t* work,
                    int64_t work_elems, void* stream);
 
 /* rs[r] = 1 / max(deg(r), 1): the mean of DenseSAGEConv, adj.sum(-1).clamp(min=1) (PyG 1.2.1) */
-int cgc_row_inv_degree(const int32_t* rowptr, int64_t rows, float* rs, void* stream);
+CGC_API int cgc_row_inv_degree(const int32_t* rowptr, int64_t rows, float* rs, void* stream);
 
 /* _re_norm_adj on the stored entries (network.py:183-191): val = p on the diagonal,
  * (1/(offdiag_degree + 1e-15)) * (1-p) elsewhere; rs[r] = 1 / max(sum_e val, 1). */
-int cgc_edge_renorm(const int32_t* rowptr, const int32_t* col, int64_t rows, float p,
+CGC_API int cgc_edge_renorm(const int32_t* rowptr, const int32_t* col, int64_t rows, double p,
                     float* val, float* rs, void* stream);
 
 /* CSR -> CSC (rows sorted within a column), val (nullable) permuted into val_t. */
-int cgc_csr_transpose(const int32_t* rowptr, const int32_t* col, const float* val, int64_t rows,
+CGC_API int cgc_csr_transpose(const int32_t* rowptr, const int32_t* col, const float* val, int64_t rows,
                       int32_t* colptr, int32_t* row, float* val_t, int32_t* work,
                       int64_t work_elems, void* stream);
 
@@ -89,7 +97,7 @@ int cgc_csr_transpose(const int32_t* rowptr, const int32_t* col, const float* va
  * = torch.matmul(adj, x) / adj.sum(-1).clamp(min=1) of DenseSAGEConv.forward (forward: CSR +
  * row_scale = rs), its transpose (backward: CSC + src_scale = rs), and A*S of _diff_pool
  * (network.py:207).  val, src_scale, row_scale nullable (= 1). */
-int cgc_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t rows,
+CGC_API int cgc_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t rows,
              const float* x, int64_t ldx, int32_t feat, const float* src_scale,
              const float* row_scale, float* out, int64_t ldo, int accumulate, void* stream);
 
@@ -100,7 +108,7 @@ int cgc_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_
  * Requires: x, out contiguous [num_graphs*nmax, feat], feat % 4 == 0, column indices of graph g
  * inside [g*nmax, (g+1)*nmax), nmax*feat*4 + staging <= 200 KB; otherwise CGC_ERR_UNSUPPORTED
  * (callers then use cgc_spmm). */
-int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, const float* val,
+CGC_API int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, const float* val,
                              const float* row_scale, const float* x, int32_t num_graphs,
                              int32_t nmax, int32_t feat, float* out, void* stream);
 
@@ -108,36 +116,36 @@ int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, const fl
  * y = relu( l2normalize(sa @ W + b) * mask )      [rows, cout]
  * DenseSAGEConv.forward lines matmul(out, weight) / + bias / F.normalize(p=2, eps=1e-12) /
  * * mask, then nn.ReLU (network.py:114-116).  sa = mean-aggregated features [rows, cin]. */
-int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w, const float* b,
+CGC_API int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w, const float* b,
                           const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
                           int32_t cout, float* y, int64_t ldy, void* stream);
 
 /* dh = d loss / d (sa @ W + b) given gy = d loss / d y.  dh may alias gy. */
-int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,
+CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,
                 const float* b, const float* y, int64_t ldy, const int32_t* num_nodes,
                 int32_t nmax, int64_t rows, int32_t cin, int32_t cout, float* dh, int64_t lddh,
                 void* stream);
 
 /* Backward of sa = rs * agg (dense stages, where rs depends on the adjacency):
  * ga = rs * dsa;  d_rs[r] += dot(dsa[r], sa[r]) / rs[r]. */
-int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows,
+CGC_API int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows,
                        int32_t c, float* ga, float* d_rs, void* stream);
 
 /* ------------------------------------------------------------------ BatchNorm1d over ALL rows
  * (padded rows count, network.py:101-107).  Training: batch mean / biased variance, running
  * stats updated with momentum and the unbiased variance. */
-int cgc_bn_stats(const float* y, int64_t ldy, int64_t rows, int32_t c, float* running_mean,
+CGC_API int cgc_bn_stats(const float* y, int64_t ldy, int64_t rows, int32_t c, float* running_mean,
                  float* running_var, float momentum, float eps, float* mean, float* invstd,
                  void* work, int64_t work_bytes, void* stream);
-int cgc_bn_eval_stats(const float* running_mean, const float* running_var, int32_t c, float eps,
+CGC_API int cgc_bn_eval_stats(const float* running_mean, const float* running_var, int32_t c, float eps,
                       float* mean, float* invstd, void* stream);
 /* out = mask * ((y - mean) * invstd * gamma + beta); mean == NULL: out = mask * y */
-int cgc_bn_apply(const float* y, int64_t ldy, const float* mean, const float* invstd,
+CGC_API int cgc_bn_apply(const float* y, int64_t ldy, const float* mean, const float* invstd,
                  const float* gamma, const float* beta, const int32_t* num_nodes, int32_t nmax,
                  int64_t rows, int32_t c, float* out, int64_t ldo, void* stream);
 /* d_gamma = sum g*xhat, d_beta = sum g (g = gx*mask);
  * gy = gamma*invstd*(g - d_beta/rows - xhat*d_gamma/rows)   (training)   or gamma*invstd*g */
-int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ldy, const float* mean,
+CGC_API int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ldy, const float* mean,
                const float* invstd, const float* gamma, const int32_t* num_nodes, int32_t nmax,
                int64_t rows, int32_t c, int training, float* gy, int64_t ldgy, float* d_gamma,
                float* d_beta, void* work, int64_t work_bytes, void* stream);
@@ -145,32 +153,33 @@ int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ldy, const
 /* ------------------------------------------------------------------ diff-pool pieces
  * s = softmax(z, -1) * mask (network.py:200-205); s_full (nullable) = softmax before masking
  * (collect_assign, :201-202); arg (nullable) = argmax_c z[r, c] = cluster index per node. */
-int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const int32_t* num_nodes,
+CGC_API int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const int32_t* num_nodes,
                     int32_t nmax, float* s, float* s_full, int32_t* arg, void* stream);
 /* gz = s * (gs - sum_c gs * s) */
-int cgc_softmax_bwd(const float* gs, const float* s, int64_t rows, int32_t c, float* gz,
+CGC_API int cgc_softmax_bwd(const float* gs, const float* s, int64_t rows, int32_t c, float* gz,
                     void* stream);
 
 /* torch.max(x, dim=1) over all nmax rows of each graph (network.py:264,275,284) */
-int cgc_colmax_fwd(const float* x, int32_t num_graphs, int32_t nmax, int32_t c, float* out,
+CGC_API int cgc_colmax_fwd(const float* x, int32_t num_graphs, int32_t nmax, int32_t c, float* out,
                    int32_t* arg, void* stream);
 /* gx[g*nmax + arg[g,c], c] += g[g,c]  (gx zero-filled by the caller) */
-int cgc_colmax_bwd(const float* g, const int32_t* arg, int32_t num_graphs, int32_t nmax,
+CGC_API int cgc_colmax_bwd(const float* g, const int32_t* arg, int32_t num_graphs, int32_t nmax,
                    int32_t c, float* gx, void* stream);
 
 /* ------------------------------------------------------------------ dense soft adjacency
  * rsum[r] = sum_j adj[r, j];  rs[r] = 1 / max(rsum[r], 1)   (DenseSAGEConv on stages 2-3) */
-int cgc_row_inv_clamped_sum(const float* adj, int64_t rows, int32_t n, float* rs, float* rsum,
+CGC_API int cgc_row_inv_clamped_sum(const float* adj, int64_t rows, int32_t n, float* rs, float* rsum,
                             void* stream);
 /* d_adj[r, :] += (rsum[r] >= 1) ? -d_rs[r] / rsum[r]^2 : 0 */
-int cgc_add_rs_grad(float* d_adj, const float* rsum, const float* d_rs, int64_t rows, int32_t n,
+CGC_API int cgc_add_rs_grad(float* d_adj, const float* rsum, const float* d_rs, int64_t rows, int32_t n,
                     void* stream);
 /* _re_norm_adj(adj, p, mask) on a dense [num_graphs, n, n] adjacency (network.py:183-191);
- * rho[r] = off-diagonal row sum + 1e-15 */
-int cgc_dense_renorm_fwd(const float* adj, int32_t num_graphs, int32_t n, float p,
+ * rho[r] = off-diagonal row sum + 1e-15.  p is a double so that (float)(1 - p) equals the
+ * reference's python-float arithmetic (1 - 0.4 -> 0.6f). */
+CGC_API int cgc_dense_renorm_fwd(const float* adj, int32_t num_graphs, int32_t n, double p,
                          const int32_t* num_nodes, float* out, float* rho, void* stream);
-int cgc_dense_renorm_bwd(const float* g, const float* out, const float* rho, int32_t num_graphs,
-                         int32_t n, float p, const int32_t* num_nodes, float* g_adj,
+CGC_API int cgc_dense_renorm_bwd(const float* g, const float* out, const float* rho, int32_t num_graphs,
+                         int32_t n, double p, const int32_t* num_nodes, float* g_adj,
                          void* stream);
 
 /* ------------------------------------------------------------------ dense contractions
@@ -182,7 +191,7 @@ int cgc_dense_renorm_bwd(const float* g, const float* out, const float* rho, int
  * torch.matmul(adj, x) of the dense stages, and all their gradients.
  * precision: 0 = fp32 FMA (exact fp32 products), 1 = tcgen05 3xTF32 (error ~1e-6 relative),
  *            -1 = library's choice (tcgen05 when the shape/alignment allows, else fp32 FMA). */
-int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t k, float alpha,
+CGC_API int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t k, float alpha,
              const float* a, int64_t lda, int64_t stride_a, const float* b, int64_t ldb,
              int64_t stride_b, float beta, float* c, int64_t ldc, int64_t stride_c,
              int32_t batch, const float* bias, const float* row_scale,
@@ -190,7 +199,7 @@ int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t k, float al
              int64_t work_bytes, void* stream);
 
 /* out[c] = sum_r mask(r) * x[r, c] */
-int cgc_colsum(const float* x, int64_t ldx, int64_t rows, int32_t c, const int32_t* num_nodes,
+CGC_API int cgc_colsum(const float* x, int64_t ldx, int64_t rows, int32_t c, const int32_t* num_nodes,
                int32_t nmax, float* out, void* work, int64_t work_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ def densify_edges(edge_index, batch):
         0, batch, torch.ones_like(batch))
     start = torch.cat([counts.new_zeros(1), counts.cumsum(0)])
     nmax = int(counts.max())
-    adj = torch.zeros(num_graphs, nmax, nmax, dtype=torch.float32)
+    adj = torch.zeros(num_graphs, nmax, nmax, dtype=torch.get_default_dtype())
     src, dst = edge_index[0], edge_index[1]
     g = batch[src]
     adj[g, src - start[g], dst - start[batch[dst]]] = 1.0
@@ -55,7 +55,7 @@ def pad_nodes(x, batch, counts):
 
 def node_mask(nmax, counts):
     """``construct_mask`` (model/network.py:172-180) without the host loop: ``[B, Nmax, 1]``."""
-    return (torch.arange(nmax)[None, :] < counts.view(-1, 1)).float().unsqueeze(2)
+    return (torch.arange(nmax)[None, :] < counts.view(-1, 1)).to(torch.get_default_dtype()).unsqueeze(2)
 
 
 def renorm_adjacency(adj, p=RENORM_P, mask=None):

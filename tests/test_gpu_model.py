@@ -1,0 +1,147 @@
+"""SoftPoolingGcnEncoder on the GPU (through libcgc_sm100.so) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): logits within 1e-4 relative fp32, cluster-assignment indices
+bit-exact (rows whose oracle top-2 margin is < 1e-6 are exempt and counted), parameter gradients
+within 1e-4 relative of the float64 oracle or within 3x the fp32 oracle's own rounding error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from cgc_net_b200 import graph, network, ops
+from oracle import restatement
+from test_oracle import _batch_from, _load
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(ours, orc, batch, dense=None):
+    ours = ours.cuda().train()
+    orc.train()
+    data_gpu = batch.to('cuda') if dense is None else tuple(t.cuda() if torch.is_tensor(t) else t for t in dense)
+    data_cpu = batch if dense is None else dense
+    lo, losso = ours(data_gpu)
+    lr, lossr = orc(data_cpu)
+    losso.backward()
+    lossr.backward()
+    torch.cuda.synchronize()
+    return lo, losso, lr, lossr
+
+
+@pytest.mark.parametrize('name', ['encoder_small_plain', 'encoder_small_normadj'])
+def test_golden_vectors(cuda_backend, name):
+    """Known answers minted from the verbatim reference (oracle/make_golden.py)."""
+    g = _load(name)
+    args = (int(g['max_nodes']), 16, 20, 20, True, True, 20, 3, float(g['ratio']), [50])
+    m = network.SoftPoolingGcnEncoder(*args, concat=True, gcn_name='SAGE', collect_assign=True,
+                                      load_data_sparse=True, norm_adj=bool(int(g['norm_adj'])))
+    m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
+    m = m.cuda().train()
+    batch = _batch_from(g).to('cuda')
+    logits, loss = m(batch)
+    assert helpers.rel_err(logits, torch.from_numpy(g['logits'])) < 1e-4
+    assert abs(float(loss.detach()) - float(g['loss'])) < 1e-5
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref = g['grad/' + k]
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 3e-4 * max(np.abs(ref).max(), 1e-3), k
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            np.testing.assert_allclose(v.cpu().numpy(), g['after/' + k], rtol=1e-4, atol=1e-6)
+    for i, idx in enumerate(m.assign_index):
+        safe = g['assign_top2_margin/%d' % i] > 1e-6
+        assert np.array_equal(idx.cpu().numpy()[safe], g['assign_argmax/%d' % i][safe])
+    m.eval()
+    with torch.no_grad():
+        assert helpers.rel_err(m(batch), torch.from_numpy(g['eval_logits'])) < 1e-4
+
+
+@pytest.mark.parametrize('norm_adj', [False, True])
+def test_ragged_batch_vs_oracle(cuda_backend, norm_adj):
+    """Ragged sizes / degrees, duplicate edges, isolated rows, unsorted COO (BASELINE config #5 shape)."""
+    graphs = helpers.make_graphs([333, 801, 57, 640, 12, 500], [5, 8, 12, 6, 3, 9], seed=4)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair(helpers.encoder_args(2000), load_data_sparse=True, norm_adj=norm_adj,
+                                   collect_assign=True)
+    lo, losso, lr, lossr = _run_pair(ours, orc, batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    assert abs(float(losso) - float(lossr)) < 1e-5
+    _, _, truth = helpers.oracle_fp64(orc, batch)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()})
+    for (k, a), (_, b) in zip(sorted(ours.named_buffers()), sorted(orc.named_buffers())):
+        assert helpers.rel_err(a.float(), b.float()) < 1e-4, k
+    for mine, s in zip(ours.assign_index, orc.assign_matrix):
+        top2 = s.topk(2, dim=-1).values
+        safe = (top2[..., 0] - top2[..., 1]) > 1e-6
+        assert torch.equal(mine.cpu()[safe].long(), s.argmax(-1)[safe])
+
+
+def test_baseline_shape_vs_oracle(cuda_backend):
+    """BASELINE configs #2/#3 at the real node count and cluster widths (1800 nodes, degree 8,
+    1140 -> 114 clusters), reduced batch so the dense CPU oracle finishes in seconds."""
+    graphs = graph.synthetic_batch(3, 1800, 8, 16, seed=2)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair((11404, 16, 20, 20, True, True, 20, 3, 0.1, [50]), load_data_sparse=True,
+                                   collect_assign=True)
+    lo, losso, lr, lossr = _run_pair(ours, orc, batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    _, _, truth = helpers.oracle_fp64(orc, batch)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()})
+    exempt = 0
+    for mine, s in zip(ours.assign_index, orc.assign_matrix):
+        top2 = s.topk(2, dim=-1).values
+        safe = (top2[..., 0] - top2[..., 1]) > 1e-6
+        exempt += int((~safe).sum())
+        assert torch.equal(mine.cpu()[safe].long(), s.argmax(-1)[safe])
+    print('assignment rows exempt for near-ties:', exempt)
+
+
+@pytest.mark.parametrize('norm_adj', [False, True])
+def test_dense_tuple_input(cuda_backend, norm_adj):
+    graphs = helpers.make_graphs([125, 240], [5, 6], seed=6)
+    b = graph.Batch.from_data_list(graphs)
+    adj, counts = restatement.densify_edges(b.edge_index, b.batch)
+    x = restatement.pad_nodes(b.x, b.batch, counts)
+    ours, orc = helpers.build_pair(helpers.encoder_args(600), load_data_sparse=False, norm_adj=norm_adj)
+    dense = (x, adj.clone(), counts, b.y)
+    lo, losso, lr, lossr = _run_pair(ours, orc, None, dense=(x, adj.clone(), counts, b.y))
+    assert helpers.rel_err(lo, lr) < 1e-4
+    _, _, truth = helpers.oracle_fp64(orc, dense)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()})
+
+
+def test_eval_is_padding_independent(cuda_backend):
+    """Eval-mode logits of a graph do not depend on what it is batched with."""
+    graphs = helpers.make_graphs([90, 300], [6, 8], seed=12, messy=False)
+    ours, _ = helpers.build_pair(helpers.encoder_args(800), load_data_sparse=True)
+    ours = ours.cuda().eval()
+    with torch.no_grad():
+        both = ours(graph.Batch.from_data_list(graphs).to('cuda'))
+        alone = ours(graph.Batch.from_data_list(graphs[:1]).to('cuda'))
+    assert helpers.rel_err(both[:1], alone) < 1e-5
+
+
+def test_full_size_properties(cuda_backend):
+    """BASELINE config #3 size (64 x 1800 nodes): size-independent invariants of the pooling path.
+    S rows sum to 1, so sum(A') = nnz(A) and sum(X') = column sums of X (checksum of checksums)."""
+    graphs = graph.synthetic_batch(64, 1800, 8, 16, seed=5)
+    batch = graph.Batch.from_data_list(graphs).to('cuda')
+    torch.manual_seed(0)
+    m = network.SoftPoolingGcnEncoder(11404, 16, 20, 20, True, True, 20, 3, 0.1, [50], concat=True,
+                                      load_data_sparse=True, collect_assign=True).cuda().train()
+    xp, g = ops.build_sparse_graph(batch.x, batch.edge_index, batch.batch, batch.num_nodes_list, False)
+    feat = m.GCN_embed_1(xp, None, g.mask, graph=g)
+    assign = m.GCN_pool_1(xp, None, g.mask, graph=g)
+    cfg = ops.GnnConfig(graph=g, num_graphs=64, nmax=1800, mask=g.mask)
+    x2, a2, s_full, arg = ops.DiffPoolFunction.apply(cfg, assign, feat, None, True)
+    torch.cuda.synchronize()
+    assert torch.allclose(s_full.sum(1), torch.ones(64 * 1800, device='cuda'), atol=1e-5)
+    assert abs(float(a2.double().sum()) - 64 * 1800 * 8) < 1.0
+    torch.testing.assert_close(x2.sum(1), feat.view(64, 1800, -1).sum(1), rtol=1e-4, atol=1e-3)
+    assert bool((arg >= 0).all()) and bool((arg < 1140).all())
+    logits, loss = m(batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(logits).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())

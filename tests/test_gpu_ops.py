@@ -1,0 +1,301 @@
+"""Every C-ABI entry point on the GPU against the per-operator CPU formulas (oracle/op_reference.py).
+
+Bit-exact for index work (CSR/CSC construction, arg-max, arg-indices); fp32 tolerance for
+floating point (stated per test).  All calls go through the ctypes binding of libcgc_sm100.so."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from cgc_net_b200 import graph, ops
+from cgc_net_b200.ops import RowMask
+from oracle import op_reference
+
+pytestmark = pytest.mark.gpu
+REF = op_reference.TorchBackend()
+
+
+def _cu(a):
+    if torch.is_tensor(a):
+        return a.cuda()
+    if isinstance(a, RowMask):
+        return RowMask(a.num_nodes.cuda(), a.nmax)
+    return a
+
+
+def both(be, name, args, outs, rtol=1e-5, atol=1e-6, exact=()):
+    """Run ``name`` on CPU formulas and on the CUDA library; compare the tensors at indices ``outs``.
+    Strided views are reproduced on the GPU by cloning the base storage."""
+    gpu_args = []
+    for a in args:
+        if torch.is_tensor(a) and a._base is not None:
+            base = a._base.cuda()
+            gpu_args.append(base.as_strided(a.shape, a.stride(), a.storage_offset()))
+        else:
+            gpu_args.append(_cu(a))
+    getattr(REF, name)(*args)
+    getattr(be, name)(*gpu_args)
+    torch.cuda.synchronize()
+    for i in outs:
+        got, want = gpu_args[i].cpu(), args[i]
+        if i in exact or not want.is_floating_point():
+            assert torch.equal(got, want), '%s: output %d differs' % (name, i)
+        else:
+            torch.testing.assert_close(got, want, rtol=rtol, atol=atol, msg=lambda m: '%s out %d: %s' % (name, i, m))
+    return gpu_args
+
+
+def _mask(b, nmax, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    nn = torch.randint(max(1, nmax // 2), nmax + 1, (b,), generator=g, dtype=torch.int32)
+    nn[0] = nmax
+    return RowMask(nn, nmax)
+
+
+def _random_csr(rows, maxdeg, seed=0, block=None):
+    """CSR with sorted unique columns; ``block`` keeps columns inside the row's graph block."""
+    g = torch.Generator().manual_seed(seed)
+    deg = torch.randint(0, maxdeg + 1, (rows,), generator=g)
+    rowptr = torch.zeros(rows + 1, dtype=torch.int32)
+    rowptr[1:] = deg.cumsum(0).to(torch.int32)
+    cols = []
+    for r in range(rows):
+        lo, hi = (0, rows) if block is None else ((r // block) * block, (r // block + 1) * block)
+        c = torch.randperm(hi - lo, generator=g)[:int(deg[r])] + lo
+        cols.append(c.sort().values)
+    col = torch.cat(cols).to(torch.int32) if cols else torch.zeros(0, dtype=torch.int32)
+    return rowptr, torch.cat([col, torch.zeros(3, dtype=torch.int32)])
+
+
+# ------------------------------------------------------------------------------- graph build
+@pytest.mark.parametrize('norm_adj', [False, True])
+@pytest.mark.parametrize('with_counts', [True, False])
+def test_graph_build_bit_exact(cuda_backend, norm_adj, with_counts):
+    graphs = helpers.make_graphs([37, 120, 64, 5, 201], [5, 8, 12, 3, 8], seed=1)
+    b = graph.Batch.from_data_list(graphs)
+    counts = b.num_nodes_list if with_counts else None
+    from cgc_net_b200 import _backend
+    _backend.use_backend_for_testing(REF)
+    xr, gr = ops.build_sparse_graph(b.x, b.edge_index, b.batch, counts, norm_adj)
+    _backend.use_backend_for_testing(None)
+    bc = b.to('cuda')
+    xg, gg = ops.build_sparse_graph(bc.x, bc.edge_index, bc.batch, counts, norm_adj)
+    torch.cuda.synchronize()
+    assert (gg.num_graphs, gg.nmax, gg.rows) == (gr.num_graphs, gr.nmax, gr.rows)
+    assert torch.equal(xg.cpu(), xr)
+    assert torch.equal(gg.num_nodes.cpu(), gr.num_nodes)
+    nnz = int(gr.rowptr[-1])
+    assert torch.equal(gg.rowptr.cpu(), gr.rowptr) and torch.equal(gg.col[:nnz].cpu(), gr.col[:nnz])
+    assert torch.equal(gg.colptr.cpu(), gr.colptr) and torch.equal(gg.row[:nnz].cpu(), gr.row[:nnz])
+    torch.testing.assert_close(gg.rs.cpu(), gr.rs, rtol=1e-6, atol=0)
+    if norm_adj:
+        torch.testing.assert_close(gg.val[:nnz].cpu(), gr.val[:nnz], rtol=1e-6, atol=0)
+        torch.testing.assert_close(gg.val_t[:nnz].cpu(), gr.val_t[:nnz], rtol=1e-6, atol=0)
+
+
+def test_graph_build_large_scan(cuda_backend):
+    """> 1024 rows per scan tile and > 256 tiles: exercises the three-kernel scan."""
+    graphs = graph.synthetic_batch(160, 1800, 8, 4, seed=3)
+    b = graph.Batch.from_data_list(graphs).to('cuda')
+    _, g = ops.build_sparse_graph(b.x, b.edge_index, b.batch, b.num_nodes_list, False)
+    torch.cuda.synchronize()
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).cpu()
+    assert int(g.rowptr[-1]) == 160 * 1800 * 8 and bool((deg == 8).all())
+    cdeg = (g.colptr[1:] - g.colptr[:-1]).cpu()
+    assert int(cdeg.sum()) == 160 * 1800 * 8
+    col = g.col[:160 * 1800 * 8].view(-1, 8).cpu()
+    assert bool((col[:, 1:] > col[:, :-1]).all())                 # sorted, unique
+    assert bool(((col // 1800) == torch.arange(160 * 1800).view(-1, 1) // 1800).all())   # block diagonal
+
+
+# ------------------------------------------------------------------------------- sparse gather
+@pytest.mark.parametrize('feat', [16, 20, 60, 7, 1140])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_spmm(cuda_backend, feat, weighted):
+    rows = 300
+    rowptr, col = _random_csr(rows, 9, seed=feat)
+    nnz = int(rowptr[-1])
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(rows, feat, generator=g)
+    val = torch.rand(nnz + 3, generator=g) if weighted else None
+    ss = torch.rand(rows, generator=g) if weighted else None
+    rsc = torch.rand(rows, generator=g)
+    out = torch.zeros(rows, feat)
+    both(cuda_backend, 'spmm', [rowptr, col, val, x, ss, rsc, out, False], [6], rtol=1e-5, atol=1e-5)
+    out2 = torch.randn(rows, feat, generator=g)
+    both(cuda_backend, 'spmm', [rowptr, col, val, x, None, None, out2, True], [6], rtol=1e-5, atol=1e-5)
+
+
+def test_spmm_strided_slices(cuda_backend):
+    """x and out as column slices of wider matrices (the concat buffer of GNN_Module)."""
+    rows = 257
+    rowptr, col = _random_csr(rows, 6, seed=2)
+    g = torch.Generator().manual_seed(6)
+    xw = torch.randn(rows, 60, generator=g)
+    ow = torch.randn(rows, 60, generator=g)
+    x, out = xw[:, 20:40], ow[:, 0:20]
+    args = both(cuda_backend, 'spmm', [rowptr, col, None, x, None, None, out, True], [6], atol=1e-5)
+    assert torch.equal(args[6]._base[:, 20:].cpu(), ow[:, 20:])      # nothing outside the slice touched
+
+
+@pytest.mark.parametrize('feat,b,nmax', [(16, 3, 70), (20, 5, 333), (16, 64, 1800), (8, 150, 40), (32, 2, 1500)])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_sage_gather_tile(cuda_backend, feat, b, nmax, weighted):
+    """TMA-staged shared-memory gather == generic gather (same sums, same order)."""
+    rows = b * nmax
+    rowptr, col = _random_csr(rows, 8, seed=nmax, block=nmax) if rows < 5000 else _knn_csr(b, nmax)
+    nnz = int(rowptr[-1])
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(rows, feat, generator=g)
+    val = torch.rand(nnz + 3, generator=g) if weighted else None
+    rsc = torch.rand(rows, generator=g) if weighted else None
+    out = torch.zeros(rows, feat)
+    both(cuda_backend, 'sage_gather_mean_fwd', [rowptr, col, val, rsc, x, b, nmax, out], [7], rtol=1e-5, atol=1e-5)
+
+
+def _knn_csr(b, nmax, k=8):
+    graphs = graph.synthetic_batch(b, nmax, k, 1, seed=11)
+    bt = graph.Batch.from_data_list(graphs)
+    from cgc_net_b200 import _backend
+    _backend.use_backend_for_testing(REF)
+    _, g = ops.build_sparse_graph(bt.x, bt.edge_index, bt.batch, bt.num_nodes_list, False)
+    _backend.use_backend_for_testing(None)
+    return g.rowptr, torch.cat([g.col, torch.zeros(3, dtype=torch.int32)])
+
+
+# ------------------------------------------------------------------------------- SAGE epilogue
+@pytest.mark.parametrize('cin,cout', [(16, 20), (20, 20), (60, 20), (20, 114), (20, 1140), (60, 300)])
+@pytest.mark.parametrize('masked', [False, True])
+def test_sage_epilogue_and_dh(cuda_backend, cin, cout, masked):
+    b, nmax = 3, 53
+    rows = b * nmax
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    sa = torch.randn(rows, cin, generator=g)
+    sa[5] = 0                                            # a row whose pre-normalisation vector is just the bias
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax) if masked else None
+    y = torch.zeros(rows, cout)
+    both(cuda_backend, 'sage_epilogue_fwd', [sa, w, bias, mask, y], [4], rtol=1e-5, atol=1e-6)
+    gy = torch.randn(rows, cout, generator=g)
+    dh = torch.zeros(rows, cout)
+    both(cuda_backend, 'sage_dh', [gy, sa, w, bias, y, mask, dh], [6], rtol=1e-4, atol=1e-5)
+    # in place (dh aliases gy), no bias, strided y
+    yw = torch.zeros(rows, cout + 8)
+    both(cuda_backend, 'sage_epilogue_fwd', [sa, w, None, mask, yw[:, 4:4 + cout]], [4], rtol=1e-5, atol=1e-6)
+
+
+def test_scale_rows_bwd(cuda_backend):
+    g = torch.Generator().manual_seed(1)
+    dsa, sa = torch.randn(500, 60, generator=g), torch.randn(500, 60, generator=g)
+    rs = torch.rand(500, generator=g) + 0.1
+    both(cuda_backend, 'scale_rows_bwd', [dsa, sa, rs, torch.zeros(500, 60), torch.randn(500, generator=g)],
+         [3, 4], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------- batch norm
+@pytest.mark.parametrize('c', [20, 114, 1140])
+@pytest.mark.parametrize('masked', [False, True])
+def test_batchnorm(cuda_backend, c, masked):
+    b, nmax = 4, 701
+    rows = b * nmax
+    g = torch.Generator().manual_seed(c)
+    y = torch.rand(rows, c, generator=g)
+    mask = _mask(b, nmax) if masked else None
+    rmean, rvar = torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5
+    mean, invstd = torch.zeros(c), torch.zeros(c)
+    both(cuda_backend, 'bn_stats', [y, rmean, rvar, 0.1, 1e-5, mean, invstd], [1, 2, 5, 6], rtol=2e-5, atol=1e-6)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    wide = torch.zeros(rows, c + 40)
+    both(cuda_backend, 'bn_apply', [y, mean, invstd, gamma, beta, mask, wide[:, 20:20 + c]], [6], rtol=1e-5, atol=1e-5)
+    both(cuda_backend, 'bn_apply', [y, None, None, None, None, mask, torch.zeros(rows, c)], [6], rtol=0, atol=0)
+    gx = torch.randn(rows, c + 40, generator=g)[:, 20:20 + c]
+    for training in (True, False):
+        both(cuda_backend, 'bn_bwd', [gx, y, mean, invstd, gamma, mask, training, torch.zeros(rows, c),
+                                      torch.zeros(c), torch.zeros(c)], [7, 8, 9], rtol=2e-4, atol=2e-4)
+    e_mean, e_inv = torch.zeros(c), torch.zeros(c)
+    both(cuda_backend, 'bn_eval_stats', [rmean, rvar, 1e-5, e_mean, e_inv], [3, 4], rtol=1e-6, atol=0)
+    both(cuda_backend, 'colsum', [gx, mask, torch.zeros(c)], [2], rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------- softmax / read-out
+@pytest.mark.parametrize('c', [3, 114, 1140])
+def test_softmax(cuda_backend, c):
+    b, nmax = 3, 97
+    rows = b * nmax
+    g = torch.Generator().manual_seed(c)
+    z = torch.randn(rows, c, generator=g) * 3
+    mask = _mask(b, nmax)
+    s, sf, arg = torch.zeros(rows, c), torch.zeros(rows, c), torch.zeros(rows, dtype=torch.int32)
+    both(cuda_backend, 'softmax_fwd', [z, mask, s, sf, arg], [2, 3, 4], rtol=1e-5, atol=1e-7)   # arg-max bit-exact
+    both(cuda_backend, 'softmax_fwd', [z, None, s, None, None], [2], rtol=1e-5, atol=1e-7)
+    gs = torch.randn(rows, c, generator=g)
+    both(cuda_backend, 'softmax_bwd', [gs, s, torch.zeros(rows, c)], [2], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('c', [60, 20, 7])
+def test_colmax(cuda_backend, c):
+    b, n = 5, 333
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(b * n, c, generator=g)
+    x[n:n + 40] = 0                                      # ties among zero rows: first index wins
+    out, arg = torch.zeros(b, c), torch.zeros(b, c, dtype=torch.int32)
+    both(cuda_backend, 'colmax_fwd', [x, b, n, out, arg], [3, 4], rtol=0, atol=0)
+    gg = torch.randn(b, c, generator=g)
+    both(cuda_backend, 'colmax_bwd', [gg, arg, b, n, torch.zeros(b * n, c)], [4], rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------- dense adjacency helpers
+@pytest.mark.parametrize('n', [114, 1140, 37])
+def test_dense_adjacency_helpers(cuda_backend, n):
+    b = 3
+    g = torch.Generator().manual_seed(n)
+    adj = torch.rand(b, n, n, generator=g) * (4.0 / n)
+    adj[0, 3] *= 0.01                                    # a row whose sum is < 1 (clamped)
+    rs, rsum = torch.zeros(b * n), torch.zeros(b * n)
+    both(cuda_backend, 'row_inv_clamped_sum', [adj, rs, rsum], [1, 2], rtol=1e-5, atol=1e-6)
+    d_adj, d_rs = torch.randn(b, n, n, generator=g), torch.randn(b * n, generator=g)
+    both(cuda_backend, 'add_rs_grad', [d_adj, rsum, d_rs], [0], rtol=1e-5, atol=1e-6)
+    for mask in (None, _mask(b, n)):
+        out, rho = torch.zeros(b, n, n), torch.zeros(b * n)
+        both(cuda_backend, 'dense_renorm_fwd', [adj, 0.4, mask, out, rho], [3, 4], rtol=1e-5, atol=1e-7)
+        gout = torch.randn(b, n, n, generator=g)
+        both(cuda_backend, 'dense_renorm_bwd', [gout, out, rho, 0.4, mask, torch.zeros(b, n, n)], [5],
+             rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------- dense contractions
+GEMM_SHAPES = [  # (batch, m, n, k)
+    (1, 200, 1140, 1180), (3, 114, 114, 300), (2, 1140, 60, 500), (1, 20, 1140, 5000), (2, 37, 154, 33),
+    (1, 1000, 20, 1140), (4, 130, 130, 20), (1, 1180, 1140, 9000),
+]
+
+
+@pytest.mark.parametrize('shape', GEMM_SHAPES)
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_fp32(cuda_backend, shape, ta, tb):
+    """fp32 FMA path (precision 0), all four transposes, unaligned shapes, split-K."""
+    batch, m, n, k = shape
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(batch, *((k, m) if ta else (m, k)), generator=g)
+    b = torch.randn(batch, *((n, k) if tb else (k, n)), generator=g)
+    c = torch.zeros(batch, m, n)
+    if batch == 1:
+        a, b, c = a[0], b[0], c[0]
+    tol = 2e-5 * k ** 0.5
+    both(cuda_backend, 'gemm', [a, b, c, ta, tb, 1.0, 0.0, None, None, None, 0], [2], rtol=1e-4, atol=tol)
+
+
+def test_gemm_epilogue_options(cuda_backend):
+    batch, m, n, k = 3, 53, 70, 41
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(batch, m, k, generator=g), torch.randn(batch, k, n, generator=g)
+    c = torch.randn(batch, m, n, generator=g)
+    bias, rsc = torch.randn(n, generator=g), torch.rand(batch * m, generator=g)
+    mask = _mask(batch, m)
+    both(cuda_backend, 'gemm', [a, b, c, False, False, 0.5, 1.0, bias, rsc, mask, 0], [2], rtol=1e-4, atol=1e-4)
+    # strided operands / output: column slices of wider buffers
+    aw, cw = torch.randn(batch * m, 100, generator=g), torch.zeros(batch * m, 90)
+    a2 = aw[:, 8:8 + k].as_strided((batch, m, k), (m * 100, 100, 1), 8)
+    c2 = cw[:, 4:4 + n].as_strided((batch, m, n), (m * 90, 90, 1), 4)
+    both(cuda_backend, 'gemm', [a2, b, c2, False, False, 1.0, 0.0, None, None, None, 0], [2], rtol=1e-4, atol=1e-4)

@@ -1,0 +1,135 @@
+"""The oracle against (a) the committed golden vectors minted from the verbatim reference and
+(b) the verbatim reference itself where /root/reference exists.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from cgc_net_b200 import graph
+from oracle import pyg_shim, reference_loader, restatement
+
+
+def _load(name):
+    return np.load(os.path.join(helpers.GOLDEN_DIR, name + '.npz'))
+
+
+def _batch_from(g):
+    return graph.Batch(torch.from_numpy(g['x']), torch.from_numpy(g['edge_index']),
+                       torch.from_numpy(g['batch']), torch.from_numpy(g['y']) if 'y' in g else None,
+                       [int(n) for n in g['num_nodes']])
+
+
+def _oracle_from(g, **kw):
+    args = (int(g['max_nodes']), 16, 20, 20, True, True, 20, 3, float(g['ratio']), [50])
+    m = restatement.OracleEncoder(*args, concat=True, gcn_name='SAGE', load_data_sparse=True,
+                                  norm_adj=bool(int(g['norm_adj'])), **kw)
+    m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
+    return m
+
+
+def test_sage_conv_golden():
+    """BASELINE config #1: single 200-node k=5 graph, one DenseSAGEConv(16->20)."""
+    g = _load('sage_conv_n200_k5')
+    adj, counts = restatement.densify_edges(torch.from_numpy(g['edge_index']), torch.zeros(200, dtype=torch.long))
+    assert np.array_equal(adj.sum(-1)[0].numpy(), g['adj_rowsum'])          # bit-exact index work
+    conv = restatement.OracleSAGEConv(16, 20)
+    conv.weight.data = torch.from_numpy(g['weight'])
+    conv.bias.data = torch.from_numpy(g['bias'])
+    out = conv(torch.from_numpy(g['x']).unsqueeze(0), adj, None)
+    np.testing.assert_allclose(out[0].detach().numpy(), g['out'], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['encoder_small_plain', 'encoder_small_normadj'])
+def test_encoder_golden(name):
+    g = _load(name)
+    m = _oracle_from(g, collect_assign=True)
+    m.train()
+    logits, loss = m(_batch_from(g))
+    np.testing.assert_allclose(logits.detach().numpy(), g['logits'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(float(loss), float(g['loss']), rtol=1e-6)
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref = g['grad/' + k]
+        assert np.abs(p.grad.numpy() - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-3), k
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            np.testing.assert_allclose(v.numpy(), g['after/' + k], rtol=1e-5, atol=1e-7)
+    for i, s in enumerate(m.assign_matrix):
+        mine = s.argmax(-1).numpy()
+        safe = g['assign_top2_margin/%d' % i] > 1e-6
+        assert np.array_equal(mine[safe], g['assign_argmax/%d' % i][safe])
+    m.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(m(_batch_from(g)).numpy(), g['eval_logits'], rtol=1e-5, atol=1e-6)
+
+
+def test_pool_stage1_golden():
+    """BASELINE config #2 (reduced): GCN_embed_1 + GCN_pool_1 + _diff_pool."""
+    g = _load('pool_stage1_small')
+    m = restatement.OracleEncoder(300, 16, 20, 20, True, True, 20, 3, 0.1, [50], load_data_sparse=True)
+    m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
+    m.train()
+    b = _batch_from(g)
+    adj, counts = restatement.densify_edges(b.edge_index, b.batch)
+    x = restatement.pad_nodes(b.x, b.batch, counts)
+    mask = restatement.node_mask(adj.shape[1], counts)
+    emb = m.GCN_embed_1(x, adj, mask)
+    assign = m.GCN_pool_1(x, adj, mask)
+    xp, ap, _ = restatement.diff_pool(emb, adj, assign, mask)
+    for mine, key in ((emb, 'embed'), (assign, 'assign'), (xp, 'pooled_x'), (ap, 'pooled_adj')):
+        np.testing.assert_allclose(mine.detach().numpy(), g[key], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason='verbatim reference not on this host')
+@pytest.mark.parametrize('norm_adj', [False, True])
+def test_oracle_equals_verbatim_reference(norm_adj):
+    graphs = helpers.make_graphs([70, 41, 55], [8, 5, 6], seed=3)
+    batch = graph.Batch.from_data_list(graphs)
+    args = helpers.encoder_args(300)
+    kw = dict(concat=True, gcn_name='SAGE', load_data_sparse=True, norm_adj=norm_adj)
+    torch.manual_seed(5)
+    ref = reference_loader.build_reference_encoder(*args, **kw)
+    orc = restatement.OracleEncoder(*args, **kw)
+    orc.load_state_dict(ref.state_dict())
+    ref.train(), orc.train()
+    lr, lossr = reference_loader.run_reference(ref, batch)
+    lo, losso = orc(batch)
+    assert torch.equal(lr, lo) or helpers.rel_err(lo, lr) < 1e-6
+    lossr.backward(), losso.backward()
+    rg = dict(ref.named_parameters())
+    for k, p in orc.named_parameters():
+        assert helpers.rel_err(p.grad, rg[k].grad) < 1e-5, k
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason='verbatim reference not on this host')
+def test_oracle_jk_and_dense_tuple_match_reference():
+    """jk=True (DenseJK) and the dense-tuple input format (network.py:254-256)."""
+    graphs = helpers.make_graphs([30, 22], [5, 5], seed=9, messy=False)
+    batch = graph.Batch.from_data_list(graphs)
+    adj, counts = restatement.densify_edges(batch.edge_index, batch.batch)
+    x = restatement.pad_nodes(batch.x, batch.batch, counts)
+    args = helpers.encoder_args(120)
+    kw = dict(concat=True, gcn_name='SAGE', load_data_sparse=False, jk=True)
+    torch.manual_seed(2)
+    ref = reference_loader.build_reference_encoder(*args, **kw)
+    orc = restatement.OracleEncoder(*args, **kw)
+    orc.load_state_dict(ref.state_dict())
+    ref.eval(), orc.eval()
+    with torch.no_grad():
+        a = reference_loader.run_reference(ref, (x, adj.clone(), counts))
+        b = orc((x, adj.clone(), counts))
+    assert helpers.rel_err(b, a) < 1e-6
+
+
+def test_shim_matches_restated_conv():
+    torch.manual_seed(0)
+    a = pyg_shim.DenseSAGEConv(16, 20)
+    b = restatement.OracleSAGEConv(16, 20)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 9, 16)
+    adj = (torch.rand(2, 9, 9) > 0.6).float()
+    mask = torch.ones(2, 9, 1)
+    mask[1, 6:] = 0
+    assert torch.equal(a(x, adj, mask, False), b(x, adj, mask, False))

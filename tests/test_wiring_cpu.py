@@ -1,0 +1,147 @@
+"""The module surface and the hand-written backward of cgc_net_b200/ops.py, checked on CPU by
+substituting the per-operator formulas of oracle/op_reference.py for the CUDA library."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from cgc_net_b200 import _backend, graph, network, ops
+from oracle import restatement
+from test_oracle import _batch_from, _load
+
+
+def _grad_check(ours, orc, batch):
+    """Gradients against the float64 oracle: 1e-4 relative, or within 3x the fp32 oracle's own error."""
+    _, _, truth = helpers.oracle_fp64(orc, batch)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()})
+
+
+@pytest.mark.parametrize('name', ['encoder_small_plain', 'encoder_small_normadj'])
+def test_module_matches_golden(torch_backend, name):
+    g = _load(name)
+    args = (int(g['max_nodes']), 16, 20, 20, True, True, 20, 3, float(g['ratio']), [50])
+    m = network.SoftPoolingGcnEncoder(*args, concat=True, gcn_name='SAGE', collect_assign=True,
+                                      load_data_sparse=True, norm_adj=bool(int(g['norm_adj'])))
+    m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
+    m.train()
+    logits, loss = m(_batch_from(g))
+    assert helpers.rel_err(logits, torch.from_numpy(g['logits'])) < 1e-4
+    assert abs(float(loss.detach()) - float(g['loss'])) < 1e-5
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref = g['grad/' + k]
+        assert np.abs(p.grad.numpy() - ref).max() <= 3e-4 * max(np.abs(ref).max(), 1e-3), k
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            np.testing.assert_allclose(v.numpy(), g['after/' + k], rtol=1e-4, atol=1e-6)
+    for i, idx in enumerate(m.assign_index):
+        safe = g['assign_top2_margin/%d' % i] > 1e-6
+        assert np.array_equal(idx.numpy()[safe], g['assign_argmax/%d' % i][safe])     # bit-exact indices
+    m.eval()
+    with torch.no_grad():
+        assert helpers.rel_err(m(_batch_from(g)), torch.from_numpy(g['eval_logits'])) < 1e-4
+
+
+@pytest.mark.parametrize('norm_adj', [False, True])
+def test_module_matches_oracle_ragged(torch_backend, norm_adj):
+    graphs = helpers.make_graphs([33, 80, 57, 12], [5, 8, 12, 3], seed=4)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair(helpers.encoder_args(300), load_data_sparse=True, norm_adj=norm_adj)
+    ours.train(), orc.train()
+    lo, losso = ours(batch)
+    lr, lossr = orc(batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    losso.backward(), lossr.backward()
+    _grad_check(ours, orc, batch)
+    for (k, a), (_, b) in zip(sorted(ours.named_buffers()), sorted(orc.named_buffers())):
+        assert helpers.rel_err(a.float(), b.float()) < 1e-4, k
+
+
+def test_batch_without_host_counts(torch_backend):
+    """A PyG-style batch carrying only x / edge_index / batch / y (no host metadata)."""
+    graphs = helpers.make_graphs([20, 31], [4, 6], seed=8)
+    b = graph.Batch.from_data_list(graphs)
+    plain = graph.Batch(b.x, b.edge_index, b.batch, b.y, None)
+    ours, orc = helpers.build_pair(helpers.encoder_args(200), load_data_sparse=True)
+    ours.eval(), orc.eval()
+    with torch.no_grad():
+        assert helpers.rel_err(ours(plain), orc(plain)) < 1e-4
+
+
+@pytest.mark.parametrize('norm_adj', [False, True])
+def test_dense_tuple_input(torch_backend, norm_adj):
+    """(x, adj, num_nodes[, label]) input of network.py:254-256."""
+    graphs = helpers.make_graphs([25, 40], [5, 6], seed=6)
+    b = graph.Batch.from_data_list(graphs)
+    adj, counts = restatement.densify_edges(b.edge_index, b.batch)
+    x = restatement.pad_nodes(b.x, b.batch, counts)
+    ours, orc = helpers.build_pair(helpers.encoder_args(200), load_data_sparse=False, norm_adj=norm_adj)
+    ours.train(), orc.train()
+    lo, losso = ours((x, adj.clone(), counts, b.y))
+    lr, lossr = orc((x, adj.clone(), counts, b.y))
+    assert helpers.rel_err(lo, lr) < 1e-4
+    losso.backward(), lossr.backward()
+    _grad_check(ours, orc, (x, adj.clone(), counts, b.y))
+
+
+def test_state_dict_names_and_size():
+    """Checkpoint compatibility: BASELINE model has 1 410 275 parameters."""
+    m = network.SoftPoolingGcnEncoder(11404, 16, 20, 20, True, True, 20, 3, 0.1, [50], concat=True)
+    o = restatement.OracleEncoder(11404, 16, 20, 20, True, True, 20, 3, 0.1, [50], concat=True)
+    assert sum(p.numel() for p in m.parameters()) == 1410275
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in o.state_dict().items()}
+    assert tuple(m.GCN_pool_1.gcn3.weight.shape) == (20, 1140)
+    assert tuple(m.GCN_pool_1.lin.weight.shape) == (1140, 1180)
+    o.load_state_dict(m.state_dict())
+
+
+def test_unbuilt_rows_raise():
+    with pytest.raises(NotImplementedError):
+        network.SoftPoolingGcnEncoder(100, 16, 20, 20, True, True, 20, 3, jk=True)
+    with pytest.raises(NotImplementedError):
+        network.SoftPoolingGcnEncoder(100, 16, 20, 20, True, True, 20, 3, gcn_name='GIN')
+
+
+def test_graph_build_matches_to_dense_adj(torch_backend):
+    """CSR/CSC against the dense adjacency of model/utils.py:3-37 (duplicates, isolated rows)."""
+    graphs = helpers.make_graphs([17, 9, 30], [4, 3, 7], seed=2)
+    b = graph.Batch.from_data_list(graphs)
+    adj, counts = restatement.densify_edges(b.edge_index, b.batch)
+    xp, g = ops.build_sparse_graph(b.x, b.edge_index, b.batch, b.num_nodes_list, False)
+    rows = g.rows
+    dense = torch.zeros(rows, rows)
+    nnz = int(g.rowptr[-1])
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).long()
+    r = torch.repeat_interleave(torch.arange(rows), deg)
+    dense[r, g.col[:nnz].long()] = 1
+    blocks = torch.block_diag(*[adj[i] for i in range(adj.shape[0])])
+    assert torch.equal(dense, blocks)
+    assert int(adj.sum()) == nnz
+    assert torch.equal(xp.view(adj.shape[0], g.nmax, -1), restatement.pad_nodes(b.x, b.batch, counts))
+    # CSC is the exact transpose
+    dt = torch.zeros(rows, rows)
+    cdeg = (g.colptr[1:] - g.colptr[:-1]).long()
+    c = torch.repeat_interleave(torch.arange(rows), cdeg)
+    dt[g.row[:nnz].long(), c] = 1
+    assert torch.equal(dt, dense)
+
+
+def test_node_balanced_split():
+    graphs = [graph.Data(x=torch.zeros(n, 1)) for n in (10, 10, 10, 10, 40, 5, 5, 30)]
+    parts = graph.split_by_node_count(graphs, 2)
+    assert sum(len(p) for p in parts) == len(graphs)
+    assert [d.num_nodes for d in parts[0]] == [10, 10, 10, 10]
+
+
+def test_product_path_has_no_cpu_fallback():
+    """CPU tensors must be rejected by the CUDA backend wrapper (and the library must exist)."""
+    _backend.use_backend_for_testing(None)
+    try:
+        be = _backend.get()
+    except _backend.CgcError:
+        pytest.skip('library not built')
+    with pytest.raises(_backend.CgcError):
+        be.row_inv_degree(torch.zeros(3, dtype=torch.int32), torch.zeros(2))
