@@ -50,16 +50,35 @@ k_colreduce(const float* __restrict__ a, int64_t lda, const float* __restrict__ 
   }
 }
 
-__global__ void k_bn_finalize(const float* __restrict__ partial, int nrb, int c, int64_t rows,
-                              float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
-                              float eps, float* __restrict__ mean, float* __restrict__ invstd) {
-  int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= c) return;
-  double t1 = 0.0, t2 = 0.0;
-  for (int rb = 0; rb < nrb; ++rb) {
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per column: lanes stride over the row-block partials (fixed order -> deterministic)
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nrb, int c, int col,
+                                                double& t1, double& t2) {
+  const int lane = threadIdx.x & 31;
+  t1 = 0.0;
+  t2 = 0.0;
+  for (int rb = lane; rb < nrb; rb += 32) {
     t1 += (double)partial[(rb * 2 + 0) * (int64_t)c + col];
     t2 += (double)partial[(rb * 2 + 1) * (int64_t)c + col];
   }
+  t1 = warp_sum_f64(t1);
+  t2 = warp_sum_f64(t2);
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_finalize(const float* __restrict__ partial, int nrb, int c, int64_t rows, float* __restrict__ running_mean,
+              float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
+              float* __restrict__ invstd) {
+  int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (col >= c) return;
+  double t1, t2;
+  reduce_partials(partial, nrb, c, col, t1, t2);
+  if ((threadIdx.x & 31) != 0) return;
   double mu = t1 / (double)rows;
   double var = t2 / (double)rows - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -73,15 +92,14 @@ __global__ void k_bn_finalize(const float* __restrict__ partial, int nrb, int c,
 }
 
 // out1[col] = sum partial[., 0, col]; out2[col] = sum partial[., 1, col]   (out2 nullable)
-__global__ void k_sum_finalize(const float* __restrict__ partial, int nrb, int c, float* __restrict__ out1,
-                               float* __restrict__ out2) {
-  int col = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_sum_finalize(const float* __restrict__ partial, int nrb, int c, float* __restrict__ out1,
+               float* __restrict__ out2) {
+  int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (col >= c) return;
-  double t1 = 0.0, t2 = 0.0;
-  for (int rb = 0; rb < nrb; ++rb) {
-    t1 += (double)partial[(rb * 2 + 0) * (int64_t)c + col];
-    t2 += (double)partial[(rb * 2 + 1) * (int64_t)c + col];
-  }
+  double t1, t2;
+  reduce_partials(partial, nrb, c, col, t1, t2);
+  if ((threadIdx.x & 31) != 0) return;
   out1[col] = (float)t1;
   if (out2) out2[col] = (float)t2;
 }
@@ -211,7 +229,7 @@ extern "C" int cgc_bn_stats(const float* y, int64_t ldy, int64_t rows, int32_t c
   k_colreduce<RED_STATS><<<grid, dim3(kRedX, kRedY), 0, st>>>(y, ldy, nullptr, 0, nullptr, nullptr, nullptr, 0, rows,
                                                               c, rpb, partial);
   CGC_CHECK_LAUNCH("k_colreduce<stats>");
-  k_bn_finalize<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nrb, c, rows, running_mean, running_var,
+  k_bn_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, rows, running_mean, running_var,
                                                             momentum, eps, mean, invstd);
   CGC_CHECK_LAUNCH("k_bn_finalize");
   return 0;
@@ -261,7 +279,7 @@ extern "C" int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t
   k_colreduce<RED_BN_BWD><<<grid, dim3(kRedX, kRedY), 0, st>>>(gx, ldgx, y, ldy, mean, invstd, num_nodes, nmax, rows,
                                                                c, rpb, partial);
   CGC_CHECK_LAUNCH("k_colreduce<bn_bwd>");
-  k_sum_finalize<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nrb, c, d_beta, d_gamma);
+  k_sum_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, d_beta, d_gamma);
   CGC_CHECK_LAUNCH("k_sum_finalize");
   k_bn_bwd_apply<<<elementwise_grid(rows * c), 256, 0, st>>>(gx, ldgx, y, ldy, mean, invstd, gamma, d_gamma, d_beta,
                                                              num_nodes, nmax, rows, c, training, gy, ldgy);
@@ -283,7 +301,7 @@ extern "C" int cgc_colsum(const float* x, int64_t ldx, int64_t rows, int32_t c, 
   k_colreduce<RED_COLSUM><<<grid, dim3(kRedX, kRedY), 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, num_nodes, nmax,
                                                                rows, c, rpb, partial);
   CGC_CHECK_LAUNCH("k_colreduce<colsum>");
-  k_sum_finalize<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nrb, c, out, nullptr);
+  k_sum_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, out, nullptr);
   CGC_CHECK_LAUNCH("k_sum_finalize");
   return 0;
 }

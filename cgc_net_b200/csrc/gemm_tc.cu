@@ -1,10 +1,469 @@
-// tcgen05 3xTF32 GEMM (placeholder until the tensor-core kernel lands: reports "unsupported").
+// tcgen05 (5th-gen tensor core) batched GEMM in 3xTF32: fp32 operands are split in-kernel into
+// hi = upper 19 bits and lo = a - hi, and D += hi*hi + lo*hi + hi*lo is accumulated in fp32 in TMEM,
+// which restores ~fp32 accuracy (relative error ~1e-6) from kind::tf32 MMAs.
+//
+// Serves the dense contractions of the hot path: lin of GNN_Module (reference model/network.py:121-124),
+// S^T (A S) and its gradients (network.py:207), dW = dY^T X.
+//
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the fp32 A / B tiles, 3-stage ring
+//   warps 4-7   split: hi (in place) / lo tiles in shared memory, fence.proxy.async, signal the MMA warp
+//   warp 1      MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8) per stage, tcgen05.commit
+//   warp 2      TMEM allocation (2 x 128 accumulator columns, double buffered)
+//   warps 8-11  epilogue: tcgen05.ld 32x32b, alpha/bias/row-scale/row-mask/beta, 128-byte row segments to global
+// Both K-major and MN-major operands are supported through the UMMA shared-memory descriptors, so no
+// transposed copies of activations are ever made.
+#include <cuda.h>
+
 #include "gemm.cuh"
 
 namespace cgc {
-bool gemm_tc_supported(const GemmParams&, int, int) { return false; }
-int gemm_tc(GemmParams, int, int, void*, int64_t, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return CGC_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int kStages = 3;
+constexpr int kOperandBytes = BM * BK * 4;            // 16 KB (BM == BN)
+constexpr int kStageBytes = 4 * kOperandBytes;        // A_hi, B_hi, A_lo, B_lo
+constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per stage
+constexpr int kThreads = 384;
+constexpr int kSplitThreads = 128;
+constexpr int kEpiThreads = 128;
+constexpr int kAccCols = BN;                          // fp32 accumulator columns per buffer
+constexpr int kTmemCols = 2 * kAccCols;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+  GemmParams g;
+  int a_mn_major, b_mn_major;
+  int tiles_m, tiles_n, total_tiles;       // total = tiles_m * tiles_n * batch * ksplit
+  int c_vec;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TC_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE;\n\t"
+      "bra TC_WAIT;\n\t"
+      "TC_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle, sm_100 version bit set.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TileCoord {
+  int bz, split, m0, n0, kbeg, kend;
+};
+__device__ __forceinline__ TileCoord tile_coord(const Params& p, int t) {
+  TileCoord c;
+  int nt = t % p.tiles_n;
+  int r = t / p.tiles_n;
+  int mt = r % p.tiles_m;
+  int z = r / p.tiles_m;                  // bz * ksplit + split
+  c.bz = z / p.g.ksplit;
+  c.split = z - c.bz * p.g.ksplit;
+  c.m0 = mt * BM;
+  c.n0 = nt * BN;
+  c.kbeg = c.split * p.g.kchunk;
+  c.kend = min(p.g.k, c.kbeg + p.g.kchunk);
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  uint64_t* full = bars;                  // TMA -> split warps
+  uint64_t* xfull = bars + kStages;       // split warps -> MMA
+  uint64_t* empty = bars + 2 * kStages;   // MMA -> TMA
+  uint64_t* tfull = bars + 3 * kStages;   // MMA -> epilogue (2)
+  uint64_t* tempty = tfull + 2;           // epilogue -> MMA (2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&xfull[s], kSplitThreads);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = tile_coord(p, t);
+        for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kTxBytes);
+          unsigned char* sa = smem + (size_t)s * kStageBytes;
+          unsigned char* sb = sa + kOperandBytes;
+          if (p.a_mn_major) {
+#pragma unroll
+            for (int ch = 0; ch < BM / 32; ++ch) tma_load_3d(sa + ch * 4096, &map_a, c.m0 + ch * 32, k0, c.bz, &full[s]);
+          } else {
+            tma_load_3d(sa, &map_a, k0, c.m0, c.bz, &full[s]);
+          }
+          if (p.b_mn_major) {
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch) tma_load_3d(sb + ch * 4096, &map_b, c.n0 + ch * 32, k0, c.bz, &full[s]);
+          } else {
+            tma_load_3d(sb, &map_b, k0, c.n0, c.bz, &full[s]);
+          }
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // MN-major: 32-element chunks 4096 B apart (LBO), 8-k groups 1024 B apart (SBO), K step = next 8-k group.
+      // K-major : 8-row groups 1024 B apart (SBO), K step = 32 B inside the 128 B swizzle row.
+      const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
+      const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const TileCoord c = tile_coord(p, t);
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+        uint32_t accumulate = 0;
+        for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
+          mbar_wait(&xfull[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
+          const uint32_t b_hi = a_hi + kOperandBytes;
+          const uint32_t a_lo = a_hi + 2 * kOperandBytes;
+          const uint32_t b_lo = a_hi + 3 * kOperandBytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t da_hi = umma_desc(a_hi + kk * a_kstep, a_lbo, 1024u);
+            const uint64_t da_lo = umma_desc(a_lo + kk * a_kstep, a_lbo, 1024u);
+            const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, 1024u);
+            const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, 1024u);
+            umma_tf32(d_tmem, da_lo, db_hi, idesc, accumulate);
+            umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+            umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+            accumulate = 1u;
+          }
+          umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);                       // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================ hi / lo split ================================
+    const int tid = threadIdx.x - 128;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord c = tile_coord(p, t);
+      for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
+        mbar_wait(&full[s], ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * kStageBytes);
+        uint4* lo = hi + (2 * kOperandBytes) / 16;
+#pragma unroll 4
+        for (int i = tid; i < (2 * kOperandBytes) / 16; i += kSplitThreads) {
+          uint4 v = hi[i];
+          uint4 h;
+          h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&xfull[s]);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================ epilogue ================================
+    const int q = warp - 8;                            // TMEM lane quarter == warp_id % 4
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = tile_coord(p, t);
+      const int acc = it & 1;
+      mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const int row = c.m0 + q * 32 + lane;
+      const GemmParams& g = p.g;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + c0), v);
+        const int col0 = c.n0 + c0;
+        if (row < g.m && col0 < g.n) {
+          if (g.ksplit > 1) {
+            float* dst = g.partial + (((int64_t)(c.bz * g.ksplit + c.split)) * g.m + row) * g.n + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.n) dst[j] = g.alpha * v[j];
+          } else {
+            const int64_t grow = (int64_t)c.bz * g.m + row;
+            const float rsc = g.row_scale ? __ldg(g.row_scale + grow) : 1.0f;
+            const bool valid = g.num_nodes ? row_valid(g.num_nodes, g.nmax, grow) : true;
+            float* dst = g.c + (int64_t)c.bz * g.stride_c + (int64_t)row * g.ldc + col0;
+            if (p.c_vec && col0 + 32 <= g.n) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float x = g.alpha * v[j + u];
+                  if (g.bias) x += __ldg(g.bias + col0 + j + u);
+                  x *= rsc;
+                  ov[u] = valid ? x : 0.f;
+                }
+                if (g.beta != 0.f) {
+                  const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                  o.x += g.beta * old.x; o.y += g.beta * old.y; o.z += g.beta * old.z; o.w += g.beta * old.w;
+                }
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < g.n) {
+                  float x = g.alpha * v[j];
+                  if (g.bias) x += __ldg(g.bias + col0 + j);
+                  x *= rsc;
+                  if (!valid) x = 0.f;
+                  if (g.beta != 0.f) x += g.beta * dst[j];
+                  dst[j] = x;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tc_splitk_reduce(GemmParams p) {
+  const int64_t per = (int64_t)p.m * p.n;
+  const int64_t total = per * p.batch;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int bz = (int)(idx / per);
+    const int64_t rem = idx - (int64_t)bz * per;
+    const int row = (int)(rem / p.n), col = (int)(rem - (int64_t)row * p.n);
+    float v = 0.f;
+    for (int s = 0; s < p.ksplit; ++s) v += p.partial[((int64_t)(bz * p.ksplit + s)) * per + rem];
+    gemm_store(p, bz, row, col, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 3-D tensor map {inner, rows, batch} over a row-major fp32 operand, 128-byte swizzle.
+static bool make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t batch, int64_t ld,
+                     int64_t batch_stride, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : (int64_t)rows * ld) * 4};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+bool gemm_tc_supported(const GemmParams& p, int ta, int tb) {
+  (void)ta;
+  (void)tb;
+  if (!p.a_vec || !p.b_vec) return false;                      // 16-byte aligned base, ld and batch stride
+  if (p.m < 96 || p.n < 96 || p.k < 64) return false;
+  if ((double)p.m * p.n * p.k * p.batch < 6.7e7) return false;   // small problems stay on the FMA path
+  if (p.lda * 4 >= (1ll << 40) || p.ldb * 4 >= (1ll << 40)) return false;
+  return tc::get_encode_fn() != nullptr;
+}
+
+int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaStream_t st) {
+  using namespace tc;
+  Params q;
+  q.a_mn_major = ta ? 1 : 0;          // A stored [k, m]: m contiguous
+  q.b_mn_major = tb ? 0 : 1;          // B stored [k, n]: n contiguous
+  q.tiles_m = (int)ceil_div(p.m, BM);
+  q.tiles_n = (int)ceil_div(p.n, BN);
+  int64_t tiles = (int64_t)q.tiles_m * q.tiles_n * p.batch;
+  p.ksplit = 1;
+  p.kchunk = p.k;
+  p.partial = nullptr;
+  if (tiles < kNumSMs && p.k >= 4096) {
+    int64_t ks = ceil_div(2 * kNumSMs, tiles);
+    int64_t kmax = p.k / 1024;
+    if (ks > kmax) ks = kmax;
+    while (ks > 1 && ks * p.batch * (int64_t)p.m * p.n * 4 > work_bytes) --ks;
+    if (ks > 1 && work != nullptr) {
+      int64_t chunk = ceil_div(ceil_div(p.k, ks), BK) * BK;
+      p.kchunk = (int)chunk;
+      p.ksplit = (int)ceil_div(p.k, chunk);
+      p.partial = reinterpret_cast<float*>(work);
+    }
+  }
+  tiles *= p.ksplit;
+  CGC_REQUIRE(tiles < (1ll << 31), CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): too many tiles");
+  q.total_tiles = (int)tiles;
+  q.c_vec = (aligned16(p.c) && p.ldc % 4 == 0 && p.stride_c % 4 == 0) ? 1 : 0;
+  q.g = p;
+
+  CUtensorMap map_a, map_b;
+  bool ok;
+  if (q.a_mn_major) ok = make_map(&map_a, p.a, (uint64_t)p.m, (uint64_t)p.k, (uint64_t)p.batch, p.lda, p.stride_a, BK);
+  else ok = make_map(&map_a, p.a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)p.batch, p.lda, p.stride_a, BM);
+  CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for A");
+  if (q.b_mn_major) ok = make_map(&map_b, p.b, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.batch, p.ldb, p.stride_b, BK);
+  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, BN);
+  CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for B");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  int grid = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
+  k_gemm_tc<<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, q);
+  CGC_CHECK_LAUNCH("k_gemm_tc");
+  if (p.ksplit > 1) {
+    int64_t total = (int64_t)p.m * p.n * p.batch;
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    k_tc_splitk_reduce<<<(unsigned)blocks, 256, 0, st>>>(p);
+    CGC_CHECK_LAUNCH("k_tc_splitk_reduce");
+  }
+  return 0;
+}
+
 }  // namespace cgc

@@ -299,3 +299,62 @@ def test_gemm_epilogue_options(cuda_backend):
     a2 = aw[:, 8:8 + k].as_strided((batch, m, k), (m * 100, 100, 1), 8)
     c2 = cw[:, 4:4 + n].as_strided((batch, m, n), (m * 90, 90, 1), 4)
     both(cuda_backend, 'gemm', [a2, b, c2, False, False, 1.0, 0.0, None, None, None, 0], [2], rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------- tcgen05 3xTF32 GEMM
+TC_SHAPES = [(1, 256, 256, 128), (1, 1000, 1140, 1180), (3, 1140, 1140, 1800), (1, 1140, 1180, 20000),
+             (2, 200, 136, 72)]
+
+
+@pytest.mark.parametrize('shape', TC_SHAPES)
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_tcgen05(cuda_backend, shape, ta, tb):
+    """precision=1 forces the tensor-core path (K-major and MN-major operands, K tails, split-K).
+    3xTF32 must be ~fp32-accurate: error bound 1e-5 * sqrt(k) * |a||b| scale (single-pass TF32 is ~50x worse)."""
+    batch, m, n, k = shape
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(batch, *((k, m) if ta else (m, k)), generator=g)
+    b = torch.randn(batch, *((n, k) if tb else (k, n)), generator=g)
+    want = ((a.transpose(1, 2) if ta else a).double() @ (b.transpose(1, 2) if tb else b).double())
+    c = torch.full((batch, m, n), float('nan')).cuda()
+    ag, bg = a.cuda(), b.cuda()
+    if batch == 1:
+        ag, bg, c, want = ag[0], bg[0], c[0], want[0]
+    cuda_backend.gemm(ag, bg, c, ta, tb, precision=1)
+    torch.cuda.synchronize()
+    err = float((c.cpu().double() - want).abs().max())
+    assert err <= 1e-5 * k ** 0.5, 'max abs err %.3e (k=%d)' % (err, k)
+
+
+def test_gemm_tcgen05_epilogue(cuda_backend):
+    """alpha / beta / bias / row_scale / row mask and strided operands on the tensor-core path."""
+    batch, m, n, k = 2, 300, 260, 200
+    g = torch.Generator().manual_seed(9)
+    aw = torch.randn(batch * m, k + 24, generator=g)
+    a = aw[:, 8:8 + k].as_strided((batch, m, k), (m * (k + 24), k + 24, 1), 8)
+    b = torch.randn(batch, k, n, generator=g)
+    c0 = torch.randn(batch, m, n, generator=g)
+    bias, rsc = torch.randn(n, generator=g), torch.rand(batch * m, generator=g)
+    mask = _mask(batch, m)
+    want = c0.clone()
+    REF.gemm(a, b, want, False, False, 0.5, 1.0, bias, rsc, mask)
+    cg = c0.cuda()
+    awg = aw.cuda()
+    ag = awg.as_strided((batch, m, k), (m * (k + 24), k + 24, 1), 8)
+    cuda_backend.gemm(ag, b.cuda(), cg, False, False, 0.5, 1.0, bias.cuda(), rsc.cuda(), _cu(mask), precision=1)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(cg.cpu(), want, rtol=1e-4, atol=2e-4)
+
+
+def test_tf32_operand_truncation_probe(cuda_backend):
+    """Records how kind::tf32 reads fp32 operands (the split writes an explicit hi so either is handled)."""
+    m = n = 128
+    k = 64
+    a = torch.zeros(m, k)
+    a[:, 0] = 1.0 + 2.0 ** -11 + 2.0 ** -12          # low bits beyond the 10-bit TF32 mantissa
+    b = torch.zeros(k, n)
+    b[0, :] = 1.0
+    c = torch.zeros(m, n).cuda()
+    cuda_backend.gemm(a.cuda(), b.cuda(), c, False, False, precision=1)
+    torch.cuda.synchronize()
+    assert float((c.cpu() - a[0, 0]).abs().max()) < 1e-7        # 3xTF32 reproduces all fp32 bits here
