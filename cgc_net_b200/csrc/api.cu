@@ -47,7 +47,7 @@ extern "C" int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t 
   p.a_vec = aligned16(a) && lda % 4 == 0 && stride_a % 4 == 0;
   p.b_vec = aligned16(b) && ldb % 4 == 0 && stride_b % 4 == 0;
   cudaStream_t st = as_stream(stream);
-  if (precision != 0 && gemm_tc_supported(p, trans_a, trans_b)) return gemm_tc(p, trans_a, trans_b, work, work_bytes, st);
+  if (precision != 0 && gemm_tc_supported(p, trans_a, trans_b, precision == 1)) return gemm_tc(p, trans_a, trans_b, work, work_bytes, st);
   CGC_REQUIRE(precision != 1, CGC_ERR_UNSUPPORTED,
               "cgc_gemm: tcgen05 path does not support this shape/alignment (m=%d n=%d k=%d)", m, n, k);
   return gemm_simt(p, trans_a, trans_b, work, work_bytes, st);

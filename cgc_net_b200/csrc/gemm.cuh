@@ -34,7 +34,7 @@ __device__ __forceinline__ void gemm_store(const GemmParams& p, int bz, int row,
 int gemm_simt(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaStream_t st);
 
 // tcgen05 3xTF32 path.  Returns 1 ("not taken") when the shape / alignment is unsupported.
-bool gemm_tc_supported(const GemmParams& p, int ta, int tb);
+bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced);
 int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaStream_t st);
 
 }  // namespace cgc

@@ -1,6 +1,9 @@
 // tcgen05 (5th-gen tensor core) batched GEMM in 3xTF32: fp32 operands are split in-kernel into
-// hi = upper 19 bits and lo = a - hi, and D += hi*hi + lo*hi + hi*lo is accumulated in fp32 in TMEM,
-// which restores ~fp32 accuracy (relative error ~1e-6) from kind::tf32 MMAs.
+// hi = upper 19 bits and lo = a - hi; hi*hi is accumulated in one TMEM accumulator and the correction
+// lo*hi + hi*lo in a second one (summed in the epilogue), which restores the fp32 products from
+// kind::tf32 MMAs.  The tensor core adds into TMEM with truncation (round-toward-zero, measured: a biased
+// ~0.5 ulp(D) per accumulation step), so the main accumulator takes ONE add per K=8 step and K is
+// chunked (split-K, <= 4096 per accumulator) with the partial sums added in fp32 round-to-nearest.
 //
 // Serves the dense contractions of the hot path: lin of GNN_Module (reference model/network.py:121-124),
 // S^T (A S) and its gradients (network.py:207), dW = dY^T X.
@@ -9,10 +12,11 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the fp32 A / B tiles, 3-stage ring
 //   warps 4-7   split: hi (in place) / lo tiles in shared memory, fence.proxy.async, signal the MMA warp
 //   warp 1      MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8) per stage, tcgen05.commit
-//   warp 2      TMEM allocation (2 x 128 accumulator columns, double buffered)
+//   warp 2      TMEM allocation (2 buffers x (main + correction) x 128 columns = all 512 columns)
 //   warps 8-11  epilogue: tcgen05.ld 32x32b, alpha/bias/row-scale/row-mask/beta, 128-byte row segments to global
-// Both K-major and MN-major operands are supported through the UMMA shared-memory descriptors, so no
-// transposed copies of activations are ever made.
+// Both K-major (128B swizzle) and MN-major (128B swizzle with 32B atoms, the only MN-major layout
+// kind::tf32 accepts) operands are supported through the UMMA shared-memory descriptors, so no transposed
+// copies of activations are ever made.
 #include <cuda.h>
 
 #include "gemm.cuh"
@@ -29,8 +33,9 @@ constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per
 constexpr int kThreads = 384;
 constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 128;
-constexpr int kAccCols = BN;                          // fp32 accumulator columns per buffer
-constexpr int kTmemCols = 2 * kAccCols;
+constexpr int kAccCols = 2 * BN;                      // main + correction accumulator columns per buffer
+constexpr int kTmemCols = 2 * kAccCols;               // double buffered: all 512 TMEM columns
+constexpr int kMaxKChunk = 4096;                      // K per accumulator (bounds the RZ accumulation bias)
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct Params {
@@ -73,14 +78,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-// UMMA shared-memory descriptor, 128-byte swizzle, sm_100 version bit set.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory descriptor (sm_100 version bit set).  layout_type: 2 = SWIZZLE_128B (K-major),
+// 1 = SWIZZLE_128B_BASE32B (MN-major tf32).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -208,9 +215,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
                              ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // MN-major: 32-element chunks 4096 B apart (LBO), 8-k groups 1024 B apart (SBO), K step = next 8-k group.
-      // K-major : 8-row groups 1024 B apart (SBO), K step = 32 B inside the 128 B swizzle row.
+      // MN-major (SW128 with 32B atoms): 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart
+      //           (SBO), one K=8 step = the next 1024 B.
+      // K-major  (SW128): 8-row groups 1024 B apart (SBO), one K=8 step = 32 B inside the 128 B swizzle row.
       const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
+      const uint32_t a_sbo = p.a_mn_major ? 512u : 1024u, b_sbo = p.b_mn_major ? 512u : 1024u;
+      const uint32_t a_lt = p.a_mn_major ? 1u : 2u, b_lt = p.b_mn_major ? 1u : 2u;
       const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
       int s = 0;
       uint32_t ph = 0;
@@ -220,7 +230,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int acc = it & 1;
         mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * kAccCols);
+        const uint32_t d_corr = d_main + (uint32_t)BN;
         uint32_t accumulate = 0;
         for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
           mbar_wait(&xfull[s], ph);
@@ -231,13 +242,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const uint32_t b_lo = a_hi + 3 * kOperandBytes;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t da_hi = umma_desc(a_hi + kk * a_kstep, a_lbo, 1024u);
-            const uint64_t da_lo = umma_desc(a_lo + kk * a_kstep, a_lbo, 1024u);
-            const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, 1024u);
-            const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, 1024u);
-            umma_tf32(d_tmem, da_lo, db_hi, idesc, accumulate);
-            umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-            umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+            const uint64_t da_hi = umma_desc(a_hi + kk * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t da_lo = umma_desc(a_lo + kk * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, b_sbo, b_lt);
+            const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, b_sbo, b_lt);
+            umma_tf32(d_corr, da_lo, db_hi, idesc, accumulate);
+            umma_tf32(d_corr, da_hi, db_lo, idesc, 1u);
+            umma_tf32(d_main, da_hi, db_hi, idesc, accumulate);
             accumulate = 1u;
           }
           umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
@@ -288,8 +299,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const GemmParams& g = p.g;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
+        float v[32], w[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + BN + c0), w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
         const int col0 = c.n0 + c0;
         if (row < g.m && col0 < g.n) {
           if (g.ksplit > 1) {
@@ -385,7 +399,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 3-D tensor map {inner, rows, batch} over a row-major fp32 operand, 128-byte swizzle.
 static bool make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t batch, int64_t ld,
-                     int64_t batch_stride, uint32_t box_rows) {
+                     int64_t batch_stride, uint32_t box_rows, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {inner, rows, batch};
@@ -393,19 +407,23 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64
   cuuint32_t box[3] = {32, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 }  // namespace tc
 
-bool gemm_tc_supported(const GemmParams& p, int ta, int tb) {
+bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
   (void)ta;
   (void)tb;
   if (!p.a_vec || !p.b_vec) return false;                      // 16-byte aligned base, ld and batch stride
-  if (p.m < 96 || p.n < 96 || p.k < 64) return false;
-  if ((double)p.m * p.n * p.k * p.batch < 6.7e7) return false;   // small problems stay on the FMA path
+  if (!forced) {                                               // small / skinny problems stay on the FMA path
+    if (p.m < 96 || p.n < 96 || p.k < 64) return false;
+    if ((double)p.m * p.n * p.k * p.batch < 6.7e7) return false;
+  }
   if (p.lda * 4 >= (1ll << 40) || p.ldb * 4 >= (1ll << 40)) return false;
   return tc::get_encode_fn() != nullptr;
 }
@@ -421,10 +439,14 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   p.ksplit = 1;
   p.kchunk = p.k;
   p.partial = nullptr;
-  if (tiles < kNumSMs && p.k >= 4096) {
-    int64_t ks = ceil_div(2 * kNumSMs, tiles);
-    int64_t kmax = p.k / 1024;
-    if (ks > kmax) ks = kmax;
+  {
+    int64_t ks = ceil_div(p.k, kMaxKChunk);                    // accuracy: <= 4096 of K per accumulator
+    if (tiles < kNumSMs && p.k >= 4096) {                      // parallelism: fill the SMs
+      int64_t want = ceil_div(2 * kNumSMs, tiles);
+      int64_t kmax = p.k / 1024;
+      if (want > kmax) want = kmax;
+      if (want > ks) ks = want;
+    }
     while (ks > 1 && ks * p.batch * (int64_t)p.m * p.n * 4 > work_bytes) --ks;
     if (ks > 1 && work != nullptr) {
       int64_t chunk = ceil_div(ceil_div(p.k, ks), BK) * BK;
@@ -441,11 +463,11 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
 
   CUtensorMap map_a, map_b;
   bool ok;
-  if (q.a_mn_major) ok = make_map(&map_a, p.a, (uint64_t)p.m, (uint64_t)p.k, (uint64_t)p.batch, p.lda, p.stride_a, BK);
-  else ok = make_map(&map_a, p.a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)p.batch, p.lda, p.stride_a, BM);
+  if (q.a_mn_major) ok = make_map(&map_a, p.a, (uint64_t)p.m, (uint64_t)p.k, (uint64_t)p.batch, p.lda, p.stride_a, BK, true);
+  else ok = make_map(&map_a, p.a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)p.batch, p.lda, p.stride_a, BM, false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for A");
-  if (q.b_mn_major) ok = make_map(&map_b, p.b, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.batch, p.ldb, p.stride_b, BK);
-  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, BN);
+  if (q.b_mn_major) ok = make_map(&map_b, p.b, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.batch, p.ldb, p.stride_b, BK, true);
+  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, BN, false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for B");
 
   static bool attr_set = false;
