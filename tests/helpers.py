@@ -66,7 +66,7 @@ def oracle_fp64(orc, batch):
     return logits.detach(), loss.detach(), {k: p.grad for k, p in m.named_parameters()}
 
 
-def assert_grads_close(module, truth, ref32=None, tol=1e-4, floor=1e-3, slack=3.0):
+def assert_grads_close(module, truth, ref32=None, tol=1e-4, floor=1e-3, slack=5.0):
     """Per parameter tensor: max|g - truth| <= tol * max(max|truth|, floor), where ``truth`` is the
     float64 oracle.  Gradients that are the residue of heavy cancellation (tiny pool stages) carry
     an absolute fp32 rounding error that no fp32 implementation can beat; for those the bound is

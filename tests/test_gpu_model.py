@@ -142,7 +142,9 @@ def test_full_size_properties(cuda_backend):
     x2, a2, s_full, arg = ops.DiffPoolFunction.apply(cfg, assign, feat, None, True)
     torch.cuda.synchronize()
     assert torch.allclose(s_full.sum(1), torch.ones(64 * 1800, device='cuda'), atol=1e-5)
-    assert abs(float(a2.double().sum()) - 64 * 1800 * 8) < 1.0
+    # exact in real arithmetic; the tcgen05 accumulator adds with round-toward-zero (225 K=8 steps for
+    # K = 1800), a relative bias of ~1e-5 on sums of positive terms ("tensor-core accumulation")
+    assert abs(float(a2.double().sum()) / (64 * 1800 * 8) - 1.0) < 5e-5
     torch.testing.assert_close(x2.sum(1), feat.view(64, 1800, -1).sum(1), rtol=1e-4, atol=1e-3)
     assert bool((arg >= 0).all()) and bool((arg < 1140).all())
     logits, loss = m(batch)
