@@ -44,7 +44,7 @@ _SIGNATURES = {
                               _c_vp, _c_i64, _c_vp],
     'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
                     _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp],
-    'cgc_scale_rows_bwd': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp],
+    'cgc_scale_rows_bwd': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp],
     'cgc_bn_stats': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp,
                      _c_vp, _c_i64, _c_vp],
     'cgc_bn_eval_stats': [_c_vp, _c_vp, _c_i32, _c_f32, _c_vp, _c_vp, _c_vp],
@@ -222,12 +222,13 @@ class CudaBackend(object):
                                          w.shape[0], w.shape[1], dp, ldd, self._stream()), 'cgc_sage_dh')
 
     def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
-        for t in (dsa, sa, ga):
+        for t in (dsa, sa):
             if not t.is_contiguous():
-                raise CgcError('cgc_scale_rows_bwd needs contiguous matrices')
+                raise CgcError('cgc_scale_rows_bwd needs contiguous dsa / sa')
+        gp, ldg = _mat(ga)
         self._check(self.lib.cgc_scale_rows_bwd(_ptr(dsa, torch.float32), _ptr(sa, torch.float32),
                                                 _ptr(rs, torch.float32), dsa.shape[0], dsa.shape[1],
-                                                _ptr(ga, torch.float32), _ptr(d_rs, torch.float32),
+                                                gp, ldg, _ptr(d_rs, torch.float32),
                                                 self._stream()), 'cgc_scale_rows_bwd')
 
     # -- batch norm

@@ -18,6 +18,7 @@
 // kind::tf32 accepts) operands are supported through the UMMA shared-memory descriptors, so no transposed
 // copies of activations are ever made.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm.cuh"
 
@@ -43,6 +44,7 @@ struct Params {
   int a_mn_major, b_mn_major;
   int tiles_m, tiles_n, total_tiles;       // total = tiles_m * tiles_n * batch * ksplit
   int c_vec;
+  int write_hi;      // 1: store the masked hi tile explicitly; 0: rely on kind::tf32 ignoring the low 13 bits
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -278,7 +280,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
           l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
           l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          hi[i] = h;
+          if (p.write_hi) hi[i] = h;
           lo[i] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -421,8 +423,12 @@ bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
   (void)tb;
   if (!p.a_vec || !p.b_vec) return false;                      // 16-byte aligned base, ld and batch stride
   if (!forced) {                                               // small / skinny problems stay on the FMA path
-    if (p.m < 96 || p.n < 96 || p.k < 64) return false;
-    if ((double)p.m * p.n * p.k * p.batch < 6.7e7) return false;
+    // skinny outputs (n or m of 16..95) are taken when K is long: those contractions are bound by
+    // streaming the big operand, which the TMA pipeline does well even with a mostly idle MMA tile
+    const int lo = p.m < p.n ? p.m : p.n, hi = p.m < p.n ? p.n : p.m;
+    if (hi < 96 || lo < 16 || p.k < 64) return false;
+    if (lo < 96 && p.k < 512) return false;
+    if ((double)hi * (lo < 96 ? 128 : lo) * p.k * p.batch < 6.7e7) return false;
   }
   if (p.lda * 4 >= (1ll << 40) || p.ldb * 4 >= (1ll << 40)) return false;
   return tc::get_encode_fn() != nullptr;
@@ -459,6 +465,11 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   CGC_REQUIRE(tiles < (1ll << 31), CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): too many tiles");
   q.total_tiles = (int)tiles;
   q.c_vec = (aligned16(p.c) && p.ldc % 4 == 0 && p.stride_c % 4 == 0) ? 1 : 0;
+  static const int write_hi = []() {
+    const char* e = getenv("CGC_TC_WRITE_HI");
+    return e ? atoi(e) : 1;
+  }();
+  q.write_hi = write_hi;
   q.g = p;
 
   CUtensorMap map_a, map_b;

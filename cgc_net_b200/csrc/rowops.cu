@@ -151,7 +151,11 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
         for (int j = 0; j < NC; ++j) {
           int c = t + kEpiThreads * j;
           float g = 0.f;
-          if (valid && c < cout && __ldg(y + r * ldy + c) > 0.f) g = gy[r * ldgy + c];
+          if (valid && c < cout) {                    // independent loads (no y -> gy dependency chain)
+            const float yv = __ldg(y + r * ldy + c);
+            const float gv = gy[r * ldgy + c];
+            g = yv > 0.f ? gv : 0.f;
+          }
           gm[rr][j] = g;
           s = fmaf(g, acc[rr][j] * inv[rr], s);
         }
@@ -296,7 +300,7 @@ k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t
 // =================================================================== small row helpers
 __global__ void __launch_bounds__(256)
 k_scale_rows_bwd(const float* __restrict__ dsa, const float* __restrict__ sa, const float* __restrict__ rs,
-                 int64_t rows, int c, float* __restrict__ ga, float* __restrict__ d_rs) {
+                 int64_t rows, int c, float* __restrict__ ga, int64_t ldga, float* __restrict__ d_rs) {
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
@@ -305,7 +309,7 @@ k_scale_rows_bwd(const float* __restrict__ dsa, const float* __restrict__ sa, co
   for (int i = lane; i < c; i += 32) {
     float d = dsa[r * c + i];
     dot = fmaf(d, sa[r * c + i], dot);
-    ga[r * c + i] = d * sc;
+    ga[r * ldga + i] = d * sc;
   }
   dot = warp_sum(dot);
   if (lane == 0 && d_rs) d_rs[r] += dot / sc;
@@ -408,9 +412,11 @@ extern "C" int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64
 }
 
 extern "C" int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows, int32_t c,
-                                  float* ga, float* d_rs, void* stream) {
-  CGC_REQUIRE(dsa && sa && rs && ga && rows > 0 && c > 0, CGC_ERR_ARG, "cgc_scale_rows_bwd: bad args");
-  k_scale_rows_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(dsa, sa, rs, rows, c, ga, d_rs);
+                                  float* ga, int64_t ldga, float* d_rs, void* stream) {
+  CGC_REQUIRE(dsa && sa && rs && ga && rows > 0 && c > 0 && ldga >= c, CGC_ERR_ARG,
+              "cgc_scale_rows_bwd: bad args");
+  k_scale_rows_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(dsa, sa, rs, rows, c, ga, ldga,
+                                                                               d_rs);
   CGC_CHECK_LAUNCH("k_scale_rows_bwd");
   return 0;
 }

@@ -138,7 +138,7 @@ def _agg_t(be, cfg, adj, g_a, src_scale, out, accumulate):
         be.spmm(g.colptr, g.row, g.val_t, g_a, src_scale, None, out, accumulate)
     else:
         b, n = cfg.num_graphs, cfg.nmax
-        be.gemm(adj, g_a.view(b, n, -1), _as3d(out, b, n), True, False,
+        be.gemm(adj, _as3d(g_a, b, n), _as3d(out, b, n), True, False,
                 beta=1.0 if accumulate else 0.0)
 
 
@@ -229,6 +229,17 @@ class GnnModuleFunction(Function):
         d_rs = torch.zeros_like(rs) if dense else None
         g_x0 = None
         offs = [0, couts[0], couts[0] + couts[1]]
+        if want_adj:
+            # dA = sum_k gA_k x_{k-1}^T as ONE contraction over the concatenated channels
+            # [layer-1 | layer-2 | layer-3]: gA_k land in slices of ga_all, the layer inputs are x0 and
+            # the first two blocks of the concat buffer.
+            cin0 = x0.shape[1]
+            goffs = [0, cin0, cin0 + couts[0]]
+            ktot = cin0 + couts[0] + couts[1]
+            ga_all = _f32(m, ktot, device=dev)
+            xc_all = _f32(m, ktot, device=dev)
+            be.bn_apply(x0, None, None, None, None, None, xc_all[:, :cin0])                       # strided copies
+            be.bn_apply(cat[:, :couts[0] + couts[1]], None, None, None, None, None, xc_all[:, cin0:])
         for k in (2, 1, 0):
             w, b, gamma, beta = conv[k]
             a, y, mean, invstd = saved[4 * k: 4 * k + 4]
@@ -252,15 +263,14 @@ class GnnModuleFunction(Function):
             be.gemm(gy, w, dsa, False, True)                    # dsa = dh W^T
             x_prev = x0 if k == 0 else cat[:, offs[k - 1]: offs[k - 1] + couts[k - 1]]
             if dense:
-                ga = _f32(m, w.shape[0], device=dev)
+                if want_adj:
+                    ga = ga_all[:, goffs[k]: goffs[k] + w.shape[0]]
+                else:
+                    ga = _f32(m, w.shape[0], device=dev)
                 be.scale_rows_bwd(dsa, a, rs, ga, d_rs)         # ga = rs*dsa ; d_rs += dsa.sa/rs
                 src_scale = None
             else:
                 ga, src_scale = dsa, rs                         # rs applied inside the CSC gather
-            if want_adj:
-                b_, n_ = cfg.num_graphs, cfg.nmax
-                be.gemm(ga.view(b_, n_, -1), _as3d(x_prev, b_, n_), d_adj, False, True,
-                        beta=0.0 if k == 2 else 1.0)           # dA += gA x^T
             if k > 0:
                 _agg_t(be, cfg, adj, ga, src_scale,
                        g_cat[:, offs[k - 1]: offs[k - 1] + couts[k - 1]], True)
@@ -268,6 +278,8 @@ class GnnModuleFunction(Function):
                 g_x0 = _f32(m, x0.shape[1], device=dev)
                 _agg_t(be, cfg, adj, ga, src_scale, g_x0, False)
         if want_adj:
+            b_, n_ = cfg.num_graphs, cfg.nmax
+            be.gemm(ga_all.view(b_, n_, -1), xc_all.view(b_, n_, -1), d_adj, False, True)   # dA = gA x^T
             # rs_i = 1 / clamp(rsum_i, 1)  ->  dA_ij += -[rsum_i >= 1] d_rs_i / rsum_i^2   (all j)
             be.add_rs_grad(d_adj, rsum, d_rs)
         return (None, g_x0, d_adj, None, None) + tuple(grads)

@@ -127,9 +127,9 @@ CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t 
                 void* stream);
 
 /* Backward of sa = rs * agg (dense stages, where rs depends on the adjacency):
- * ga = rs * dsa;  d_rs[r] += dot(dsa[r], sa[r]) / rs[r]. */
+ * ga = rs * dsa (leading dimension ldga);  d_rs[r] += dot(dsa[r], sa[r]) / rs[r]. */
 CGC_API int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows,
-                       int32_t c, float* ga, float* d_rs, void* stream);
+                       int32_t c, float* ga, int64_t ldga, float* d_rs, void* stream);
 
 /* ------------------------------------------------------------------ BatchNorm1d over ALL rows
  * (padded rows count, network.py:101-107).  Training: batch mean / biased variance, running
