@@ -1,22 +1,27 @@
-// tcgen05 (5th-gen tensor core) batched GEMM in 3xTF32: fp32 operands are split in-kernel into
-// hi = upper 19 bits and lo = a - hi; hi*hi is accumulated in one TMEM accumulator and the correction
-// lo*hi + hi*lo in a second one (summed in the epilogue), which restores the fp32 products from
-// kind::tf32 MMAs.  The tensor core adds into TMEM with truncation (round-toward-zero, measured: a biased
-// ~0.5 ulp(D) per accumulation step), so the main accumulator takes ONE add per K=8 step and K is
-// chunked (split-K, <= 4096 per accumulator) with the partial sums added in fp32 round-to-nearest.
+// tcgen05 (5th-gen tensor core) batched GEMM in 3xTF32 with fp32 "promotion" of the accumulator.
 //
-// Serves the dense contractions of the hot path: lin of GNN_Module (reference model/network.py:121-124),
-// S^T (A S) and its gradients (network.py:207), dW = dY^T X.
+// fp32 operands are split in-kernel into hi (what kind::tf32 reads: the upper 19 bits, the hardware
+// ignores the low 13 mantissa bits -- verified by tests/test_gpu_ops.py) and lo = a - hi, and
+// D += lo*hi + hi*lo + hi*hi restores the fp32 products.  The tensor core adds into TMEM with truncation
+// (round toward zero; measured: a biased ~0.5 ulp(D) per accumulation step), which over a
+// K = 1000..100000 contraction would cost 1e-5..1e-3 relative.  So the accumulator is drained every
+// 4 K-blocks (K = 128, 48 MMA adds): the epilogue warps read the chunk from TMEM and add it to fp32
+// registers with round-to-nearest while the MMA warp fills the other TMEM buffer.  The result is
+// fp32-grade (~3e-6 relative), which is what lets every dense contraction of the path use this kernel.
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the fp32 A / B tiles, 3-stage ring
-//   warps 4-7   split: hi (in place) / lo tiles in shared memory, fence.proxy.async, signal the MMA warp
-//   warp 1      MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8) per stage, tcgen05.commit
-//   warp 2      TMEM allocation (2 buffers x (main + correction) x 128 columns = all 512 columns)
-//   warps 8-11  epilogue: tcgen05.ld 32x32b, alpha/bias/row-scale/row-mask/beta, 128-byte row segments to global
-// Both K-major (128B swizzle) and MN-major (128B swizzle with 32B atoms, the only MN-major layout
-// kind::tf32 accepts) operands are supported through the UMMA shared-memory descriptors, so no transposed
-// copies of activations are ever made.
+// Serves lin of GNN_Module (reference model/network.py:121-124), S^T X / S^T (A S) of _diff_pool
+// (network.py:206-207), matmul(adj, x) of DenseSAGEConv on the dense stages, and all their gradients.
+//
+// Structure (one persistent CTA per SM, 512 threads, warp-specialised):
+//   warp 0       TMA producer: cp.async.bulk.tensor of the fp32 A / B tiles into a 3-stage ring
+//   warps 4-7    split: lo tile written next to the TMA-landed tile, fence.proxy.async, signal the MMA warp
+//   warp 1       MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8) per stage;
+//                tcgen05.commit frees the stage and, every 4 stages, hands the accumulator to the epilogue
+//   warp 2       TMEM allocation (2 accumulator buffers x 128 columns)
+//   warps 8-15   promotion + epilogue: tcgen05.ld 32x32b chunks -> fp32 registers (+=), at the end of the tile
+//                alpha / bias / row-scale / row-mask / beta and 128-byte row segments to global
+// K-major operands use the 128B swizzle, MN-major operands the 128B swizzle with 32B atoms (the only
+// MN-major layout kind::tf32 accepts), so no transposed copy of an activation is ever made.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -29,14 +34,14 @@ namespace tc {
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int kStages = 3;
 constexpr int kOperandBytes = BM * BK * 4;            // 16 KB (BM == BN)
-constexpr int kStageBytes = 4 * kOperandBytes;        // A_hi, B_hi, A_lo, B_lo
+constexpr int kStageBytes = 4 * kOperandBytes;        // A, B (as landed = hi), A_lo, B_lo
 constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per stage
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kSplitThreads = 128;
-constexpr int kEpiThreads = 128;
-constexpr int kAccCols = 2 * BN;                      // main + correction accumulator columns per buffer
-constexpr int kTmemCols = 2 * kAccCols;               // double buffered: all 512 TMEM columns
-constexpr int kMaxKChunk = 4096;                      // K per accumulator (bounds the RZ accumulation bias)
+constexpr int kEpiThreads = 256;
+constexpr int kChunkBlocks = 4;                       // K-blocks accumulated in TMEM before promotion to fp32 registers
+constexpr int kAccCols = BN;
+constexpr int kTmemCols = 2 * kAccCols;
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct Params {
@@ -44,7 +49,7 @@ struct Params {
   int a_mn_major, b_mn_major;
   int tiles_m, tiles_n, total_tiles;       // total = tiles_m * tiles_n * batch * ksplit
   int c_vec;
-  int write_hi;      // 1: store the masked hi tile explicitly; 0: rely on kind::tf32 ignoring the low 13 bits
+  int write_hi;      // 1: also store the masked hi tile (not needed: kind::tf32 ignores the low 13 bits)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,7 +116,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+// acc[0..31] += TMEM[lane, col .. col+31]
+__device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float* acc) {
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -124,7 +130,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
 }
 
 struct TileCoord {
@@ -145,6 +151,54 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, int t) {
   return c;
 }
 
+// final write of 32 consecutive columns of one output row (v already holds the fp32 sums)
+__device__ __forceinline__ void store_segment(const Params& p, const TileCoord& c, int row, int col0, const float* v) {
+  const GemmParams& g = p.g;
+  if (row >= g.m || col0 >= g.n) return;
+  if (g.ksplit > 1) {
+    float* dst = g.partial + (((int64_t)(c.bz * g.ksplit + c.split)) * g.m + row) * g.n + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < g.n) dst[j] = g.alpha * v[j];
+    return;
+  }
+  const int64_t grow = (int64_t)c.bz * g.m + row;
+  const float rsc = g.row_scale ? __ldg(g.row_scale + grow) : 1.0f;
+  const bool valid = g.num_nodes ? row_valid(g.num_nodes, g.nmax, grow) : true;
+  float* dst = g.c + (int64_t)c.bz * g.stride_c + (int64_t)row * g.ldc + col0;
+  if (p.c_vec && col0 + 32 <= g.n) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 o;
+      float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float x = g.alpha * v[j + u];
+        if (g.bias) x += __ldg(g.bias + col0 + j + u);
+        x *= rsc;
+        ov[u] = valid ? x : 0.f;
+      }
+      if (g.beta != 0.f) {
+        const float4 old = *reinterpret_cast<const float4*>(dst + j);
+        o.x += g.beta * old.x; o.y += g.beta * old.y; o.z += g.beta * old.z; o.w += g.beta * old.w;
+      }
+      *reinterpret_cast<float4*>(dst + j) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col0 + j < g.n) {
+        float x = g.alpha * v[j];
+        if (g.bias) x += __ldg(g.bias + col0 + j);
+        x *= rsc;
+        if (!valid) x = 0.f;
+        if (g.beta != 0.f) x += g.beta * dst[j];
+        dst[j] = x;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   extern __shared__ unsigned char smem_raw[];
@@ -153,8 +207,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* full = bars;                  // TMA -> split warps
   uint64_t* xfull = bars + kStages;       // split warps -> MMA
   uint64_t* empty = bars + 2 * kStages;   // MMA -> TMA
-  uint64_t* tfull = bars + 3 * kStages;   // MMA -> epilogue (2)
-  uint64_t* tempty = tfull + 2;           // epilogue -> MMA (2)
+  uint64_t* tfull = bars + 3 * kStages;   // MMA -> promotion warps (2 accumulator buffers)
+  uint64_t* tempty = tfull + 2;           // promotion warps -> MMA (2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,37 +280,40 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
       int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      uint32_t chunk_it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = tile_coord(p, t);
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(acc * kAccCols);
-        const uint32_t d_corr = d_main + (uint32_t)BN;
-        uint32_t accumulate = 0;
-        for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
-          mbar_wait(&xfull[s], ph);
+        int k0 = c.kbeg;
+        while (k0 < c.kend) {
+          const uint32_t buf = chunk_it & 1u;
+          mbar_wait(&tempty[buf], ((chunk_it >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
-          const uint32_t b_hi = a_hi + kOperandBytes;
-          const uint32_t a_lo = a_hi + 2 * kOperandBytes;
-          const uint32_t b_lo = a_hi + 3 * kOperandBytes;
+          const uint32_t d_tmem = tmem_base + buf * (uint32_t)kAccCols;
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < kChunkBlocks && k0 < c.kend; ++kb, k0 += BK) {
+            mbar_wait(&xfull[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
+            const uint32_t b_hi = a_hi + kOperandBytes;
+            const uint32_t a_lo = a_hi + 2 * kOperandBytes;
+            const uint32_t b_lo = a_hi + 3 * kOperandBytes;
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t da_hi = umma_desc(a_hi + kk * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t da_lo = umma_desc(a_lo + kk * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, b_sbo, b_lt);
-            const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, b_sbo, b_lt);
-            umma_tf32(d_corr, da_lo, db_hi, idesc, accumulate);
-            umma_tf32(d_corr, da_hi, db_lo, idesc, 1u);
-            umma_tf32(d_main, da_hi, db_hi, idesc, accumulate);
-            accumulate = 1u;
+            for (int kk = 0; kk < BK / 8; ++kk) {
+              const uint64_t da_hi = umma_desc(a_hi + kk * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t da_lo = umma_desc(a_lo + kk * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, b_sbo, b_lt);
+              umma_tf32(d_tmem, da_lo, db_hi, idesc, accumulate);
+              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit(&empty[s]);                     // frees the stage once these MMAs have read it
+            if (++s == kStages) { s = 0; ph ^= 1; }
           }
-          umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
-          if (++s == kStages) { s = 0; ph ^= 1; }
+          umma_commit(&tfull[buf]);                     // chunk complete -> promotion warps
+          ++chunk_it;
         }
-        umma_commit(&tfull[acc]);                       // accumulator complete -> epilogue
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -272,7 +329,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint4* lo = hi + (2 * kOperandBytes) / 16;
 #pragma unroll 4
         for (int i = tid; i < (2 * kOperandBytes) / 16; i += kSplitThreads) {
-          uint4 v = hi[i];
+          const uint4 v = hi[i];
           uint4 h;
           h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
           uint4 l;
@@ -289,71 +346,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 8) {
-    // ================================ epilogue ================================
-    const int q = warp - 8;                            // TMEM lane quarter == warp_id % 4
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    // ================================ promotion + epilogue ================================
+    const int q = (warp - 8) & 3;                      // TMEM lane quarter == warp_id % 4
+    const int half = (warp - 8) >> 2;                  // which 64 accumulator columns this warp owns
+    uint32_t chunk_it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = tile_coord(p, t);
-      const int acc = it & 1;
-      mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
-      tc_fence_after();
-      const int row = c.m0 + q * 32 + lane;
-      const GemmParams& g = p.g;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32], w[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + c0), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + BN + c0), w);
+      float acc[64];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-        const int col0 = c.n0 + c0;
-        if (row < g.m && col0 < g.n) {
-          if (g.ksplit > 1) {
-            float* dst = g.partial + (((int64_t)(c.bz * g.ksplit + c.split)) * g.m + row) * g.n + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.n) dst[j] = g.alpha * v[j];
-          } else {
-            const int64_t grow = (int64_t)c.bz * g.m + row;
-            const float rsc = g.row_scale ? __ldg(g.row_scale + grow) : 1.0f;
-            const bool valid = g.num_nodes ? row_valid(g.num_nodes, g.nmax, grow) : true;
-            float* dst = g.c + (int64_t)c.bz * g.stride_c + (int64_t)row * g.ldc + col0;
-            if (p.c_vec && col0 + 32 <= g.n) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                float* ov = reinterpret_cast<float*>(&o);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  float x = g.alpha * v[j + u];
-                  if (g.bias) x += __ldg(g.bias + col0 + j + u);
-                  x *= rsc;
-                  ov[u] = valid ? x : 0.f;
-                }
-                if (g.beta != 0.f) {
-                  const float4 old = *reinterpret_cast<const float4*>(dst + j);
-                  o.x += g.beta * old.x; o.y += g.beta * old.y; o.z += g.beta * old.z; o.w += g.beta * old.w;
-                }
-                *reinterpret_cast<float4*>(dst + j) = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (col0 + j < g.n) {
-                  float x = g.alpha * v[j];
-                  if (g.bias) x += __ldg(g.bias + col0 + j);
-                  x *= rsc;
-                  if (!valid) x = 0.f;
-                  if (g.beta != 0.f) x += g.beta * dst[j];
-                  dst[j] = x;
-                }
-              }
-            }
-          }
-        }
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int k0 = c.kbeg; k0 < c.kend; k0 += kChunkBlocks * BK) {
+        const uint32_t buf = chunk_it & 1u;
+        mbar_wait(&tfull[buf], (chunk_it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * 64);
+        tmem_ld32_add(taddr, acc);
+        tmem_ld32_add(taddr + 32u, acc + 32);
+        tc_fence_before();
+        mbar_arrive(&tempty[buf]);
+        ++chunk_it;
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      const int row = c.m0 + q * 32 + lane;
+      store_segment(p, c, row, c.n0 + half * 64, acc);
+      store_segment(p, c, row, c.n0 + half * 64 + 32, acc + 32);
     }
   }
 
@@ -399,7 +414,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 3-D tensor map {inner, rows, batch} over a row-major fp32 operand, 128-byte swizzle.
+// 3-D tensor map {inner, rows, batch} over a row-major fp32 operand.
 static bool make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t batch, int64_t ld,
                      int64_t batch_stride, uint32_t box_rows, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();
@@ -411,8 +426,7 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -422,7 +436,7 @@ bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
   (void)ta;
   (void)tb;
   if (!p.a_vec || !p.b_vec) return false;                      // 16-byte aligned base, ld and batch stride
-  if (!forced) {                                               // small / skinny problems stay on the FMA path
+  if (!forced) {                                               // small problems stay on the FMA path
     // skinny outputs (n or m of 16..95) are taken when K is long: those contractions are bound by
     // streaming the big operand, which the TMA pipeline does well even with a mostly idle MMA tile
     const int lo = p.m < p.n ? p.m : p.n, hi = p.m < p.n ? p.n : p.m;
@@ -445,17 +459,13 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   p.ksplit = 1;
   p.kchunk = p.k;
   p.partial = nullptr;
-  {
-    int64_t ks = ceil_div(p.k, kMaxKChunk);                    // accuracy: <= 4096 of K per accumulator
-    if (tiles < kNumSMs && p.k >= 4096) {                      // parallelism: fill the SMs
-      int64_t want = ceil_div(2 * kNumSMs, tiles);
-      int64_t kmax = p.k / 1024;
-      if (want > kmax) want = kmax;
-      if (want > ks) ks = want;
-    }
+  if (tiles < kNumSMs && p.k >= 4096 && work != nullptr) {      // split K to fill the SMs
+    int64_t ks = ceil_div(2 * kNumSMs, tiles);
+    int64_t kmax = p.k / 1024;
+    if (ks > kmax) ks = kmax;
     while (ks > 1 && ks * p.batch * (int64_t)p.m * p.n * 4 > work_bytes) --ks;
-    if (ks > 1 && work != nullptr) {
-      int64_t chunk = ceil_div(ceil_div(p.k, ks), BK) * BK;
+    if (ks > 1) {
+      int64_t chunk = ceil_div(ceil_div(p.k, ks), kChunkBlocks * BK) * (kChunkBlocks * BK);
       p.kchunk = (int)chunk;
       p.ksplit = (int)ceil_div(p.k, chunk);
       p.partial = reinterpret_cast<float*>(work);
@@ -467,7 +477,7 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   q.c_vec = (aligned16(p.c) && p.ldc % 4 == 0 && p.stride_c % 4 == 0) ? 1 : 0;
   static const int write_hi = []() {
     const char* e = getenv("CGC_TC_WRITE_HI");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   q.write_hi = write_hi;
   q.g = p;
@@ -481,11 +491,7 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, BN, false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for B");
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
-  }
+  CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   int grid = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
   k_gemm_tc<<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, q);
   CGC_CHECK_LAUNCH("k_gemm_tc");

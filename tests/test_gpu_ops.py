@@ -323,9 +323,10 @@ def test_gemm_tcgen05(cuda_backend, shape, ta, tb):
     cuda_backend.gemm(ag, bg, c, ta, tb, precision=1)
     torch.cuda.synchronize()
     err = float((c.cpu().double() - want).abs().max())
-    # the tensor core accumulates into TMEM with round-toward-zero: a biased ~0.5 ulp per K=8 step
-    # (<= 512 steps per accumulator) -> relative to the output scale ~1e-5; single-pass TF32 is ~1e-3
-    assert err <= 3e-5 * float(want.abs().max()), 'max abs err %.3e vs scale %.3e (k=%d)' % (
+    # the tensor core accumulates into TMEM with round-toward-zero, so the kernel promotes the accumulator
+    # to fp32 registers every K = 128; what is left is fp32-grade: < 5e-6 of the output scale
+    # (un-promoted 3xTF32 measured ~1.3e-5, single-pass TF32 ~1e-3)
+    assert err <= 5e-6 * float(want.abs().max()), 'max abs err %.3e vs scale %.3e (k=%d)' % (
         err, float(want.abs().max()), k)
 
 
