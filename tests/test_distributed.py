@@ -1,0 +1,91 @@
+"""Data-parallel path on CPU: world_size 2 over gloo (host logic of cgc_net_b200/parallel.py).
+
+Two ranks each take a shard of the graphs, run forward/backward (per-operator CPU formulas injected as the
+backend), all-reduce ONE flat gradient bucket and must end up with the mean of the per-replica gradients --
+the reference's DataParallel semantics (mean of per-replica mean losses, train.py:179; per-replica BatchNorm)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers
+from cgc_net_b200 import _backend, graph, network, parallel
+from oracle import op_reference
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _make_model():
+    torch.manual_seed(3)
+    return network.SoftPoolingGcnEncoder(*helpers.encoder_args(300), concat=True, load_data_sparse=True).train()
+
+
+def _graphs():
+    return helpers.make_graphs([40, 55, 33, 61], [5, 6, 4, 8], seed=9)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    _backend.use_backend_for_testing(op_reference.TorchBackend())
+    model = _make_model()
+    if rank != 0:                                     # ranks start different, rank 0's weights win
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    parallel.broadcast_parameters(model, src=0)
+    bucket = parallel.FlatGradBucket(model.parameters())
+    shard = parallel.shard_for_rank(_graphs(), rank, world)
+    bucket.zero()
+    _, loss = model(graph.Batch.from_data_list(shard))
+    loss.backward()
+    bucket.all_reduce_mean()
+    if rank == 0:
+        torch.save({'flat': bucket.flat.clone(), 'loss': loss.detach()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gradient_allreduce(tmp_path, torch_backend):
+    out = str(tmp_path / 'rank0.pt')
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    # single-process reference: mean over the two shards of each shard's own gradient
+    graphs = _graphs()
+    flats = []
+    for rank in range(2):
+        model = _make_model()
+        bucket = parallel.FlatGradBucket(model.parameters())
+        bucket.zero()
+        _, loss = model(graph.Batch.from_data_list(parallel.shard_for_rank(graphs, rank, 2)))
+        loss.backward()
+        flats.append(bucket.flat.clone())
+    want = (flats[0] + flats[1]) / 2
+    assert got['flat'].numel() == sum(p.numel() for p in _make_model().parameters())
+    torch.testing.assert_close(got['flat'], want, rtol=1e-5, atol=1e-7)
+
+
+def test_flat_bucket_views_and_sharding():
+    model = _make_model()
+    bucket = parallel.FlatGradBucket(model.parameters())
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
+    bucket.flat.fill_(2.0)
+    assert all(float(p.grad.min()) == 2.0 for p in model.parameters())
+    bucket.zero()
+    assert float(bucket.flat.abs().sum()) == 0.0
+    bucket.all_reduce_mean()                           # no process group: a no-op
+    graphs = _graphs()
+    assert sum(len(parallel.shard_for_rank(graphs, r, 2)) for r in range(2)) == len(graphs)
+    by_nodes = [parallel.shard_for_rank(graphs, r, 2, by_nodes=True) for r in range(2)]
+    assert sum(len(s) for s in by_nodes) == len(graphs)
