@@ -41,7 +41,7 @@ FEAT = 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch-per-gpu', type=int, default=64)
@@ -61,7 +61,7 @@ def workload_name(args):
 
 # ----------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
@@ -70,7 +70,7 @@ class ClockSampler(object):
         self.rows, self.proc, self.thread = [], None, None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -126,7 +126,7 @@ def cpu_oracle_rate(args, steps, warmup):
         _, loss = model(batch)
         loss.backward()
         opt.step()
-        return float(loss)
+        return loss.item()
 
     for _ in range(warmup):
         one()
@@ -272,7 +272,7 @@ def run_ours(args):
 
     def e2e_step():
         loss = step(host_batch.to(device, non_blocking=True))
-        return float(loss)                      # D2H read of the step's result
+        return loss.item()                      # D2H read of the step's result
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)

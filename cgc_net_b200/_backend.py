@@ -52,8 +52,8 @@ _SIGNATURES = {
                      _c_vp, _c_i64, _c_vp],
     'cgc_bn_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64,
                    _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
-    'cgc_softmax_fwd': [_c_vp, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp],
-    'cgc_softmax_bwd': [_c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp],
+    'cgc_softmax_fwd': [_c_vp, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp],
+    'cgc_softmax_bwd': [_c_vp, _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp],
     'cgc_colmax_fwd': [_c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_vp],
     'cgc_colmax_bwd': [_c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp],
     'cgc_row_inv_clamped_sum': [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp],
@@ -269,14 +269,20 @@ class CudaBackend(object):
     # -- softmax / readout
     def softmax_fwd(self, z, mask, s, s_full, arg):
         nn, nmax = _mask(mask)
+        if not z.is_contiguous() or (s_full is not None and not s_full.is_contiguous()):
+            raise CgcError('cgc_softmax_fwd needs contiguous z / s_full')
+        sp, lds = _mat(s)
         self._check(self.lib.cgc_softmax_fwd(_ptr(z, torch.float32), z.shape[0], z.shape[1], nn, nmax,
-                                             _ptr(s, torch.float32), _ptr(s_full, torch.float32),
+                                             sp, lds, _ptr(s_full, torch.float32),
                                              _ptr(arg, torch.int32), self._stream()), 'cgc_softmax_fwd')
 
     def softmax_bwd(self, gs, s, gz):
-        self._check(self.lib.cgc_softmax_bwd(_ptr(gs, torch.float32), _ptr(s, torch.float32), s.shape[0],
-                                             s.shape[1], _ptr(gz, torch.float32), self._stream()),
-                    'cgc_softmax_bwd')
+        gp, ldg = _mat(gs)
+        sp, lds = _mat(s)
+        if ldg != lds or not gz.is_contiguous():
+            raise CgcError('cgc_softmax_bwd: gs and s must share their leading dimension, gz contiguous')
+        self._check(self.lib.cgc_softmax_bwd(gp, sp, lds, s.shape[0], s.shape[1], _ptr(gz, torch.float32),
+                                             self._stream()), 'cgc_softmax_bwd')
 
     def colmax_fwd(self, x, b, n, out, arg):
         self._check(self.lib.cgc_colmax_fwd(_ptr(x, torch.float32), b, n, x.shape[1],

@@ -440,7 +440,7 @@ bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
     // skinny outputs (n or m of 16..95) are taken when K is long: those contractions are bound by
     // streaming the big operand, which the TMA pipeline does well even with a mostly idle MMA tile
     const int lo = p.m < p.n ? p.m : p.n, hi = p.m < p.n ? p.n : p.m;
-    if (hi < 96 || lo < 16 || p.k < 64) return false;
+    if (hi < 96 || lo < 16 || p.k < 32) return false;
     if (lo < 96 && p.k < 512) return false;
     if ((double)hi * (lo < 96 ? 128 : lo) * p.k * p.batch < 6.7e7) return false;
   }

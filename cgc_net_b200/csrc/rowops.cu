@@ -238,7 +238,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
 template <int NREG>
 __global__ void __launch_bounds__(256)
 k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* __restrict__ num_nodes, int nmax,
-              float* __restrict__ s, float* __restrict__ s_full, int32_t* __restrict__ arg) {
+              float* __restrict__ s, int64_t lds, float* __restrict__ s_full, int32_t* __restrict__ arg) {
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
@@ -268,7 +268,7 @@ k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* _
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
   const bool valid = row_valid(num_nodes, nmax, r);
-  float* sr = s + r * (int64_t)c;
+  float* sr = s + r * lds;
   float* fr = s_full ? s_full + r * (int64_t)c : nullptr;
 #pragma unroll
   for (int j = 0; j < NREG; ++j) {
@@ -283,13 +283,13 @@ k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* _
 }
 
 __global__ void __launch_bounds__(256)
-k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t rows, int c,
+k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t lds, int64_t rows, int c,
               float* __restrict__ gz) {
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
-  const float* g = gs + r * (int64_t)c;
-  const float* p = s + r * (int64_t)c;
+  const float* g = gs + r * lds;
+  const float* p = s + r * lds;
   float dot = 0.f;
   for (int i = lane; i < c; i += 32) dot = fmaf(__ldg(g + i), __ldg(p + i), dot);
   dot = warp_sum(dot);
@@ -422,25 +422,25 @@ extern "C" int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float
 }
 
 extern "C" int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const int32_t* num_nodes, int32_t nmax,
-                               float* s, float* s_full, int32_t* arg, void* stream) {
-  CGC_REQUIRE(z && s && rows > 0 && c > 0, CGC_ERR_ARG, "cgc_softmax_fwd: bad args");
+                               float* s, int64_t lds, float* s_full, int32_t* arg, void* stream) {
+  CGC_REQUIRE(z && s && rows > 0 && c > 0 && lds >= c, CGC_ERR_ARG, "cgc_softmax_fwd: bad args");
   CGC_REQUIRE(c <= 32 * 40, CGC_ERR_UNSUPPORTED, "cgc_softmax_fwd: %d clusters > 1280", c);
   cudaStream_t st = as_stream(stream);
   unsigned grid = (unsigned)ceil_div(rows, 8);
   if (c <= 128)
-    k_softmax_fwd<4><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, s_full, arg);
+    k_softmax_fwd<4><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
   else if (c <= 512)
-    k_softmax_fwd<16><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, s_full, arg);
+    k_softmax_fwd<16><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
   else
-    k_softmax_fwd<40><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, s_full, arg);
+    k_softmax_fwd<40><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
   CGC_CHECK_LAUNCH("k_softmax_fwd");
   return 0;
 }
 
-extern "C" int cgc_softmax_bwd(const float* gs, const float* s, int64_t rows, int32_t c, float* gz,
+extern "C" int cgc_softmax_bwd(const float* gs, const float* s, int64_t lds, int64_t rows, int32_t c, float* gz,
                                void* stream) {
-  CGC_REQUIRE(gs && s && gz && rows > 0 && c > 0, CGC_ERR_ARG, "cgc_softmax_bwd: bad args");
-  k_softmax_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(gs, s, rows, c, gz);
+  CGC_REQUIRE(gs && s && gz && rows > 0 && c > 0 && lds >= c, CGC_ERR_ARG, "cgc_softmax_bwd: bad args");
+  k_softmax_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(gs, s, lds, rows, c, gz);
   CGC_CHECK_LAUNCH("k_softmax_bwd");
   return 0;
 }

@@ -36,6 +36,14 @@ def _f32(*shape, device):
     return torch.empty(*shape, dtype=torch.float32, device=device)
 
 
+def _mat(rows, cols, device):
+    """``[rows, cols]`` fp32 matrix whose leading dimension is padded to a multiple of 4 floats
+    (16 bytes): the alignment the TMA / tcgen05 contraction path needs (e.g. 114 clusters -> ld 116)."""
+    ld = (cols + 3) // 4 * 4
+    buf = torch.empty(rows, ld, dtype=torch.float32, device=device)
+    return buf if ld == cols else buf[:, :cols]
+
+
 class RowMask(object):
     """Validity of padded rows: row ``r`` is real iff ``r % nmax < num_nodes[r // nmax]``."""
 
@@ -299,21 +307,21 @@ class DiffPoolFunction(Function):
         dev = z.device
         m, c = z.shape
         b, n = cfg.num_graphs, cfg.nmax
-        s = _f32(m, c, device=dev)
+        s = _mat(m, c, dev)                      # leading dimension padded to 4 floats (TMA operand)
         s_full = _f32(m, c, device=dev) if collect else None
         arg = torch.empty(m, dtype=torch.int32, device=dev) if collect else None
         be.softmax_fwd(z.contiguous(), cfg.mask, s, s_full, arg)
         x = x.contiguous()
         xp = _f32(b, c, x.shape[1], device=dev)
-        be.gemm(s.view(b, n, c), x.view(b, n, -1), xp, True, False)
-        p = _f32(m, c, device=dev)
+        be.gemm(_as3d(s, b, n), x.view(b, n, -1), xp, True, False)
+        p = _mat(m, c, dev)
         if cfg.graph is not None:
             g = cfg.graph
             be.spmm(g.rowptr, g.col, g.val, s, None, None, p, False)
         else:
-            be.gemm(adj, s.view(b, n, c), p.view(b, n, c), False, False)
+            be.gemm(adj, _as3d(s, b, n), _as3d(p, b, n), False, False)
         ap = _f32(b, c, c, device=dev)
-        be.gemm(s.view(b, n, c), p.view(b, n, c), ap, True, False)
+        be.gemm(_as3d(s, b, n), _as3d(p, b, n), ap, True, False)
         ctx.cfg, ctx.s, ctx.p, ctx.x, ctx.adj = cfg, s, p, x, adj
         ctx.want_adj = adj is not None and ctx.needs_input_grad[3]
         outs = (xp, ap, s_full, arg)
@@ -329,22 +337,22 @@ class DiffPoolFunction(Function):
         b, n = cfg.num_graphs, cfg.nmax
         g_ap = g_ap.contiguous() if g_ap is not None else torch.zeros(b, c, c, device=dev)
         g_xp = g_xp.contiguous() if g_xp is not None else torch.zeros(b, c, x.shape[1], device=dev)
-        g_s = _f32(m, c, device=dev)
-        be.gemm(p.view(b, n, c), g_ap, g_s.view(b, n, c), False, True)                 # P gA'^T
-        be.gemm(x.view(b, n, -1), g_xp, g_s.view(b, n, c), False, True, beta=1.0)      # + X gX'^T
-        g_p = _f32(m, c, device=dev)
-        be.gemm(s.view(b, n, c), g_ap, g_p.view(b, n, c), False, False)                # S gA'
+        g_s = _mat(m, c, dev)
+        be.gemm(_as3d(p, b, n), g_ap, _as3d(g_s, b, n), False, True)                   # P gA'^T
+        be.gemm(x.view(b, n, -1), g_xp, _as3d(g_s, b, n), False, True, beta=1.0)       # + X gX'^T
+        g_p = _mat(m, c, dev)
+        be.gemm(_as3d(s, b, n), g_ap, _as3d(g_p, b, n), False, False)                  # S gA'
         g_adj = None
         if cfg.graph is not None:
             g = cfg.graph
-            be.spmm(g.colptr, g.row, g.val_t, g_p, None, None, g_s, True)                          # + A^T gP
+            be.spmm(g.colptr, g.row, g.val_t, g_p, None, None, g_s, True)              # + A^T gP
         else:
-            be.gemm(adj, g_p.view(b, n, c), g_s.view(b, n, c), True, False, beta=1.0)
+            be.gemm(adj, _as3d(g_p, b, n), _as3d(g_s, b, n), True, False, beta=1.0)
             if ctx.want_adj:
                 g_adj = torch.empty_like(adj)
-                be.gemm(g_p.view(b, n, c), s.view(b, n, c), g_adj, False, True)        # gP S^T
+                be.gemm(_as3d(g_p, b, n), _as3d(s, b, n), g_adj, False, True)          # gP S^T
         g_x = _f32(m, x.shape[1], device=dev)
-        be.gemm(s.view(b, n, c), g_xp, g_x.view(b, n, -1), False, False)               # S gX'
+        be.gemm(_as3d(s, b, n), g_xp, g_x.view(b, n, -1), False, False)                # S gX'
         g_z = _f32(m, c, device=dev)
         be.softmax_bwd(g_s, s, g_z)
         return None, g_z, g_x, g_adj, None

@@ -152,12 +152,13 @@ CGC_API int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ld
 
 /* ------------------------------------------------------------------ diff-pool pieces
  * s = softmax(z, -1) * mask (network.py:200-205); s_full (nullable) = softmax before masking
- * (collect_assign, :201-202); arg (nullable) = argmax_c z[r, c] = cluster index per node. */
+ * (collect_assign, :201-202); arg (nullable) = argmax_c z[r, c] = cluster index per node.
+ * z and s_full are contiguous [rows, c]; s has leading dimension lds (>= c, padded for TMA). */
 CGC_API int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const int32_t* num_nodes,
-                    int32_t nmax, float* s, float* s_full, int32_t* arg, void* stream);
-/* gz = s * (gs - sum_c gs * s) */
-CGC_API int cgc_softmax_bwd(const float* gs, const float* s, int64_t rows, int32_t c, float* gz,
-                    void* stream);
+                    int32_t nmax, float* s, int64_t lds, float* s_full, int32_t* arg, void* stream);
+/* gz = s * (gs - sum_c gs * s);  gs and s share the leading dimension lds, gz is contiguous */
+CGC_API int cgc_softmax_bwd(const float* gs, const float* s, int64_t lds, int64_t rows, int32_t c,
+                    float* gz, void* stream);
 
 /* torch.max(x, dim=1) over all nmax rows of each graph (network.py:264,275,284) */
 CGC_API int cgc_colmax_fwd(const float* x, int32_t num_graphs, int32_t nmax, int32_t c, float* out,

@@ -231,6 +231,11 @@ def test_softmax(cuda_backend, c):
     both(cuda_backend, 'softmax_fwd', [z, None, s, None, None], [2], rtol=1e-5, atol=1e-7)
     gs = torch.randn(rows, c, generator=g)
     both(cuda_backend, 'softmax_bwd', [gs, s, torch.zeros(rows, c)], [2], rtol=1e-4, atol=1e-6)
+    # padded leading dimension (what ops._mat hands out for 114 clusters: ld 116)
+    ld = (c + 3) // 4 * 4 + 4
+    sp, gsp = torch.zeros(rows, ld)[:, :c], torch.randn(rows, ld, generator=g)[:, :c]
+    both(cuda_backend, 'softmax_fwd', [z, mask, sp, None, None], [2], rtol=1e-5, atol=1e-7)
+    both(cuda_backend, 'softmax_bwd', [gsp, sp, torch.zeros(rows, c)], [2], rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize('c', [60, 20, 7])
