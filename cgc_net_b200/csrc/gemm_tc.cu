@@ -32,16 +32,18 @@ namespace cgc {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kOperandBytes = BM * BK * 4;            // 16 KB (BM == BN)
-constexpr int kStageBytes = 4 * kOperandBytes;        // A, B (as landed = hi), A_lo, B_lo
+constexpr int kStageBytes = 3 * kOperandBytes;        // A (as landed), B (as landed = B_hi), B_lo
 constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per stage
 constexpr int kThreads = 512;
 constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 256;
 constexpr int kChunkBlocks = 2;                      // K-blocks accumulated in TMEM before promotion to fp32 registers
-constexpr int kAccCols = BN;
-constexpr int kTmemCols = 2 * kAccCols;
+constexpr int kAccCols = BN;                          // accumulator columns per buffer (2 buffers)
+constexpr int kATmemBase = 2 * kAccCols;              // A operand tiles live in TMEM: per stage hi[32] | lo[32]
+constexpr int kATmemCols = 2 * BK;
+constexpr int kTmemCols = 512;                        // 2 * 128 accumulator + 4 * 64 operand columns
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct Params {
@@ -107,6 +109,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand from tensor memory (lane = row of the tile, column = K index), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive TMEM columns of this thread's lane <- 32 registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -269,15 +295,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
-                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // MN-major (SW128 with 32B atoms): 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart
+      // A is fed from TMEM (always "K-major" there: lane = row, column = k), B from shared memory.
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.b_mn_major << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // B MN-major (SW128 with 32B atoms): 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart
       //           (SBO), one K=8 step = the next 1024 B.
-      // K-major  (SW128): 8-row groups 1024 B apart (SBO), one K=8 step = 32 B inside the 128 B swizzle row.
-      const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
-      const uint32_t a_sbo = p.a_mn_major ? 512u : 1024u, b_sbo = p.b_mn_major ? 512u : 1024u;
-      const uint32_t a_lt = p.a_mn_major ? 1u : 2u, b_lt = p.b_mn_major ? 1u : 2u;
-      const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
+      // B K-major  (SW128): 8-row groups 1024 B apart (SBO), one K=8 step = 32 B inside the 128 B swizzle row.
+      const uint32_t b_lbo = p.b_mn_major ? 4096u : 16u;
+      const uint32_t b_sbo = p.b_mn_major ? 512u : 1024u;
+      const uint32_t b_lt = p.b_mn_major ? 1u : 2u;
+      const uint32_t b_kstep = p.b_mn_major ? 1024u : 32u;
       int s = 0;
       uint32_t ph = 0;
       uint32_t chunk_it = 0;
@@ -293,19 +320,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           for (int kb = 0; kb < kChunkBlocks && k0 < c.kend; ++kb, k0 += BK) {
             mbar_wait(&xfull[s], ph);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
-            const uint32_t b_hi = a_hi + kOperandBytes;
-            const uint32_t a_lo = a_hi + 2 * kOperandBytes;
-            const uint32_t b_lo = a_hi + 3 * kOperandBytes;
+            const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes) + kOperandBytes;
+            const uint32_t b_lo = b_hi + kOperandBytes;
+            const uint32_t a_hi = tmem_base + (uint32_t)(kATmemBase + s * kATmemCols);
+            const uint32_t a_lo = a_hi + (uint32_t)BK;
 #pragma unroll
             for (int kk = 0; kk < BK / 8; ++kk) {
-              const uint64_t da_hi = umma_desc(a_hi + kk * a_kstep, a_lbo, a_sbo, a_lt);
-              const uint64_t da_lo = umma_desc(a_lo + kk * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, b_sbo, b_lt);
               const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, b_sbo, b_lt);
-              umma_tf32(d_tmem, da_lo, db_hi, idesc, accumulate);
-              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-              umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, idesc, accumulate);
+              umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, idesc, 1u);
               accumulate = 1u;
             }
             umma_commit(&empty[s]);                     // frees the stage once these MMAs have read it
@@ -325,21 +350,55 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const TileCoord c = tile_coord(p, t);
       for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
         mbar_wait(&full[s], ph);
-        uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * kStageBytes);
-        uint4* lo = hi + (2 * kOperandBytes) / 16;
+        unsigned char* sa = smem + (size_t)s * kStageBytes;
+        // ---- B: lo tile next to the landed tile (element-wise, layout preserving)
+        uint4* bhi = reinterpret_cast<uint4*>(sa + kOperandBytes);
+        uint4* blo = bhi + kOperandBytes / 16;
 #pragma unroll 4
-        for (int i = tid; i < (2 * kOperandBytes) / 16; i += kSplitThreads) {
-          const uint4 v = hi[i];
-          uint4 h;
-          h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+        for (int i = tid; i < kOperandBytes / 16; i += kSplitThreads) {
+          const uint4 v = bhi[i];
           uint4 l;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          if (p.write_hi) hi[i] = h;
-          lo[i] = l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+          if (p.write_hi) {
+            uint4 h;
+            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+            bhi[i] = h;
+          }
+          blo[i] = l;
         }
+        // ---- A: thread `tid` owns row `tid` of the tile: gather its 32 k-values out of the swizzled
+        //      shared-memory tile, split, and store hi | lo into this lane's TMEM columns.
+        uint32_t ah[BK], al[BK];
+        if (p.a_mn_major) {
+          // box (tid / 32) of 4096 B; k-row k at k * 128 B; 32-byte units XOR-swizzled with (k & 3)
+          const unsigned char* base = sa + (tid >> 5) * 4096 + (tid & 7) * 4;
+          const int unit = (tid & 31) >> 3;
+#pragma unroll
+          for (int k = 0; k < BK; ++k)
+            ah[k] = *reinterpret_cast<const uint32_t*>(base + k * 128 + ((unit ^ (k & 3)) << 5));
+        } else {
+          // row tid at tid * 128 B; 16-byte chunks XOR-swizzled with (tid & 7)
+          const uint4* rowp = reinterpret_cast<const uint4*>(sa + tid * 128);
+#pragma unroll
+          for (int ch = 0; ch < BK / 4; ++ch) {
+            const uint4 v = rowp[ch ^ (tid & 7)];
+            ah[4 * ch + 0] = v.x; ah[4 * ch + 1] = v.y; ah[4 * ch + 2] = v.z; ah[4 * ch + 3] = v.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          const uint32_t h = ah[k] & 0xFFFFE000u;
+          al[k] = __float_as_uint(__uint_as_float(ah[k]) - __uint_as_float(h));
+          ah[k] = h;
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kATmemBase + s * kATmemCols);
+        tmem_st32(ta, ah);
+        tmem_st32(ta + (uint32_t)BK, al);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&xfull[s]);
         if (++s == kStages) { s = 0; ph ^= 1; }

@@ -158,12 +158,9 @@ k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, 
   int* s_col = s_ptr + (kGatherMaxRows + 4);
   float* s_val = reinterpret_cast<float*>(s_col + col_cap);
   __shared__ __align__(8) uint64_t bar;
-  __shared__ int s_e[2];
 
   const int* gptr = rowptr + grow0 + r0;
   if (threadIdx.x == 0) {
-    // the two row pointers that bound this CTA's edges: issued first, consumed after the TMA is in flight
-    const int e_lo = __ldg(gptr), e_hi = __ldg(gptr + nrows);
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&bar, tile_bytes);
@@ -172,15 +169,13 @@ k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, 
       uint32_t n = min(kBulkChunk, tile_bytes - off);
       bulk_g2s(smem_raw + off, src + off, n, &bar);
     }
-    s_e[0] = e_lo;
-    s_e[1] = e_hi;
   }
-  __syncthreads();
-  // while the tile is in flight: stage this CTA's rowptr slice and column indices (one round of loads)
-  const int e0 = s_e[0];
-  const int nnz = s_e[1] - e0;
-  const bool staged = nnz <= col_cap;
+  // While the tile is in flight: the two row pointers bounding this CTA's edges (broadcast loads, in
+  // flight together with the rowptr slice), then the column indices.  No barrier until everything landed.
+  const int e0 = __ldg(gptr);
+  const int nnz = __ldg(gptr + nrows) - e0;
   stage_words(s_ptr, gptr, nrows + 1);
+  const bool staged = nnz <= col_cap;
   if (staged) {
     stage_words(s_col, col + e0, nnz);
     if (val != nullptr) stage_words(s_val, val + e0, nnz);
@@ -193,36 +188,36 @@ k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, 
   constexpr int kGroups = kGatherThreads / LPR;
   const bool lane_on = sl * 4 < feat;
   const int base_col = (int)grow0;
-  // groups of one warp read the column lists of consecutive rows: rotating the start edge for the upper
-  // half of the groups keeps their smem words in different banks (deg 8: 8 groups x 8 words wrap at 32)
+  // The groups of one warp read the column lists of consecutive rows; starting the upper half of the
+  // groups 4 edges later keeps their smem words in different banks (deg 8: 8 groups x 8 words wrap at 32).
   const int rot_req = ((grp % (32 / LPR)) >= (16 / LPR)) ? 4 : 0;
   for (int r = grp; r < nrows; r += kGroups) {
     const int b = s_ptr[r] - e0, e = s_ptr[r + 1] - e0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane_on) {
-      const int mid = b + min(rot_req, e - b);
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const int lo = pass == 0 ? mid : b, hi = pass == 0 ? e : mid;
+      const int deg = e - b;
+      const int rot = deg > rot_req ? rot_req : 0;
 #pragma unroll 4
-        for (int i = lo; i < hi; ++i) {
-          int j;
-          float w = 1.0f;
-          if (staged) {
-            j = s_col[i] - base_col;
-            if (val != nullptr) w = s_val[i];
-          } else {
-            j = __ldg(col + e0 + i) - base_col;
-            if (val != nullptr) w = __ldg(val + e0 + i);
-          }
-          const float4 v = *reinterpret_cast<const float4*>(s_x + (size_t)j * feat + sl * 4);
-          acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-          acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      for (int t = 0; t < deg; ++t) {
+        int tt = t + rot;
+        if (tt >= deg) tt -= deg;
+        const int i = b + tt;
+        int j;
+        float w = 1.0f;
+        if (staged) {
+          j = s_col[i] - base_col;
+          if (val != nullptr) w = s_val[i];
+        } else {
+          j = __ldg(col + e0 + i) - base_col;
+          if (val != nullptr) w = __ldg(val + e0 + i);
         }
+        const float4 v = *reinterpret_cast<const float4*>(s_x + (size_t)j * feat + sl * 4);
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
       }
       float s;
       if (row_scale != nullptr) s = __ldg(row_scale + grow0 + r0 + r);
-      else if (val == nullptr) s = 1.0f / fmaxf((float)(e - b), 1.0f);
+      else if (val == nullptr) s = 1.0f / fmaxf((float)deg, 1.0f);
       else s = 1.0f;
       acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s;
       *reinterpret_cast<float4*>(out + (grow0 + r0 + r) * feat + sl * 4) = acc;
