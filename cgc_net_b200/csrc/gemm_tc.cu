@@ -13,16 +13,12 @@
 // (network.py:206-207), matmul(adj, x) of DenseSAGEConv on the dense stages, and all their gradients.
 //
 // Structure (one persistent CTA per SM, 512 threads, warp-specialised):
-//   warp 0       TMA producer: cp.async.bulk.tensor of the fp32 A / B tiles into a 4-stage ring
-//   warps 4-7    A operand: each thread gathers its row of the swizzled A tile from shared memory, splits it and
-//                stores hi | lo into TENSOR MEMORY (tcgen05.st) -- the MMA then reads A from TMEM, which
-//                halves the shared-memory bandwidth the contraction needs (the measured limiter)
-//   warp 1       MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8, A from TMEM, B from
-//                shared memory) per stage; tcgen05.commit frees the stage and, every 2 stages, hands the
-//                accumulator to the promotion warps
-//   warp 2       TMEM allocation (2 accumulator buffers x 128 columns + 4 x 64 operand columns = 512)
-//   warps 8-15   B operand lo tile (element-wise in shared memory) for every stage; one chunk later:
-//                promotion (tcgen05.ld 32x32b -> fp32 registers, +=); at the end of the tile the epilogue
+//   warp 0       TMA producer: cp.async.bulk.tensor of the fp32 A / B tiles into a 3-stage ring
+//   warps 4-7    split: lo tile written next to the TMA-landed tile, fence.proxy.async, signal the MMA warp
+//   warp 1       MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8) per stage;
+//                tcgen05.commit frees the stage and, every 2 stages, hands the accumulator to the epilogue
+//   warp 2       TMEM allocation (2 accumulator buffers x 128 columns)
+//   warps 8-15   promotion + epilogue: tcgen05.ld 32x32b chunks -> fp32 registers (+=), at the end of the tile
 //                alpha / bias / row-scale / row-mask / beta and 128-byte row segments to global
 // K-major operands use the 128B swizzle, MN-major operands the 128B swizzle with 32B atoms (the only
 // MN-major layout kind::tf32 accepts), so no transposed copy of an activation is ever made.
@@ -246,7 +242,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&xfull[s], kSplitThreads + kEpiThreads);
+      mbar_init(&xfull[s], kSplitThreads);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -355,6 +351,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + (size_t)s * kStageBytes;
+        // ---- B: lo tile next to the landed tile (element-wise, layout preserving)
+        uint4* bhi = reinterpret_cast<uint4*>(sa + kOperandBytes);
+        uint4* blo = bhi + kOperandBytes / 16;
+#pragma unroll 4
+        for (int i = tid; i < kOperandBytes / 16; i += kSplitThreads) {
+          const uint4 v = bhi[i];
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+          if (p.write_hi) {
+            uint4 h;
+            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+            bhi[i] = h;
+          }
+          blo[i] = l;
+        }
         // ---- A: thread `tid` owns row `tid` of the tile: gather its 32 k-values out of the swizzled
         //      shared-memory tile, split, and store hi | lo into this lane's TMEM columns.
         uint32_t ah[BK], al[BK];
@@ -385,78 +399,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         tmem_st32(ta + (uint32_t)BK, al);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&xfull[s]);
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= 8) {
-    // ================================ B split + promotion + epilogue ================================
-    // These 8 warps (a) write the lo tile of B for every stage, and (b) one chunk later drain the finished
-    // TMEM accumulator into fp32 registers; at the end of a tile they apply the epilogue and store.
+    // ================================ promotion + epilogue ================================
     const int q = (warp - 8) & 3;                      // TMEM lane quarter == warp_id % 4
     const int half = (warp - 8) >> 2;                  // which 64 accumulator columns this warp owns
-    const int tid = threadIdx.x - 256;
-    int s = 0;
-    uint32_t ph = 0;
     uint32_t chunk_it = 0;
-    float acc[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-    bool pending = false, pending_last = false;
-    TileCoord pc = tile_coord(p, 0);
-
-    auto drain = [&]() {                               // promote chunk (chunk_it - 1) and finish its tile if it was the last
-      const uint32_t it = chunk_it - 1u, buf = it & 1u;
-      mbar_wait(&tfull[buf], (it >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * 64);
-      tmem_ld32_add(taddr, acc);
-      tmem_ld32_add(taddr + 32u, acc + 32);
-      tc_fence_before();
-      mbar_arrive(&tempty[buf]);
-      if (pending_last) {
-        const int row = pc.m0 + q * 32 + lane;
-        store_segment(p, pc, row, pc.n0 + half * 64, acc);
-        store_segment(p, pc, row, pc.n0 + half * 64 + 32, acc + 32);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-      }
-    };
-
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = tile_coord(p, t);
-      for (int k0 = c.kbeg; k0 < c.kend; k0 += kChunkBlocks * BK) {
-        for (int kb = 0; kb < kChunkBlocks && k0 + kb * BK < c.kend; ++kb) {
-          mbar_wait(&full[s], ph);
-          uint4* bhi = reinterpret_cast<uint4*>(smem + (size_t)s * kStageBytes + kOperandBytes);
-          uint4* blo = bhi + kOperandBytes / 16;
+      float acc[64];
 #pragma unroll
-          for (int i = tid; i < kOperandBytes / 16; i += kEpiThreads) {
-            const uint4 v = bhi[i];
-            uint4 l;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
-            if (p.write_hi) {
-              uint4 h;
-              h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-              bhi[i] = h;
-            }
-            blo[i] = l;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&xfull[s]);
-          if (++s == kStages) { s = 0; ph ^= 1; }
-        }
-        if (pending) drain();
-        pending = true;
-        pending_last = (k0 + kChunkBlocks * BK >= c.kend);
-        pc = c;
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int k0 = c.kbeg; k0 < c.kend; k0 += kChunkBlocks * BK) {
+        const uint32_t buf = chunk_it & 1u;
+        mbar_wait(&tfull[buf], (chunk_it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * 64);
+        tmem_ld32_add(taddr, acc);
+        tmem_ld32_add(taddr + 32u, acc + 32);
+        tc_fence_before();
+        mbar_arrive(&tempty[buf]);
         ++chunk_it;
       }
+      const int row = c.m0 + q * 32 + lane;
+      store_segment(p, c, row, c.n0 + half * 64, acc);
+      store_segment(p, c, row, c.n0 + half * 64 + 32, acc + 32);
     }
-    if (pending) drain();
   }
 
   tc_fence_before();
