@@ -25,16 +25,22 @@ k_colreduce(const float* __restrict__ a, int64_t lda, const float* __restrict__ 
   if (col < c) {
     float mu = 0.f, is = 1.f;
     if (MODE == RED_BN_BWD) { mu = mean[col]; is = invstd[col]; }
-    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += kRedY) {
-      if (MODE == RED_STATS) {
-        float v = __ldg(a + r * lda + col);
-        acc1 += v;
-        acc2 = fmaf(v, v, acc2);
-      } else {
-        if (!row_valid(num_nodes, nmax, r)) continue;
-        float g = __ldg(a + r * lda + col);
-        acc1 += g;
-        if (MODE == RED_BN_BWD) acc2 = fmaf(g, (__ldg(y + r * ldy + col) - mu) * is, acc2);
+    // kUnroll independent loads in flight per thread (the loop is latency-bound otherwise)
+    constexpr int kUnroll = 8;
+    for (int64_t r0 = r_begin + threadIdx.y; r0 < r_end; r0 += (int64_t)kRedY * kUnroll) {
+      float va[kUnroll], vy[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t r = r0 + (int64_t)u * kRedY;
+        const bool ok = r < r_end && (MODE == RED_STATS || row_valid(num_nodes, nmax, r));
+        va[u] = ok ? __ldg(a + r * lda + col) : 0.f;
+        vy[u] = (MODE == RED_BN_BWD && ok) ? __ldg(y + r * ldy + col) : mu;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        acc1 += va[u];
+        if (MODE == RED_STATS) acc2 = fmaf(va[u], va[u], acc2);
+        if (MODE == RED_BN_BWD) acc2 = fmaf(va[u], (vy[u] - mu) * is, acc2);
       }
     }
   }
@@ -113,48 +119,147 @@ __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __res
 }
 
 // out = mask * ((y - mean) * invstd * gamma + beta)      (mean == nullptr: out = mask * y)
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 k_bn_apply(const float* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
            const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
            const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c, float* __restrict__ out,
            int64_t ldo) {
-  const int64_t total = rows * c;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = idx / c;
-    const int col = (int)(idx - r * c);
+  const IdxT total = (IdxT)(rows * c);
+  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT r = idx / (IdxT)c;
+    const int col = (int)(idx - r * (IdxT)c);
     float v = 0.f;
-    if (row_valid(num_nodes, nmax, r)) {
-      v = y[r * ldy + col];
+    if (row_valid(num_nodes, nmax, (int64_t)r)) {
+      v = y[(int64_t)r * ldy + col];
       if (mean != nullptr) v = (v - mean[col]) * invstd[col] * gamma[col] + beta[col];
     }
-    out[r * ldo + col] = v;
+    out[(int64_t)r * ldo + col] = v;
+  }
+}
+
+// float4 variant for wide, 16-byte aligned matrices: block (32 chunks x 8 rows), kRowUnroll rows in flight
+constexpr int kRowUnroll = 4;
+__global__ void __launch_bounds__(256)
+k_bn_apply_v4(const float* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c4, float* __restrict__ out,
+              int64_t ldo) {
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  if (ch >= c4) return;
+  if (mean != nullptr) {
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + ch);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + ch);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + ch);
+    // (v - mu) * is * ga + be, evaluated in that order to stay bit-identical with the scalar kernel
+    for (int64_t r0 = (int64_t)blockIdx.y * 8 + threadIdx.y; r0 < rows; r0 += (int64_t)gridDim.y * 8 * kRowUnroll) {
+      float4 v[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) {
+        const int64_t r = r0 + (int64_t)u * gridDim.y * 8;
+        if (r < rows) v[u] = __ldg(reinterpret_cast<const float4*>(y + r * ldy) + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) {
+        const int64_t r = r0 + (int64_t)u * gridDim.y * 8;
+        if (r >= rows) continue;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_valid(num_nodes, nmax, r)) {
+          o.x = (v[u].x - mu.x) * is.x * ga.x + be.x;
+          o.y = (v[u].y - mu.y) * is.y * ga.y + be.y;
+          o.z = (v[u].z - mu.z) * is.z * ga.z + be.z;
+          o.w = (v[u].w - mu.w) * is.w * ga.w + be.w;
+        }
+        *(reinterpret_cast<float4*>(out + r * ldo) + ch) = o;
+      }
+    }
+    return;
+  }
+  for (int64_t r0 = (int64_t)blockIdx.y * 8 + threadIdx.y; r0 < rows; r0 += (int64_t)gridDim.y * 8 * kRowUnroll) {
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const int64_t r = r0 + (int64_t)u * gridDim.y * 8;
+      if (r >= rows) continue;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_valid(num_nodes, nmax, r)) o = __ldg(reinterpret_cast<const float4*>(y + r * ldy) + ch);
+      *(reinterpret_cast<float4*>(out + r * ldo) + ch) = o;
+    }
   }
 }
 
 // gy = gamma*invstd*(g - d_beta/rows - xhat*d_gamma/rows)   (training) | gamma*invstd*g   (eval)
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float* __restrict__ gx, int64_t ldgx, const float* __restrict__ y, int64_t ldy,
                const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
                const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c, int training,
                float* __restrict__ gy, int64_t ldgy) {
-  const int64_t total = rows * c;
+  const IdxT total = (IdxT)(rows * c);
   const float inv_rows = 1.0f / (float)rows;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = idx / c;
-    const int col = (int)(idx - r * c);
-    const float g = row_valid(num_nodes, nmax, r) ? gx[r * ldgx + col] : 0.f;
+  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT r = idx / (IdxT)c;
+    const int col = (int)(idx - r * (IdxT)c);
+    const float g = row_valid(num_nodes, nmax, (int64_t)r) ? gx[(int64_t)r * ldgx + col] : 0.f;
     const float is = invstd[col];
     float v;
     if (training) {
-      const float xhat = (y[r * ldy + col] - mean[col]) * is;
+      const float xhat = (y[(int64_t)r * ldy + col] - mean[col]) * is;
       v = gamma[col] * is * (g - d_beta[col] * inv_rows - xhat * d_gamma[col] * inv_rows);
     } else {
       v = gamma[col] * is * g;
     }
-    gy[r * ldgy + col] = v;
+    gy[(int64_t)r * ldgy + col] = v;
+  }
+}
+
+__device__ __forceinline__ float bn_bwd_elem(float g, float yv, float mu, float is, float ga, float dg, float db,
+                                             float inv_rows, int training) {
+  if (training) {
+    const float xhat = (yv - mu) * is;
+    return ga * is * (g - db * inv_rows - xhat * dg * inv_rows);
+  }
+  return ga * is * g;
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply_v4(const float* __restrict__ gx, int64_t ldgx, const float* __restrict__ y, int64_t ldy,
+                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                  const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
+                  const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c4, int training,
+                  float* __restrict__ gy, int64_t ldgy) {
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  if (ch >= c4) return;
+  const float inv_rows = 1.0f / (float)rows;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + ch);
+  const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + ch);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
+  const float4 dg = __ldg(reinterpret_cast<const float4*>(d_gamma) + ch);
+  const float4 db = __ldg(reinterpret_cast<const float4*>(d_beta) + ch);
+  for (int64_t r0 = (int64_t)blockIdx.y * 8 + threadIdx.y; r0 < rows; r0 += (int64_t)gridDim.y * 8 * kRowUnroll) {
+    float4 g[kRowUnroll], yv[kRowUnroll];
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const int64_t r = r0 + (int64_t)u * gridDim.y * 8;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      yv[u] = mu;
+      if (r < rows) {
+        if (row_valid(num_nodes, nmax, r)) g[u] = __ldg(reinterpret_cast<const float4*>(gx + r * ldgx) + ch);
+        if (training) yv[u] = __ldg(reinterpret_cast<const float4*>(y + r * ldy) + ch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const int64_t r = r0 + (int64_t)u * gridDim.y * 8;
+      if (r >= rows) continue;
+      float4 o;
+      o.x = bn_bwd_elem(g[u].x, yv[u].x, mu.x, is.x, ga.x, dg.x, db.x, inv_rows, training);
+      o.y = bn_bwd_elem(g[u].y, yv[u].y, mu.y, is.y, ga.y, dg.y, db.y, inv_rows, training);
+      o.z = bn_bwd_elem(g[u].z, yv[u].z, mu.z, is.z, ga.z, dg.z, db.z, inv_rows, training);
+      o.w = bn_bwd_elem(g[u].w, yv[u].w, mu.w, is.w, ga.w, dg.w, db.w, inv_rows, training);
+      *(reinterpret_cast<float4*>(gy + r * ldgy) + ch) = o;
+    }
   }
 }
 
@@ -201,11 +306,11 @@ __global__ void k_colmax_bwd(const float* __restrict__ g, const int32_t* __restr
 // ---------------------------------------------------------------------------------------------
 static void reduce_geometry(int64_t rows, int c, int& nrb, int64_t& rows_per_block, dim3& grid) {
   int colblocks = (int)ceil_div(c, kRedX);
-  int64_t want = ceil_div((int64_t)kNumSMs * 8, colblocks);
-  int64_t max_by_rows = ceil_div(rows, kRedY * 4);      // at least ~4 rows per thread
+  int64_t want = ceil_div((int64_t)kNumSMs * 6, colblocks);
+  int64_t max_by_rows = ceil_div(rows, kRedY * 8);      // at least one unrolled batch per thread
   if (want > max_by_rows) want = max_by_rows;
   if (want < 1) want = 1;
-  if (want > 1024) want = 1024;
+  if (want > 512) want = 512;
   rows_per_block = ceil_div(rows, want);
   nrb = (int)ceil_div(rows, rows_per_block);
   grid = dim3((unsigned)colblocks, (unsigned)nrb);
@@ -244,6 +349,17 @@ extern "C" int cgc_bn_eval_stats(const float* running_mean, const float* running
   return 0;
 }
 
+// grid for the float4 row-streaming kernels: x = 32-chunk column groups, y = row blocks (~8 CTAs per SM)
+static dim3 wide_grid(int64_t rows, int c4) {
+  int gx = (int)ceil_div(c4, 32);
+  int64_t gy = ceil_div((int64_t)kNumSMs * 8, gx);
+  int64_t maxy = ceil_div(rows, 8 * kRowUnroll);
+  if (gy > maxy) gy = maxy;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  return dim3((unsigned)gx, (unsigned)gy);
+}
+
 static unsigned elementwise_grid(int64_t total) {
   int64_t blocks = ceil_div(total, 256);
   int64_t cap = (int64_t)kNumSMs * 32;
@@ -256,8 +372,19 @@ extern "C" int cgc_bn_apply(const float* y, int64_t ldy, const float* mean, cons
   CGC_REQUIRE(y && out && rows > 0 && c > 0 && ldy >= c && ldo >= c, CGC_ERR_ARG, "cgc_bn_apply: bad args");
   CGC_REQUIRE(mean == nullptr || (invstd && gamma && beta), CGC_ERR_ARG, "cgc_bn_apply: incomplete BN params");
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_bn_apply: mask without nmax");
-  k_bn_apply<<<elementwise_grid(rows * c), 256, 0, as_stream(stream)>>>(y, ldy, mean, invstd, gamma, beta,
-                                                                        num_nodes, nmax, rows, c, out, ldo);
+  cudaStream_t st = as_stream(stream);
+  const bool vec = c >= 64 && c % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0 && aligned16(y) && aligned16(out) &&
+                   (mean == nullptr || (aligned16(mean) && aligned16(invstd) && aligned16(gamma) && aligned16(beta)));
+  if (vec) {
+    k_bn_apply_v4<<<wide_grid(rows, c / 4), dim3(32, 8), 0, st>>>(y, ldy, mean, invstd, gamma, beta, num_nodes, nmax,
+                                                                 rows, c / 4, out, ldo);
+  } else if (rows * c < (1ll << 31)) {
+    k_bn_apply<uint32_t><<<elementwise_grid(rows * c), 256, 0, st>>>(y, ldy, mean, invstd, gamma, beta, num_nodes,
+                                                                     nmax, rows, c, out, ldo);
+  } else {
+    k_bn_apply<int64_t><<<elementwise_grid(rows * c), 256, 0, st>>>(y, ldy, mean, invstd, gamma, beta, num_nodes,
+                                                                    nmax, rows, c, out, ldo);
+  }
   CGC_CHECK_LAUNCH("k_bn_apply");
   return 0;
 }
@@ -281,8 +408,22 @@ extern "C" int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t
   CGC_CHECK_LAUNCH("k_colreduce<bn_bwd>");
   k_sum_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, d_beta, d_gamma);
   CGC_CHECK_LAUNCH("k_sum_finalize");
-  k_bn_bwd_apply<<<elementwise_grid(rows * c), 256, 0, st>>>(gx, ldgx, y, ldy, mean, invstd, gamma, d_gamma, d_beta,
-                                                             num_nodes, nmax, rows, c, training, gy, ldgy);
+  const bool vec = c >= 64 && c % 4 == 0 && ldgx % 4 == 0 && ldy % 4 == 0 && ldgy % 4 == 0 && aligned16(gx) &&
+                   aligned16(y) && aligned16(gy) && aligned16(mean) && aligned16(invstd) && aligned16(gamma) &&
+                   aligned16(d_gamma) && aligned16(d_beta);
+  if (vec) {
+    k_bn_bwd_apply_v4<<<wide_grid(rows, c / 4), dim3(32, 8), 0, st>>>(gx, ldgx, y, ldy, mean, invstd, gamma, d_gamma,
+                                                                     d_beta, num_nodes, nmax, rows, c / 4, training,
+                                                                     gy, ldgy);
+  } else if (rows * c < (1ll << 31)) {
+    k_bn_bwd_apply<uint32_t><<<elementwise_grid(rows * c), 256, 0, st>>>(gx, ldgx, y, ldy, mean, invstd, gamma,
+                                                                         d_gamma, d_beta, num_nodes, nmax, rows, c,
+                                                                         training, gy, ldgy);
+  } else {
+    k_bn_bwd_apply<int64_t><<<elementwise_grid(rows * c), 256, 0, st>>>(gx, ldgx, y, ldy, mean, invstd, gamma,
+                                                                        d_gamma, d_beta, num_nodes, nmax, rows, c,
+                                                                        training, gy, ldgy);
+  }
   CGC_CHECK_LAUNCH("k_bn_bwd_apply");
   return 0;
 }

@@ -198,7 +198,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     size_t smem = sizeof(float) * (size_t)(cin * cout + cout);
     int64_t warps_needed = rows;
     int64_t blocks = ceil_div(warps_needed, 8);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;   // latency-bound per row: keep many warps in flight
     k_epi_narrow<BWD><<<(unsigned)blocks, 256, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy,
                                                            gy, ldgy, dh, lddh);
     CGC_CHECK_LAUNCH("k_epi_narrow");
