@@ -36,8 +36,8 @@ constexpr int kStages = 4;
 constexpr int kOperandBytes = BM * BK * 4;            // 16 KB (BM == BN)
 constexpr int kStageBytes = 3 * kOperandBytes;        // A (as landed), B (as landed = B_hi), B_lo
 constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per stage
-constexpr int kThreads = 512;
-constexpr int kSplitThreads = 128;
+constexpr int kThreads = 640;                         // warps 0-3 misc, 4-7 + 16-19 split, 8-15 promotion/epilogue
+constexpr int kSplitThreads = 256;
 constexpr int kEpiThreads = 256;
 constexpr int kChunkBlocks = 2;                      // K-blocks accumulated in TMEM before promotion to fp32 registers
 constexpr int kAccCols = BN;                          // accumulator columns per buffer (2 buffers)
@@ -135,6 +135,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// 16 consecutive TMEM columns of this thread's lane <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -142,6 +151,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// acc[0..15] += TMEM[lane, col .. col+15]
+__device__ __forceinline__ void tmem_ld16_add(uint32_t taddr, float* acc) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+}
 // acc[0..31] += TMEM[lane, col .. col+31]
 __device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float* acc) {
   uint32_t r[32];
@@ -341,9 +363,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================ hi / lo split ================================
-    const int tid = threadIdx.x - 128;
+  } else if ((warp >= 4 && warp < 8) || warp >= 16) {
+    // ================================ hi / lo split (two sets of 4 warps) ================================
+    // set 0 (warps 4-7) owns k columns 0-15 of every A row, set 1 (warps 16-19) columns 16-31; thread
+    // `row` = TMEM lane.  The element-wise B split is shared by all 256 threads.
+    const int sset = warp >= 16 ? 1 : 0;
+    const int row = (warp & 3) * 32 + lane;
+    const int tid = sset * 128 + row;
     int s = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -351,10 +377,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + (size_t)s * kStageBytes;
+        // ---- A: gather this row's 16 k-values out of the swizzled shared-memory tile (issued first so
+        //      the loads overlap the B pass), split, store hi | lo into this lane's TMEM columns.
+        uint32_t ah[16], al[16];
+        if (p.a_mn_major) {
+          // box (row / 32) of 4096 B; k-row k at k * 128 B; 32-byte units XOR-swizzled with (k & 3)
+          const unsigned char* base = sa + (row >> 5) * 4096 + (row & 7) * 4 + sset * 16 * 128;
+          const int unit = (row & 31) >> 3;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            ah[k] = *reinterpret_cast<const uint32_t*>(base + k * 128 + ((unit ^ (k & 3)) << 5));
+        } else {
+          // row at row * 128 B; 16-byte chunks XOR-swizzled with (row & 7)
+          const uint4* rowp = reinterpret_cast<const uint4*>(sa + row * 128);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint4 v = rowp[(ch + 4 * sset) ^ (row & 7)];
+            ah[4 * ch + 0] = v.x; ah[4 * ch + 1] = v.y; ah[4 * ch + 2] = v.z; ah[4 * ch + 3] = v.w;
+          }
+        }
         // ---- B: lo tile next to the landed tile (element-wise, layout preserving)
         uint4* bhi = reinterpret_cast<uint4*>(sa + kOperandBytes);
         uint4* blo = bhi + kOperandBytes / 16;
-#pragma unroll 4
+#pragma unroll
         for (int i = tid; i < kOperandBytes / 16; i += kSplitThreads) {
           const uint4 v = bhi[i];
           uint4 l;
@@ -369,34 +414,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           blo[i] = l;
         }
-        // ---- A: thread `tid` owns row `tid` of the tile: gather its 32 k-values out of the swizzled
-        //      shared-memory tile, split, and store hi | lo into this lane's TMEM columns.
-        uint32_t ah[BK], al[BK];
-        if (p.a_mn_major) {
-          // box (tid / 32) of 4096 B; k-row k at k * 128 B; 32-byte units XOR-swizzled with (k & 3)
-          const unsigned char* base = sa + (tid >> 5) * 4096 + (tid & 7) * 4;
-          const int unit = (tid & 31) >> 3;
 #pragma unroll
-          for (int k = 0; k < BK; ++k)
-            ah[k] = *reinterpret_cast<const uint32_t*>(base + k * 128 + ((unit ^ (k & 3)) << 5));
-        } else {
-          // row tid at tid * 128 B; 16-byte chunks XOR-swizzled with (tid & 7)
-          const uint4* rowp = reinterpret_cast<const uint4*>(sa + tid * 128);
-#pragma unroll
-          for (int ch = 0; ch < BK / 4; ++ch) {
-            const uint4 v = rowp[ch ^ (tid & 7)];
-            ah[4 * ch + 0] = v.x; ah[4 * ch + 1] = v.y; ah[4 * ch + 2] = v.z; ah[4 * ch + 3] = v.w;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
+        for (int k = 0; k < 16; ++k) {
           const uint32_t h = ah[k] & 0xFFFFE000u;
           al[k] = __float_as_uint(__uint_as_float(ah[k]) - __uint_as_float(h));
           ah[k] = h;
         }
-        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kATmemBase + s * kATmemCols);
-        tmem_st32(ta, ah);
-        tmem_st32(ta + (uint32_t)BK, al);
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                            (uint32_t)(kATmemBase + s * kATmemCols + sset * 16);
+        tmem_st16(ta, ah);
+        tmem_st16(ta + (uint32_t)BK, al);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -404,7 +431,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 16) {
     // ================================ promotion + epilogue ================================
     const int q = (warp - 8) & 3;                      // TMEM lane quarter == warp_id % 4
     const int half = (warp - 8) >> 2;                  // which 64 accumulator columns this warp owns
@@ -419,8 +446,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         mbar_wait(&tfull[buf], (chunk_it >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * 64);
-        tmem_ld32_add(taddr, acc);
-        tmem_ld32_add(taddr + 32u, acc + 32);
+        tmem_ld16_add(taddr, acc);
+        tmem_ld16_add(taddr + 16u, acc + 16);
+        tmem_ld16_add(taddr + 32u, acc + 32);
+        tmem_ld16_add(taddr + 48u, acc + 48);
         tc_fence_before();
         mbar_arrive(&tempty[buf]);
         ++chunk_it;
