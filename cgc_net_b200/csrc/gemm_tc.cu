@@ -36,10 +36,10 @@ constexpr int kStages = 4;
 constexpr int kOperandBytes = BM * BK * 4;            // 16 KB (BM == BN)
 constexpr int kStageBytes = 3 * kOperandBytes;        // A (as landed), B (as landed = B_hi), B_lo
 constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per stage
-constexpr int kThreads = 640;                         // warps 0-3 misc, 4-7 + 16-19 split, 8-15 promotion/epilogue
-constexpr int kSplitThreads = 256;
+constexpr int kThreads = 512;
+constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 256;
-constexpr int kChunkBlocks = 2;                      // K-blocks accumulated in TMEM before promotion to fp32 registers
+constexpr int kDefaultChunkBlocks = 2;               // K-blocks accumulated in TMEM before promotion to fp32 registers
 constexpr int kAccCols = BN;                          // accumulator columns per buffer (2 buffers)
 constexpr int kATmemBase = 2 * kAccCols;              // A operand tiles live in TMEM: per stage hi[32] | lo[32]
 constexpr int kATmemCols = 2 * BK;
@@ -52,6 +52,7 @@ struct Params {
   int tiles_m, tiles_n, total_tiles;       // total = tiles_m * tiles_n * batch * ksplit
   int c_vec;
   int write_hi;      // 1: also store the masked hi tile (not needed: kind::tf32 ignores the low 13 bits)
+  int chunk_blocks;  // K-blocks per TMEM accumulation chunk (promotion period), CGC_TC_CHUNK overrides
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,6 +124,31 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, with the B descriptor passed as two 32-bit halves (no 64-bit arithmetic in the issue loop)
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // 32 consecutive TMEM columns of this thread's lane <- 32 registers
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -135,15 +161,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-// 16 consecutive TMEM columns of this thread's lane <- 16 registers
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -151,19 +168,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// acc[0..15] += TMEM[lane, col .. col+15]
-__device__ __forceinline__ void tmem_ld16_add(uint32_t taddr, float* acc) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
-}
 // acc[0..31] += TMEM[lane, col .. col+31]
 __device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float* acc) {
   uint32_t r[32];
@@ -316,8 +320,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      // A is fed from TMEM (always "K-major" there: lane = row, column = k), B from shared memory.
+    // The whole warp runs the loop (so addresses / descriptors stay warp-uniform and cheap to form);
+    // one elected lane issues.  A is fed from TMEM (lane = row, column = k), B from shared memory.
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.b_mn_major << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // B MN-major (SW128 with 32B atoms): 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart
@@ -326,7 +331,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const uint32_t b_lbo = p.b_mn_major ? 4096u : 16u;
       const uint32_t b_sbo = p.b_mn_major ? 512u : 1024u;
       const uint32_t b_lt = p.b_mn_major ? 1u : 2u;
-      const uint32_t b_kstep = p.b_mn_major ? 1024u : 32u;
+      const uint32_t b_kstep16 = (p.b_mn_major ? 1024u : 32u) >> 4;       // K step in descriptor address units
+      // descriptor = {lo: addr>>4 | lbo>>4 << 16, hi: sbo>>4 | version 1 << 14 | layout << 29}
+      const uint32_t desc_hi = (b_sbo >> 4) | (1u << 14) | (b_lt << 29);
+      const uint32_t desc_lo_base = (b_lbo >> 4) << 16;
+      const uint32_t smem_base16 = smem_u32(smem) >> 4;
       int s = 0;
       uint32_t ph = 0;
       uint32_t chunk_it = 0;
@@ -339,37 +348,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * (uint32_t)kAccCols;
           uint32_t accumulate = 0;
-          for (int kb = 0; kb < kChunkBlocks && k0 < c.kend; ++kb, k0 += BK) {
+          for (int kb = 0; kb < p.chunk_blocks && k0 < c.kend; ++kb, k0 += BK) {
             mbar_wait(&xfull[s], ph);
             tc_fence_after();
-            const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes) + kOperandBytes;
-            const uint32_t b_lo = b_hi + kOperandBytes;
-            const uint32_t a_hi = tmem_base + (uint32_t)(kATmemBase + s * kATmemCols);
-            const uint32_t a_lo = a_hi + (uint32_t)BK;
+            if (elect_one()) {
+              const uint32_t bh = desc_lo_base | (smem_base16 + (uint32_t)((s * kStageBytes + kOperandBytes) >> 4));
+              const uint32_t bl = bh + (uint32_t)(kOperandBytes >> 4);
+              const uint32_t a_hi = tmem_base + (uint32_t)(kATmemBase + s * kATmemCols);
+              const uint32_t a_lo = a_hi + (uint32_t)BK;
 #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk) {
-              const uint64_t db_hi = umma_desc(b_hi + kk * b_kstep, b_lbo, b_sbo, b_lt);
-              const uint64_t db_lo = umma_desc(b_lo + kk * b_kstep, b_lbo, b_sbo, b_lt);
-              umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, idesc, accumulate);
-              umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, idesc, 1u);
-              umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, idesc, 1u);
-              accumulate = 1u;
+              for (int kk = 0; kk < BK / 8; ++kk) {
+                umma_tf32_ts2(d_tmem, a_lo + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
+                umma_tf32_ts2(d_tmem, a_hi + kk * 8, bl + kk * b_kstep16, desc_hi, idesc, 1u);
+                umma_tf32_ts2(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, 1u);
+              }
+              umma_commit(&empty[s]);                   // frees the stage once these MMAs have read it
             }
-            umma_commit(&empty[s]);                     // frees the stage once these MMAs have read it
+            __syncwarp();
+            accumulate = 1u;
             if (++s == kStages) { s = 0; ph ^= 1; }
           }
-          umma_commit(&tfull[buf]);                     // chunk complete -> promotion warps
+          if (elect_one()) umma_commit(&tfull[buf]);    // chunk complete -> promotion warps
+          __syncwarp();
           ++chunk_it;
         }
       }
     }
-  } else if ((warp >= 4 && warp < 8) || warp >= 16) {
-    // ================================ hi / lo split (two sets of 4 warps) ================================
-    // set 0 (warps 4-7) owns k columns 0-15 of every A row, set 1 (warps 16-19) columns 16-31; thread
-    // `row` = TMEM lane.  The element-wise B split is shared by all 256 threads.
-    const int sset = warp >= 16 ? 1 : 0;
-    const int row = (warp & 3) * 32 + lane;
-    const int tid = sset * 128 + row;
+  } else if (warp >= 4 && warp < 8) {
+    // ================================ hi / lo split ================================
+    const int tid = threadIdx.x - 128;
     int s = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -377,29 +384,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + (size_t)s * kStageBytes;
-        // ---- A: gather this row's 16 k-values out of the swizzled shared-memory tile (issued first so
-        //      the loads overlap the B pass), split, store hi | lo into this lane's TMEM columns.
-        uint32_t ah[16], al[16];
-        if (p.a_mn_major) {
-          // box (row / 32) of 4096 B; k-row k at k * 128 B; 32-byte units XOR-swizzled with (k & 3)
-          const unsigned char* base = sa + (row >> 5) * 4096 + (row & 7) * 4 + sset * 16 * 128;
-          const int unit = (row & 31) >> 3;
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            ah[k] = *reinterpret_cast<const uint32_t*>(base + k * 128 + ((unit ^ (k & 3)) << 5));
-        } else {
-          // row at row * 128 B; 16-byte chunks XOR-swizzled with (row & 7)
-          const uint4* rowp = reinterpret_cast<const uint4*>(sa + row * 128);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const uint4 v = rowp[(ch + 4 * sset) ^ (row & 7)];
-            ah[4 * ch + 0] = v.x; ah[4 * ch + 1] = v.y; ah[4 * ch + 2] = v.z; ah[4 * ch + 3] = v.w;
-          }
-        }
         // ---- B: lo tile next to the landed tile (element-wise, layout preserving)
         uint4* bhi = reinterpret_cast<uint4*>(sa + kOperandBytes);
         uint4* blo = bhi + kOperandBytes / 16;
-#pragma unroll
+#pragma unroll 4
         for (int i = tid; i < kOperandBytes / 16; i += kSplitThreads) {
           const uint4 v = bhi[i];
           uint4 l;
@@ -414,16 +402,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           blo[i] = l;
         }
+        // ---- A: thread `tid` owns row `tid` of the tile: gather its 32 k-values out of the swizzled
+        //      shared-memory tile, split, and store hi | lo into this lane's TMEM columns.
+        uint32_t ah[BK], al[BK];
+        if (p.a_mn_major) {
+          // box (tid / 32) of 4096 B; k-row k at k * 128 B; 32-byte units XOR-swizzled with (k & 3)
+          const unsigned char* base = sa + (tid >> 5) * 4096 + (tid & 7) * 4;
+          const int unit = (tid & 31) >> 3;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+          for (int k = 0; k < BK; ++k)
+            ah[k] = *reinterpret_cast<const uint32_t*>(base + k * 128 + ((unit ^ (k & 3)) << 5));
+        } else {
+          // row tid at tid * 128 B; 16-byte chunks XOR-swizzled with (tid & 7)
+          const uint4* rowp = reinterpret_cast<const uint4*>(sa + tid * 128);
+#pragma unroll
+          for (int ch = 0; ch < BK / 4; ++ch) {
+            const uint4 v = rowp[ch ^ (tid & 7)];
+            ah[4 * ch + 0] = v.x; ah[4 * ch + 1] = v.y; ah[4 * ch + 2] = v.z; ah[4 * ch + 3] = v.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
           const uint32_t h = ah[k] & 0xFFFFE000u;
           al[k] = __float_as_uint(__uint_as_float(ah[k]) - __uint_as_float(h));
           ah[k] = h;
         }
-        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
-                            (uint32_t)(kATmemBase + s * kATmemCols + sset * 16);
-        tmem_st16(ta, ah);
-        tmem_st16(ta + (uint32_t)BK, al);
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kATmemBase + s * kATmemCols);
+        tmem_st32(ta, ah);
+        tmem_st32(ta + (uint32_t)BK, al);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -431,7 +437,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 8 && warp < 16) {
+  } else if (warp >= 8) {
     // ================================ promotion + epilogue ================================
     const int q = (warp - 8) & 3;                      // TMEM lane quarter == warp_id % 4
     const int half = (warp - 8) >> 2;                  // which 64 accumulator columns this warp owns
@@ -441,15 +447,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       float acc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-      for (int k0 = c.kbeg; k0 < c.kend; k0 += kChunkBlocks * BK) {
+      for (int k0 = c.kbeg; k0 < c.kend; k0 += p.chunk_blocks * BK) {
         const uint32_t buf = chunk_it & 1u;
         mbar_wait(&tfull[buf], (chunk_it >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * 64);
-        tmem_ld16_add(taddr, acc);
-        tmem_ld16_add(taddr + 16u, acc + 16);
-        tmem_ld16_add(taddr + 32u, acc + 32);
-        tmem_ld16_add(taddr + 48u, acc + 48);
+        tmem_ld32_add(taddr, acc);
+        tmem_ld32_add(taddr + 32u, acc + 32);
         tc_fence_before();
         mbar_arrive(&tempty[buf]);
         ++chunk_it;
@@ -538,7 +542,13 @@ bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
 
 int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaStream_t st) {
   using namespace tc;
+  static const int chunk_blocks = []() {
+    const char* e = getenv("CGC_TC_CHUNK");
+    int v = e ? atoi(e) : kDefaultChunkBlocks;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
+  }();
   Params q;
+  q.chunk_blocks = chunk_blocks;
   q.a_mn_major = ta ? 1 : 0;          // A stored [k, m]: m contiguous
   q.b_mn_major = tb ? 0 : 1;          // B stored [k, n]: n contiguous
   q.tiles_m = (int)ceil_div(p.m, BM);
@@ -553,7 +563,7 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
     if (ks > kmax) ks = kmax;
     while (ks > 1 && ks * p.batch * (int64_t)p.m * p.n * 4 > work_bytes) --ks;
     if (ks > 1) {
-      int64_t chunk = ceil_div(ceil_div(p.k, ks), kChunkBlocks * BK) * (kChunkBlocks * BK);
+      int64_t chunk = ceil_div(ceil_div(p.k, ks), chunk_blocks * BK) * (chunk_blocks * BK);
       p.kchunk = (int)chunk;
       p.ksplit = (int)ceil_div(p.k, chunk);
       p.partial = reinterpret_cast<float*>(work);
