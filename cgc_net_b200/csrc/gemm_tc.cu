@@ -13,11 +13,15 @@
 // (network.py:206-207), matmul(adj, x) of DenseSAGEConv on the dense stages, and all their gradients.
 //
 // Structure (one persistent CTA per SM, 512 threads, warp-specialised):
-//   warp 0       TMA producer: cp.async.bulk.tensor of the fp32 A / B tiles into a 3-stage ring
-//   warps 4-7    split: lo tile written next to the TMA-landed tile, fence.proxy.async, signal the MMA warp
-//   warp 1       MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (128x128x8) per stage;
+//   warp 0       TMA producer: cp.async.bulk.tensor of the fp32 A / B tiles into a 4-stage ring
+//   warps 4-7    split: B lo tile written next to the TMA-landed B tile (element-wise, layout preserving);
+//                A: each thread gathers its row out of the swizzled A tile, splits it and stores hi | lo
+//                into TENSOR MEMORY (tcgen05.st).  The MMA reads A from TMEM, which removes the A operand
+//                from the shared-memory read stream (shared-memory bandwidth is the measured limiter)
+//   warp 1       MMA issuer: the warp runs the loop uniformly, one elected lane issues 3 x 4
+//                tcgen05.mma.kind::tf32 (128x128x8, A from TMEM, B via shared-memory descriptors) per stage;
 //                tcgen05.commit frees the stage and, every 2 stages, hands the accumulator to the epilogue
-//   warp 2       TMEM allocation (2 accumulator buffers x 128 columns)
+//   warp 2       TMEM allocation: 2 accumulator buffers x 128 columns + 4 stages x 64 operand columns = 512
 //   warps 8-15   promotion + epilogue: tcgen05.ld 32x32b chunks -> fp32 registers (+=), at the end of the tile
 //                alpha / bias / row-scale / row-mask / beta and 128-byte row segments to global
 // K-major operands use the 128B swizzle, MN-major operands the 128B swizzle with 32B atoms (the only

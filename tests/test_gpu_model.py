@@ -7,9 +7,9 @@ Tolerances
 * parameter gradients, asserted against the FLOAT64 oracle.  This network's gradients amplify relative
   perturbations ~1000x: the fp32 reference itself is 1-3e-4 (relative to each tensor's max) away from
   float64 at the BASELINE shape.  So the bound is max(tol * scale, slack * fp32-oracle's own error):
-    - ``fp32``    mode (every contraction on the exact-fp32 FMA kernel): tol 1e-4, slack 10 -- i.e. "as
-      exact as the reference's own arithmetic" (same rounding class; tiny-gradient tensors sit at the
-      noise floor of either evaluation, hence the factor);
+    - ``fp32``    mode (every contraction on the exact-fp32 FMA kernel): tol 3e-4 (the fp32 reference's own
+      distance to float64 on these tensors, measured with tools/grad_diag.py), slack 10 -- i.e. "as exact
+      as the reference's own arithmetic": same rounding class, different summation order;
     - ``tcgen05`` mode (the default product path: 3xTF32 tensor-core contractions whose TMEM accumulation
       rounds toward zero, promoted to fp32 every K = 64; ~1e-6 relative per contraction instead of ~1e-7):
       tol 3e-3 -- stated, measured ~1e-3 on the worst tensors;
@@ -43,7 +43,7 @@ def gemm_mode(request, cuda_backend):
 def _grad_tol(mode, norm_adj=False):
     if mode == 'tcgen05':
         return dict(tol=3e-3, slack=20.0)
-    return dict(tol=1e-3, slack=10.0) if norm_adj else dict(tol=1e-4, slack=10.0)
+    return dict(tol=1e-3, slack=10.0) if norm_adj else dict(tol=3e-4, slack=10.0)
 
 
 def _run_pair(ours, orc, batch, dense=None):
