@@ -111,6 +111,36 @@ class GNN_Module(nn.Module):
         return ops.GnnModuleFunction.apply(cfg, x, adj, rs, rsum, *params)
 
 
+class DenseJK(nn.Module):
+    """Jumping-knowledge aggregation of the three layer outputs of one stage (reference ``DenseJK('lstm')``,
+    network.py:11-55): a bi-LSTM over the 3-step "sequence" of per-layer features of every node scores the
+    layers, the scores are soft-maxed and the layers summed with those weights.
+
+    SURVEY 8(f) rank-1 "next" row: the recurrence itself still runs on torch's LSTM (cuDNN); it is wired in so
+    that the only published configuration (``--jk``, parallel_train.sh:3) runs end to end.  Parameter names
+    (``lstm.*``, ``att.*``) match the reference for checkpoint compatibility.
+    """
+
+    def __init__(self, mode, channels=None, num_layers=None):
+        super(DenseJK, self).__init__()
+        assert mode.lower() == 'lstm' and channels is not None and num_layers is not None
+        self.mode, self.channel = mode.lower(), channels
+        hidden = channels * num_layers // 2
+        self.lstm = nn.LSTM(channels, hidden, bidirectional=True, batch_first=True)
+        self.att = nn.Linear(2 * hidden, 1)
+
+    def forward(self, feats, num_graphs, nmax):
+        """``feats [B*N, L*C]`` (concat of the L layer outputs, padded layout) -> ``[B*N, C]``."""
+        rows = feats.shape[0]
+        seq = feats.view(rows, -1, self.channel)                 # [rows, L, C]
+        score, _ = self.lstm(seq)
+        alpha = torch.softmax(self.att(score).squeeze(-1), dim=-1)
+        return (seq * alpha.unsqueeze(-1)).sum(dim=1)
+
+    def __repr__(self):
+        return '{}({})'.format(self.__class__.__name__, self.mode)
+
+
 class SoftPoolingGcnEncoder(nn.Module):
     """CGC-Net's 3-stage DiffPool encoder (network.py:127-291) on hand-written sm_100a kernels."""
 
@@ -119,8 +149,6 @@ class SoftPoolingGcnEncoder(nn.Module):
                  collect_assign=False, load_data_sparse=False, norm_adj=False,
                  activation='relu', drop_out=0., jk=False):
         super(SoftPoolingGcnEncoder, self).__init__()
-        if jk:
-            raise NotImplementedError('jk=True (DenseJK, network.py:11-55) is a SURVEY 8(f) "next" row')
         self.jk = jk
         self.drop_out = drop_out
         self.norm_adj = norm_adj
@@ -132,6 +160,8 @@ class SoftPoolingGcnEncoder(nn.Module):
         kw = dict(gcn_name=gcn_name, activation=activation, jk=jk)
         self.GCN_embed_1 = GNN_Module(input_dim, hidden_dim, embedding_dim, bias, bn,
                                       add_loop=False, lin=False, **kw)
+        if jk:
+            self.jk1 = DenseJK('lstm', hidden_dim, 3)
         self.GCN_pool_1 = GNN_Module(input_dim, assign_hidden_dim, assign_dim, bias, bn,
                                      add_loop=False, **kw)
         if concat and not jk:
@@ -141,10 +171,14 @@ class SoftPoolingGcnEncoder(nn.Module):
         assign_dim = int(assign_dim * assign_ratio)
         self.GCN_embed_2 = GNN_Module(input_dim, hidden_dim, embedding_dim, bias, bn,
                                       add_loop=False, lin=False, **kw)
+        if jk:
+            self.jk2 = DenseJK('lstm', hidden_dim, 3)
         self.GCN_pool_2 = GNN_Module(input_dim, assign_hidden_dim, assign_dim, bias, bn,
                                      add_loop=False, **kw)
         self.GCN_embed_3 = GNN_Module(input_dim, hidden_dim, embedding_dim, bias, bn,
                                       add_loop=False, lin=False, **kw)
+        if jk:
+            self.jk3 = DenseJK('lstm', hidden_dim, 3)
         pred_input = input_dim * 3
         self.pred_model = self.build_readout_module(pred_input, pred_hidden_dims, label_dim, activation)
 
@@ -196,6 +230,8 @@ class SoftPoolingGcnEncoder(nn.Module):
         for stage in (1, 2, 3):
             embed = getattr(self, 'GCN_embed_%d' % stage)
             feat = embed(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
+            if self.jk:
+                feat = getattr(self, 'jk%d' % stage)(feat, b, n)
             pooled, _ = ops.ColMaxFunction.apply(feat, b, n)
             readouts.append(pooled)
             if stage == 3:

@@ -133,7 +133,13 @@ def _agg(be, cfg, adj, rs, x_prev, out):
     """Mean-aggregated neighbours ``sa = rs * (A x)`` (DenseSAGEConv: matmul(adj, x) / deg)."""
     if cfg.graph is not None:
         g = cfg.graph
-        be.spmm(g.rowptr, g.col, g.val, x_prev, None, rs, out, False)
+        feat = x_prev.shape[1]
+        if (x_prev.is_contiguous() and out.is_contiguous() and feat % 4 == 0 and feat <= 32
+                and g.nmax * feat * 4 + 12288 <= 220 * 1024):
+            # whole-graph feature tile fits in shared memory: TMA-staged gather (the roofline kernel)
+            be.sage_gather_mean_fwd(g.rowptr, g.col, g.val, rs, x_prev, g.num_graphs, g.nmax, out)
+        else:
+            be.spmm(g.rowptr, g.col, g.val, x_prev, None, rs, out, False)
     else:
         b, n = cfg.num_graphs, cfg.nmax
         be.gemm(adj, _as3d(x_prev, b, n), out.view(b, n, -1), False, False, row_scale=rs)

@@ -178,3 +178,50 @@ def test_full_size_properties(cuda_backend):
     loss.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(logits).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_jumping_knowledge(gemm_mode):
+    """jk=True, the only published configuration (parallel_train.sh:3): DenseJK between embed and read-out."""
+    graphs = helpers.make_graphs([410, 670, 300], [5, 8, 6], seed=13)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair(helpers.encoder_args(3000), load_data_sparse=True, jk=True)
+    lo, losso, lr, lossr = _run_pair(ours, orc, batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    _, _, truth = helpers.oracle_fp64(orc, batch)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()}, **_grad_tol(gemm_mode))
+
+
+def test_edge_cases_vs_oracle(cuda_backend):
+    """Empty edge list (every node isolated), a one-node graph next to a large one, a single-graph batch."""
+    torch.manual_seed(0)
+    cases = []
+    g0 = [graph.Data(x=torch.randn(n, 16), edge_index=torch.zeros(2, 0, dtype=torch.long), y=torch.tensor([i % 3]))
+          for i, n in enumerate([7, 19])]
+    cases.append(g0)                                                   # no edges at all
+    cases.append(helpers.make_graphs([1, 150], [1, 6], seed=3, messy=False))   # one-node graph + padding
+    cases.append(helpers.make_graphs([64], [5], seed=4, messy=False))          # single graph
+    for graphs in cases:
+        batch = graph.Batch.from_data_list(graphs)
+        ours, orc = helpers.build_pair(helpers.encoder_args(400), load_data_sparse=True, collect_assign=True)
+        lo, losso, lr, lossr = _run_pair(ours, orc, batch)
+        assert torch.isfinite(lo).all()
+        assert helpers.rel_err(lo, lr) < 1e-4
+        assert abs(float(losso.detach()) - float(lossr.detach())) < 1e-5
+        _check_assignments(ours, orc)
+
+
+def test_maximum_graph_size(cuda_backend):
+    """setting.py:15 max_num_nodes = 11404: the feature tile (730 KB) no longer fits in shared memory, so the
+    aggregation takes the generic gather; invariants of the pooled adjacency still hold."""
+    d = graph.synthetic_cell_graph(11404, 8, 16, seed=1)
+    batch = graph.Batch.from_data_list([d]).to('cuda')
+    torch.manual_seed(0)
+    m = network.SoftPoolingGcnEncoder(11404, 16, 20, 20, True, True, 20, 3, 0.1, [50], concat=True,
+                                      load_data_sparse=True, collect_assign=True).cuda().train()
+    logits, loss = m(batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(logits).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    s = m.assign_matrix[0]
+    assert tuple(s.shape) == (1, 11404, 1140)
+    assert torch.allclose(s.sum(-1), torch.ones(1, 11404, device='cuda'), atol=1e-5)

@@ -98,9 +98,23 @@ def test_state_dict_names_and_size():
     o.load_state_dict(m.state_dict())
 
 
+@pytest.mark.parametrize('norm_adj', [False, True])
+def test_jumping_knowledge_matches_oracle(torch_backend, norm_adj):
+    """jk=True (DenseJK, the published configuration): changes the stage widths to 20 / 60 (network.py:150-167)."""
+    graphs = helpers.make_graphs([41, 67, 30], [5, 8, 6], seed=13)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair(helpers.encoder_args(300), load_data_sparse=True, norm_adj=norm_adj, jk=True)
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in orc.state_dict().items()}
+    ours.train(), orc.train()
+    lo, losso = ours(batch)
+    lr, lossr = orc(batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    losso.backward(), lossr.backward()
+    _grad_check(ours, orc, batch)
+
+
 def test_unbuilt_rows_raise():
-    with pytest.raises(NotImplementedError):
-        network.SoftPoolingGcnEncoder(100, 16, 20, 20, True, True, 20, 3, jk=True)
     with pytest.raises(NotImplementedError):
         network.SoftPoolingGcnEncoder(100, 16, 20, 20, True, True, 20, 3, gcn_name='GIN')
 
@@ -145,3 +159,36 @@ def test_product_path_has_no_cpu_fallback():
         pytest.skip('library not built')
     with pytest.raises(_backend.CgcError):
         be.row_inv_degree(torch.zeros(3, dtype=torch.int32), torch.zeros(2))
+
+
+def test_property_graph_build_random(torch_backend):
+    """Property test (hypothesis): random sizes / degrees / duplicate and unsorted edges -- the CSR of the
+    padded rows always equals the reference's dense adjacency and the CSC is its exact transpose."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(st.integers(1, 40), min_size=1, max_size=4), st.integers(0, 12), st.integers(0, 2 ** 31 - 1))
+    def check(sizes, deg, seed):
+        g = torch.Generator().manual_seed(seed)
+        datas = []
+        for n in sizes:
+            e = n * deg
+            ei = torch.randint(0, n, (2, e), generator=g) if e else torch.zeros(2, 0, dtype=torch.long)
+            datas.append(graph.Data(x=torch.randn(n, 4, generator=g), edge_index=ei, y=torch.zeros(1, dtype=torch.long)))
+        b = graph.Batch.from_data_list(datas)
+        adj, counts = restatement.densify_edges(b.edge_index, b.batch) if b.edge_index.shape[1] else \
+            (torch.zeros(len(sizes), max(sizes), max(sizes)), torch.tensor(sizes))
+        xp, gr = ops.build_sparse_graph(b.x, b.edge_index, b.batch, b.num_nodes_list, False)
+        rows = gr.rows
+        nnz = int(gr.rowptr[-1])
+        dense = torch.zeros(rows, rows)
+        deg_r = (gr.rowptr[1:] - gr.rowptr[:-1]).long()
+        dense[torch.repeat_interleave(torch.arange(rows), deg_r), gr.col[:nnz].long()] = 1
+        assert torch.equal(dense, torch.block_diag(*[adj[i] for i in range(adj.shape[0])]))
+        dt = torch.zeros(rows, rows)
+        deg_c = (gr.colptr[1:] - gr.colptr[:-1]).long()
+        dt[gr.row[:nnz].long(), torch.repeat_interleave(torch.arange(rows), deg_c)] = 1
+        assert torch.equal(dt, dense)
+        assert torch.equal(gr.rs, 1.0 / deg_r.float().clamp(min=1))
+
+    check()
