@@ -133,7 +133,9 @@ class DenseJK(nn.Module):
         """``feats [B*N, L*C]`` (concat of the L layer outputs, padded layout) -> ``[B*N, C]``."""
         rows = feats.shape[0]
         seq = feats.view(rows, -1, self.channel)                 # [rows, L, C]
-        score, _ = self.lstm(seq)
+        # fp32 parity with the reference: cuDNN's RNN would otherwise run its matmuls in single-pass TF32
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            score, _ = self.lstm(seq)
         alpha = torch.softmax(self.att(score).squeeze(-1), dim=-1)
         return (seq * alpha.unsqueeze(-1)).sum(dim=1)
 
