@@ -44,6 +44,8 @@ _SIGNATURES = {
                               _c_vp, _c_i64, _c_vp],
     'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
                     _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp],
+    'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
+                                  _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_scale_rows_bwd': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp],
     'cgc_bn_stats': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp,
                      _c_vp, _c_i64, _c_vp],
@@ -220,6 +222,19 @@ class CudaBackend(object):
         self._check(self.lib.cgc_sage_dh(gp, ldg, sp, lds, _ptr(w.contiguous(), torch.float32),
                                          _ptr(b, torch.float32), yp, ldy, nn, nmax, sa.shape[0],
                                          w.shape[0], w.shape[1], dp, ldd, self._stream()), 'cgc_sage_dh')
+
+    def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b):
+        gp, ldg = _mat(gy)
+        sp, lds = _mat(sa)
+        yp, ldy = _mat(y)
+        dp, ldd = _mat(dsa)
+        nn, nmax = _mask(mask)
+        wp, wb = self._workspace(sa.device)
+        self._check(self.lib.cgc_sage_layer_bwd_narrow(gp, ldg, sp, lds, _ptr(w.contiguous(), torch.float32),
+                                                       _ptr(b, torch.float32), yp, ldy, nn, nmax, sa.shape[0],
+                                                       w.shape[0], w.shape[1], dp, ldd,
+                                                       _ptr(d_w, torch.float32), _ptr(d_b, torch.float32), wp, wb,
+                                                       self._stream()), 'cgc_sage_layer_bwd_narrow')
 
     def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
         for t in (dsa, sa):

@@ -265,16 +265,19 @@ class GnnModuleFunction(Function):
                 grads[4 * k + 2], grads[4 * k + 3] = d_gamma, d_beta
             else:
                 be.bn_apply(gx, None, None, None, None, cfg.mask, gy)     # gy = gx * mask
-            be.sage_dh(gy, a, w, b, y, cfg.mask, gy)            # gy <- dh = dL/d(sa W + b), in place
             d_w = torch.empty_like(w)
-            be.gemm(a, gy, d_w, True, False)                    # dW = sa^T dh   (K = M)
-            grads[4 * k] = d_w
-            if b is not None:
-                d_b = torch.empty_like(b)
-                be.colsum(gy, None, d_b)
-                grads[4 * k + 1] = d_b
+            d_b = torch.empty_like(b) if b is not None else None
             dsa = _f32(m, w.shape[0], device=dev)
-            be.gemm(gy, w, dsa, False, True)                    # dsa = dh W^T
+            if w.shape[1] <= 32 and w.shape[0] <= 64:
+                # narrow layer: dh, dW, db and dsa = dh W^T in ONE pass over the rows
+                be.sage_layer_bwd_narrow(gy, a, w, b, y, cfg.mask, dsa, d_w, d_b)
+            else:
+                be.sage_dh(gy, a, w, b, y, cfg.mask, gy)        # gy <- dh = dL/d(sa W + b), in place
+                be.gemm(a, gy, d_w, True, False)                # dW = sa^T dh   (K = M)
+                if d_b is not None:
+                    be.colsum(gy, None, d_b)
+                be.gemm(gy, w, dsa, False, True)                # dsa = dh W^T
+            grads[4 * k], grads[4 * k + 1] = d_w, d_b
             x_prev = x0 if k == 0 else cat[:, offs[k - 1]: offs[k - 1] + couts[k - 1]]
             if dense:
                 if want_adj:

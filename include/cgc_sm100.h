@@ -126,6 +126,16 @@ CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t 
                 int32_t nmax, int64_t rows, int32_t cin, int32_t cout, float* dh, int64_t lddh,
                 void* stream);
 
+/* Fused backward of a narrow layer epilogue (cout <= 32, cin <= 64) in one pass over the rows:
+ * dsa = dh W^T [rows, cin], d_w = sa^T dh [cin, cout], d_b = sum_rows dh (nullable), with
+ * dh = d loss / d (sa @ W + b) as in cgc_sage_dh (not materialised).  Deterministic (per-CTA partials in
+ * `work`, fixed-order finalize). */
+CGC_API int cgc_sage_layer_bwd_narrow(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa,
+                              const float* w, const float* b, const float* y, int64_t ldy,
+                              const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
+                              int32_t cout, float* dsa, int64_t lddsa, float* d_w, float* d_b,
+                              void* work, int64_t work_bytes, void* stream);
+
 /* Backward of sa = rs * agg (dense stages, where rs depends on the adjacency):
  * ga = rs * dsa (leading dimension ldga);  d_rs[r] += dot(dsa[r], sa[r]) / rs[r]. */
 CGC_API int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows,

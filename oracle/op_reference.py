@@ -147,6 +147,14 @@ class TorchBackend(object):
         # y = h / max(|h|, eps): d/dh = (g - hn (hn . g)) / |h|   when |h| >= eps, g / eps otherwise
         dh.copy_(torch.where(nrm >= L2_EPS, (gm - hn * dot) * inv, gm * inv))
 
+    def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b):
+        dh = torch.empty_like(y)
+        self.sage_dh(gy, sa, w, b, y, mask, dh)
+        dsa.copy_(dh @ w.t())
+        d_w.copy_(sa.t() @ dh)
+        if d_b is not None:
+            d_b.copy_(dh.sum(0))
+
     def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
         ga.copy_(dsa * rs[:, None])
         d_rs += (dsa * sa).sum(1) / rs

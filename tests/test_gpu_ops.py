@@ -185,6 +185,26 @@ def test_sage_epilogue_and_dh(cuda_backend, cin, cout, masked):
     both(cuda_backend, 'sage_epilogue_fwd', [sa, w, None, mask, yw[:, 4:4 + cout]], [4], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('cin,cout', [(16, 20), (20, 20), (60, 20), (33, 32), (5, 3)])
+@pytest.mark.parametrize('masked', [False, True])
+def test_sage_layer_bwd_narrow(cuda_backend, cin, cout, masked):
+    """Fused narrow backward (dh, dW, db, dsa in one pass) == the unfused formulas."""
+    b, nmax = 4, 611
+    rows = b * nmax
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    sa = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax) if masked else None
+    y = torch.zeros(rows, cout)
+    REF.sage_epilogue_fwd(sa, w, bias, mask, y)
+    gyw = torch.randn(rows, cout + 12, generator=g)
+    gy = gyw[:, 4:4 + cout]                              # strided like a slice of the concat gradient
+    both(cuda_backend, 'sage_layer_bwd_narrow',
+         [gy, sa, w, bias, y, mask, torch.zeros(rows, cin), torch.zeros(cin, cout), torch.zeros(cout)],
+         [6, 7, 8], rtol=2e-4, atol=2e-4)
+
+
 def test_scale_rows_bwd(cuda_backend):
     g = torch.Generator().manual_seed(1)
     dsa, sa = torch.randn(500, 60, generator=g), torch.randn(500, 60, generator=g)
