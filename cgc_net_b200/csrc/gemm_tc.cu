@@ -35,20 +35,18 @@ namespace cgc {
 
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int BM = 128, BK = 32;                      // BN is a template parameter: 128, 64 or 32
 constexpr int kStages = 4;
-constexpr int kOperandBytes = BM * BK * 4;            // 16 KB (BM == BN)
-constexpr int kStageBytes = 3 * kOperandBytes;        // A (as landed), B (as landed = B_hi), B_lo
-constexpr int kTxBytes = 2 * kOperandBytes;           // bytes landed by TMA per stage
+constexpr int kOperandBytes = BM * BK * 4;            // A tile: 16 KB.  Stage = A (as landed) | B (as landed = B_hi) | B_lo
 constexpr int kThreads = 512;
 constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 256;
 constexpr int kDefaultChunkBlocks = 2;               // K-blocks accumulated in TMEM before promotion to fp32 registers
-constexpr int kAccCols = BN;                          // accumulator columns per buffer (2 buffers)
-constexpr int kATmemBase = 2 * kAccCols;              // A operand tiles live in TMEM: per stage hi[32] | lo[32]
+constexpr int kATmemBase = 256;                       // accumulators: 2 buffers x BN columns in [0, 256); then the A operand
+                                                      // tiles: per stage hi[32] | lo[32]
 constexpr int kATmemCols = 2 * BK;
 constexpr int kTmemCols = 512;                        // 2 * 128 accumulator + 4 * 64 operand columns
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t smem_bytes(int bn) { return (size_t)kStages * (kOperandBytes + 2 * bn * BK * 4) + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct Params {
   GemmParams g;
@@ -57,6 +55,7 @@ struct Params {
   int c_vec;
   int write_hi;      // 1: also store the masked hi tile (not needed: kind::tf32 ignores the low 13 bits)
   int chunk_blocks;  // K-blocks per TMEM accumulation chunk (promotion period), CGC_TC_CHUNK overrides
+  int bn;            // N tile (= the kernel's BN template argument)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,6 +171,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// acc[0..15] += TMEM[lane, col .. col+15]
+__device__ __forceinline__ void tmem_ld16_add(uint32_t taddr, float* acc) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+}
 // acc[0..31] += TMEM[lane, col .. col+31]
 __device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float* acc) {
   uint32_t r[32];
@@ -201,20 +213,21 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, int t) {
   c.bz = z / p.g.ksplit;
   c.split = z - c.bz * p.g.ksplit;
   c.m0 = mt * BM;
-  c.n0 = nt * BN;
+  c.n0 = nt * p.bn;
   c.kbeg = c.split * p.g.kchunk;
   c.kend = min(p.g.k, c.kbeg + p.g.kchunk);
   return c;
 }
 
-// final write of 32 consecutive columns of one output row (v already holds the fp32 sums)
+// final write of NC (16 or 32) consecutive columns of one output row (v already holds the fp32 sums)
+template <int NC>
 __device__ __forceinline__ void store_segment(const Params& p, const TileCoord& c, int row, int col0, const float* v) {
   const GemmParams& g = p.g;
   if (row >= g.m || col0 >= g.n) return;
   if (g.ksplit > 1) {
     float* dst = g.partial + (((int64_t)(c.bz * g.ksplit + c.split)) * g.m + row) * g.n + col0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < NC; ++j)
       if (col0 + j < g.n) dst[j] = g.alpha * v[j];
     return;
   }
@@ -222,9 +235,9 @@ __device__ __forceinline__ void store_segment(const Params& p, const TileCoord& 
   const float rsc = g.row_scale ? __ldg(g.row_scale + grow) : 1.0f;
   const bool valid = g.num_nodes ? row_valid(g.num_nodes, g.nmax, grow) : true;
   float* dst = g.c + (int64_t)c.bz * g.stride_c + (int64_t)row * g.ldc + col0;
-  if (p.c_vec && col0 + 32 <= g.n) {
+  if (p.c_vec && col0 + NC <= g.n) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < NC; j += 4) {
       float4 o;
       float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
@@ -242,7 +255,7 @@ __device__ __forceinline__ void store_segment(const Params& p, const TileCoord& 
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < NC; ++j) {
       if (col0 + j < g.n) {
         float x = g.alpha * v[j];
         if (g.bias) x += __ldg(g.bias + col0 + j);
@@ -255,8 +268,13 @@ __device__ __forceinline__ void store_segment(const Params& p, const TileCoord& 
   }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  constexpr int kBBytes = BN * BK * 4;
+  constexpr int kStageBytes = kOperandBytes + 2 * kBBytes;
+  constexpr int kTxBytes = kOperandBytes + kBBytes;
+  constexpr int kAccCols = BN;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by offset (keeps the pointer in the shared address space: LDS/STS, not generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -358,7 +376,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tc_fence_after();
             if (elect_one()) {
               const uint32_t bh = desc_lo_base | (smem_base16 + (uint32_t)((s * kStageBytes + kOperandBytes) >> 4));
-              const uint32_t bl = bh + (uint32_t)(kOperandBytes >> 4);
+              const uint32_t bl = bh + (uint32_t)(kBBytes >> 4);
               const uint32_t a_hi = tmem_base + (uint32_t)(kATmemBase + s * kATmemCols);
               const uint32_t a_lo = a_hi + (uint32_t)BK;
 #pragma unroll
@@ -391,9 +409,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         unsigned char* sa = smem + (size_t)s * kStageBytes;
         // ---- B: lo tile next to the landed tile (element-wise, layout preserving)
         uint4* bhi = reinterpret_cast<uint4*>(sa + kOperandBytes);
-        uint4* blo = bhi + kOperandBytes / 16;
+        uint4* blo = bhi + kBBytes / 16;
 #pragma unroll 4
-        for (int i = tid; i < kOperandBytes / 16; i += kSplitThreads) {
+        for (int i = tid; i < kBBytes / 16; i += kSplitThreads) {
           const uint4 v = bhi[i];
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
@@ -445,27 +463,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   } else if (warp >= 8) {
     // ================================ promotion + epilogue ================================
     const int q = (warp - 8) & 3;                      // TMEM lane quarter == warp_id % 4
-    const int half = (warp - 8) >> 2;                  // which 64 accumulator columns this warp owns
+    const int half = (warp - 8) >> 2;                  // which BN/2 accumulator columns this warp owns
+    constexpr int kCols = BN / 2;                      // 64, 32 or 16
     uint32_t chunk_it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = tile_coord(p, t);
-      float acc[64];
+      float acc[kCols];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int j = 0; j < kCols; ++j) acc[j] = 0.f;
       for (int k0 = c.kbeg; k0 < c.kend; k0 += p.chunk_blocks * BK) {
         const uint32_t buf = chunk_it & 1u;
         mbar_wait(&tfull[buf], (chunk_it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * 64);
-        tmem_ld32_add(taddr, acc);
-        tmem_ld32_add(taddr + 32u, acc + 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * kCols);
+        if constexpr (kCols == 16) {
+          tmem_ld16_add(taddr, acc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCols; j += 32) tmem_ld32_add(taddr + (uint32_t)j, acc + j);
+        }
         tc_fence_before();
         mbar_arrive(&tempty[buf]);
         ++chunk_it;
       }
       const int row = c.m0 + q * 32 + lane;
-      store_segment(p, c, row, c.n0 + half * 64, acc);
-      store_segment(p, c, row, c.n0 + half * 64 + 32, acc + 32);
+      if constexpr (kCols == 16) {
+        store_segment<16>(p, c, row, c.n0 + half * kCols, acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kCols; j += 32) store_segment<32>(p, c, row, c.n0 + half * kCols + j, acc + j);
+      }
     }
   }
 
@@ -557,7 +584,9 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   q.a_mn_major = ta ? 1 : 0;          // A stored [k, m]: m contiguous
   q.b_mn_major = tb ? 0 : 1;          // B stored [k, n]: n contiguous
   q.tiles_m = (int)ceil_div(p.m, BM);
-  q.tiles_n = (int)ceil_div(p.n, BN);
+  const int bn = p.n <= 32 ? 32 : (p.n <= 64 ? 64 : 128);      // skinny outputs: narrow MMA tile, same A stream
+  q.bn = bn;
+  q.tiles_n = (int)ceil_div(p.n, bn);
   int64_t tiles = (int64_t)q.tiles_m * q.tiles_n * p.batch;
   p.ksplit = 1;
   p.kchunk = p.k;
@@ -591,12 +620,22 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   else ok = make_map(&map_a, p.a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)p.batch, p.lda, p.stride_a, BM, false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for A");
   if (q.b_mn_major) ok = make_map(&map_b, p.b, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.batch, p.ldb, p.stride_b, BK, true);
-  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, BN, false);
+  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, (uint32_t)bn, false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for B");
 
-  CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   int grid = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
-  k_gemm_tc<<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, q);
+  const size_t smem = smem_bytes(bn);
+#define CGC_TC_CASE(N)                                                                                   \
+  case N:                                                                                                \
+    CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_gemm_tc<N><<<grid, kThreads, smem, st>>>(map_a, map_b, q);                                         \
+    break;
+  switch (bn) {
+    CGC_TC_CASE(32)
+    CGC_TC_CASE(64)
+    CGC_TC_CASE(128)
+  }
+#undef CGC_TC_CASE
   CGC_CHECK_LAUNCH("k_gemm_tc");
   if (p.ksplit > 1) {
     int64_t total = (int64_t)p.m * p.n * p.batch;

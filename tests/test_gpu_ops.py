@@ -328,7 +328,9 @@ def test_gemm_epilogue_options(cuda_backend):
 
 # ------------------------------------------------------------------------------- tcgen05 3xTF32 GEMM
 TC_SHAPES = [(1, 256, 256, 128), (1, 1000, 1140, 1180), (3, 1140, 1140, 1800), (1, 1140, 1180, 20000),
-             (2, 200, 136, 72)]
+             (2, 200, 136, 72),
+             # skinny outputs -> the BN=32 / BN=64 instantiations (dense-stage A'x, S gX', split-K variants)
+             (3, 1140, 20, 1140), (2, 1800, 60, 1140), (1, 300, 32, 9000), (2, 132, 64, 520), (1, 1140, 36, 20000)]
 
 
 @pytest.mark.parametrize('shape', TC_SHAPES)
