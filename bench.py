@@ -158,9 +158,10 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- gather roofline
-def gather_roofline(args, device):
+def gather_roofline(args, device, variant='ell', parity=True):
     """The SAGE gather kernel alone (F = 16, unfused): CUDA-graph replay over rotating input copies whose
-    total footprint exceeds L2, timed with CUDA events on the launching stream."""
+    total footprint exceeds L2, timed with CUDA events on the launching stream.
+    variant 'ell' = cgc_sage_gather_ell_fwd (fixed-pitch index table), 'csr' = cgc_sage_gather_mean_fwd."""
     from cgc_net_b200 import _backend, graph, ops
     be = _backend.get()
     b, n, k = args.batch_per_gpu, args.nodes, args.degree
@@ -174,18 +175,30 @@ def gather_roofline(args, device):
     per_copy = alg_bytes
     copies = max(2, int(320e6 // per_copy) + 1)                                # > 2x the 126 MB L2
     xs = [xp.clone() for _ in range(copies)]
-    cols = [g.col.clone() for _ in range(copies)]
-    ptrs = [g.rowptr.clone() for _ in range(copies)]
     outs = [torch.empty_like(xp) for _ in range(copies)]
+    if variant == 'ell':
+        assert g.ell is not None, 'no ELL16 table was built for this batch'
+        ell0 = g.ell
+        if not parity:
+            ell0 = torch.empty_like(g.ell)
+            be.csr_to_ell16(g.rowptr, g.col, None, b, n, g.ell_width, False, ell0, None)
+        ells = [ell0.clone() for _ in range(copies)]
 
-    def launch(i):
-        be.sage_gather_mean_fwd(ptrs[i], cols[i], None, None, xs[i], b, n, outs[i])
+        def launch(i):
+            be.sage_gather_ell_fwd(ells[i], None, g.ell_width, None, g.rowptr, g.col, None, xs[i], b, n, outs[i])
+    else:
+        cols = [g.col.clone() for _ in range(copies)]
+        ptrs = [g.rowptr.clone() for _ in range(copies)]
+
+        def launch(i):
+            be.sage_gather_mean_fwd(ptrs[i], cols[i], None, None, xs[i], b, n, outs[i])
 
     launch(0)
     torch.cuda.synchronize()
-    ref = torch.empty_like(xp)
-    be.spmm(g.rowptr, g.col, None, xp, None, g.rs, ref, False)
-    assert torch.allclose(outs[0], ref, rtol=1e-5, atol=1e-6), 'gather kernel disagrees with the generic gather'
+    if not os.environ.get('CGC_GATHER_STAGE'):
+        ref = torch.empty_like(xp)
+        be.spmm(g.rowptr, g.col, None, xp, None, g.rs, ref, False)
+        assert torch.allclose(outs[0], ref, rtol=1e-5, atol=1e-6), 'gather kernel disagrees with the generic gather'
     stream = torch.cuda.Stream(device)
     stream.wait_stream(torch.cuda.current_stream())
     graph_obj = torch.cuda.CUDAGraph()
@@ -301,7 +314,7 @@ def run_ours(args):
             peak, which = 6650.0, 'fallback (B200_PROFILING.md)'
         alg_bytes, us, copies = gather_roofline(args, device)
         achieved = alg_bytes / (us * 1e-6) / 1e9
-        line['roofline'] = {'kernel': 'k_sage_gather_tile (cgc_sage_gather_mean_fwd, F=16, unfused)', 'bound': 'hbm',
+        line['roofline'] = {'kernel': 'k_sage_gather_ell (cgc_sage_gather_ell_fwd, F=16, unfused)', 'bound': 'hbm',
                             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                             'traffic': None, 'peak_source': which, 'algorithmic_bytes_per_launch': alg_bytes,
                             'us_per_launch': us,

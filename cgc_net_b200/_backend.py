@@ -40,6 +40,9 @@ _SIGNATURES = {
                  _c_int, _c_vp],
     'cgc_sage_gather_mean_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp,
                                  _c_vp],
+    'cgc_csr_to_ell16': [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_int, _c_vp, _c_vp, _c_vp],
+    'cgc_sage_gather_ell_fwd': [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32,
+                                _c_vp, _c_vp],
     'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32,
                               _c_vp, _c_i64, _c_vp],
     'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
@@ -202,6 +205,24 @@ class CudaBackend(object):
                                                       _ptr(x, torch.float32), num_graphs, nmax,
                                                       x.shape[1], _ptr(out, torch.float32),
                                                       self._stream()), 'cgc_sage_gather_mean_fwd')
+
+    def csr_to_ell16(self, rowptr, col, val, num_graphs, nmax, width, parity_order, ell, ell_val):
+        if ell.dtype != torch.int16 or ell.numel() < num_graphs * nmax * width:
+            raise CgcError('cgc_csr_to_ell16: ell must be an int16 tensor of num_graphs * nmax * width elements')
+        self._check(self.lib.cgc_csr_to_ell16(_ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                              _ptr(val, torch.float32), num_graphs, nmax, width,
+                                              int(parity_order), _ptr(ell, torch.int16),
+                                              _ptr(ell_val, torch.float32), self._stream()), 'cgc_csr_to_ell16')
+
+    def sage_gather_ell_fwd(self, ell, ell_val, width, row_scale, rowptr, col, val, x, num_graphs, nmax, out):
+        if not (x.is_contiguous() and out.is_contiguous()):
+            raise CgcError('cgc_sage_gather_ell_fwd needs contiguous x / out')
+        self._check(self.lib.cgc_sage_gather_ell_fwd(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32), width,
+                                                     _ptr(row_scale, torch.float32), _ptr(rowptr, torch.int32),
+                                                     _ptr(col, torch.int32), _ptr(val, torch.float32),
+                                                     _ptr(x, torch.float32), num_graphs, nmax, x.shape[1],
+                                                     _ptr(out, torch.float32), self._stream()),
+                    'cgc_sage_gather_ell_fwd')
 
     # -- SAGE epilogue
     def sage_epilogue_fwd(self, sa, w, b, mask, y):

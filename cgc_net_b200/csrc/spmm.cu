@@ -8,6 +8,8 @@
 //
 // Reference arithmetic: torch.matmul(adj, x) / adj.sum(-1).clamp(min=1) of PyG 1.2.1
 // DenseSAGEConv.forward (call sites model/network.py:114-116) and adj @ s of _diff_pool (:207).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cgc {
@@ -225,6 +227,209 @@ k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, 
   }
 }
 
+
+// ------------------------------------------------------------------ ELL16 gather (fixed row pitch)
+// Row-padded CSR ("ELL16"): every padded row owns W slots of uint16 LOCAL column ids (column - g*nmax);
+// unused slots hold `nmax`, which addresses an all-zero row appended to the shared-memory tile.  A row whose
+// degree exceeds W is marked by slot 0 == nmax + 1 (a second zero row) and walked through the CSR instead.  The fixed pitch removes
+// the rowptr -> column-index dependency: a row's whole index list is ONE 16-byte load whose address is known
+// at kernel start, so index loads fly together with the TMA tile copy and nothing is staged through smem.
+//
+// Bank conflicts: a 64-byte feature row covers half of the 32 banks, chosen by the parity of its index.  The
+// two rows served by one quarter-warp (lanes 8q..8q+7) collide iff their current neighbours have equal parity,
+// so the builder orders the slots of even local rows "even columns first" and of odd local rows "odd columns
+// first" (stable within a parity class): slots pair up with opposite parities except for |a - b| of them.
+__global__ void __launch_bounds__(256) k_csr_to_ell16(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                      const float* __restrict__ val, int64_t rows, int nmax, int W,
+                                                      int parity_order, uint16_t* __restrict__ ell,
+                                                      float* __restrict__ ellw) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int64_t g = r / nmax;
+  const int lr = (int)(r - g * nmax);
+  const int base = (int)(g * nmax);
+  const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+  uint16_t* o = ell + r * W;
+  float* ow = ellw ? ellw + r * W : nullptr;
+  int pos = 0;
+  if (e - b > W) {
+    o[pos++] = (uint16_t)(nmax + 1);          // overflow: the gather walks the CSR for this row
+    if (ow) ow[0] = 0.f;
+  } else if (parity_order) {
+    const int first = lr & 1;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int want = pass == 0 ? first : 1 - first;
+      for (int i = b; i < e; ++i) {
+        const int c = __ldg(col + i) - base;
+        if ((c & 1) == want) {
+          if (ow) ow[pos] = __ldg(val + i);
+          o[pos++] = (uint16_t)c;
+        }
+      }
+    }
+  } else {
+    for (int i = b; i < e; ++i) {
+      if (ow) ow[pos] = __ldg(val + i);
+      o[pos++] = (uint16_t)(__ldg(col + i) - base);
+    }
+  }
+  for (; pos < W; ++pos) {
+    o[pos] = (uint16_t)nmax;
+    if (ow) ow[pos] = 0.f;
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ldg_f4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// slot t (compile-time after unrolling) of a row's packed uint16 index words
+__device__ __forceinline__ uint32_t ell_slot(const uint32_t* words, int t) {
+  const uint32_t w = words[t >> 1];
+  return (t & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// grid = num_graphs * parts; CTA (g, p) owns local rows [p*rpp, min((p+1)*rpp, nmax)) of graph g (rpp % 8 == 0).
+// LPR lanes per row, one float4 of the feature row per lane; group grp = tid / LPR serves rows grp, grp+G, ...
+// RB rows per thread form one batch: their index vectors are loaded (next batch: prefetched) before the
+// branch-free slot loop, so the shared-memory pipe always has RB * W independent reads per thread to chew on.
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ ellw,
+                  const float* __restrict__ row_scale, const int* __restrict__ rowptr,
+                  const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ x,
+                  int nmax, int feat, int parts, int rpp, float* __restrict__ out, int stage_limit) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int G = THREADS / LPR;
+  constexpr int NW = W / 2;                            // 32-bit index words per row
+  const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
+  const int r0 = p * rpp;
+  const int nrows = min(rpp, nmax - r0);
+  if (nrows <= 0 || stage_limit == 1) return;
+  const int64_t grow0 = (int64_t)g * nmax;
+  const uint32_t row_bytes = (uint32_t)feat * 4u;
+  const uint32_t tile_bytes = (uint32_t)nmax * row_bytes;
+  float* s_x = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bar;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar, tile_bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + grow0 * feat);
+    for (uint32_t off = 0; off < tile_bytes; off += kBulkChunk) {
+      uint32_t n = min(kBulkChunk, tile_bytes - off);
+      bulk_g2s(smem_raw + off, src + off, n, &bar);
+    }
+  }
+  // two zero rows behind the tile: index nmax = empty slot, nmax + 1 = overflow mark
+  if (threadIdx.x < 2 * feat) s_x[(size_t)nmax * feat + threadIdx.x] = 0.f;
+
+  const int sl = threadIdx.x % LPR;
+  const int grp = threadIdx.x / LPR;
+  const bool lane_on = sl * 4 < feat;
+  const uint32_t lane_base = smem_u32(smem_raw) + (lane_on ? sl : 0) * 16u;
+  const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
+  const uint32_t ovf_mark = (uint32_t)nmax + 1u;
+
+  uint32_t idx[RB][NW];
+  float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
+  float rsc[RB];
+  auto load_batch = [&](int i0) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = (i0 + i) * G + grp;
+      const bool on = r < nrows;
+      const int64_t row = grow0 + r0 + (on ? r : 0);
+#pragma unroll
+      for (int q = 0; q < NW / 4; ++q) {
+        uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
+        if (on) v = ldg_u4(ell + row * W + q * 8);
+        idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
+      }
+      if (WEIGHTED) {
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on) v = ldg_f4(ellw + row * W + q * 4);
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
+        }
+      }
+      rsc[i] = (row_scale != nullptr && on) ? __ldg(row_scale + row) : 1.0f;
+    }
+  };
+
+  load_batch(0);
+  __syncthreads();                                     // zero rows visible, barrier initialised
+  mbar_wait(&bar, 0);
+  if (stage_limit == 2) return;
+
+  for (int i0 = 0; i0 * G < nrows; i0 += RB) {
+    float4 acc[RB];
+    int cnt[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cnt[i] = 0;
+#pragma unroll
+      for (int t = 0; t < W; ++t) {
+        const uint32_t j = ell_slot(idx[i], t);
+        if (!WEIGHTED) cnt[i] += (j != (uint32_t)nmax) ? 1 : 0;
+        const float4 v = lds_f4(lane_base + j * row_bytes);
+        if (WEIGHTED) {
+          const float w = wgt[WEIGHTED ? i : 0][WEIGHTED ? t : 0];
+          acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
+          acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+        } else {
+          acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+        }
+      }
+    }
+    uint32_t ovf = 0;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = (i0 + i) * G + grp;
+      if ((idx[i][0] & 0xFFFFu) == ovf_mark) ovf |= 1u << i;
+      float s = rsc[i];
+      if (!WEIGHTED && row_scale == nullptr) s = 1.0f / fmaxf((float)cnt[i], 1.0f);
+      if (r < nrows && lane_on) {
+        float4 o = acc[i];
+        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+        *reinterpret_cast<float4*>(out + (grow0 + r0 + r) * feat + sl * 4) = o;
+      }
+    }
+    if (ovf != 0) {
+      // rows whose degree exceeds W: walk the CSR (column ids are global padded rows); overwrites the row
+      for (int i = 0; i < RB; ++i) {
+        if (!((ovf >> i) & 1u)) continue;
+        const int64_t row = grow0 + r0 + (i0 + i) * G + grp;
+        const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = b; k < e; ++k) {
+          const uint32_t j = (uint32_t)(__ldg(col + k) - (int)grow0);
+          const float w = WEIGHTED ? __ldg(val + k) : 1.0f;
+          const float4 v = lds_f4(lane_base + j * row_bytes);
+          a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+        }
+        float s = row_scale != nullptr ? __ldg(row_scale + row) : 1.0f;
+        if (!WEIGHTED && row_scale == nullptr) s = 1.0f / fmaxf((float)(e - b), 1.0f);
+        if (lane_on) {
+          a.x *= s; a.y *= s; a.z *= s; a.w *= s;
+          *reinterpret_cast<float4*>(out + row * feat + sl * 4) = a;
+        }
+      }
+    }
+    if ((i0 + RB) * G < nrows) load_batch(i0 + RB);
+  }
+}
+
 }  // namespace cgc
 
 using namespace cgc;
@@ -299,4 +504,92 @@ extern "C" int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* co
                                                          (int)cap, out);
   CGC_CHECK_LAUNCH("k_sage_gather_tile");
   return 0;
+}
+
+extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const float* val, int32_t num_graphs,
+                                int32_t nmax, int32_t width, int parity_order, uint16_t* ell, float* ell_val,
+                                void* stream) {
+  CGC_REQUIRE(rowptr && col && ell && num_graphs > 0 && nmax > 0, CGC_ERR_ARG, "cgc_csr_to_ell16: bad args");
+  CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: width must be 8 or 16 (got %d)",
+              width);
+  CGC_REQUIRE(nmax + 1 <= 0xFFFF, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: nmax %d does not fit uint16 local ids", nmax);
+  CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
+              "cgc_csr_to_ell16: val and ell_val must be given together");
+  const int64_t rows = (int64_t)num_graphs * nmax;
+  k_csr_to_ell16<<<(unsigned)ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, rows, nmax, width,
+                                                                                parity_order, ell, ell_val);
+  CGC_CHECK_LAUNCH("k_csr_to_ell16");
+  return 0;
+}
+
+static int ell_stage_limit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CGC_GATHER_STAGE");      // profiling aid: 1 = exit at entry, 2 = exit after the tile copy
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static int ell_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CGC_GATHER_THREADS");    // tuning aid: 512 or 1024 threads per CTA
+    v = e ? atoi(e) : 1024;
+  }
+  return v;
+}
+
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
+static int launch_ell(const uint16_t* ell, const float* ellw, const float* row_scale, const int32_t* rowptr,
+                      const int32_t* col, const float* val, const float* x, int num_graphs, int nmax, int feat,
+                      float* out, cudaStream_t st) {
+  const size_t smem = ((size_t)nmax + 2) * feat * 4;
+  CGC_REQUIRE(smem + 1024 <= 227 * 1024, CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_ell_fwd: feature tile of %lld B does not fit in shared memory", (long long)smem);
+  int parts = kNumSMs / num_graphs;
+  if (parts < 1) parts = 1;
+  int rpp = (int)ceil_div(nmax, parts);
+  rpp = (rpp + 7) & ~7;                                 // quarter-warp row pairs stay aligned
+  parts = (int)ceil_div(nmax, rpp);
+  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS>;
+  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<num_graphs * parts, THREADS, smem, st>>>(ell, ellw, row_scale, rowptr, col, val, x, nmax, feat, parts, rpp,
+                                                  out, ell_stage_limit());
+  CGC_CHECK_LAUNCH("k_sage_gather_ell");
+  return 0;
+}
+
+extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, int32_t width,
+                                       const float* row_scale, const int32_t* rowptr, const int32_t* col,
+                                       const float* val, const float* x, int32_t num_graphs, int32_t nmax,
+                                       int32_t feat, float* out, void* stream) {
+  CGC_REQUIRE(ell && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
+              "cgc_sage_gather_ell_fwd: bad args");
+  CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_sage_gather_ell_fwd: width must be 8 or 16");
+  CGC_REQUIRE(feat % 4 == 0 && feat <= 32 && aligned16(x) && aligned16(out) && aligned16(ell), CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_ell_fwd: feat must be a multiple of 4 and <= 32 (got %d), 16B-aligned x/out/ell", feat);
+  CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
+              "cgc_sage_gather_ell_fwd: val and ell_val must be given together");
+  CGC_REQUIRE(ell_val == nullptr || aligned16(ell_val), CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_ell_fwd: ell_val must be 16B-aligned");
+  cudaStream_t st = as_stream(stream);
+  const bool wt = ell_val != nullptr;
+  const bool big = ell_threads() >= 1024;
+#define CGC_ELL(W_, LPR_, WT_, RB_, TH_) \
+  return launch_ell<W_, LPR_, WT_, RB_, TH_>(ell, ell_val, row_scale, rowptr, col, val, x, num_graphs, nmax, feat, \
+                                            out, st)
+  if (feat <= 16) {
+    if (width == 8) {
+      if (wt) CGC_ELL(8, 4, true, 2, 512);
+      else if (big) CGC_ELL(8, 4, false, 4, 1024);
+      else CGC_ELL(8, 4, false, 8, 512);
+    } else {
+      if (wt) CGC_ELL(16, 4, true, 1, 512); else CGC_ELL(16, 4, false, 4, 512);
+    }
+  } else {
+    if (width == 8) { if (wt) CGC_ELL(8, 8, true, 2, 512); else CGC_ELL(8, 8, false, 4, 512); }
+    else            { if (wt) CGC_ELL(16, 8, true, 1, 512); else CGC_ELL(16, 8, false, 4, 512); }
+  }
+#undef CGC_ELL
 }

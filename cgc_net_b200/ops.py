@@ -66,6 +66,8 @@ class SparseGraph(object):
         self.colptr = self.row = self.val_t = None
         self.rs = None
         self.mask = None
+        self.ell = self.ell_val = None      # row-padded CSR, uint16 local ids (cgc_csr_to_ell16)
+        self.ell_width = 0
 
 
 def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False):
@@ -112,6 +114,16 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
     g.row = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
     g.val_t = _f32(max(cap, 1), device=dev) if norm_adj else None
     be.csr_transpose(g.rowptr, g.col, g.val, g.colptr, g.row, g.val_t, work)
+    # Fixed-pitch index table of the shared-memory gather: pitch 8 when the mean row degree allows it, else 16;
+    # rows above the pitch are flagged and walk the CSR.  The slot-parity order pays off for 64-byte rows.
+    feat = x.shape[1]
+    real_rows = max(n_total, 1)
+    if nmax < 0xFFFF and cap <= 16 * real_rows and feat % 4 == 0 and feat <= 32 \
+            and (nmax + 1) * feat * 4 + 1024 <= 227 * 1024:
+        g.ell_width = 8 if cap <= 8 * real_rows else 16
+        g.ell = torch.empty(rows * g.ell_width, dtype=torch.int16, device=dev)
+        g.ell_val = _f32(rows * g.ell_width, device=dev) if norm_adj else None
+        be.csr_to_ell16(g.rowptr, g.col, g.val, num_graphs, nmax, g.ell_width, feat == 16, g.ell, g.ell_val)
     return xp, g
 
 
@@ -134,8 +146,12 @@ def _agg(be, cfg, adj, rs, x_prev, out):
     if cfg.graph is not None:
         g = cfg.graph
         feat = x_prev.shape[1]
-        if (x_prev.is_contiguous() and out.is_contiguous() and feat % 4 == 0 and feat <= 32
-                and g.nmax * feat * 4 + 12288 <= 220 * 1024):
+        dense_io = x_prev.is_contiguous() and out.is_contiguous() and feat % 4 == 0 and feat <= 32
+        if dense_io and g.ell is not None and (g.nmax + 1) * feat * 4 + 1024 <= 227 * 1024:
+            # fixed-pitch index table + TMA-staged feature tile (the roofline kernel)
+            be.sage_gather_ell_fwd(g.ell, g.ell_val, g.ell_width, rs, g.rowptr, g.col, g.val, x_prev,
+                                   g.num_graphs, g.nmax, out)
+        elif dense_io and g.nmax * feat * 4 + 12288 <= 220 * 1024:
             # whole-graph feature tile fits in shared memory: TMA-staged gather (the roofline kernel)
             be.sage_gather_mean_fwd(g.rowptr, g.col, g.val, rs, x_prev, g.num_graphs, g.nmax, out)
         else:

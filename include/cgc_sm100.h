@@ -112,6 +112,29 @@ CGC_API int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, 
                              const float* row_scale, const float* x, int32_t num_graphs,
                              int32_t nmax, int32_t feat, float* out, void* stream);
 
+/* Row-padded CSR ("ELL16") of the stage-1 adjacency, the index layout of cgc_sage_gather_ell_fwd:
+ * ell[r * width + t] = LOCAL column id (column - g*nmax, uint16) of the t-th stored entry of padded row r,
+ * `nmax` in unused slots; a row with more than `width` entries gets ell[r*width] = nmax + 1 (the gather then
+ * walks the CSR for it).  ell_val (nullable, with val) carries the entry weights, 0 in unused slots.
+ * parity_order != 0 orders the slots of even local rows "even columns first" and of odd local rows "odd
+ * columns first" (stable inside a parity class): with 64-byte feature rows the two rows a quarter-warp serves
+ * then read opposite shared-memory bank halves.  Same adjacency as to_dense_adj (model/utils.py:29-33); only
+ * the summation order of a row's neighbours changes.  width is 8 or 16. */
+CGC_API int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const float* val, int32_t num_graphs,
+                     int32_t nmax, int32_t width, int parity_order, uint16_t* ell, float* ell_val,
+                     void* stream);
+
+/* The roofline kernel, fixed-pitch variant (BASELINE.json metric): same result as cgc_sage_gather_mean_fwd,
+ * out[r,:] = (1/max(deg,1)) * sum_e x[col[e],:] (ell_val == NULL, row_scale == NULL), or
+ * row_scale[r] * sum_e val[e] * x[col[e],:].  The per-graph feature tile is staged in shared memory by bulk
+ * async copies (TMA); each row's whole index list is one 16-byte load issued at kernel start (no rowptr ->
+ * column dependency, nothing but the tile goes through shared memory).  rowptr / col / val are read only for
+ * rows marked as overflowing `width`.  Requires (nmax + 2) * feat * 4 <= 226 KB, feat % 4 == 0, feat <= 32. */
+CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, int32_t width,
+                            const float* row_scale, const int32_t* rowptr, const int32_t* col,
+                            const float* val, const float* x, int32_t num_graphs, int32_t nmax,
+                            int32_t feat, float* out, void* stream);
+
 /* ------------------------------------------------------------------ SAGE layer epilogue
  * y = relu( l2normalize(sa @ W + b) * mask )      [rows, cout]
  * DenseSAGEConv.forward lines matmul(out, weight) / + bias / F.normalize(p=2, eps=1e-12) /

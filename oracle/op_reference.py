@@ -125,6 +125,59 @@ class TorchBackend(object):
             row_scale = 1.0 / deg.clamp(min=1)
         self.spmm(rowptr, col, val, x, None, row_scale, out, False)
 
+    def csr_to_ell16(self, rowptr, col, val, num_graphs, nmax, width, parity_order, ell, ell_val):
+        """Row-padded CSR with uint16 local column ids (held in an int16 tensor): unused slots = nmax,
+        overflow rows (degree > width) marked by slot 0 = nmax + 1; optional parity slot order."""
+        rows = num_graphs * nmax
+        rp = rowptr.tolist()
+        cl = col.tolist()
+        vl = val.tolist() if val is not None else None
+        table = torch.full((rows, width), nmax, dtype=torch.int64)
+        wtab = torch.zeros(rows, width, dtype=torch.float32)
+        for r in range(rows):
+            b, e = rp[r], rp[r + 1]
+            base = (r // nmax) * nmax
+            if e - b > width:
+                table[r, 0] = nmax + 1
+                continue
+            ent = [(cl[i] - base, vl[i] if vl is not None else 0.0) for i in range(b, e)]
+            if parity_order:
+                first = (r - base) & 1
+                ent = [t for t in ent if (t[0] & 1) == first] + [t for t in ent if (t[0] & 1) != first]
+            for t, (c, w) in enumerate(ent):
+                table[r, t] = c
+                wtab[r, t] = w
+        table = torch.where(table >= 32768, table - 65536, table).to(torch.int16)
+        ell.view(-1)[:rows * width].copy_(table.view(-1))
+        if ell_val is not None:
+            ell_val.view(-1)[:rows * width].copy_(wtab.view(-1))
+
+    def sage_gather_ell_fwd(self, ell, ell_val, width, row_scale, rowptr, col, val, x, num_graphs, nmax, out):
+        """Same sums as sage_gather_mean_fwd, taken over the ELL16 table (overflow rows over the CSR)."""
+        rows = num_graphs * nmax
+        idx = ell.view(-1)[:rows * width].view(rows, width).long() & 0xFFFF
+        over = idx[:, 0] == nmax + 1
+        xz = torch.cat([x.view(num_graphs, nmax, -1),
+                        torch.zeros(num_graphs, 1, x.shape[1], dtype=x.dtype)], dim=1)     # zero row at nmax
+        gid = (torch.arange(rows) // nmax).view(-1, 1)
+        src = xz[gid, idx.clamp(max=nmax)]                                                # [rows, width, F]
+        if ell_val is not None:
+            res = (src * ell_val.view(-1)[:rows * width].view(rows, width, 1)).sum(1)
+        else:
+            res = src.sum(1)
+        if row_scale is not None:
+            scale = row_scale
+        elif ell_val is None:
+            scale = 1.0 / (idx != nmax).sum(1).clamp(min=1).float()
+        else:
+            scale = torch.ones(rows)
+        res = res * scale[:, None]
+        if bool(over.any()):
+            full = torch.zeros_like(res)
+            self.sage_gather_mean_fwd(rowptr, col, val, row_scale, x, num_graphs, nmax, full)
+            res[over] = full[over]
+        out.copy_(res)
+
     # ---------------------------------------------------------------- SAGE epilogue
     def _epilogue(self, sa, w, b, mask):
         h = sa @ w

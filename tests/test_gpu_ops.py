@@ -153,6 +153,51 @@ def test_sage_gather_tile(cuda_backend, feat, b, nmax, weighted):
     both(cuda_backend, 'sage_gather_mean_fwd', [rowptr, col, val, rsc, x, b, nmax, out], [7], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('width,maxdeg', [(8, 8), (8, 11), (16, 16), (16, 19)])
+@pytest.mark.parametrize('parity', [0, 1])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_csr_to_ell16_bit_exact(cuda_backend, width, maxdeg, parity, weighted):
+    """Row-padded CSR table: indices bit-exact (incl. pad slots, overflow marks, parity slot order)."""
+    b, nmax = 3, 57
+    rows = b * nmax
+    rowptr, col = _random_csr(rows, maxdeg, seed=width + maxdeg, block=nmax)
+    nnz = int(rowptr[-1])
+    val = torch.rand(nnz + 3, generator=torch.Generator().manual_seed(1)) if weighted else None
+    ell = torch.zeros(rows * width, dtype=torch.int16)
+    ellw = torch.zeros(rows * width) if weighted else None
+    both(cuda_backend, 'csr_to_ell16', [rowptr, col, val, b, nmax, width, parity, ell, ellw],
+         [7, 8] if weighted else [7], exact=(7, 8))
+    table = (ell.view(rows, width).long() & 0xFFFF)
+    deg = (rowptr[1:] - rowptr[:-1]).long()
+    assert bool(((table[:, 0] == nmax + 1) == (deg > width)).all())
+    ok = deg <= width
+    assert bool(((table[ok] != nmax).sum(1) == deg[ok]).all())
+
+
+@pytest.mark.parametrize('feat,b,nmax,width,maxdeg', [(16, 3, 70, 8, 8), (16, 5, 333, 8, 10), (16, 64, 1800, 8, 8),
+                                                      (8, 150, 40, 16, 16), (32, 2, 1500, 16, 18),
+                                                      (20, 4, 1100, 8, 8), (16, 2, 2999, 8, 8)])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_sage_gather_ell(cuda_backend, feat, b, nmax, width, maxdeg, weighted):
+    """Fixed-pitch TMA-staged gather == CPU formulas == generic CSR gather (fp32 tolerance: slot order differs)."""
+    rows = b * nmax
+    rowptr, col = _random_csr(rows, maxdeg, seed=nmax, block=nmax) if rows < 5000 else _knn_csr(b, nmax)
+    nnz = int(rowptr[-1])
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(rows, feat, generator=g)
+    val = torch.rand(nnz + 3, generator=g) if weighted else None
+    rsc = torch.rand(rows, generator=g) if weighted else None
+    ell = torch.zeros(rows * width, dtype=torch.int16)
+    ellw = torch.zeros(rows * width) if weighted else None
+    REF.csr_to_ell16(rowptr, col, val, b, nmax, width, int(feat == 16), ell, ellw)
+    out = torch.zeros(rows, feat)
+    both(cuda_backend, 'sage_gather_ell_fwd', [ell, ellw, width, rsc, rowptr, col, val, x, b, nmax, out], [10],
+         rtol=1e-5, atol=1e-5)
+    want = torch.zeros(rows, feat)
+    REF.sage_gather_mean_fwd(rowptr, col, val, rsc, x, b, nmax, want)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+
+
 def _knn_csr(b, nmax, k=8):
     graphs = graph.synthetic_batch(b, nmax, k, 1, seed=11)
     bt = graph.Batch.from_data_list(graphs)

@@ -14,8 +14,12 @@ batch = graph.Batch.from_data_list(graphs).to('cuda')
 xp, g = ops.build_sparse_graph(batch.x, batch.edge_index, batch.batch, batch.num_nodes_list, False)
 out = torch.empty_like(xp)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+variant = os.environ.get('VARIANT', 'ell')
 for _ in range(3):
     flush.zero_()
-    be.sage_gather_mean_fwd(g.rowptr, g.col, None, None, xp, b, n, out)
+    if variant == 'ell':
+        be.sage_gather_ell_fwd(g.ell, None, g.ell_width, None, g.rowptr, g.col, None, xp, b, n, out)
+    else:
+        be.sage_gather_mean_fwd(g.rowptr, g.col, None, None, xp, b, n, out)
 torch.cuda.synchronize()
 print('done')
