@@ -158,7 +158,7 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- gather roofline
-def gather_roofline(args, device, variant='ell', parity=True):
+def gather_roofline(args, device, variant='ell', parity=True, scale=True):
     """The SAGE gather kernel alone (F = 16, unfused): CUDA-graph replay over rotating input copies whose
     total footprint exceeds L2, timed with CUDA events on the launching stream.
     variant 'ell' = cgc_sage_gather_ell_fwd (fixed-pitch index table), 'csr' = cgc_sage_gather_mean_fwd."""
@@ -183,9 +183,10 @@ def gather_roofline(args, device, variant='ell', parity=True):
             ell0 = torch.empty_like(g.ell)
             be.csr_to_ell16(g.rowptr, g.col, None, b, n, g.ell_width, False, ell0, None)
         ells = [ell0.clone() for _ in range(copies)]
+        rss = [g.rs.clone() if scale else None for _ in range(copies)]     # 1/deg per row, as the model passes it
 
         def launch(i):
-            be.sage_gather_ell_fwd(ells[i], None, g.ell_width, None, g.rowptr, g.col, None, xs[i], b, n, outs[i])
+            be.sage_gather_ell_fwd(ells[i], None, g.ell_width, rss[i], g.rowptr, g.col, None, xs[i], b, n, outs[i])
     else:
         cols = [g.col.clone() for _ in range(copies)]
         ptrs = [g.rowptr.clone() for _ in range(copies)]

@@ -286,6 +286,31 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+// 16 bytes of shared memory as two packed f32x2 registers (operands of FADD2 / FFMA2)
+struct F32x4 {
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ F32x4 lds_x4(uint32_t addr) {
+  F32x4 v;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void add_x4(F32x4& acc, const F32x4& v) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.lo) : "l"(v.lo));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.hi) : "l"(v.hi));
+}
+__device__ __forceinline__ void fma_x4(F32x4& acc, float w, const F32x4& v) {
+  unsigned long long ww;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.lo) : "l"(v.lo), "l"(ww));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.hi) : "l"(v.hi), "l"(ww));
+}
+__device__ __forceinline__ float4 unpack_x4(const F32x4& v) {
+  float4 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(v.lo));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.z), "=f"(o.w) : "l"(v.hi));
+  return o;
+}
 
 // slot t (compile-time after unrolling) of a row's packed uint16 index words
 __device__ __forceinline__ uint32_t ell_slot(const uint32_t* words, int t) {
@@ -295,14 +320,15 @@ __device__ __forceinline__ uint32_t ell_slot(const uint32_t* words, int t) {
 
 // grid = num_graphs * parts; CTA (g, p) owns local rows [p*rpp, min((p+1)*rpp, nmax)) of graph g (rpp % 8 == 0).
 // LPR lanes per row, one float4 of the feature row per lane; group grp = tid / LPR serves rows grp, grp+G, ...
-// RB rows per thread form one batch: their index vectors are loaded (next batch: prefetched) before the
-// branch-free slot loop, so the shared-memory pipe always has RB * W independent reads per thread to chew on.
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
+// The index vectors (and weights / row scales) of RB rows per thread are loaded before the tile barrier (next
+// batch: prefetched), so the slot loop is pure LDS.128 + packed FADD2/FFMA2 on registers.
+// HAS_SCALE: row_scale given (else, unweighted: 1 / max(#valid slots, 1)).
+template <int W, int LPR, bool WEIGHTED, bool HAS_SCALE, int RB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ ellw,
                   const float* __restrict__ row_scale, const int* __restrict__ rowptr,
                   const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ x,
-                  int nmax, int feat, int parts, int rpp, float* __restrict__ out, int stage_limit) {
+                  int nmax, int feat, int parts, int rpp, float* __restrict__ out, int stage_limit, uint32_t chunk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int G = THREADS / LPR;
   constexpr int NW = W / 2;                            // 32-bit index words per row
@@ -319,10 +345,17 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&bar, tile_bytes);
+    uint32_t lo = 0, hi = tile_bytes;
+    if (stage_limit == 3) {                            // lab: each CTA copies only its share of the tile
+      const uint32_t share = (tile_bytes / parts) & ~15u;
+      lo = p * share; hi = lo + share;
+    } else if (stage_limit >= 4) {                     // lab: every CTA copies the first 1/(stage-2) of the tile
+      hi = (tile_bytes / (stage_limit - 2)) & ~15u;
+    }
+    mbar_expect_tx(&bar, hi - lo);
     const unsigned char* src = reinterpret_cast<const unsigned char*>(x + grow0 * feat);
-    for (uint32_t off = 0; off < tile_bytes; off += kBulkChunk) {
-      uint32_t n = min(kBulkChunk, tile_bytes - off);
+    for (uint32_t off = lo; off < hi; off += chunk) {
+      uint32_t n = min(chunk, hi - off);
       bulk_g2s(smem_raw + off, src + off, n, &bar);
     }
   }
@@ -362,68 +395,52 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
         }
       }
-      rsc[i] = (row_scale != nullptr && on) ? __ldg(row_scale + row) : 1.0f;
+      rsc[i] = (HAS_SCALE && on) ? __ldg(row_scale + row) : 1.0f;
     }
   };
 
   load_batch(0);
   __syncthreads();                                     // zero rows visible, barrier initialised
   mbar_wait(&bar, 0);
-  if (stage_limit == 2) return;
+  if (stage_limit >= 2) return;
 
   for (int i0 = 0; i0 * G < nrows; i0 += RB) {
-    float4 acc[RB];
-    int cnt[RB];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      cnt[i] = 0;
-#pragma unroll
-      for (int t = 0; t < W; ++t) {
-        const uint32_t j = ell_slot(idx[i], t);
-        if (!WEIGHTED) cnt[i] += (j != (uint32_t)nmax) ? 1 : 0;
-        const float4 v = lds_f4(lane_base + j * row_bytes);
-        if (WEIGHTED) {
-          const float w = wgt[WEIGHTED ? i : 0][WEIGHTED ? t : 0];
-          acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
-          acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
-        } else {
-          acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
-        }
-      }
-    }
-    uint32_t ovf = 0;
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
       const int r = (i0 + i) * G + grp;
-      if ((idx[i][0] & 0xFFFFu) == ovf_mark) ovf |= 1u << i;
+      if (r >= nrows) continue;                        // whole quarter-warps at a time (rpp % 8 == 0)
+      const int64_t row = grow0 + r0 + r;
+      float4 o;
       float s = rsc[i];
-      if (!WEIGHTED && row_scale == nullptr) s = 1.0f / fmaxf((float)cnt[i], 1.0f);
-      if (r < nrows && lane_on) {
-        float4 o = acc[i];
-        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-        *reinterpret_cast<float4*>(out + (grow0 + r0 + r) * feat + sl * 4) = o;
-      }
-    }
-    if (ovf != 0) {
-      // rows whose degree exceeds W: walk the CSR (column ids are global padded rows); overwrites the row
-      for (int i = 0; i < RB; ++i) {
-        if (!((ovf >> i) & 1u)) continue;
-        const int64_t row = grow0 + r0 + (i0 + i) * G + grp;
+      if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
+        F32x4 acc;
+        acc.lo = 0ull; acc.hi = 0ull;
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+          const uint32_t j = ell_slot(idx[i], t);
+          if (!WEIGHTED && !HAS_SCALE) cnt += (j != (uint32_t)nmax) ? 1 : 0;
+          const F32x4 v = lds_x4(lane_base + j * row_bytes);
+          if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? t : 0], v);
+          else add_x4(acc, v);
+        }
+        if (!WEIGHTED && !HAS_SCALE) s = 1.0f / fmaxf((float)cnt, 1.0f);
+        o = unpack_x4(acc);
+      } else {
+        // degree > W: walk the CSR (column ids are global padded rows)
         const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        o = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = b; k < e; ++k) {
           const uint32_t j = (uint32_t)(__ldg(col + k) - (int)grow0);
           const float w = WEIGHTED ? __ldg(val + k) : 1.0f;
           const float4 v = lds_f4(lane_base + j * row_bytes);
-          a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+          o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y); o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
         }
-        float s = row_scale != nullptr ? __ldg(row_scale + row) : 1.0f;
-        if (!WEIGHTED && row_scale == nullptr) s = 1.0f / fmaxf((float)(e - b), 1.0f);
-        if (lane_on) {
-          a.x *= s; a.y *= s; a.z *= s; a.w *= s;
-          *reinterpret_cast<float4*>(out + row * feat + sl * 4) = a;
-        }
+        if (!WEIGHTED && !HAS_SCALE) s = 1.0f / fmaxf((float)(e - b), 1.0f);
+      }
+      if (lane_on) {
+        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+        *reinterpret_cast<float4*>(out + row * feat + sl * 4) = o;
       }
     }
     if ((i0 + RB) * G < nrows) load_batch(i0 + RB);
@@ -535,12 +552,12 @@ static int ell_threads() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CGC_GATHER_THREADS");    // tuning aid: 512 or 1024 threads per CTA
-    v = e ? atoi(e) : 1024;
+    v = e ? atoi(e) : 512;
   }
   return v;
 }
 
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
+template <int W, int LPR, bool WEIGHTED, bool HAS_SCALE, int RB, int THREADS>
 static int launch_ell(const uint16_t* ell, const float* ellw, const float* row_scale, const int32_t* rowptr,
                       const int32_t* col, const float* val, const float* x, int num_graphs, int nmax, int feat,
                       float* out, cudaStream_t st) {
@@ -548,14 +565,17 @@ static int launch_ell(const uint16_t* ell, const float* ellw, const float* row_s
   CGC_REQUIRE(smem + 1024 <= 227 * 1024, CGC_ERR_UNSUPPORTED,
               "cgc_sage_gather_ell_fwd: feature tile of %lld B does not fit in shared memory", (long long)smem);
   int parts = kNumSMs / num_graphs;
+  if (const char* e = getenv("CGC_GATHER_PARTS")) parts = atoi(e);
   if (parts < 1) parts = 1;
   int rpp = (int)ceil_div(nmax, parts);
   rpp = (rpp + 7) & ~7;                                 // quarter-warp row pairs stay aligned
   parts = (int)ceil_div(nmax, rpp);
-  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS>;
+  uint32_t chunk = kBulkChunk;
+  if (const char* e = getenv("CGC_GATHER_CHUNK")) chunk = (uint32_t)atoi(e);
+  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, HAS_SCALE, RB, THREADS>;
   CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<num_graphs * parts, THREADS, smem, st>>>(ell, ellw, row_scale, rowptr, col, val, x, nmax, feat, parts, rpp,
-                                                  out, ell_stage_limit());
+                                                  out, ell_stage_limit(), chunk);
   CGC_CHECK_LAUNCH("k_sage_gather_ell");
   return 0;
 }
@@ -576,9 +596,15 @@ extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val
   cudaStream_t st = as_stream(stream);
   const bool wt = ell_val != nullptr;
   const bool big = ell_threads() >= 1024;
-#define CGC_ELL(W_, LPR_, WT_, RB_, TH_) \
-  return launch_ell<W_, LPR_, WT_, RB_, TH_>(ell, ell_val, row_scale, rowptr, col, val, x, num_graphs, nmax, feat, \
-                                            out, st)
+  const bool sc = row_scale != nullptr;
+#define CGC_ELL(W_, LPR_, WT_, RB_, TH_)                                                                             \
+  do {                                                                                                              \
+    if (sc)                                                                                                         \
+      return launch_ell<W_, LPR_, WT_, true, RB_, TH_>(ell, ell_val, row_scale, rowptr, col, val, x, num_graphs,    \
+                                                       nmax, feat, out, st);                                        \
+    return launch_ell<W_, LPR_, WT_, false, RB_, TH_>(ell, ell_val, row_scale, rowptr, col, val, x, num_graphs,     \
+                                                      nmax, feat, out, st);                                         \
+  } while (0)
   if (feat <= 16) {
     if (width == 8) {
       if (wt) CGC_ELL(8, 4, true, 2, 512);
