@@ -43,12 +43,11 @@ _SIGNATURES = {
     'cgc_csr_to_ell16': [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_int, _c_vp, _c_vp, _c_vp],
     'cgc_sage_gather_ell_fwd': [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32,
                                 _c_vp, _c_vp],
-    'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32,
-                              _c_vp, _c_i64, _c_vp],
-    'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
-                    _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp],
-    'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32,
-                                  _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
+    'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
+    'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    'cgc_act_fwd': [_c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
+    'cgc_act_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_scale_rows_bwd': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp],
     'cgc_bn_stats': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp,
                      _c_vp, _c_i64, _c_vp],
@@ -225,16 +224,16 @@ class CudaBackend(object):
                     'cgc_sage_gather_ell_fwd')
 
     # -- SAGE epilogue
-    def sage_epilogue_fwd(self, sa, w, b, mask, y):
+    def sage_epilogue_fwd(self, sa, w, b, mask, y, act=0):
         sp, lds = _mat(sa)
         yp, ldy = _mat(y)
         nn, nmax = _mask(mask)
         self._check(self.lib.cgc_sage_epilogue_fwd(sp, lds, _ptr(w.contiguous(), torch.float32),
                                                    _ptr(b, torch.float32), nn, nmax, sa.shape[0],
-                                                   w.shape[0], w.shape[1], yp, ldy, self._stream()),
+                                                   w.shape[0], w.shape[1], int(act), yp, ldy, self._stream()),
                     'cgc_sage_epilogue_fwd')
 
-    def sage_dh(self, gy, sa, w, b, y, mask, dh):
+    def sage_dh(self, gy, sa, w, b, y, mask, dh, act=0):
         gp, ldg = _mat(gy)
         sp, lds = _mat(sa)
         yp, ldy = _mat(y)
@@ -242,9 +241,9 @@ class CudaBackend(object):
         nn, nmax = _mask(mask)
         self._check(self.lib.cgc_sage_dh(gp, ldg, sp, lds, _ptr(w.contiguous(), torch.float32),
                                          _ptr(b, torch.float32), yp, ldy, nn, nmax, sa.shape[0],
-                                         w.shape[0], w.shape[1], dp, ldd, self._stream()), 'cgc_sage_dh')
+                                         w.shape[0], w.shape[1], int(act), dp, ldd, self._stream()), 'cgc_sage_dh')
 
-    def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b):
+    def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b, act=0):
         gp, ldg = _mat(gy)
         sp, lds = _mat(sa)
         yp, ldy = _mat(y)
@@ -253,9 +252,22 @@ class CudaBackend(object):
         wp, wb = self._workspace(sa.device)
         self._check(self.lib.cgc_sage_layer_bwd_narrow(gp, ldg, sp, lds, _ptr(w.contiguous(), torch.float32),
                                                        _ptr(b, torch.float32), yp, ldy, nn, nmax, sa.shape[0],
-                                                       w.shape[0], w.shape[1], dp, ldd,
+                                                       w.shape[0], w.shape[1], int(act), dp, ldd,
                                                        _ptr(d_w, torch.float32), _ptr(d_b, torch.float32), wp, wb,
                                                        self._stream()), 'cgc_sage_layer_bwd_narrow')
+
+    def act_fwd(self, x, act, y):
+        xp, ldx = _mat(x)
+        yp, ldy = _mat(y)
+        self._check(self.lib.cgc_act_fwd(xp, ldx, x.shape[0], x.shape[1], int(act), yp, ldy, self._stream()),
+                    'cgc_act_fwd')
+
+    def act_bwd(self, gy, y, act, gx):
+        gp, ldg = _mat(gy)
+        yp, ldy = _mat(y)
+        op, ldo = _mat(gx)
+        self._check(self.lib.cgc_act_bwd(gp, ldg, yp, ldy, y.shape[0], y.shape[1], int(act), op, ldo,
+                                         self._stream()), 'cgc_act_bwd')
 
     def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
         for t in (dsa, sa):

@@ -52,6 +52,19 @@ __device__ __forceinline__ bool row_valid(const int32_t* __restrict__ num_nodes,
   return (int)(r - g * nmax) < __ldg(num_nodes + g);
 }
 
+// Activation that follows a conv (GNN_Module._activation, network.py:82-90): 0 relu, 1 elu (alpha 1), 2 leaky relu
+// (slope 0.01).  The gradient is written in terms of the OUTPUT y, as the reference's in-place modules do.
+__device__ __forceinline__ float act_fwd(int act, float v) {
+  if (act == CGC_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == CGC_ACT_ELU) return v > 0.f ? v : expm1f(v);
+  return v > 0.f ? v : 0.01f * v;
+}
+__device__ __forceinline__ float act_grad(int act, float y) {
+  if (act == CGC_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == CGC_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+  return y > 0.f ? 1.f : 0.01f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256)
 k_epi_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
              const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
              float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
-             float* __restrict__ dh, int64_t lddh) {
+             float* __restrict__ dh, int64_t lddh, int act) {
   extern __shared__ float s_w[];          // [cin][cout] then bias[cout]
   float* s_b = s_w + cin * cout;
   for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = w[i];
@@ -39,11 +39,11 @@ k_epi_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict
     const float inv = 1.0f / fmaxf(nrm, kL2NormEps);
     const bool valid = row_valid(num_nodes, nmax, r);
     if (!BWD) {
-      if (lane < cout) y[r * ldy + lane] = valid ? fmaxf(h * inv, 0.f) : 0.f;
+      if (lane < cout) y[r * ldy + lane] = valid ? act_fwd(act, h * inv) : 0.f;
     } else {
       float hn = h * inv;
       float g = 0.f;
-      if (lane < cout && valid && __ldg(y + r * ldy + lane) > 0.f) g = gy[r * ldgy + lane];
+      if (lane < cout && valid) g = gy[r * ldgy + lane] * act_grad(act, __ldg(y + r * ldy + lane));
       const float dot = warp_sum(g * hn);
       float d = (nrm >= kL2NormEps) ? (g - hn * dot) * inv : g * inv;
       if (lane < cout) dh[r * lddh + lane] = d;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kEpiThreads)
 k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
            const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
            float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
-           float* __restrict__ dh, int64_t lddh) {
+           float* __restrict__ dh, int64_t lddh, int act) {
   extern __shared__ float smem[];
   float* s_w = smem;                                 // [cin][cout]
   float* s_a = s_w + cin * cout;                     // [cin][kEpiRows]  (transposed row tile)
@@ -136,7 +136,7 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
           int c = t + kEpiThreads * j;
-          if (c < cout) y[r * ldy + c] = valid ? fmaxf(acc[rr][j] * inv[rr], 0.f) : 0.f;
+          if (c < cout) y[r * ldy + c] = valid ? act_fwd(act, acc[rr][j] * inv[rr]) : 0.f;
         }
       }
     } else {
@@ -154,7 +154,7 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
           if (valid && c < cout) {                    // independent loads (no y -> gy dependency chain)
             const float yv = __ldg(y + r * ldy + c);
             const float gv = gy[r * ldgy + c];
-            g = yv > 0.f ? gv : 0.f;
+            g = gv * act_grad(act, yv);
           }
           gm[rr][j] = g;
           s = fmaf(g, acc[rr][j] * inv[rr], s);
@@ -191,8 +191,9 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
 template <bool BWD>
 static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const float* b,
                            const int32_t* num_nodes, int nmax, int64_t rows, int cin, int cout, float* y,
-                           int64_t ldy, const float* gy, int64_t ldgy, float* dh, int64_t lddh,
+                           int64_t ldy, const float* gy, int64_t ldgy, float* dh, int64_t lddh, int act,
                            cudaStream_t st) {
+  CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG, "sage epilogue: unknown activation %d", act);
   if (cout <= 32) {
     CGC_REQUIRE(cin <= 64, CGC_ERR_UNSUPPORTED, "sage epilogue: cin=%d > 64", cin);
     size_t smem = sizeof(float) * (size_t)(cin * cout + cout);
@@ -200,7 +201,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     int64_t blocks = ceil_div(warps_needed, 8);
     if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;   // latency-bound per row: keep many warps in flight
     k_epi_narrow<BWD><<<(unsigned)blocks, 256, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy,
-                                                           gy, ldgy, dh, lddh);
+                                                           gy, ldgy, dh, lddh, act);
     CGC_CHECK_LAUNCH("k_epi_narrow");
     return 0;
   }
@@ -219,7 +220,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     auto kern = k_epi_wide<N, BWD>;                                                                           \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     kern<<<(unsigned)blocks, kEpiThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, \
-                                                      gy, ldgy, dh, lddh);                                    \
+                                                      gy, ldgy, dh, lddh, act);                               \
   } break;
   switch (nc) {
     CGC_EPI_CASE(1)
@@ -388,27 +389,64 @@ k_dense_renorm_bwd(const float* __restrict__ g, const float* __restrict__ out, c
   for (int i = lane; i < n; i += 32) o[i] = (i == diag) ? 0.f : sc * (gr[i] - dot);
 }
 
+// elementwise activation on a [rows, c] matrix with leading dimensions (GIN's MLP and post-conv activation)
+template <bool BWD>
+__global__ void __launch_bounds__(256) k_act(const float* __restrict__ a, int64_t lda, const float* __restrict__ y,
+                                             int64_t ldy, int64_t rows, int c, int act, float* __restrict__ o,
+                                             int64_t ldo) {
+  const int64_t n = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c;
+    const int k = (int)(i - r * c);
+    if (!BWD) o[r * ldo + k] = act_fwd(act, a[r * lda + k]);
+    else o[r * ldo + k] = a[r * lda + k] * act_grad(act, __ldg(y + r * ldy + k));
+  }
+}
+
 }  // namespace cgc
 
 using namespace cgc;
 
+extern "C" int cgc_act_fwd(const float* x, int64_t ldx, int64_t rows, int32_t c, int act, float* y, int64_t ldy,
+                           void* stream) {
+  CGC_REQUIRE(x && y && rows > 0 && c > 0 && ldx >= c && ldy >= c, CGC_ERR_ARG, "cgc_act_fwd: bad args");
+  CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG, "cgc_act_fwd: unknown activation %d", act);
+  int64_t blocks = ceil_div(rows * c, 256 * 4);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  k_act<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, ldx, nullptr, 0, rows, c, act, y, ldy);
+  CGC_CHECK_LAUNCH("k_act");
+  return 0;
+}
+
+extern "C" int cgc_act_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy, int64_t rows, int32_t c,
+                           int act, float* gx, int64_t ldgx, void* stream) {
+  CGC_REQUIRE(gy && y && gx && rows > 0 && c > 0 && ldgy >= c && ldy >= c && ldgx >= c, CGC_ERR_ARG,
+              "cgc_act_bwd: bad args");
+  CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG, "cgc_act_bwd: unknown activation %d", act);
+  int64_t blocks = ceil_div(rows * c, 256 * 4);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  k_act<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(gy, ldgy, y, ldy, rows, c, act, gx, ldgx);
+  CGC_CHECK_LAUNCH("k_act");
+  return 0;
+}
+
 extern "C" int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w, const float* b,
                                      const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
-                                     int32_t cout, float* y, int64_t ldy, void* stream) {
+                                     int32_t cout, int act, float* y, int64_t ldy, void* stream) {
   CGC_REQUIRE(sa && w && y && rows > 0 && cin > 0 && cout > 0 && ldsa >= cin && ldy >= cout, CGC_ERR_ARG,
               "cgc_sage_epilogue_fwd: bad args");
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_epilogue_fwd: mask without nmax");
   return launch_epilogue<false>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, nullptr, 0, nullptr, 0,
-                                as_stream(stream));
+                                act, as_stream(stream));
 }
 
 extern "C" int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,
                            const float* b, const float* y, int64_t ldy, const int32_t* num_nodes, int32_t nmax,
-                           int64_t rows, int32_t cin, int32_t cout, float* dh, int64_t lddh, void* stream) {
+                           int64_t rows, int32_t cin, int32_t cout, int act, float* dh, int64_t lddh, void* stream) {
   CGC_REQUIRE(gy && sa && w && y && dh && rows > 0 && cin > 0 && cout > 0, CGC_ERR_ARG, "cgc_sage_dh: bad args");
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_dh: mask without nmax");
   return launch_epilogue<true>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, const_cast<float*>(y), ldy, gy,
-                               ldgy, dh, lddh, as_stream(stream));
+                               ldgy, dh, lddh, act, as_stream(stream));
 }
 
 extern "C" int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows, int32_t c,

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kNbThreads, 3)
 k_sage_bwd_narrow(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ sa, int64_t ldsa,
                   const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ y,
                   int64_t ldy, const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
-                  float* __restrict__ dsa, int64_t lddsa, float* __restrict__ partial, int cinp, int vec) {
+                  float* __restrict__ dsa, int64_t lddsa, float* __restrict__ partial, int cinp, int vec, int act) {
   extern __shared__ __align__(16) float smem[];
   const int cin_r = (cin + 3) & ~3;          // W rows staged (zero padded)
   const int cin_e = (cin + 4) & ~3;          // sa columns of the dW contraction: cin, the ones column, zero pad
@@ -122,16 +122,16 @@ k_sage_bwd_narrow(const float* __restrict__ gy, int64_t ldgy, const float* __res
           if (vec) {
             const float4 yv = __ldg(reinterpret_cast<const float4*>(yrow) + c4);
             const float4 gv = __ldg(reinterpret_cast<const float4*>(grow) + c4);
-            g4.x = yv.x > 0.f ? gv.x : 0.f;
-            g4.y = yv.y > 0.f ? gv.y : 0.f;
-            g4.z = yv.z > 0.f ? gv.z : 0.f;
-            g4.w = yv.w > 0.f ? gv.w : 0.f;
+            g4.x = gv.x * act_grad(act, yv.x);
+            g4.y = gv.y * act_grad(act, yv.y);
+            g4.z = gv.z * act_grad(act, yv.z);
+            g4.w = gv.w * act_grad(act, yv.w);
           } else {
             float gs[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int c = 4 * c4 + j;
-              gs[j] = (c < cout && __ldg(yrow + c) > 0.f) ? __ldg(grow + c) : 0.f;
+              gs[j] = c < cout ? __ldg(grow + c) * act_grad(act, __ldg(yrow + c)) : 0.f;
             }
             g4 = make_float4(gs[0], gs[1], gs[2], gs[3]);
           }
@@ -261,13 +261,15 @@ using namespace cgc;
 extern "C" int cgc_sage_layer_bwd_narrow(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa,
                                          const float* w, const float* b, const float* y, int64_t ldy,
                                          const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
-                                         int32_t cout, float* dsa, int64_t lddsa, float* d_w, float* d_b,
+                                         int32_t cout, int act, float* dsa, int64_t lddsa, float* d_w, float* d_b,
                                          void* work, int64_t work_bytes, void* stream) {
   CGC_REQUIRE(gy && sa && w && y && dsa && d_w && work && rows > 0 && cin > 0 && cout > 0, CGC_ERR_ARG,
               "cgc_sage_layer_bwd_narrow: bad args");
   CGC_REQUIRE(cout <= 32 && cin <= 64, CGC_ERR_UNSUPPORTED,
               "cgc_sage_layer_bwd_narrow: needs cout <= 32 and cin <= 64 (got %d, %d)", cout, cin);
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_layer_bwd_narrow: mask without nmax");
+  CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG,
+              "cgc_sage_layer_bwd_narrow: unknown activation %d", act);
   const int cinp = cin <= 16 ? 16 : (cin <= 32 ? 32 : 64);
   const int c4 = cout <= 8 ? 2 : (cout <= 20 ? 5 : 8);
   const int cin_r = (cin + 3) & ~3;
@@ -290,7 +292,7 @@ extern "C" int cgc_sage_layer_bwd_narrow(const float* gy, int64_t ldgy, const fl
     auto kern = k_sage_bwd_narrow<N>;                                                                           \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
     kern<<<(unsigned)blocks, kNbThreads, smem, st>>>(gy, ldgy, sa, ldsa, w, b, y, ldy, num_nodes, nmax, rows, cin, \
-                                                     cout, dsa, lddsa, partial, cinp, vec);                     \
+                                                     cout, dsa, lddsa, partial, cinp, vec, act);                \
   } break;
   switch (c4) {
     CGC_NB_CASE(2)

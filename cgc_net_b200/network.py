@@ -54,25 +54,44 @@ class DenseSAGEConv(nn.Module):
                 self.bias.uniform_(-bound, bound)
 
 
+class DenseGINConv(nn.Module):
+    """Parameter holder with PyG 1.2.1 ``DenseGINConv`` names (``nn.0.*``, ``nn.2.*`` of the 2-layer MLP built at
+    network.py:97-98, and the ``eps`` buffer).  With ``add_loop=False`` (every reference call) ``eps`` is unused:
+    ``out = MLP(adj @ x) * mask``.  The arithmetic runs through ``ops`` (see ``GNN_Module._forward_gin``)."""
+
+    def __init__(self, in_channels, out_channels, eps=0.0):
+        super(DenseGINConv, self).__init__()
+        # the middle module is the activation in the reference (no parameters): an Identity placeholder keeps
+        # the Sequential indices 0 / 2 of the two Linear layers
+        self.nn = nn.Sequential(nn.Linear(in_channels, out_channels), nn.Identity(),
+                                nn.Linear(out_channels, out_channels))
+        self.register_buffer('eps', torch.tensor([float(eps)]))
+
+
 class GNN_Module(nn.Module):
-    """Three SAGE conv -> ReLU -> BatchNorm1d blocks, concat, optional Linear (network.py:57-125)."""
+    """Three conv -> activation -> BatchNorm1d blocks, concat, optional Linear (network.py:57-125); conv is
+    DenseSAGEConv (``gcn_name='SAGE'``) or DenseGINConv around a 2-layer MLP (anything else, network.py:92-99)."""
 
     def __init__(self, input_dim, hidden_dim, embedding_dim, bias, bn, add_loop, lin=True,
                  gcn_name='SAGE', sync=False, activation='relu', jk=False):
         super(GNN_Module, self).__init__()
-        if gcn_name != 'SAGE':
-            raise NotImplementedError('gcn_name=%r: only the SAGE path (network.py:94-95) is built; '
-                                      'DenseGINConv is a SURVEY 8(f) "next" row' % (gcn_name,))
-        if activation != 'relu':
-            raise NotImplementedError('activation=%r: only relu has a CUDA epilogue' % (activation,))
+        if activation not in ops.ACTIVATIONS:
+            raise ValueError('activation must be one of %s (network.py:83)' % sorted(ops.ACTIVATIONS))
         if add_loop:
             raise NotImplementedError('add_loop=True is never used by the reference '
                                       '(network.py:144,148,157,161,164)')
         self.jk = jk
         self.add_loop = add_loop
-        self.gcn1 = DenseSAGEConv(input_dim, hidden_dim, normalize=True, bias=bias)
-        self.gcn2 = DenseSAGEConv(hidden_dim, hidden_dim, normalize=True, bias=bias)
-        self.gcn3 = DenseSAGEConv(hidden_dim, embedding_dim, normalize=True, bias=bias)
+        self.act = ops.ACTIVATIONS[activation]
+        self.gin = gcn_name != 'SAGE'
+        if self.gin:
+            self.gcn1 = DenseGINConv(input_dim, hidden_dim)
+            self.gcn2 = DenseGINConv(hidden_dim, hidden_dim)
+            self.gcn3 = DenseGINConv(hidden_dim, embedding_dim)
+        else:
+            self.gcn1 = DenseSAGEConv(input_dim, hidden_dim, normalize=True, bias=bias)
+            self.gcn2 = DenseSAGEConv(hidden_dim, hidden_dim, normalize=True, bias=bias)
+            self.gcn3 = DenseSAGEConv(hidden_dim, embedding_dim, normalize=True, bias=bias)
         self.has_bn = bool(bn)
         if bn:
             self.bn1 = nn.BatchNorm1d(hidden_dim)
@@ -86,6 +105,8 @@ class GNN_Module(nn.Module):
     def forward(self, x, adj, mask=None, graph=None, num_graphs=None, nmax=None, scale=None):
         """``x [M, Cin]`` in the padded node layout.  Either ``graph`` (``ops.SparseGraph``,
         stage 1) or a dense ``adj [B, N, N]`` with ``scale = ops.dense_row_scale(adj)``."""
+        if self.gin:
+            return self._forward_gin(x, adj, mask, graph, num_graphs, nmax)
         params, buffers = [], []
         for k in (1, 2, 3):
             conv = getattr(self, 'gcn%d' % k)
@@ -102,13 +123,42 @@ class GNN_Module(nn.Module):
         if graph is not None:
             cfg = ops.GnnConfig(graph=graph, num_graphs=graph.num_graphs, nmax=graph.nmax,
                                 mask=graph.mask, training=self.training, has_bn=self.has_bn,
-                                has_lin=self.lin is not None, bn_buffers=buffers)
+                                has_lin=self.lin is not None, bn_buffers=buffers, act=self.act)
             return ops.GnnModuleFunction.apply(cfg, x, None, graph.rs, None, *params)
         rs, rsum = scale
         cfg = ops.GnnConfig(graph=None, num_graphs=num_graphs, nmax=nmax, mask=mask,
                             training=self.training, has_bn=self.has_bn,
-                            has_lin=self.lin is not None, bn_buffers=buffers)
+                            has_lin=self.lin is not None, bn_buffers=buffers, act=self.act)
         return ops.GnnModuleFunction.apply(cfg, x, adj, rs, rsum, *params)
+
+    def _forward_gin(self, x, adj, mask, graph, num_graphs, nmax):
+        """DenseGINConv path (network.py:96-99,109-125): ``x_k = BN_k(act(MLP_k(A x_{k-1}) * mask))``.  Built
+        from the same C-ABI kernels (neighbour-sum gather / contraction, tcgen05 or fp32 GEMM with fused bias
+        and row mask, activation, BatchNorm), chained by autograd."""
+        if graph is not None:
+            num_graphs, nmax, mask = graph.num_graphs, graph.nmax, graph.mask
+        cfg = ops.GnnConfig(graph=graph, num_graphs=num_graphs, nmax=nmax, mask=mask, training=self.training)
+        feats = []
+        h = x
+        for k in (1, 2, 3):
+            conv = getattr(self, 'gcn%d' % k)
+            agg = ops.NeighbourSumFunction.apply(cfg, h, adj)
+            z = ops.LinearFunction.apply(agg, conv.nn[0].weight, conv.nn[0].bias, None)
+            z = ops.ActFunction.apply(z, self.act)
+            z = ops.LinearFunction.apply(z, conv.nn[2].weight, conv.nn[2].bias, mask)
+            z = ops.ActFunction.apply(z, self.act)
+            if self.has_bn:
+                bn = getattr(self, 'bn%d' % k)
+                if self.training:
+                    bn.num_batches_tracked += 1
+                z = ops.BatchNormFunction.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                self.training, mask)
+            feats.append(z)
+            h = z
+        out = torch.cat(feats, dim=1)
+        if self.lin is not None:
+            out = ops.LinearFunction.apply(out, self.lin.weight, self.lin.bias, mask)
+        return out
 
 
 class DenseJK(nn.Module):
@@ -191,7 +241,7 @@ class SoftPoolingGcnEncoder(nn.Module):
         layers = []
         for pred_dim in pred_hidden_dims:
             layers.append(nn.Linear(pred_input_dim, pred_dim))
-            layers.append(nn.ReLU(inplace=True))
+            layers.append({'relu': nn.ReLU, 'elu': nn.ELU, 'leakyrelu': nn.LeakyReLU}[activation](inplace=True))
             pred_input_dim = pred_dim
             if self.drop_out > 0:
                 layers.append(nn.Dropout(self.drop_out))

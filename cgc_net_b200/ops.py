@@ -28,6 +28,7 @@ from torch.autograd import Function
 from . import _backend
 
 RENORM_P = 0.4       # model/network.py:260,271,280
+ACTIVATIONS = {'relu': 0, 'elu': 1, 'leakyrelu': 2}     # GNN_Module._activation (network.py:82-90) -> CGC_ACT_*
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -132,13 +133,14 @@ class GnnConfig(object):
     """Static description of one ``GNN_Module`` call (not a tensor; passed through autograd)."""
 
     def __init__(self, graph=None, num_graphs=0, nmax=0, mask=None, training=True, has_bn=True,
-                 has_lin=False, bn_buffers=None, need_adj_grad=False):
+                 has_lin=False, bn_buffers=None, need_adj_grad=False, act=0):
         self.graph = graph              # SparseGraph, or None when the adjacency is dense
         self.num_graphs, self.nmax = num_graphs, nmax
         self.mask = mask                # RowMask or None
         self.training, self.has_bn, self.has_lin = training, has_bn, has_lin
         self.bn_buffers = bn_buffers    # [(running_mean, running_var)] * 3 (updated in place)
         self.need_adj_grad = need_adj_grad
+        self.act = act                  # ACTIVATIONS[name]: 0 relu, 1 elu, 2 leakyrelu (network.py:82-90)
 
 
 def _agg(be, cfg, adj, rs, x_prev, out):
@@ -204,7 +206,7 @@ class GnnModuleFunction(Function):
             a = _f32(m, w.shape[0], device=dev)          # sa = rs * (A x)
             _agg(be, cfg, adj, rs, x_prev, a)
             y = _f32(m, couts[k], device=dev)
-            be.sage_epilogue_fwd(a, w, b, cfg.mask, y)
+            be.sage_epilogue_fwd(a, w, b, cfg.mask, y, cfg.act)
             dst = cat[:, off: off + couts[k]]
             mean = invstd = None
             if cfg.has_bn:
@@ -286,9 +288,9 @@ class GnnModuleFunction(Function):
             dsa = _f32(m, w.shape[0], device=dev)
             if w.shape[1] <= 32 and w.shape[0] <= 64:
                 # narrow layer: dh, dW, db and dsa = dh W^T in ONE pass over the rows
-                be.sage_layer_bwd_narrow(gy, a, w, b, y, cfg.mask, dsa, d_w, d_b)
+                be.sage_layer_bwd_narrow(gy, a, w, b, y, cfg.mask, dsa, d_w, d_b, cfg.act)
             else:
-                be.sage_dh(gy, a, w, b, y, cfg.mask, gy)        # gy <- dh = dL/d(sa W + b), in place
+                be.sage_dh(gy, a, w, b, y, cfg.mask, gy, cfg.act)   # gy <- dh = dL/d(sa W + b), in place
                 be.gemm(a, gy, d_w, True, False)                # dW = sa^T dh   (K = M)
                 if d_b is not None:
                     be.colsum(gy, None, d_b)
@@ -316,6 +318,135 @@ class GnnModuleFunction(Function):
             # rs_i = 1 / clamp(rsum_i, 1)  ->  dA_ij += -[rsum_i >= 1] d_rs_i / rsum_i^2   (all j)
             be.add_rs_grad(d_adj, rsum, d_rs)
         return (None, g_x0, d_adj, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------- GIN variant (composable pieces)
+class NeighbourSumFunction(Function):
+    """``torch.matmul(adj, x)`` of DenseGINConv (PyG 1.2.1; reference call site network.py:99,114): the plain
+    neighbour SUM (no mean, no self term since the reference passes ``add_loop=False``).  Sparse stage 1: CSR
+    gather forward, CSC gather backward; dense stages: batched contraction with a gradient for the adjacency."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, adj):
+        be = _backend.get()
+        out = _f32(x.shape[0], x.shape[1], device=x.device)
+        if cfg.graph is not None:
+            g = cfg.graph
+            be.spmm(g.rowptr, g.col, g.val, x, None, None, out, False)
+        else:
+            b, n = cfg.num_graphs, cfg.nmax
+            be.gemm(adj, _as3d(x, b, n), out.view(b, n, -1), False, False)
+        ctx.cfg = cfg
+        ctx.save_for_backward(x, adj)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        be = _backend.get()
+        cfg = ctx.cfg
+        x, adj = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        gx = g_adj = None
+        if cfg.graph is not None:
+            if ctx.needs_input_grad[1]:
+                g = cfg.graph
+                gx = _f32(x.shape[0], x.shape[1], device=x.device)
+                be.spmm(g.colptr, g.row, g.val_t, g_out, None, None, gx, False)
+        else:
+            b, n = cfg.num_graphs, cfg.nmax
+            if ctx.needs_input_grad[1]:
+                gx = _f32(x.shape[0], x.shape[1], device=x.device)
+                be.gemm(adj, _as3d(g_out, b, n), gx.view(b, n, -1), True, False)           # A^T g
+            if ctx.needs_input_grad[2]:
+                g_adj = torch.empty_like(adj)
+                be.gemm(_as3d(g_out, b, n), _as3d(x.contiguous(), b, n), g_adj, False, True)   # g x^T
+        return None, gx, g_adj
+
+
+class LinearFunction(Function):
+    """``nn.Linear`` of the GIN MLP (network.py:97-98): ``y = (x W^T + b) [* mask]``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask):
+        be = _backend.get()
+        x = x.contiguous()
+        y = _f32(x.shape[0], weight.shape[0], device=x.device)
+        be.gemm(x, weight, y, False, True, bias=bias, rowmask=mask)
+        ctx.mask = mask
+        ctx.save_for_backward(x, weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        be = _backend.get()
+        x, weight, bias = ctx.saved_tensors
+        gy = gy.contiguous()
+        if ctx.mask is not None:
+            gm = torch.empty_like(gy)
+            be.bn_apply(gy, None, None, None, None, ctx.mask, gm)      # gy * mask
+            gy = gm
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _f32(x.shape[0], x.shape[1], device=x.device)
+            be.gemm(gy, weight, gx, False, False)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(weight)
+            be.gemm(gy, x, gw, True, False)
+        if bias is not None and ctx.needs_input_grad[2]:
+            gb = torch.empty_like(bias)
+            be.colsum(gy, None, gb)
+        return gx, gw, gb, None
+
+
+class ActFunction(Function):
+    """relu / elu / leakyrelu (``GNN_Module._activation``, network.py:82-90); gradient from the output."""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        be = _backend.get()
+        y = torch.empty_like(x, memory_format=torch.contiguous_format)
+        be.act_fwd(x.contiguous(), act, y)
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        be = _backend.get()
+        y, = ctx.saved_tensors
+        gx = torch.empty_like(y)
+        be.act_bwd(gy.contiguous(), y, ctx.act, gx)
+        return gx, None
+
+
+class BatchNormFunction(Function):
+    """``nn.BatchNorm1d`` over all padded rows (network.py:101-107), output multiplied by the row mask
+    (network.py:119-120 applies it to the concat; padded rows never reach real rows before that)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, rmean, rvar, training, mask):
+        be = _backend.get()
+        y = y.contiguous()
+        c = y.shape[1]
+        mean, invstd = _f32(c, device=y.device), _f32(c, device=y.device)
+        if training:
+            be.bn_stats(y, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
+        else:
+            be.bn_eval_stats(rmean, rvar, BN_EPS, mean, invstd)
+        out = torch.empty_like(y)
+        be.bn_apply(y, mean, invstd, gamma, beta, mask, out)
+        ctx.training, ctx.mask = training, mask
+        ctx.save_for_backward(y, mean, invstd, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        be = _backend.get()
+        y, mean, invstd, gamma = ctx.saved_tensors
+        gy = torch.empty_like(y)
+        d_gamma, d_beta = torch.empty_like(gamma), torch.empty_like(gamma)
+        be.bn_bwd(g.contiguous(), y, mean, invstd, gamma, ctx.mask, ctx.training, gy, d_gamma, d_beta)
+        return gy, d_gamma, d_beta, None, None, None, None
 
 
 # ----------------------------------------------------------------------------- diff-pool

@@ -46,6 +46,11 @@ extern "C" {
 #define CGC_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are instantiated for  */
 #define CGC_ERR_WORKSPACE (-3)  /* workspace too small                                   */
 
+/* activation after a conv (GNN_Module._activation, model/network.py:82-90), `act` arguments below */
+#define CGC_ACT_RELU 0
+#define CGC_ACT_ELU 1          /* alpha = 1 (nn.ELU default)           */
+#define CGC_ACT_LEAKY_RELU 2   /* slope 0.01 (nn.LeakyReLU default)    */
+
 CGC_API int cgc_version(void);
 CGC_API const char* cgc_last_error(void);
 /* Bytes of scratch that is enough for every entry point below at any supported shape. */
@@ -136,18 +141,19 @@ CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, i
                             int32_t feat, float* out, void* stream);
 
 /* ------------------------------------------------------------------ SAGE layer epilogue
- * y = relu( l2normalize(sa @ W + b) * mask )      [rows, cout]
+ * y = act( l2normalize(sa @ W + b) * mask )      [rows, cout]
  * DenseSAGEConv.forward lines matmul(out, weight) / + bias / F.normalize(p=2, eps=1e-12) /
- * * mask, then nn.ReLU (network.py:114-116).  sa = mean-aggregated features [rows, cin]. */
+ * * mask, then the in-place activation (network.py:82-90,114-116; act = CGC_ACT_*).
+ * sa = mean-aggregated features [rows, cin]. */
 CGC_API int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w, const float* b,
                           const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
-                          int32_t cout, float* y, int64_t ldy, void* stream);
+                          int32_t cout, int act, float* y, int64_t ldy, void* stream);
 
 /* dh = d loss / d (sa @ W + b) given gy = d loss / d y.  dh may alias gy. */
 CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,
                 const float* b, const float* y, int64_t ldy, const int32_t* num_nodes,
-                int32_t nmax, int64_t rows, int32_t cin, int32_t cout, float* dh, int64_t lddh,
-                void* stream);
+                int32_t nmax, int64_t rows, int32_t cin, int32_t cout, int act, float* dh,
+                int64_t lddh, void* stream);
 
 /* Fused backward of a narrow layer epilogue (cout <= 32, cin <= 64) in one pass over the rows:
  * dsa = dh W^T [rows, cin], d_w = sa^T dh [cin, cout], d_b = sum_rows dh (nullable), with
@@ -156,8 +162,16 @@ CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t 
 CGC_API int cgc_sage_layer_bwd_narrow(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa,
                               const float* w, const float* b, const float* y, int64_t ldy,
                               const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
-                              int32_t cout, float* dsa, int64_t lddsa, float* d_w, float* d_b,
+                              int32_t cout, int act, float* dsa, int64_t lddsa, float* d_w, float* d_b,
                               void* work, int64_t work_bytes, void* stream);
+
+/* Element-wise activation y = act(x) and its gradient gx = gy * act'(y) (in terms of the output, as the
+ * reference's in-place modules): the activation inside DenseGINConv's MLP and after it (network.py:96-99,114).
+ * y may alias x; gx may alias gy. */
+CGC_API int cgc_act_fwd(const float* x, int64_t ldx, int64_t rows, int32_t c, int act, float* y, int64_t ldy,
+                void* stream);
+CGC_API int cgc_act_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy, int64_t rows, int32_t c,
+                int act, float* gx, int64_t ldgx, void* stream);
 
 /* Backward of sa = rs * agg (dense stages, where rs depends on the adjacency):
  * ga = rs * dsa (leading dimension ldga);  d_rs[r] += dot(dsa[r], sa[r]) / rs[r]. */

@@ -179,6 +179,28 @@ class TorchBackend(object):
         out.copy_(res)
 
     # ---------------------------------------------------------------- SAGE epilogue
+    @staticmethod
+    def _act(act, v):
+        if act == 0:
+            return v.clamp(min=0)
+        if act == 1:
+            return torch.where(v > 0, v, torch.expm1(v))
+        return torch.where(v > 0, v, 0.01 * v)
+
+    @staticmethod
+    def _act_grad(act, y):
+        if act == 0:
+            return (y > 0).float()
+        if act == 1:
+            return torch.where(y > 0, torch.ones_like(y), y + 1)
+        return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.01))
+
+    def act_fwd(self, x, act, y):
+        y.copy_(self._act(act, x))
+
+    def act_bwd(self, gy, y, act, gx):
+        gx.copy_(gy * self._act_grad(act, y))
+
     def _epilogue(self, sa, w, b, mask):
         h = sa @ w
         if b is not None:
@@ -188,21 +210,21 @@ class TorchBackend(object):
         valid = _valid_rows(mask, sa.shape[0], sa.device)[:, None].float()
         return h, nrm, inv, valid
 
-    def sage_epilogue_fwd(self, sa, w, b, mask, y):
+    def sage_epilogue_fwd(self, sa, w, b, mask, y, act=0):
         h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
-        y.copy_(torch.relu(h * inv * valid))
+        y.copy_(self._act(act, h * inv * valid))
 
-    def sage_dh(self, gy, sa, w, b, y, mask, dh):
+    def sage_dh(self, gy, sa, w, b, y, mask, dh, act=0):
         h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
         hn = h * inv
-        gm = gy * (y > 0).float() * valid                # ReLU (output sign) and row mask
+        gm = gy * self._act_grad(act, y) * valid         # activation gradient (from the output) and row mask
         dot = (gm * hn).sum(1, keepdim=True)
         # y = h / max(|h|, eps): d/dh = (g - hn (hn . g)) / |h|   when |h| >= eps, g / eps otherwise
         dh.copy_(torch.where(nrm >= L2_EPS, (gm - hn * dot) * inv, gm * inv))
 
-    def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b):
+    def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b, act=0):
         dh = torch.empty_like(y)
-        self.sage_dh(gy, sa, w, b, y, mask, dh)
+        self.sage_dh(gy, sa, w, b, y, mask, dh, act)
         dsa.copy_(dh @ w.t())
         d_w.copy_(sa.t() @ dh)
         if d_b is not None:

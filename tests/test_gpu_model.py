@@ -225,3 +225,20 @@ def test_maximum_graph_size(cuda_backend):
     s = m.assign_matrix[0]
     assert tuple(s.shape) == (1, 11404, 1140)
     assert torch.allclose(s.sum(-1), torch.ones(1, 11404, device='cuda'), atol=1e-5)
+
+
+@pytest.mark.parametrize('gcn_name,activation,norm_adj', [('GIN', 'relu', False), ('GIN', 'elu', True),
+                                                           ('SAGE', 'elu', False), ('SAGE', 'leakyrelu', True)])
+def test_gin_and_activations_vs_oracle(gemm_mode, gcn_name, activation, norm_adj):
+    """DenseGINConv variant (network.py:96-99) and elu / leakyrelu (network.py:82-90) on the GPU."""
+    graphs = helpers.make_graphs([333, 801, 57, 640], [5, 8, 12, 6], seed=9)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair(helpers.encoder_args(2000), load_data_sparse=True, norm_adj=norm_adj,
+                                   collect_assign=True, gcn_name=gcn_name, activation=activation)
+    lo, losso, lr, lossr = _run_pair(ours, orc, batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    assert abs(float(losso.detach()) - float(lossr.detach())) < 1e-5
+    _, _, truth = helpers.oracle_fp64(orc, batch)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()},
+                               **_grad_tol(gemm_mode, norm_adj))
+    _check_assignments(ours, orc)

@@ -230,6 +230,50 @@ def test_sage_epilogue_and_dh(cuda_backend, cin, cout, masked):
     both(cuda_backend, 'sage_epilogue_fwd', [sa, w, None, mask, yw[:, 4:4 + cout]], [4], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('act', [1, 2])
+@pytest.mark.parametrize('cin,cout', [(16, 20), (20, 300)])
+def test_sage_epilogue_activations(cuda_backend, act, cin, cout):
+    """elu / leakyrelu epilogues and their gradients (narrow, wide and fused-narrow kernels)."""
+    b, nmax = 3, 53
+    rows = b * nmax
+    g = torch.Generator().manual_seed(act * 100 + cout)
+    sa = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax)
+    y = torch.zeros(rows, cout)
+    getattr(REF, 'sage_epilogue_fwd')(sa, w, bias, mask, y, act)
+    yg = torch.zeros(rows, cout).cuda()
+    cuda_backend.sage_epilogue_fwd(sa.cuda(), w.cuda(), bias.cuda(), _cu(mask), yg, act)
+    torch.testing.assert_close(yg.cpu(), y, rtol=1e-5, atol=1e-6)
+    assert bool((y < 0).any())                                   # the negative branch is exercised
+    gy = torch.randn(rows, cout, generator=g)
+    dh = torch.zeros(rows, cout)
+    REF.sage_dh(gy, sa, w, bias, y, mask, dh, act)
+    dhg = torch.zeros(rows, cout).cuda()
+    cuda_backend.sage_dh(gy.cuda(), sa.cuda(), w.cuda(), bias.cuda(), yg, _cu(mask), dhg, act)
+    torch.testing.assert_close(dhg.cpu(), dh, rtol=1e-4, atol=1e-5)
+    if cout <= 32:
+        dsa, d_w, d_b = torch.zeros(rows, cin), torch.zeros(cin, cout), torch.zeros(cout)
+        REF.sage_layer_bwd_narrow(gy, sa, w, bias, y, mask, dsa, d_w, d_b, act)
+        outs = [torch.zeros_like(t).cuda() for t in (dsa, d_w, d_b)]
+        cuda_backend.sage_layer_bwd_narrow(gy.cuda(), sa.cuda(), w.cuda(), bias.cuda(), yg, _cu(mask), *outs, act)
+        for got, want in zip(outs, (dsa, d_w, d_b)):
+            torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('act', [0, 1, 2])
+def test_act_fwd_bwd(cuda_backend, act):
+    g = torch.Generator().manual_seed(act)
+    xw = torch.randn(211, 70, generator=g)
+    x = xw[:, 3:64]                                              # strided view
+    y = torch.zeros(211, 61)
+    both(cuda_backend, 'act_fwd', [x, act, y], [2], rtol=1e-6, atol=1e-7)
+    gy = torch.randn(211, 61, generator=g)
+    gx = torch.zeros(211, 61)
+    both(cuda_backend, 'act_bwd', [gy, y, act, gx], [3], rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize('cin,cout', [(16, 20), (20, 20), (60, 20), (33, 32), (5, 3)])
 @pytest.mark.parametrize('masked', [False, True])
 def test_sage_layer_bwd_narrow(cuda_backend, cin, cout, masked):

@@ -114,9 +114,47 @@ def test_jumping_knowledge_matches_oracle(torch_backend, norm_adj):
     _grad_check(ours, orc, batch)
 
 
-def test_unbuilt_rows_raise():
-    with pytest.raises(NotImplementedError):
-        network.SoftPoolingGcnEncoder(100, 16, 20, 20, True, True, 20, 3, gcn_name='GIN')
+@pytest.mark.parametrize('gcn_name,activation,norm_adj', [('GIN', 'relu', False), ('GIN', 'elu', True),
+                                                           ('SAGE', 'elu', False), ('SAGE', 'leakyrelu', True),
+                                                           ('GIN', 'leakyrelu', False)])
+def test_gin_and_activations_match_oracle(torch_backend, gcn_name, activation, norm_adj):
+    """DenseGINConv variant (network.py:96-99) and the elu / leakyrelu activations (network.py:82-90)."""
+    graphs = helpers.make_graphs([41, 67, 30], [5, 8, 6], seed=21)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair(helpers.encoder_args(300), load_data_sparse=True, norm_adj=norm_adj,
+                                   gcn_name=gcn_name, activation=activation)
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in orc.state_dict().items()}
+    ours.train(), orc.train()
+    lo, losso = ours(batch)
+    lr, lossr = orc(batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    losso.backward(), lossr.backward()
+    _grad_check(ours, orc, batch)
+    for (k, a), (_, b) in zip(sorted(ours.named_buffers()), sorted(orc.named_buffers())):
+        assert helpers.rel_err(a.float(), b.float()) < 1e-4, k
+    ours.eval(), orc.eval()
+    with torch.no_grad():
+        assert helpers.rel_err(ours(batch), orc(batch)) < 1e-4
+
+
+def test_gin_dense_tuple_input(torch_backend):
+    graphs = helpers.make_graphs([25, 40], [5, 6], seed=6)
+    b = graph.Batch.from_data_list(graphs)
+    adj, counts = restatement.densify_edges(b.edge_index, b.batch)
+    x = restatement.pad_nodes(b.x, b.batch, counts)
+    ours, orc = helpers.build_pair(helpers.encoder_args(200), load_data_sparse=False, gcn_name='GIN')
+    ours.train(), orc.train()
+    lo, losso = ours((x, adj.clone(), counts, b.y))
+    lr, lossr = orc((x, adj.clone(), counts, b.y))
+    assert helpers.rel_err(lo, lr) < 1e-4
+    losso.backward(), lossr.backward()
+    _grad_check(ours, orc, (x, adj.clone(), counts, b.y))
+
+
+def test_unknown_activation_raises():
+    with pytest.raises(ValueError):
+        network.SoftPoolingGcnEncoder(100, 16, 20, 20, True, True, 20, 3, activation='gelu')
 
 
 def test_graph_build_matches_to_dense_adj(torch_backend):
