@@ -180,13 +180,17 @@ def gather_roofline(args, device, variant='ell', parity=True, scale=True):
         assert g.ell is not None, 'no ELL16 table was built for this batch'
         ell0 = g.ell
         if not parity:
-            ell0 = torch.empty_like(g.ell)
-            be.csr_to_ell16(g.rowptr, g.col, None, b, n, g.ell_width, False, ell0, None)
+            ell0, perm0, sc0 = torch.empty_like(g.ell), torch.empty_like(g.ell_perm), torch.empty_like(g.ell_scale)
+            be.csr_to_ell16(g.rowptr, g.col, None, g.rs, b, n, g.ell_width, False, ell0, None, sc0, perm0)
+        else:
+            perm0, sc0 = g.ell_perm, g.ell_scale
         ells = [ell0.clone() for _ in range(copies)]
-        rss = [g.rs.clone() if scale else None for _ in range(copies)]     # 1/deg per row, as the model passes it
+        perms = [perm0.clone() for _ in range(copies)]
+        scs = [sc0.clone() for _ in range(copies)]
 
         def launch(i):
-            be.sage_gather_ell_fwd(ells[i], None, g.ell_width, rss[i], g.rowptr, g.col, None, xs[i], b, n, outs[i])
+            be.sage_gather_ell_fwd(ells[i], None, scs[i], perms[i], g.ell_width, g.rowptr, g.col, None, xs[i], b, n,
+                                   outs[i])
     else:
         cols = [g.col.clone() for _ in range(copies)]
         ptrs = [g.rowptr.clone() for _ in range(copies)]
@@ -210,19 +214,23 @@ def gather_roofline(args, device, variant='ell', parity=True, scale=True):
         with torch.cuda.graph(graph_obj, stream=stream):
             for i in range(copies):
                 launch(i)
-    reps = 20
+    reps, blocks = 20, 5
+    samples = []
     with torch.cuda.stream(stream):
         for _ in range(3):
             graph_obj.replay()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(reps):
-            graph_obj.replay()
-        e1.record(stream)
-        torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / (reps * copies)
-    return alg_bytes, us, copies
+        for _ in range(blocks):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(reps):
+                graph_obj.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            samples.append(e0.elapsed_time(e1) * 1e3 / (reps * copies))
+    samples.sort()
+    gather_roofline.samples = samples
+    return alg_bytes, samples[len(samples) // 2], copies       # median of 5 blocks of 20 x `copies` launches
 
 
 # ----------------------------------------------------------------------------------- our arm

@@ -40,9 +40,11 @@ _SIGNATURES = {
                  _c_int, _c_vp],
     'cgc_sage_gather_mean_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp,
                                  _c_vp],
-    'cgc_csr_to_ell16': [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_int, _c_vp, _c_vp, _c_vp],
-    'cgc_sage_gather_ell_fwd': [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32,
-                                _c_vp, _c_vp],
+    'cgc_ell16_rows': [_c_i32, _c_i32],
+    'cgc_csr_to_ell16': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+                         _c_vp],
+    'cgc_sage_gather_ell_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32,
+                                _c_i32, _c_vp, _c_vp],
     'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
@@ -70,7 +72,7 @@ _SIGNATURES = {
     'cgc_colsum': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp],
 }
 _RESTYPES = {'cgc_last_error': ctypes.c_char_p, 'cgc_workspace_bytes': _c_i64, 'cgc_launch_count': _c_i64,
-             'cgc_coo_to_csr_workspace': _c_i64}
+             'cgc_coo_to_csr_workspace': _c_i64, 'cgc_ell16_rows': _c_i64}
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 
@@ -205,19 +207,29 @@ class CudaBackend(object):
                                                       x.shape[1], _ptr(out, torch.float32),
                                                       self._stream()), 'cgc_sage_gather_mean_fwd')
 
-    def csr_to_ell16(self, rowptr, col, val, num_graphs, nmax, width, parity_order, ell, ell_val):
-        if ell.dtype != torch.int16 or ell.numel() < num_graphs * nmax * width:
-            raise CgcError('cgc_csr_to_ell16: ell must be an int16 tensor of num_graphs * nmax * width elements')
-        self._check(self.lib.cgc_csr_to_ell16(_ptr(rowptr, torch.int32), _ptr(col, torch.int32),
-                                              _ptr(val, torch.float32), num_graphs, nmax, width,
-                                              int(parity_order), _ptr(ell, torch.int16),
-                                              _ptr(ell_val, torch.float32), self._stream()), 'cgc_csr_to_ell16')
+    def ell16_rows(self, num_graphs, nmax):
+        return int(self.lib.cgc_ell16_rows(num_graphs, nmax))
 
-    def sage_gather_ell_fwd(self, ell, ell_val, width, row_scale, rowptr, col, val, x, num_graphs, nmax, out):
+    def csr_to_ell16(self, rowptr, col, val, row_scale, num_graphs, nmax, width, pair_rows, ell, ell_val,
+                     ell_scale, perm):
+        rows = self.ell16_rows(num_graphs, nmax)
+        if ell.dtype != torch.int16 or ell.numel() < rows * width or perm.numel() < rows // 8 \
+                or ell_scale.numel() < rows:
+            raise CgcError('cgc_csr_to_ell16: ell must hold ell16_rows * width int16, ell_scale ell16_rows '
+                           'floats, perm ell16_rows / 8 int32')
+        self._check(self.lib.cgc_csr_to_ell16(_ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                              _ptr(val, torch.float32), _ptr(row_scale, torch.float32),
+                                              num_graphs, nmax, width, int(pair_rows), _ptr(ell, torch.int16),
+                                              _ptr(ell_val, torch.float32), _ptr(ell_scale, torch.float32),
+                                              _ptr(perm, torch.int32), self._stream()), 'cgc_csr_to_ell16')
+
+    def sage_gather_ell_fwd(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax,
+                            out):
         if not (x.is_contiguous() and out.is_contiguous()):
             raise CgcError('cgc_sage_gather_ell_fwd needs contiguous x / out')
-        self._check(self.lib.cgc_sage_gather_ell_fwd(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32), width,
-                                                     _ptr(row_scale, torch.float32), _ptr(rowptr, torch.int32),
+        self._check(self.lib.cgc_sage_gather_ell_fwd(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32),
+                                                     _ptr(ell_scale, torch.float32), _ptr(perm, torch.int32),
+                                                     width, _ptr(rowptr, torch.int32),
                                                      _ptr(col, torch.int32), _ptr(val, torch.float32),
                                                      _ptr(x, torch.float32), num_graphs, nmax, x.shape[1],
                                                      _ptr(out, torch.float32), self._stream()),

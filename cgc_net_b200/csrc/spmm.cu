@@ -231,52 +231,103 @@ k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, 
 // ------------------------------------------------------------------ ELL16 gather (fixed row pitch)
 // Row-padded CSR ("ELL16"): every padded row owns W slots of uint16 LOCAL column ids (column - g*nmax);
 // unused slots hold `nmax`, which addresses an all-zero row appended to the shared-memory tile.  A row whose
-// degree exceeds W is marked by slot 0 == nmax + 1 (a second zero row) and walked through the CSR instead.  The fixed pitch removes
-// the rowptr -> column-index dependency: a row's whole index list is ONE 16-byte load whose address is known
-// at kernel start, so index loads fly together with the TMA tile copy and nothing is staged through smem.
+// degree exceeds W is marked by slot 0 == nmax + 1 (a second zero row) and walked through the CSR instead.  The
+// fixed pitch removes the rowptr -> column-index dependency: a row's whole index list is ONE 16-byte load whose
+// address is known at kernel start, so index loads fly together with the TMA tile copy and nothing but the
+// feature tile is staged through shared memory.
 //
-// Bank conflicts: a 64-byte feature row covers half of the 32 banks, chosen by the parity of its index.  The
-// two rows served by one quarter-warp (lanes 8q..8q+7) collide iff their current neighbours have equal parity,
-// so the builder orders the slots of even local rows "even columns first" and of odd local rows "odd columns
-// first" (stable within a parity class): slots pair up with opposite parities except for |a - b| of them.
-__global__ void __launch_bounds__(256) k_csr_to_ell16(const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                      const float* __restrict__ val, int64_t rows, int nmax, int W,
-                                                      int parity_order, uint16_t* __restrict__ ell,
-                                                      float* __restrict__ ellw) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const int64_t g = r / nmax;
-  const int lr = (int)(r - g * nmax);
-  const int base = (int)(g * nmax);
-  const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
-  uint16_t* o = ell + r * W;
-  float* ow = ellw ? ellw + r * W : nullptr;
-  int pos = 0;
-  if (e - b > W) {
-    o[pos++] = (uint16_t)(nmax + 1);          // overflow: the gather walks the CSR for this row
-    if (ow) ow[0] = 0.f;
-  } else if (parity_order) {
-    const int first = lr & 1;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int want = pass == 0 ? first : 1 - first;
-      for (int i = b; i < e; ++i) {
-        const int c = __ldg(col + i) - base;
-        if ((c & 1) == want) {
+// Layout: graph g owns nrow8 = round_up(nmax, 8) table rows; table row g*nrow8 + 8*blk + p is the row served by
+// lane group p of the warp that handles block blk, and perm[g*nrow8/8 + blk] (3 bits per position) names the
+// local row 8*blk + ((perm >> 3p) & 7) it belongs to.
+//
+// Neighbour rows are read from the shared-memory tile, where a 64-byte feature row covers half of the 32 banks,
+// chosen by the parity of its index: the two rows served by one quarter-warp (positions 2k, 2k+1) collide iff
+// their current neighbours have equal parity.  With `pair_rows` the builder therefore
+//   * orders the slots "even columns first" on even positions and "odd columns first" on odd positions,
+//   * sorts the 8 rows of a block by their number e of even columns and pairs smallest with largest, so that
+//     e_A + e_B is as close to W as the block allows: the pair then collides in only |e_A + e_B - W| slots.
+// (Fetching one neighbour per row straight from global memory during the tile copy was tried and lost: the
+// dependent 64-byte reads go to DRAM at random and delay the tile barrier by 2 us.)
+// Only the summation order inside a row changes; the adjacency is exactly that of to_dense_adj (utils.py:29-33).
+constexpr int kEllMaxW = 16;
+
+__global__ void __launch_bounds__(128) k_csr_to_ell16(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                      const float* __restrict__ val,
+                                                      const float* __restrict__ row_scale, int num_graphs, int nmax,
+                                                      int W, int pair_rows, uint16_t* __restrict__ ell,
+                                                      float* __restrict__ ellw, float* __restrict__ ell_scale,
+                                                      uint32_t* __restrict__ perm) {
+  const int nrow8 = (nmax + 7) & ~7;
+  const int nb8 = nrow8 >> 3;
+  const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= (int64_t)num_graphs * nb8) return;
+  const int g = (int)(blk / nb8), lb = (int)(blk - (int64_t)g * nb8);
+  const int base = g * nmax;
+  const int n = W;
+  const int pad_par = nmax & 1;
+  int deg[8], key[8];
+  for (int q = 0; q < 8; ++q) {
+    const int lr = lb * 8 + q;
+    deg[q] = -1;                      // row does not exist (beyond nmax)
+    key[q] = n / 2;
+    if (lr >= nmax) continue;
+    const int64_t r = (int64_t)base + lr;
+    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    deg[q] = e - b;
+    if (deg[q] > W) continue;         // overflow row
+    if (deg[q] == 0) { key[q] = pad_par == 0 ? n : 0; continue; }
+    int ev = 0;
+    for (int i = b; i < e; ++i) ev += ((__ldg(col + i) - base) & 1) == 0;
+    const int pads = W - deg[q];
+    key[q] = ev + (pad_par == 0 ? pads : 0);
+  }
+  int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  if (pair_rows) {
+    for (int i = 1; i < 8; ++i) {     // stable insertion sort by key
+      const int o = order[i];
+      int j = i - 1;
+      while (j >= 0 && key[order[j]] > key[o]) { order[j + 1] = order[j]; --j; }
+      order[j + 1] = o;
+    }
+  }
+  uint32_t pw = 0;
+  for (int p = 0; p < 8; ++p) {
+    const int q = pair_rows ? ((p & 1) ? order[7 - (p >> 1)] : order[p >> 1]) : p;
+    pw |= (uint32_t)q << (3 * p);
+    uint16_t* o = ell + (blk * 8 + p) * W;
+    float* ow = ellw ? ellw + (blk * 8 + p) * W : nullptr;
+    // the row's output scale, in table order: row_scale[row], else the mean of the binary adjacency (DenseSAGEConv)
+    float sc = 1.0f;
+    if (deg[q] >= 0) {
+      if (row_scale) sc = __ldg(row_scale + base + lb * 8 + q);
+      else if (!val) sc = 1.0f / fmaxf((float)deg[q], 1.0f);
+    }
+    ell_scale[blk * 8 + p] = sc;
+    int pos = 0;
+    if (deg[q] > W) {
+      o[pos] = (uint16_t)(nmax + 1);
+      if (ow) ow[pos] = 0.f;
+      ++pos;
+    } else if (deg[q] > 0) {
+      const int64_t r = (int64_t)base + lb * 8 + q;
+      const int b = __ldg(rowptr + r), e = b + deg[q];
+      const int npass = pair_rows ? 2 : 1;
+      for (int pass = 0; pass < npass; ++pass) {
+        const int want = pass == 0 ? (p & 1) : 1 - (p & 1);
+        for (int i = b; i < e; ++i) {
+          const int c = __ldg(col + i) - base;
+          if (pair_rows && (c & 1) != want) continue;
           if (ow) ow[pos] = __ldg(val + i);
           o[pos++] = (uint16_t)c;
         }
       }
     }
-  } else {
-    for (int i = b; i < e; ++i) {
-      if (ow) ow[pos] = __ldg(val + i);
-      o[pos++] = (uint16_t)(__ldg(col + i) - base);
+    for (; pos < W; ++pos) {
+      o[pos] = (uint16_t)nmax;
+      if (ow) ow[pos] = 0.f;
     }
   }
-  for (; pos < W; ++pos) {
-    o[pos] = (uint16_t)nmax;
-    if (ow) ow[pos] = 0.f;
-  }
+  perm[blk] = pw;
 }
 
 __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -318,25 +369,29 @@ __device__ __forceinline__ uint32_t ell_slot(const uint32_t* words, int t) {
   return (t & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-// grid = num_graphs * parts; CTA (g, p) owns local rows [p*rpp, min((p+1)*rpp, nmax)) of graph g (rpp % 8 == 0).
-// LPR lanes per row, one float4 of the feature row per lane; group grp = tid / LPR serves rows grp, grp+G, ...
-// The index vectors (and weights / row scales) of RB rows per thread are loaded before the tile barrier (next
-// batch: prefetched), so the slot loop is pure LDS.128 + packed FADD2/FFMA2 on registers.
-// HAS_SCALE: row_scale given (else, unweighted: 1 / max(#valid slots, 1)).
-template <int W, int LPR, bool WEIGHTED, bool HAS_SCALE, int RB, int THREADS>
+// grid = num_graphs * parts; CTA (g, p) owns table rows [p*rpp, min((p+1)*rpp, nrow8)) of graph g (rpp % 8 == 0).
+// LPR lanes per row, one float4 of the feature row per lane; group grp = tid / LPR serves table rows grp, grp+G, ...
+// Before the tile barrier every thread loads the index vectors (weights, row scales) of its RB rows (next batch:
+// prefetched); after it the slot loop is pure LDS.128 + packed FADD2 / FFMA2 on registers.
+// Everything a thread reads before the barrier (indices, weights, scale, position map) is addressed by the table
+// row alone: no load depends on another.
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ ellw,
-                  const float* __restrict__ row_scale, const int* __restrict__ rowptr,
+                  const float* __restrict__ ell_scale, const uint32_t* __restrict__ perm,
+                  const int* __restrict__ rowptr,
                   const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ x,
                   int nmax, int feat, int parts, int rpp, float* __restrict__ out, int stage_limit, uint32_t chunk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int G = THREADS / LPR;
   constexpr int NW = W / 2;                            // 32-bit index words per row
+  const int nrow8 = (nmax + 7) & ~7;
   const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
   const int r0 = p * rpp;
-  const int nrows = min(rpp, nmax - r0);
+  const int nrows = min(rpp, nrow8 - r0);
   if (nrows <= 0 || stage_limit == 1) return;
-  const int64_t grow0 = (int64_t)g * nmax;
+  const int64_t grow0 = (int64_t)g * nmax;             // first padded row of the graph (x / out / rowptr)
+  const int64_t trow0 = (int64_t)g * nrow8 + r0;       // first table row of this CTA
   const uint32_t row_bytes = (uint32_t)feat * 4u;
   const uint32_t tile_bytes = (uint32_t)nmax * row_bytes;
   float* s_x = reinterpret_cast<float*>(smem_raw);
@@ -372,30 +427,32 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
   uint32_t idx[RB][NW];
   float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
   float rsc[RB];
+  uint32_t pw[RB];                                     // position map word of the row's block
   auto load_batch = [&](int i0) {
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
-      const int r = (i0 + i) * G + grp;
-      const bool on = r < nrows;
-      const int64_t row = grow0 + r0 + (on ? r : 0);
+      const int t = (i0 + i) * G + grp;                // table row inside the CTA
+      const bool on = t < nrows;
+      const int64_t trow = trow0 + (on ? t : 0);
+      pw[i] = on ? __ldg(perm + (trow >> 3)) : 0xFFFFFFFFu;
+      rsc[i] = on ? __ldg(ell_scale + trow) : 1.0f;
 #pragma unroll
       for (int q = 0; q < NW / 4; ++q) {
         uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
-        if (on) v = ldg_u4(ell + row * W + q * 8);
+        if (on) v = ldg_u4(ell + trow * W + q * 8);
         idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
       }
       if (WEIGHTED) {
 #pragma unroll
         for (int q = 0; q < W / 4; ++q) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on) v = ldg_f4(ellw + row * W + q * 4);
+          if (on) v = ldg_f4(ellw + trow * W + q * 4);
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
         }
       }
-      rsc[i] = (HAS_SCALE && on) ? __ldg(row_scale + row) : 1.0f;
     }
   };
 
@@ -407,24 +464,23 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
   for (int i0 = 0; i0 * G < nrows; i0 += RB) {
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
-      const int r = (i0 + i) * G + grp;
-      if (r >= nrows) continue;                        // whole quarter-warps at a time (rpp % 8 == 0)
-      const int64_t row = grow0 + r0 + r;
+      const int t = (i0 + i) * G + grp;
+      if (t >= nrows) continue;                        // whole quarter-warps at a time
+      const int lrow = ((r0 + t) & ~7) + (int)((pw[i] >> (3 * (t & 7))) & 7u);
+      if (lrow >= nmax) continue;                      // padding of the graph's last 8-row block
+      const int64_t row = grow0 + lrow;
       float4 o;
-      float s = rsc[i];
+      const float s = rsc[i];
       if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
         F32x4 acc;
         acc.lo = 0ull; acc.hi = 0ull;
-        int cnt = 0;
 #pragma unroll
-        for (int t = 0; t < W; ++t) {
-          const uint32_t j = ell_slot(idx[i], t);
-          if (!WEIGHTED && !HAS_SCALE) cnt += (j != (uint32_t)nmax) ? 1 : 0;
+        for (int u = 0; u < W; ++u) {
+          const uint32_t j = ell_slot(idx[i], u);
           const F32x4 v = lds_x4(lane_base + j * row_bytes);
-          if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? t : 0], v);
+          if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
           else add_x4(acc, v);
         }
-        if (!WEIGHTED && !HAS_SCALE) s = 1.0f / fmaxf((float)cnt, 1.0f);
         o = unpack_x4(acc);
       } else {
         // degree > W: walk the CSR (column ids are global padded rows)
@@ -436,7 +492,6 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
           const float4 v = lds_f4(lane_base + j * row_bytes);
           o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y); o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
         }
-        if (!WEIGHTED && !HAS_SCALE) s = 1.0f / fmaxf((float)(e - b), 1.0f);
       }
       if (lane_on) {
         o.x *= s; o.y *= s; o.z *= s; o.w *= s;
@@ -523,18 +578,24 @@ extern "C" int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* co
   return 0;
 }
 
-extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const float* val, int32_t num_graphs,
-                                int32_t nmax, int32_t width, int parity_order, uint16_t* ell, float* ell_val,
-                                void* stream) {
-  CGC_REQUIRE(rowptr && col && ell && num_graphs > 0 && nmax > 0, CGC_ERR_ARG, "cgc_csr_to_ell16: bad args");
+extern "C" int64_t cgc_ell16_rows(int32_t num_graphs, int32_t nmax) {
+  return (int64_t)num_graphs * ((nmax + 7) & ~7);
+}
+
+extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const float* val, const float* row_scale,
+                                int32_t num_graphs, int32_t nmax, int32_t width, int pair_rows, uint16_t* ell,
+                                float* ell_val, float* ell_scale, uint32_t* perm, void* stream) {
+  CGC_REQUIRE(rowptr && col && ell && ell_scale && perm && num_graphs > 0 && nmax > 0, CGC_ERR_ARG,
+              "cgc_csr_to_ell16: bad args");
   CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: width must be 8 or 16 (got %d)",
               width);
   CGC_REQUIRE(nmax + 1 <= 0xFFFF, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: nmax %d does not fit uint16 local ids", nmax);
   CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
               "cgc_csr_to_ell16: val and ell_val must be given together");
-  const int64_t rows = (int64_t)num_graphs * nmax;
-  k_csr_to_ell16<<<(unsigned)ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, rows, nmax, width,
-                                                                                parity_order, ell, ell_val);
+  const int64_t blocks8 = cgc_ell16_rows(num_graphs, nmax) / 8;
+  k_csr_to_ell16<<<(unsigned)ceil_div(blocks8, 128), 128, 0, as_stream(stream)>>>(rowptr, col, val, row_scale, num_graphs,
+                                                                                  nmax, width, pair_rows, ell, ell_val,
+                                                                                  ell_scale, perm);
   CGC_CHECK_LAUNCH("k_csr_to_ell16");
   return 0;
 }
@@ -552,13 +613,14 @@ static int ell_threads() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CGC_GATHER_THREADS");    // tuning aid: 512 or 1024 threads per CTA
-    v = e ? atoi(e) : 512;
+    v = e ? atoi(e) : 1024;
   }
   return v;
 }
 
-template <int W, int LPR, bool WEIGHTED, bool HAS_SCALE, int RB, int THREADS>
-static int launch_ell(const uint16_t* ell, const float* ellw, const float* row_scale, const int32_t* rowptr,
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
+static int launch_ell(const uint16_t* ell, const float* ellw, const float* ell_scale, const uint32_t* perm,
+                      const int32_t* rowptr,
                       const int32_t* col, const float* val, const float* x, int num_graphs, int nmax, int feat,
                       float* out, cudaStream_t st) {
   const size_t smem = ((size_t)nmax + 2) * feat * 4;
@@ -567,24 +629,25 @@ static int launch_ell(const uint16_t* ell, const float* ellw, const float* row_s
   int parts = kNumSMs / num_graphs;
   if (const char* e = getenv("CGC_GATHER_PARTS")) parts = atoi(e);
   if (parts < 1) parts = 1;
-  int rpp = (int)ceil_div(nmax, parts);
-  rpp = (rpp + 7) & ~7;                                 // quarter-warp row pairs stay aligned
-  parts = (int)ceil_div(nmax, rpp);
+  const int nrow8 = (nmax + 7) & ~7;
+  int rpp = (int)ceil_div(nrow8, parts);
+  rpp = (rpp + 7) & ~7;                                 // CTAs own whole 8-row blocks of the table
+  parts = (int)ceil_div(nrow8, rpp);
   uint32_t chunk = kBulkChunk;
   if (const char* e = getenv("CGC_GATHER_CHUNK")) chunk = (uint32_t)atoi(e);
-  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, HAS_SCALE, RB, THREADS>;
+  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS>;
   CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<num_graphs * parts, THREADS, smem, st>>>(ell, ellw, row_scale, rowptr, col, val, x, nmax, feat, parts, rpp,
+  kern<<<num_graphs * parts, THREADS, smem, st>>>(ell, ellw, ell_scale, perm, rowptr, col, val, x, nmax, feat, parts, rpp,
                                                   out, ell_stage_limit(), chunk);
   CGC_CHECK_LAUNCH("k_sage_gather_ell");
   return 0;
 }
 
-extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, int32_t width,
-                                       const float* row_scale, const int32_t* rowptr, const int32_t* col,
+extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                                       const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
                                        const float* val, const float* x, int32_t num_graphs, int32_t nmax,
                                        int32_t feat, float* out, void* stream) {
-  CGC_REQUIRE(ell && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
+  CGC_REQUIRE(ell && ell_scale && perm && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
               "cgc_sage_gather_ell_fwd: bad args");
   CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_sage_gather_ell_fwd: width must be 8 or 16");
   CGC_REQUIRE(feat % 4 == 0 && feat <= 32 && aligned16(x) && aligned16(out) && aligned16(ell), CGC_ERR_UNSUPPORTED,
@@ -596,15 +659,9 @@ extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val
   cudaStream_t st = as_stream(stream);
   const bool wt = ell_val != nullptr;
   const bool big = ell_threads() >= 1024;
-  const bool sc = row_scale != nullptr;
 #define CGC_ELL(W_, LPR_, WT_, RB_, TH_)                                                                             \
-  do {                                                                                                              \
-    if (sc)                                                                                                         \
-      return launch_ell<W_, LPR_, WT_, true, RB_, TH_>(ell, ell_val, row_scale, rowptr, col, val, x, num_graphs,    \
-                                                       nmax, feat, out, st);                                        \
-    return launch_ell<W_, LPR_, WT_, false, RB_, TH_>(ell, ell_val, row_scale, rowptr, col, val, x, num_graphs,     \
-                                                      nmax, feat, out, st);                                         \
-  } while (0)
+  return launch_ell<W_, LPR_, WT_, RB_, TH_>(ell, ell_val, ell_scale, perm, rowptr, col, val, x, num_graphs, nmax,   \
+                                            feat, out, st)
   if (feat <= 16) {
     if (width == 8) {
       if (wt) CGC_ELL(8, 4, true, 2, 512);

@@ -67,7 +67,7 @@ class SparseGraph(object):
         self.colptr = self.row = self.val_t = None
         self.rs = None
         self.mask = None
-        self.ell = self.ell_val = None      # row-padded CSR, uint16 local ids (cgc_csr_to_ell16)
+        self.ell = self.ell_val = self.ell_scale = self.ell_perm = None   # row-padded CSR (cgc_csr_to_ell16)
         self.ell_width = 0
 
 
@@ -120,11 +120,15 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
     feat = x.shape[1]
     real_rows = max(n_total, 1)
     if nmax < 0xFFFF and cap <= 16 * real_rows and feat % 4 == 0 and feat <= 32 \
-            and (nmax + 1) * feat * 4 + 1024 <= 227 * 1024:
+            and (nmax + 2) * feat * 4 + 1024 <= 227 * 1024:
         g.ell_width = 8 if cap <= 8 * real_rows else 16
-        g.ell = torch.empty(rows * g.ell_width, dtype=torch.int16, device=dev)
-        g.ell_val = _f32(rows * g.ell_width, device=dev) if norm_adj else None
-        be.csr_to_ell16(g.rowptr, g.col, g.val, num_graphs, nmax, g.ell_width, feat == 16, g.ell, g.ell_val)
+        trows = be.ell16_rows(num_graphs, nmax)
+        g.ell = torch.empty(trows * g.ell_width, dtype=torch.int16, device=dev)
+        g.ell_val = _f32(trows * g.ell_width, device=dev) if norm_adj else None
+        g.ell_scale = _f32(trows, device=dev)
+        g.ell_perm = torch.empty(trows // 8, dtype=torch.int32, device=dev)
+        be.csr_to_ell16(g.rowptr, g.col, g.val, g.rs, num_graphs, nmax, g.ell_width, feat == 16, g.ell, g.ell_val,
+                        g.ell_scale, g.ell_perm)
     return xp, g
 
 
@@ -149,10 +153,10 @@ def _agg(be, cfg, adj, rs, x_prev, out):
         g = cfg.graph
         feat = x_prev.shape[1]
         dense_io = x_prev.is_contiguous() and out.is_contiguous() and feat % 4 == 0 and feat <= 32
-        if dense_io and g.ell is not None and (g.nmax + 1) * feat * 4 + 1024 <= 227 * 1024:
-            # fixed-pitch index table + TMA-staged feature tile (the roofline kernel)
-            be.sage_gather_ell_fwd(g.ell, g.ell_val, g.ell_width, rs, g.rowptr, g.col, g.val, x_prev,
-                                   g.num_graphs, g.nmax, out)
+        if dense_io and g.ell is not None and rs is g.rs and (g.nmax + 2) * feat * 4 + 1024 <= 227 * 1024:
+            # fixed-pitch index table (rs baked in) + TMA-staged feature tile (the roofline kernel)
+            be.sage_gather_ell_fwd(g.ell, g.ell_val, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val,
+                                   x_prev, g.num_graphs, g.nmax, out)
         elif dense_io and g.nmax * feat * 4 + 12288 <= 220 * 1024:
             # whole-graph feature tile fits in shared memory: TMA-staged gather (the roofline kernel)
             be.sage_gather_mean_fwd(g.rowptr, g.col, g.val, rs, x_prev, g.num_graphs, g.nmax, out)

@@ -117,28 +117,39 @@ CGC_API int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, 
                              const float* row_scale, const float* x, int32_t num_graphs,
                              int32_t nmax, int32_t feat, float* out, void* stream);
 
-/* Row-padded CSR ("ELL16") of the stage-1 adjacency, the index layout of cgc_sage_gather_ell_fwd:
- * ell[r * width + t] = LOCAL column id (column - g*nmax, uint16) of the t-th stored entry of padded row r,
- * `nmax` in unused slots; a row with more than `width` entries gets ell[r*width] = nmax + 1 (the gather then
- * walks the CSR for it).  ell_val (nullable, with val) carries the entry weights, 0 in unused slots.
- * parity_order != 0 orders the slots of even local rows "even columns first" and of odd local rows "odd
- * columns first" (stable inside a parity class): with 64-byte feature rows the two rows a quarter-warp serves
- * then read opposite shared-memory bank halves.  Same adjacency as to_dense_adj (model/utils.py:29-33); only
- * the summation order of a row's neighbours changes.  width is 8 or 16. */
-CGC_API int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const float* val, int32_t num_graphs,
-                     int32_t nmax, int32_t width, int parity_order, uint16_t* ell, float* ell_val,
+/* Row-padded CSR ("ELL16") of the stage-1 adjacency, the index layout of cgc_sage_gather_ell_fwd.
+ * Graph g owns nrow8 = round_up(nmax, 8) table rows (cgc_ell16_rows() = num_graphs * nrow8 in total); table row
+ * g*nrow8 + 8*blk + p holds the entries of local row 8*blk + ((perm[g*nrow8/8 + blk] >> 3p) & 7):
+ *   ell[row * width + t] = LOCAL column id (column - g*nmax, uint16) of its t-th entry, `nmax` in unused slots
+ *   (and everywhere for rows beyond nmax); a row with more than `width` entries gets slot 0 = nmax + 1 and the
+ *   gather walks the CSR for it.  ell_val (nullable, with val) carries the entry weights, 0 in unused slots.
+ * pair_rows != 0 chooses the slot order and the row-to-position map that minimise shared-memory bank conflicts
+ * for 64-byte feature rows (slots go "even columns first" on even positions / "odd first" on odd ones; the
+ * 8 rows of a block are paired smallest-with-largest even count); pair_rows == 0 keeps CSR order and the
+ * identity map.  Same
+ * adjacency as to_dense_adj (model/utils.py:29-33); only the summation order inside a row changes.
+ * ell_scale[row] = the output scale of that table row: row_scale[r] when given (rs of cgc_edge_renorm /
+ * cgc_row_inv_degree), else 1/max(deg,1) for a binary adjacency (val == NULL), else 1.
+ * width is 8 or 16.  ell: cgc_ell16_rows()*width uint16; ell_scale: cgc_ell16_rows() floats;
+ * perm: cgc_ell16_rows()/8 uint32. */
+CGC_API int64_t cgc_ell16_rows(int32_t num_graphs, int32_t nmax);
+CGC_API int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const float* val,
+                     const float* row_scale, int32_t num_graphs, int32_t nmax, int32_t width,
+                     int pair_rows, uint16_t* ell, float* ell_val, float* ell_scale, uint32_t* perm,
                      void* stream);
 
 /* The roofline kernel, fixed-pitch variant (BASELINE.json metric): same result as cgc_sage_gather_mean_fwd,
- * out[r,:] = (1/max(deg,1)) * sum_e x[col[e],:] (ell_val == NULL, row_scale == NULL), or
- * row_scale[r] * sum_e val[e] * x[col[e],:].  The per-graph feature tile is staged in shared memory by bulk
- * async copies (TMA); each row's whole index list is one 16-byte load issued at kernel start (no rowptr ->
- * column dependency, nothing but the tile goes through shared memory).  rowptr / col / val are read only for
- * rows marked as overflowing `width`.  Requires (nmax + 2) * feat * 4 <= 226 KB, feat % 4 == 0, feat <= 32. */
-CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, int32_t width,
-                            const float* row_scale, const int32_t* rowptr, const int32_t* col,
-                            const float* val, const float* x, int32_t num_graphs, int32_t nmax,
-                            int32_t feat, float* out, void* stream);
+ * out[r,:] = scale[r] * sum_e val[e] * x[col[e],:] with scale / val as baked into the table by
+ * cgc_csr_to_ell16 (binary adjacency: the DenseSAGEConv mean).  The per-graph feature tile is staged in
+ * shared memory by bulk async copies (TMA); everything else a row needs (its whole index list = one 16-byte
+ * load, weights, scale, position map) is addressed by the table row alone and issued at kernel start: no
+ * rowptr -> column dependency, nothing but the tile goes through shared memory.  rowptr / col / val are read only for
+ * rows marked as
+ * overflowing `width`.  Requires (nmax + 2) * feat * 4 <= 226 KB, feat % 4 == 0, feat <= 32. */
+CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                            const uint32_t* perm, int32_t width, const int32_t* rowptr,
+                            const int32_t* col, const float* val, const float* x, int32_t num_graphs,
+                            int32_t nmax, int32_t feat, float* out, void* stream);
 
 /* ------------------------------------------------------------------ SAGE layer epilogue
  * y = act( l2normalize(sa @ W + b) * mask )      [rows, cout]

@@ -125,60 +125,102 @@ class TorchBackend(object):
             row_scale = 1.0 / deg.clamp(min=1)
         self.spmm(rowptr, col, val, x, None, row_scale, out, False)
 
-    def csr_to_ell16(self, rowptr, col, val, num_graphs, nmax, width, parity_order, ell, ell_val):
-        """Row-padded CSR with uint16 local column ids (held in an int16 tensor): unused slots = nmax,
-        overflow rows (degree > width) marked by slot 0 = nmax + 1; optional parity slot order."""
-        rows = num_graphs * nmax
-        rp = rowptr.tolist()
-        cl = col.tolist()
-        vl = val.tolist() if val is not None else None
-        table = torch.full((rows, width), nmax, dtype=torch.int64)
-        wtab = torch.zeros(rows, width, dtype=torch.float32)
-        for r in range(rows):
-            b, e = rp[r], rp[r + 1]
-            base = (r // nmax) * nmax
-            if e - b > width:
-                table[r, 0] = nmax + 1
-                continue
-            ent = [(cl[i] - base, vl[i] if vl is not None else 0.0) for i in range(b, e)]
-            if parity_order:
-                first = (r - base) & 1
-                ent = [t for t in ent if (t[0] & 1) == first] + [t for t in ent if (t[0] & 1) != first]
-            for t, (c, w) in enumerate(ent):
-                table[r, t] = c
-                wtab[r, t] = w
-        table = torch.where(table >= 32768, table - 65536, table).to(torch.int16)
-        ell.view(-1)[:rows * width].copy_(table.view(-1))
-        if ell_val is not None:
-            ell_val.view(-1)[:rows * width].copy_(wtab.view(-1))
+    def ell16_rows(self, num_graphs, nmax):
+        return num_graphs * ((nmax + 7) // 8 * 8)
 
-    def sage_gather_ell_fwd(self, ell, ell_val, width, row_scale, rowptr, col, val, x, num_graphs, nmax, out):
-        """Same sums as sage_gather_mean_fwd, taken over the ELL16 table (overflow rows over the CSR)."""
-        rows = num_graphs * nmax
-        idx = ell.view(-1)[:rows * width].view(rows, width).long() & 0xFFFF
-        over = idx[:, 0] == nmax + 1
-        xz = torch.cat([x.view(num_graphs, nmax, -1),
-                        torch.zeros(num_graphs, 1, x.shape[1], dtype=x.dtype)], dim=1)     # zero row at nmax
-        gid = (torch.arange(rows) // nmax).view(-1, 1)
-        src = xz[gid, idx.clamp(max=nmax)]                                                # [rows, width, F]
+    def csr_to_ell16(self, rowptr, col, val, row_scale, num_graphs, nmax, width, pair_rows, ell, ell_val,
+                     ell_scale, perm):
+        """Row-padded CSR with uint16 local column ids (held in an int16 tensor), see include/cgc_sm100.h:
+        slots parity-ordered by position and the 8 rows of a block paired smallest-with-largest even count
+        (``pair_rows``); unused slots = nmax; overflow rows
+        (degree > width) marked by slot 0 = nmax + 1; ``perm`` = 3 bits per position -> local row in the block."""
+        nrow8 = (nmax + 7) // 8 * 8
+        nb8 = nrow8 // 8
+        rp, cl = rowptr.tolist(), col.tolist()
+        vl = val.tolist() if val is not None else None
+        table = torch.full((num_graphs * nrow8, width), nmax, dtype=torch.int64)
+        wtab = torch.zeros(num_graphs * nrow8, width, dtype=torch.float32)
+        stab = torch.ones(num_graphs * nrow8, dtype=torch.float32)
+        pw_all = []
+        n, pad_par = width, nmax & 1
+        for blk in range(num_graphs * nb8):
+            g, lb = divmod(blk, nb8)
+            base = g * nmax
+            deg, key = [-1] * 8, [n // 2] * 8
+            for q in range(8):
+                lr = lb * 8 + q
+                if lr >= nmax:
+                    continue
+                b, e = rp[base + lr], rp[base + lr + 1]
+                deg[q] = e - b
+                if deg[q] > width:
+                    continue
+                if deg[q] == 0:
+                    key[q] = n if pad_par == 0 else 0
+                    continue
+                ev = sum(1 for i in range(b, e) if ((cl[i] - base) & 1) == 0)
+                key[q] = ev + ((width - deg[q]) if pad_par == 0 else 0)
+            order = sorted(range(8), key=lambda q: key[q]) if pair_rows else list(range(8))   # stable
+            pw = 0
+            for p in range(8):
+                q = (order[7 - (p >> 1)] if (p & 1) else order[p >> 1]) if pair_rows else p
+                pw |= q << (3 * p)
+                trow = blk * 8 + p
+                if deg[q] >= 0:
+                    if row_scale is not None:
+                        stab[trow] = row_scale[base + lb * 8 + q]
+                    elif val is None:
+                        stab[trow] = 1.0 / torch.tensor(float(max(deg[q], 1)), dtype=torch.float32)
+                if deg[q] > width:
+                    table[trow, 0] = nmax + 1
+                elif deg[q] > 0:
+                    b = rp[base + lb * 8 + q]
+                    e = b + deg[q]
+                    ent = list(range(b, e))
+                    if pair_rows:
+                        want = p & 1
+                        ent = [i for i in ent if ((cl[i] - base) & 1) == want] + \
+                              [i for i in ent if ((cl[i] - base) & 1) != want]
+                    for t, i in enumerate(ent):
+                        table[trow, t] = cl[i] - base
+                        if vl is not None:
+                            wtab[trow, t] = vl[i]
+            pw_all.append(pw)
+        table = torch.where(table >= 32768, table - 65536, table).to(torch.int16)
+        ell.view(-1)[:table.numel()].copy_(table.view(-1))
         if ell_val is not None:
-            res = (src * ell_val.view(-1)[:rows * width].view(rows, width, 1)).sum(1)
+            ell_val.view(-1)[:wtab.numel()].copy_(wtab.view(-1))
+        ell_scale.view(-1)[:stab.numel()].copy_(stab)
+        perm.view(-1)[:len(pw_all)].copy_(torch.tensor(pw_all, dtype=torch.int64).to(torch.int32))
+
+    def sage_gather_ell_fwd(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax,
+                            out):
+        """Same sums as sage_gather_mean_fwd, taken over the ELL16 table (overflow rows over the CSR)."""
+        nrow8 = (nmax + 7) // 8 * 8
+        trows = num_graphs * nrow8
+        idx = ell.view(-1)[:trows * width].view(trows, width).long() & 0xFFFF
+        pw = perm.view(-1)[:trows // 8].long() & 0xFFFFFF
+        pos = torch.arange(trows)
+        lrow = (pos % nrow8) // 8 * 8 + ((pw[pos // 8] >> (3 * (pos % 8))) & 7)             # local row per table row
+        gid = pos // nrow8
+        real = lrow < nmax
+        xz = torch.cat([x.view(num_graphs, nmax, -1),
+                        torch.zeros(num_graphs, 2, x.shape[1], dtype=x.dtype)], dim=1)     # zero rows at nmax, nmax+1
+        src = xz[gid.view(-1, 1), idx.clamp(max=nmax + 1)]                                # [trows, width, F]
+        if ell_val is not None:
+            res = (src * ell_val.view(-1)[:trows * width].view(trows, width, 1)).sum(1)
         else:
             res = src.sum(1)
-        if row_scale is not None:
-            scale = row_scale
-        elif ell_val is None:
-            scale = 1.0 / (idx != nmax).sum(1).clamp(min=1).float()
-        else:
-            scale = torch.ones(rows)
+        grow = gid * nmax + lrow.clamp(max=nmax - 1)
+        scale = ell_scale.view(-1)[:trows]
         res = res * scale[:, None]
-        if bool(over.any()):
-            full = torch.zeros_like(res)
-            self.sage_gather_mean_fwd(rowptr, col, val, row_scale, x, num_graphs, nmax, full)
-            res[over] = full[over]
-        out.copy_(res)
+        out[grow[real]] = res[real]
+        over = real & (idx[:, 0] == nmax + 1)
+        if bool(over.any()):                    # rows above the pitch: plain CSR sum, same table scale
+            full = torch.zeros(num_graphs * nmax, x.shape[1], dtype=x.dtype)
+            self.spmm(rowptr, col, val, x, None, None, full, False)
+            out[grow[over]] = full[grow[over]] * scale[over][:, None]
 
-    # ---------------------------------------------------------------- SAGE epilogue
     @staticmethod
     def _act(act, v):
         if act == 0:

@@ -154,24 +154,40 @@ def test_sage_gather_tile(cuda_backend, feat, b, nmax, weighted):
 
 
 @pytest.mark.parametrize('width,maxdeg', [(8, 8), (8, 11), (16, 16), (16, 19)])
-@pytest.mark.parametrize('parity', [0, 1])
+@pytest.mark.parametrize('pair', [0, 1])
 @pytest.mark.parametrize('weighted', [False, True])
-def test_csr_to_ell16_bit_exact(cuda_backend, width, maxdeg, parity, weighted):
-    """Row-padded CSR table: indices bit-exact (incl. pad slots, overflow marks, parity slot order)."""
+def test_csr_to_ell16_bit_exact(cuda_backend, width, maxdeg, pair, weighted):
+    """Row-padded CSR table: indices, weights and the position map bit-exact (pad slots, overflow marks,
+    slot-0 choice, parity slot order, in-block row pairing); nmax not a multiple of 8."""
     b, nmax = 3, 57
     rows = b * nmax
     rowptr, col = _random_csr(rows, maxdeg, seed=width + maxdeg, block=nmax)
     nnz = int(rowptr[-1])
     val = torch.rand(nnz + 3, generator=torch.Generator().manual_seed(1)) if weighted else None
-    ell = torch.zeros(rows * width, dtype=torch.int16)
-    ellw = torch.zeros(rows * width) if weighted else None
-    both(cuda_backend, 'csr_to_ell16', [rowptr, col, val, b, nmax, width, parity, ell, ellw],
-         [7, 8] if weighted else [7], exact=(7, 8))
-    table = (ell.view(rows, width).long() & 0xFFFF)
+    trows = REF.ell16_rows(b, nmax)
+    assert trows == cuda_backend.ell16_rows(b, nmax) == 3 * 64
+    ell = torch.zeros(trows * width, dtype=torch.int16)
+    ellw = torch.zeros(trows * width) if weighted else None
+    ells = torch.zeros(trows)
+    perm = torch.zeros(trows // 8, dtype=torch.int32)
+    rsc = torch.rand(rows, generator=torch.Generator().manual_seed(2)) if weighted else None
+    both(cuda_backend, 'csr_to_ell16', [rowptr, col, val, rsc, b, nmax, width, pair, ell, ellw, ells, perm],
+         [8, 9, 10, 11] if weighted else [8, 10, 11], exact=(8, 9, 10, 11))
+    # every row's entry set survives the re-ordering
+    table = (ell.view(trows, width).long() & 0xFFFF)
+    pos = torch.arange(trows)
+    lrow = (pos % 64) // 8 * 8 + ((perm.long()[pos // 8] >> (3 * (pos % 8))) & 7)
     deg = (rowptr[1:] - rowptr[:-1]).long()
-    assert bool(((table[:, 0] == nmax + 1) == (deg > width)).all())
-    ok = deg <= width
-    assert bool(((table[ok] != nmax).sum(1) == deg[ok]).all())
+    for t in range(trows):
+        if int(lrow[t]) >= nmax:
+            assert bool((table[t] == nmax).all())
+            continue
+        r = (t // 64) * nmax + int(lrow[t])
+        if int(deg[r]) > width:
+            assert int(table[t, 0]) == nmax + 1
+        else:
+            want = sorted((col[int(rowptr[r]):int(rowptr[r + 1])].long() - (t // 64) * nmax).tolist())
+            assert sorted(v for v in table[t].tolist() if v != nmax) == want
 
 
 @pytest.mark.parametrize('feat,b,nmax,width,maxdeg', [(16, 3, 70, 8, 8), (16, 5, 333, 8, 10), (16, 64, 1800, 8, 8),
@@ -187,11 +203,14 @@ def test_sage_gather_ell(cuda_backend, feat, b, nmax, width, maxdeg, weighted):
     x = torch.randn(rows, feat, generator=g)
     val = torch.rand(nnz + 3, generator=g) if weighted else None
     rsc = torch.rand(rows, generator=g) if weighted else None
-    ell = torch.zeros(rows * width, dtype=torch.int16)
-    ellw = torch.zeros(rows * width) if weighted else None
-    REF.csr_to_ell16(rowptr, col, val, b, nmax, width, int(feat == 16), ell, ellw)
+    trows = REF.ell16_rows(b, nmax)
+    ell = torch.zeros(trows * width, dtype=torch.int16)
+    ellw = torch.zeros(trows * width) if weighted else None
+    ells = torch.zeros(trows)
+    perm = torch.zeros(trows // 8, dtype=torch.int32)
+    REF.csr_to_ell16(rowptr, col, val, rsc, b, nmax, width, int(feat == 16), ell, ellw, ells, perm)
     out = torch.zeros(rows, feat)
-    both(cuda_backend, 'sage_gather_ell_fwd', [ell, ellw, width, rsc, rowptr, col, val, x, b, nmax, out], [10],
+    both(cuda_backend, 'sage_gather_ell_fwd', [ell, ellw, ells, perm, width, rowptr, col, val, x, b, nmax, out], [11],
          rtol=1e-5, atol=1e-5)
     want = torch.zeros(rows, feat)
     REF.sage_gather_mean_fwd(rowptr, col, val, rsc, x, b, nmax, want)

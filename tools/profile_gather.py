@@ -18,7 +18,7 @@ variant = os.environ.get('VARIANT', 'ell')
 for _ in range(3):
     flush.zero_()
     if variant == 'ell':
-        be.sage_gather_ell_fwd(g.ell, None, g.ell_width, None, g.rowptr, g.col, None, xp, b, n, out)
+        be.sage_gather_ell_fwd(g.ell, None, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, None, xp, b, n, out)
     else:
         be.sage_gather_mean_fwd(g.rowptr, g.col, None, None, xp, b, n, out)
 torch.cuda.synchronize()
