@@ -50,6 +50,11 @@ _SIGNATURES = {
     'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_act_fwd': [_c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_act_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
+    'cgc_jk_supported': [_c_i32, _c_i32],
+    'cgc_jk_tape_floats': [_c_i64, _c_i32, _c_i32],
+    'cgc_jk_lstm_fwd': [_c_vp, _c_i64, _c_i64, _c_i32, _c_i32] + [_c_vp] * 10 + [_c_vp, _c_i64, _c_vp, _c_vp],
+    'cgc_jk_lstm_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32, _c_i32] + [_c_vp] * 6 +
+                       [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp],
     'cgc_scale_rows_bwd': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp],
     'cgc_bn_stats': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp,
                      _c_vp, _c_i64, _c_vp],
@@ -72,7 +77,7 @@ _SIGNATURES = {
     'cgc_colsum': [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp],
 }
 _RESTYPES = {'cgc_last_error': ctypes.c_char_p, 'cgc_workspace_bytes': _c_i64, 'cgc_launch_count': _c_i64,
-             'cgc_coo_to_csr_workspace': _c_i64, 'cgc_ell16_rows': _c_i64}
+             'cgc_coo_to_csr_workspace': _c_i64, 'cgc_ell16_rows': _c_i64, 'cgc_jk_tape_floats': _c_i64}
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 
@@ -280,6 +285,32 @@ class CudaBackend(object):
         op, ldo = _mat(gx)
         self._check(self.lib.cgc_act_bwd(gp, ldg, yp, ldy, y.shape[0], y.shape[1], int(act), op, ldo,
                                          self._stream()), 'cgc_act_bwd')
+
+    # -- DenseJK
+    def jk_supported(self, channels, layers):
+        return bool(self.lib.cgc_jk_supported(channels, layers))
+
+    def jk_tape_floats(self, rows, channels, layers):
+        return int(self.lib.cgc_jk_tape_floats(rows, channels, layers))
+
+    def jk_lstm_fwd(self, feats, channels, layers, lstm_params, att_w, att_b, out, tape):
+        fp, ld = _mat(feats)
+        op, ldo = _mat(out)
+        ptrs = [_ptr(p.contiguous(), torch.float32) for p in lstm_params]
+        self._check(self.lib.cgc_jk_lstm_fwd(fp, ld, feats.shape[0], channels, layers, *ptrs,
+                                             _ptr(att_w.contiguous(), torch.float32), _ptr(att_b, torch.float32),
+                                             op, ldo, _ptr(tape, torch.float32), self._stream()),
+                    'cgc_jk_lstm_fwd')
+
+    def jk_lstm_bwd(self, g_out, feats, channels, layers, lstm_params, att_w, tape, g_feats, dgates, dscore):
+        gp, ldg = _mat(g_out)
+        fp, ld = _mat(feats)
+        op, ldo = _mat(g_feats)
+        w = [_ptr(lstm_params[i].contiguous(), torch.float32) for i in (0, 1, 4, 5)]
+        self._check(self.lib.cgc_jk_lstm_bwd(gp, ldg, fp, ld, feats.shape[0], channels, layers, *w,
+                                             _ptr(att_w.contiguous(), torch.float32), _ptr(tape, torch.float32),
+                                             op, ldo, _ptr(dgates, torch.float32), _ptr(dscore, torch.float32),
+                                             self._stream()), 'cgc_jk_lstm_bwd')
 
     def scale_rows_bwd(self, dsa, sa, rs, ga, d_rs):
         for t in (dsa, sa):

@@ -166,9 +166,10 @@ class DenseJK(nn.Module):
     network.py:11-55): a bi-LSTM over the 3-step "sequence" of per-layer features of every node scores the
     layers, the scores are soft-maxed and the layers summed with those weights.
 
-    SURVEY 8(f) rank-1 "next" row: the recurrence itself still runs on torch's LSTM (cuDNN); it is wired in so
-    that the only published configuration (``--jk``, parallel_train.sh:3) runs end to end.  Parameter names
-    (``lstm.*``, ``att.*``) match the reference for checkpoint compatibility.
+    SURVEY 8(f) rank-1 row: for the reference's shape (20 channels x 3 layers) the whole aggregation is ONE
+    hand-written kernel per direction of autograd (``ops.DenseJKFunction`` -> ``cgc_jk_lstm_fwd / bwd``); other
+    shapes keep torch's LSTM (cuDNN, TF32 off).  Parameter names (``lstm.*``, ``att.*``) match the reference for
+    checkpoint compatibility (the ``nn.LSTM`` / ``nn.Linear`` modules are kept as parameter holders).
     """
 
     def __init__(self, mode, channels=None, num_layers=None):
@@ -181,6 +182,14 @@ class DenseJK(nn.Module):
 
     def forward(self, feats, num_graphs, nmax):
         """``feats [B*N, L*C]`` (concat of the L layer outputs, padded layout) -> ``[B*N, C]``."""
+        from . import _backend
+        be = _backend.get()
+        layers = feats.shape[1] // self.channel
+        if be.jk_supported(self.channel, layers):
+            # fused per-node kernel (cgc_jk_lstm_fwd / bwd): no cuDNN launch, no [rows, L, 2H] intermediates
+            names = ['weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0']
+            params = [getattr(self.lstm, n) for n in names] + [getattr(self.lstm, n + '_reverse') for n in names]
+            return ops.DenseJKFunction.apply(feats, self.channel, layers, self.att.weight, self.att.bias, *params)
         rows = feats.shape[0]
         seq = feats.view(rows, -1, self.channel)                 # [rows, L, C]
         # fp32 parity with the reference: cuDNN's RNN would otherwise run its matmuls in single-pass TF32

@@ -453,6 +453,69 @@ class BatchNormFunction(Function):
         return gy, d_gamma, d_beta, None, None, None, None
 
 
+# ----------------------------------------------------------------------------- DenseJK
+class DenseJKFunction(Function):
+    """``DenseJK.forward`` (network.py:36-52) as one fused kernel per direction of autograd: forward writes a
+    tape in training mode, backward turns it into ``d feats`` plus gate / score gradients whose contractions over
+    the nodes (the weight and bias gradients) run on the library GEMM.
+
+    ``lstm_params`` = (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, weight_ih_l0_reverse, ...)."""
+
+    @staticmethod
+    def forward(ctx, feats, channels, layers, att_w, att_b, *lstm_params):
+        be = _backend.get()
+        feats = feats.contiguous()
+        rows = feats.shape[0]
+        out = _f32(rows, channels, device=feats.device)
+        need_tape = any(ctx.needs_input_grad)           # inference: no tape is written
+        tape = _f32(be.jk_tape_floats(rows, channels, layers), device=feats.device) if need_tape else None
+        be.jk_lstm_fwd(feats, channels, layers, lstm_params, att_w, att_b, out, tape)
+        ctx.dims = (channels, layers)
+        ctx.tape = tape
+        ctx.save_for_backward(feats, att_w, *lstm_params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        be = _backend.get()
+        channels, layers = ctx.dims
+        feats, att_w = ctx.saved_tensors[:2]
+        lstm_params = ctx.saved_tensors[2:]
+        tape = ctx.tape
+        dev = feats.device
+        rows = feats.shape[0]
+        hid = channels * layers // 2
+        g_feats = _f32(rows, layers * channels, device=dev)
+        dgates = _f32(2, layers, 4 * hid, rows, device=dev)
+        dscore = _f32(layers, rows, device=dev)
+        be.jk_lstm_bwd(g_out.contiguous(), feats, channels, layers, lstm_params, att_w, tape, g_feats, dgates, dscore)
+        n_g = 2 * layers * 5 * hid * rows
+        hs = tape[n_g:n_g + 2 * layers * hid * rows].view(2, layers, hid, rows)
+        ones = torch.ones(rows, 1, dtype=torch.float32, device=dev)
+        grads = []
+        d_att_w = torch.empty(1, 2 * hid, dtype=torch.float32, device=dev)
+        for d in range(2):
+            order = list(range(layers)) if d == 0 else list(range(layers - 1, -1, -1))
+            d_wih = _f32(4 * hid, channels, device=dev)
+            d_whh = _f32(4 * hid, hid, device=dev)
+            d_b = _f32(4 * hid, 1, device=dev)
+            for i, t in enumerate(order):
+                first = i == 0
+                x_t = feats[:, t * channels:(t + 1) * channels]
+                be.gemm(dgates[d, t], x_t, d_wih, False, False, beta=0.0 if first else 1.0)     # K = rows
+                be.gemm(dgates[d, t], ones, d_b, False, False, beta=0.0 if first else 1.0)
+                if i > 0:                                    # h_prev of the first computed step is zero
+                    be.gemm(dgates[d, t], hs[d, order[i - 1]], d_whh, False, True, beta=0.0 if i == 1 else 1.0)
+                be.gemm(dscore[t:t + 1], hs[d, t], d_att_w[:, d * hid:(d + 1) * hid], False, True,
+                        beta=0.0 if first else 1.0)
+            if layers == 1:
+                d_whh.zero_()
+            grads += [d_wih, d_whh, d_b.view(-1), d_b.view(-1).clone()]
+        d_att_b = torch.empty(1, dtype=torch.float32, device=dev)
+        be.colsum(dscore.view(-1, 1), None, d_att_b)
+        return (g_feats, None, None, d_att_w, d_att_b) + tuple(grads)
+
+
 # ----------------------------------------------------------------------------- diff-pool
 class DiffPoolFunction(Function):
     """``_diff_pool`` (network.py:194-208): ``S = softmax(Z) * mask``; ``X' = S^T X``; ``A' = S^T (A S)``.

@@ -189,6 +189,31 @@ CGC_API int cgc_act_bwd(const float* gy, int64_t ldgy, const float* y, int64_t l
 CGC_API int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows,
                        int32_t c, float* ga, int64_t ldga, float* d_rs, void* stream);
 
+/* ------------------------------------------------------------------ DenseJK (jumping knowledge, iff jk)
+ * DenseJK.forward (model/network.py:36-52): x_t = feats[:, t*C:(t+1)*C] (t < layers); a bidirectional
+ * LSTM(C -> H = C*layers/2, PyTorch gate order i,f,g,o, zero initial state) over the `layers` steps of every
+ * node; score_t = att_w . [h_fwd_t, h_bwd_t] + att_b; alpha = softmax_t(score); out = sum_t alpha_t x_t.
+ * Weight pointers are the nn.LSTM / nn.Linear parameters as PyTorch stores them (weight_ih_l0 [4H, C],
+ * weight_hh_l0 [4H, H], bias_ih_l0, bias_hh_l0 [4H], the *_reverse set, att.weight [1, 2H], att.bias [1]).
+ * tape (nullable = inference): cgc_jk_tape_floats() floats, sections gates [2][layers][5][H][rows] (i,f,g,o,c),
+ * hs [2][layers][H][rows], alpha [layers][rows].  cgc_jk_supported() != 0 for the instantiated shapes
+ * (channels = 20, layers = 3: the reference's hidden_dim); otherwise CGC_ERR_UNSUPPORTED. */
+CGC_API int cgc_jk_supported(int32_t channels, int32_t layers);
+CGC_API int64_t cgc_jk_tape_floats(int64_t rows, int32_t channels, int32_t layers);
+CGC_API int cgc_jk_lstm_fwd(const float* feats, int64_t ld, int64_t rows, int32_t channels, int32_t layers,
+                    const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                    const float* w_ih_b, const float* w_hh_b, const float* b_ih_b, const float* b_hh_b,
+                    const float* att_w, const float* att_b, float* out, int64_t ldo, float* tape,
+                    void* stream);
+/* Backward from the tape: g_feats [rows, layers*C]; dgates [2][layers][4H][rows] = d loss / d gate
+ * pre-activations and dscore [layers][rows] = d loss / d score, from which the caller contracts the weight
+ * gradients over the nodes (dW_ih = sum_t dgates_t x_t, dW_hh = sum_t dgates_t h_prev_t^T, db = row sums,
+ * d att_w = sum_t hs_t dscore_t, d att_b = sum dscore) with cgc_gemm / cgc_colsum. */
+CGC_API int cgc_jk_lstm_bwd(const float* g_out, int64_t ldg, const float* feats, int64_t ld, int64_t rows,
+                    int32_t channels, int32_t layers, const float* w_ih_f, const float* w_hh_f,
+                    const float* w_ih_b, const float* w_hh_b, const float* att_w, const float* tape,
+                    float* g_feats, int64_t ldgf, float* dgates, float* dscore, void* stream);
+
 /* ------------------------------------------------------------------ BatchNorm1d over ALL rows
  * (padded rows count, network.py:101-107).  Training: batch mean / biased variance, running
  * stats updated with momentum and the unbiased variance. */

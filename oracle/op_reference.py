@@ -276,6 +276,91 @@ class TorchBackend(object):
         ga.copy_(dsa * rs[:, None])
         d_rs += (dsa * sa).sum(1) / rs
 
+    # ---------------------------------------------------------------- DenseJK (bi-LSTM attention over layers)
+    @staticmethod
+    def jk_supported(channels, layers):
+        return (channels * layers) % 2 == 0
+
+    @staticmethod
+    def jk_tape_floats(rows, channels, layers):
+        hid = channels * layers // 2
+        return rows * (2 * layers * 5 * hid + 2 * layers * hid + layers)
+
+    @staticmethod
+    def _jk_tape_views(tape, rows, channels, layers):
+        hid = channels * layers // 2
+        n_g = 2 * layers * 5 * hid * rows
+        n_h = 2 * layers * hid * rows
+        gates = tape[:n_g].view(2, layers, 5, hid, rows)                  # i, f, g, o, c  (node fastest)
+        hs = tape[n_g:n_g + n_h].view(2, layers, hid, rows)
+        alpha = tape[n_g + n_h:n_g + n_h + layers * rows].view(layers, rows)
+        return gates, hs, alpha
+
+    def jk_lstm_fwd(self, feats, channels, layers, lstm_params, att_w, att_b, out, tape):
+        """DenseJK.forward (model/network.py:36-52): bi-LSTM(C -> H = C*L/2) over the L per-layer features of every
+        node (PyTorch gate order i, f, g, o), Linear(2H -> 1) score, softmax over layers, weighted sum."""
+        rows = feats.shape[0]
+        hid = channels * layers // 2
+        xs = [feats[:, t * channels:(t + 1) * channels] for t in range(layers)]
+        if tape is not None:
+            gates, hs, alpha_t = self._jk_tape_views(tape, rows, channels, layers)
+        hall = torch.zeros(2, layers, rows, hid, dtype=feats.dtype)
+        for d in range(2):
+            w_ih, w_hh, b_ih, b_hh = lstm_params[4 * d:4 * d + 4]
+            h = torch.zeros(rows, hid, dtype=feats.dtype)
+            c = torch.zeros(rows, hid, dtype=feats.dtype)
+            order = range(layers) if d == 0 else range(layers - 1, -1, -1)
+            for t in order:
+                a = xs[t] @ w_ih.t() + h @ w_hh.t() + (b_ih + b_hh)
+                i, f = torch.sigmoid(a[:, :hid]), torch.sigmoid(a[:, hid:2 * hid])
+                g, o = torch.tanh(a[:, 2 * hid:3 * hid]), torch.sigmoid(a[:, 3 * hid:])
+                c = f * c + i * g
+                h = o * torch.tanh(c)
+                hall[d, t] = h
+                if tape is not None:
+                    for q, v in enumerate((i, f, g, o, c)):
+                        gates[d, t, q].copy_(v.t())
+                    hs[d, t].copy_(h.t())
+        score = torch.stack([torch.cat([hall[0, t], hall[1, t]], 1) @ att_w.view(-1) + att_b.view(())
+                             for t in range(layers)], 1)                       # [rows, L]
+        alpha = torch.softmax(score, dim=1)
+        if tape is not None:
+            alpha_t.copy_(alpha.t())
+        out.copy_(sum(alpha[:, t:t + 1] * xs[t] for t in range(layers)))
+
+    def jk_lstm_bwd(self, g_out, feats, channels, layers, lstm_params, att_w, tape, g_feats, dgates, dscore):
+        """Backward of jk_lstm_fwd from the tape: g_feats [rows, L*C]; dgates [2, L, 4H, rows] = d loss / d gate
+        pre-activations (weight / bias gradients are contractions of these, done by the caller); dscore [L, rows]."""
+        rows = feats.shape[0]
+        hid = channels * layers // 2
+        gates, hs, alpha = self._jk_tape_views(tape, rows, channels, layers)
+        xs = [feats[:, t * channels:(t + 1) * channels] for t in range(layers)]
+        d_alpha = torch.stack([(g_out * xs[t]).sum(1) for t in range(layers)], 0)          # [L, rows]
+        dot = (alpha * d_alpha).sum(0, keepdim=True)
+        ds = alpha * (d_alpha - dot)
+        dscore.copy_(ds)
+        gx = [alpha[t][:, None] * g_out for t in range(layers)]
+        aw = att_w.view(-1)
+        for d in range(2):
+            w_ih, w_hh = lstm_params[4 * d], lstm_params[4 * d + 1]
+            order = list(range(layers)) if d == 0 else list(range(layers - 1, -1, -1))
+            dh_next = torch.zeros(rows, hid, dtype=feats.dtype)
+            dc_next = torch.zeros(rows, hid, dtype=feats.dtype)
+            for pos in range(layers - 1, -1, -1):
+                t = order[pos]
+                i, f, g, o, c = [gates[d, t, q].t() for q in range(5)]
+                c_prev = gates[d, order[pos - 1], 4].t() if pos > 0 else torch.zeros_like(c)
+                dh = ds[t][:, None] * aw[d * hid:(d + 1) * hid][None, :] + dh_next
+                tc = torch.tanh(c)
+                dc = dh * o * (1 - tc * tc) + dc_next
+                da = torch.cat([dc * g * i * (1 - i), dc * c_prev * f * (1 - f), dc * i * (1 - g * g),
+                                dh * tc * o * (1 - o)], 1)                                # [rows, 4H]
+                dgates[d, t].copy_(da.t())
+                dc_next = dc * f
+                dh_next = da @ w_hh
+                gx[t] = gx[t] + da @ w_ih
+        g_feats.copy_(torch.cat(gx, 1))
+
     # ---------------------------------------------------------------- batch norm
     def bn_stats(self, y, rmean, rvar, momentum, eps, mean, invstd):
         m = y.shape[0]

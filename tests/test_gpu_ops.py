@@ -497,3 +497,41 @@ def test_tf32_operand_truncation_probe(cuda_backend):
     cuda_backend.gemm(a.cuda(), b.cuda(), c, False, False, precision=1)
     torch.cuda.synchronize()
     assert float((c.cpu() - a[0, 0]).abs().max()) < 1e-7        # 3xTF32 reproduces all fp32 bits here
+
+
+# ------------------------------------------------------------------------------- DenseJK (fused bi-LSTM attention)
+@pytest.mark.parametrize('rows', [1, 200, 1000])
+def test_jk_lstm_fwd_bwd(cuda_backend, rows):
+    """cgc_jk_lstm_fwd / bwd against the CPU formulas (themselves pinned to torch.nn.LSTM autograd, see
+    test_oracle.py::test_jk_reference_formulas_match_autograd); strided feats (a slice of a wider buffer)."""
+    c, layers = 20, 3
+    hid = c * layers // 2
+    assert cuda_backend.jk_supported(c, layers) and not cuda_backend.jk_supported(16, 3)
+    torch.manual_seed(rows)
+    lstm = torch.nn.LSTM(c, hid, bidirectional=True, batch_first=True)
+    att = torch.nn.Linear(2 * hid, 1)
+    names = ['weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0']
+    params = [getattr(lstm, n).detach() for n in names] + [getattr(lstm, n + '_reverse').detach() for n in names]
+    wide = torch.randn(rows, layers * c + 8)
+    feats = wide[:, 4:4 + layers * c]
+    out, tape = torch.zeros(rows, c), torch.zeros(REF.jk_tape_floats(rows, c, layers))
+    assert cuda_backend.jk_tape_floats(rows, c, layers) == tape.numel()
+    REF.jk_lstm_fwd(feats, c, layers, params, att.weight.detach(), att.bias.detach(), out, tape)
+    fg = wide.cuda()[:, 4:4 + layers * c]
+    pg = [p.cuda() for p in params]
+    outg, tapeg = torch.zeros(rows, c).cuda(), torch.zeros(tape.numel()).cuda()
+    cuda_backend.jk_lstm_fwd(fg, c, layers, pg, att.weight.detach().cuda(), att.bias.detach().cuda(), outg, tapeg)
+    torch.testing.assert_close(outg.cpu(), out, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(tapeg.cpu(), tape, rtol=1e-5, atol=2e-6)
+    # inference call (no tape) gives the same output
+    out2 = torch.zeros(rows, c).cuda()
+    cuda_backend.jk_lstm_fwd(fg, c, layers, pg, att.weight.detach().cuda(), att.bias.detach().cuda(), out2, None)
+    assert torch.equal(out2, outg)
+    g_out = torch.randn(rows, c)
+    gf, dg, dsc = torch.zeros(rows, layers * c), torch.zeros(2, layers, 4 * hid, rows), torch.zeros(layers, rows)
+    REF.jk_lstm_bwd(g_out, feats, c, layers, params, att.weight.detach(), tape, gf, dg, dsc)
+    gfg, dgg, dscg = [torch.zeros_like(t).cuda() for t in (gf, dg, dsc)]
+    cuda_backend.jk_lstm_bwd(g_out.cuda(), fg, c, layers, pg, att.weight.detach().cuda(), tape.cuda(), gfg, dgg, dscg)
+    torch.testing.assert_close(gfg.cpu(), gf, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dgg.cpu(), dg, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dscg.cpu(), dsc, rtol=1e-4, atol=1e-6)

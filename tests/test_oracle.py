@@ -133,3 +133,46 @@ def test_shim_matches_restated_conv():
     mask = torch.ones(2, 9, 1)
     mask[1, 6:] = 0
     assert torch.equal(a(x, adj, mask, False), b(x, adj, mask, False))
+
+
+def test_jk_reference_formulas_match_autograd():
+    """The per-operator DenseJK formulas (forward, hand-written backward, weight-gradient contractions) of
+    oracle/op_reference.py against torch.nn.LSTM + autograd in float64 (DenseJK.forward, network.py:36-52)."""
+    from oracle import op_reference
+    ref = op_reference.TorchBackend()
+    torch.manual_seed(0)
+    c, layers, m = 20, 3, 37
+    hid = c * layers // 2
+    lstm = torch.nn.LSTM(c, hid, bidirectional=True, batch_first=True).double()
+    att = torch.nn.Linear(2 * hid, 1).double()
+    feats = torch.randn(m, layers * c, dtype=torch.double, requires_grad=True)
+    seq = feats.view(m, layers, c)
+    score, _ = lstm(seq)
+    alpha = torch.softmax(att(score).squeeze(-1), -1)
+    y = (seq * alpha.unsqueeze(-1)).sum(1)
+    g = torch.randn(m, c, dtype=torch.double)
+    y.backward(g)
+    names = ['weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0']
+    params = [getattr(lstm, n).detach() for n in names] + [getattr(lstm, n + '_reverse').detach() for n in names]
+    out = torch.zeros(m, c, dtype=torch.double)
+    tape = torch.zeros(ref.jk_tape_floats(m, c, layers), dtype=torch.double)
+    ref.jk_lstm_fwd(feats.detach(), c, layers, params, att.weight.detach(), att.bias.detach(), out, tape)
+    assert float((out - y.detach()).abs().max()) < 1e-12
+    gf = torch.zeros(m, layers * c, dtype=torch.double)
+    dg = torch.zeros(2, layers, 4 * hid, m, dtype=torch.double)
+    dsc = torch.zeros(layers, m, dtype=torch.double)
+    ref.jk_lstm_bwd(g, feats.detach(), c, layers, params, att.weight.detach(), tape, gf, dg, dsc)
+    assert float((gf - feats.grad).abs().max()) < 1e-12
+    _, hs, _ = ref._jk_tape_views(tape, m, c, layers)
+    xs = [feats.detach()[:, t * c:(t + 1) * c] for t in range(layers)]
+    for d, suf in enumerate(['', '_reverse']):
+        order = list(range(layers)) if d == 0 else list(range(layers - 1, -1, -1))
+        d_wih = sum(dg[d, t] @ xs[t] for t in range(layers))
+        d_whh = sum(dg[d, order[p]] @ hs[d, order[p - 1]].t() for p in range(1, layers))
+        d_b = sum(dg[d, t].sum(1) for t in range(layers))
+        assert float((d_wih - getattr(lstm, 'weight_ih_l0' + suf).grad).abs().max()) < 1e-12
+        assert float((d_whh - getattr(lstm, 'weight_hh_l0' + suf).grad).abs().max()) < 1e-12
+        assert float((d_b - getattr(lstm, 'bias_hh_l0' + suf).grad).abs().max()) < 1e-12
+    d_aw = torch.cat([sum(hs[d, t] @ dsc[t] for t in range(layers)) for d in range(2)])
+    assert float((d_aw - att.weight.grad.view(-1)).abs().max()) < 1e-12
+    assert float((dsc.sum() - att.bias.grad).abs().max()) < 1e-12
