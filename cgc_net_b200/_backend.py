@@ -36,6 +36,8 @@ _SIGNATURES = {
     'cgc_row_inv_degree': [_c_vp, _c_i64, _c_vp, _c_vp],
     'cgc_edge_renorm': [_c_vp, _c_vp, _c_i64, _c_f64, _c_vp, _c_vp, _c_vp],
     'cgc_csr_transpose': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    'cgc_radius_graph': [_c_vp, _c_vp, _c_i32, _c_i32, _c_f64, _c_i32, _c_int, _c_vp, _c_vp, _c_vp],
+    'cgc_knn_to_coo': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp],
     'cgc_spmm': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64,
                  _c_int, _c_vp],
     'cgc_sage_gather_mean_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp,
@@ -192,6 +194,19 @@ class CudaBackend(object):
                                                _ptr(colptr, torch.int32), _ptr(row, torch.int32),
                                                _ptr(val_t, torch.float32), _ptr(work, torch.int32),
                                                work.numel(), self._stream()), 'cgc_csr_transpose')
+
+    # -- cell-graph construction
+    def radius_graph(self, pos, start, num_graphs, nmax, r, k, loop, nbr, deg):
+        if not pos.is_contiguous() or pos.dim() != 2 or pos.shape[1] != 2:
+            raise CgcError('cgc_radius_graph needs contiguous [n, 2] positions')
+        self._check(self.lib.cgc_radius_graph(_ptr(pos, torch.float32), _ptr(start, torch.int32), num_graphs, nmax,
+                                              float(r), int(k), int(bool(loop)), _ptr(nbr, torch.int32),
+                                              _ptr(deg, torch.int32), self._stream()), 'cgc_radius_graph')
+
+    def knn_to_coo(self, nbr, deg, offsets, k, num_edges, edge_index):
+        self._check(self.lib.cgc_knn_to_coo(_ptr(nbr, torch.int32), _ptr(deg, torch.int32),
+                                            _ptr(offsets, torch.int64), deg.numel(), int(k), int(num_edges),
+                                            _ptr(edge_index, torch.int64), self._stream()), 'cgc_knn_to_coo')
 
     # -- sparse gather
     def spmm(self, rowptr, col, val, x, src_scale, row_scale, out, accumulate):

@@ -123,3 +123,35 @@ def split_by_node_count(data_list, world_size):
     mid = (cum - counts / 2.0) * world_size / cum[-1]
     dev = mid.floor().long().clamp_(max=world_size - 1)
     return [[d for d, r in zip(data_list, dev.tolist()) if r == rank] for rank in range(world_size)]
+
+
+def radius_graph(pos, r, batch=None, loop=False, max_num_neighbors=32, num_nodes_list=None):
+    """``torch_cluster.radius_graph(pos, r, batch, loop, max_num_neighbors)`` (flow ``source_to_target``) as the
+    reference's loaders call it (dataflow/data.py:246,255,297,348 with ``loop=True, max_num_neighbors=8``), on
+    the GPU: ``edge_index[0]`` = neighbour, ``edge_index[1]`` = centre, <= k nearest within ``r`` per centre,
+    centre-major, nearest first.  ``pos [N, 2]`` CUDA float tensor; ``batch`` sorted graph ids (or ``None`` for a
+    single graph); ``num_nodes_list`` avoids the device->host sync for the sizes."""
+    from . import _backend
+    be = _backend.get()
+    dev = pos.device
+    n_total = pos.shape[0]
+    if num_nodes_list is None:
+        if batch is None:
+            num_nodes_list = [n_total]
+        else:
+            num_nodes_list = torch.bincount(batch).tolist()
+    counts = torch.tensor(num_nodes_list, dtype=torch.int32)
+    start = torch.zeros(len(num_nodes_list) + 1, dtype=torch.int32)
+    start[1:] = torch.cumsum(counts, 0)
+    start = start.to(dev)
+    k = int(max_num_neighbors)
+    nbr = torch.empty(n_total, k, dtype=torch.int32, device=dev)
+    deg = torch.empty(n_total, dtype=torch.int32, device=dev)
+    be.radius_graph(pos.contiguous().float(), start, len(num_nodes_list), int(max(num_nodes_list)), r, k, loop, nbr, deg)
+    ends = torch.cumsum(deg.long(), 0)
+    num_edges = int(ends[-1])                       # output size is data dependent, like the reference op
+    offsets = ends - deg.long()
+    edge_index = torch.empty(2, num_edges, dtype=torch.long, device=dev)
+    if num_edges:
+        be.knn_to_coo(nbr, deg, offsets, k, num_edges, edge_index)
+    return edge_index

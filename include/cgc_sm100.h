@@ -97,6 +97,19 @@ CGC_API int cgc_csr_transpose(const int32_t* rowptr, const int32_t* col, const f
                       int32_t* colptr, int32_t* row, float* val_t, int32_t* work,
                       int64_t work_elems, void* stream);
 
+/* ------------------------------------------------------------------ cell-graph construction (loader side)
+ * radius_graph(pos, r, batch, loop, max_num_neighbors = k) of torch_cluster 1.4.2 as called at
+ * dataflow/data.py:246,255,297,348: for every centre c the <= k nearest nodes of the same graph with distance
+ * < r (the centre itself first when loop != 0), nearest first, ties by lower index; distances in double on the
+ * float positions (the CPU path is scipy cKDTree.query).  pos [n_total, 2]; start [num_graphs + 1] node offsets;
+ * nbr [n_total, k] global node ids (-1 = none), deg [n_total] = valid entries per centre. */
+CGC_API int cgc_radius_graph(const float* pos, const int32_t* start, int32_t num_graphs, int32_t nmax, double r,
+                     int32_t k, int loop, int32_t* nbr, int32_t* deg, void* stream);
+/* (nbr, deg, offsets = exclusive scan of deg) -> the reference's COO edge_index [2, num_edges] (int64):
+ * edge_index[0] = neighbour, edge_index[1] = centre (flow = source_to_target), centre-major order. */
+CGC_API int cgc_knn_to_coo(const int32_t* nbr, const int32_t* deg, const int64_t* offsets, int64_t n_total,
+                   int32_t k, int64_t num_edges, int64_t* edge_index, void* stream);
+
 /* ------------------------------------------------------------------ sparse neighbour gather
  * out[r,:] (+)= row_scale[r] * sum_{e in row r} val[e] * src_scale[col[e]] * x[col[e], :]
  * = torch.matmul(adj, x) / adj.sum(-1).clamp(min=1) of DenseSAGEConv.forward (forward: CSR +

@@ -99,6 +99,37 @@ class TorchBackend(object):
         if val is not None:
             val_t[:nnz] = val[:nnz][order]
 
+    # ---------------------------------------------------------------- cell-graph construction
+    def radius_graph(self, pos, start, num_graphs, nmax, r, k, loop, nbr, deg):
+        """torch_cluster 1.4.2 radius_graph on CPU = scipy cKDTree.query(k, distance_upper_bound=r) per graph
+        (float64 distances on the float positions), nearest first, the centre itself first when ``loop``."""
+        from scipy.spatial import cKDTree
+        import numpy as np
+        nbr.fill_(-1)
+        st = start.tolist()
+        for g in range(num_graphs):
+            p = pos[st[g]:st[g + 1]].double().numpy()
+            n = p.shape[0]
+            if n == 0:
+                continue
+            kk = min(k + (0 if loop else 1), n)
+            dist, idx = cKDTree(p).query(p, k=kk, distance_upper_bound=float(r))
+            dist, idx = dist.reshape(n, kk), idx.reshape(n, kk)
+            for c in range(n):
+                cand = [(dist[c, s], int(idx[c, s])) for s in range(kk) if np.isfinite(dist[c, s])]
+                if not loop:
+                    cand = [t for t in cand if t[1] != c]
+                cand = sorted(cand)[:k]
+                for s, (_, j) in enumerate(cand):
+                    nbr[st[g] + c, s] = st[g] + j
+                deg[st[g] + c] = len(cand)
+
+    def knn_to_coo(self, nbr, deg, offsets, k, num_edges, edge_index):
+        valid = nbr >= 0
+        centre = torch.arange(nbr.shape[0]).view(-1, 1).expand_as(nbr)
+        edge_index[0, :num_edges] = nbr[valid].long()
+        edge_index[1, :num_edges] = centre[valid]
+
     # ---------------------------------------------------------------- sparse gather
     def spmm(self, rowptr, col, val, x, src_scale, row_scale, out, accumulate):
         rows = rowptr.numel() - 1

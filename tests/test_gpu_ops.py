@@ -535,3 +535,25 @@ def test_jk_lstm_fwd_bwd(cuda_backend, rows):
     torch.testing.assert_close(gfg.cpu(), gf, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(dgg.cpu(), dg, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(dscg.cpu(), dsc, rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------- radius_graph (loader side)
+@pytest.mark.parametrize('sizes,r,k,loop', [([1800, 1800, 700], 100.0, 8, True), ([300, 41, 1], 30.0, 8, True),
+                                            ([500, 260], 60.0, 12, False), ([2999], 45.0, 20, True)])
+def test_radius_graph_matches_ckdtree(cuda_backend, sizes, r, k, loop):
+    """GPU radius_graph == scipy cKDTree.query (the CPU path of torch_cluster 1.4.2), bit-exact neighbour lists
+    (nearest first), then the COO edge_index the reference's loaders emit (dataflow/data.py:348)."""
+    g = torch.Generator().manual_seed(len(sizes) * 1000 + k)
+    pos = torch.rand(sum(sizes), 2, generator=g) * 1000.0
+    start = torch.zeros(len(sizes) + 1, dtype=torch.int32)
+    start[1:] = torch.tensor(sizes).cumsum(0).to(torch.int32)
+    nbr = torch.zeros(sum(sizes), k, dtype=torch.int32)
+    deg = torch.zeros(sum(sizes), dtype=torch.int32)
+    both(cuda_backend, 'radius_graph', [pos, start, len(sizes), max(sizes), r, k, loop, nbr, deg], [7, 8])
+    assert int(deg.max()) <= k and (loop is False or int(deg.min()) >= 1)
+    ei = graph.radius_graph(pos.cuda(), r, None, loop, k, num_nodes_list=sizes).cpu()
+    valid = nbr >= 0
+    centre = torch.arange(sum(sizes)).view(-1, 1).expand_as(nbr)
+    assert torch.equal(ei[0], nbr[valid].long()) and torch.equal(ei[1], centre[valid])
+    if loop:
+        assert torch.equal(nbr[:, 0].long(), torch.arange(sum(sizes)))      # the centre itself comes first

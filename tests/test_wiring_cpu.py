@@ -230,3 +230,32 @@ def test_property_graph_build_random(torch_backend):
         assert torch.equal(gr.rs, 1.0 / deg_r.float().clamp(min=1))
 
     check()
+
+
+def test_radius_graph_wrapper_feeds_the_encoder(torch_backend):
+    """graph.radius_graph (reference call: radius_graph(pos, 100, None, True, 8), dataflow/data.py:348) produces
+    an edge_index the encoder consumes: neighbour -> centre pairs, self loop first, <= k per centre."""
+    g = torch.Generator().manual_seed(5)
+    sizes = [60, 35]
+    pos = torch.rand(sum(sizes), 2, generator=g) * 300.0
+    ei = graph.radius_graph(pos, 100.0, None, True, 8, num_nodes_list=sizes)
+    assert ei.dtype == torch.long and ei.shape[0] == 2
+    indeg = torch.bincount(ei[1], minlength=sum(sizes))
+    assert int(indeg.max()) <= 8 and int(indeg.min()) >= 1
+    d = (pos[ei[0]] - pos[ei[1]]).norm(dim=1)
+    assert float(d.max()) < 100.0
+    same_graph = (ei[0] < 60) == (ei[1] < 60)
+    assert bool(same_graph.all())
+    # brute force: every centre's list equals its k nearest within r
+    dm = torch.cdist(pos.double(), pos.double())
+    dm[:60, 60:] = float('inf')
+    dm[60:, :60] = float('inf')
+    for c in (0, 17, 59, 60, 94):
+        want = [int(j) for j in dm[c].argsort()[:8] if dm[c, j] < 100.0]
+        assert ei[0][ei[1] == c].tolist() == want
+    batch = graph.Batch(torch.randn(sum(sizes), 16, generator=g), ei,
+                        torch.cat([torch.full((n,), i) for i, n in enumerate(sizes)]), torch.tensor([0, 2]), sizes)
+    ours, orc = helpers.build_pair(helpers.encoder_args(200), load_data_sparse=True)
+    ours.eval(), orc.eval()
+    with torch.no_grad():
+        assert helpers.rel_err(ours(batch), orc(batch)) < 1e-4
