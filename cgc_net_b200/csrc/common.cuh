@@ -64,6 +64,14 @@ __device__ __forceinline__ float act_grad(int act, float y) {
   if (act == CGC_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
   return y > 0.f ? 1.f : 0.01f;
 }
+// Branch-free form for the hot backward loops: act'(y) = y > 0 ? 1 : a0 + a1 * y with (a0, a1) = (0, 0) relu,
+// (1, 1) elu, (0.01, 0) leaky relu -- one select + one FMA per element, no control flow between the loads.
+struct ActGrad {
+  float a0, a1;
+  __device__ __forceinline__ explicit ActGrad(int act)
+      : a0(act == CGC_ACT_RELU ? 0.f : (act == CGC_ACT_ELU ? 1.f : 0.01f)), a1(act == CGC_ACT_ELU ? 1.f : 0.f) {}
+  __device__ __forceinline__ float operator()(float y) const { return y > 0.f ? 1.f : fmaf(a1, y, a0); }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -17,6 +17,7 @@ k_epi_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict
              float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
              float* __restrict__ dh, int64_t lddh, int act) {
   extern __shared__ float s_w[];          // [cin][cout] then bias[cout]
+  const ActGrad agrad(act);
   float* s_b = s_w + cin * cout;
   for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = w[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
@@ -43,7 +44,7 @@ k_epi_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict
     } else {
       float hn = h * inv;
       float g = 0.f;
-      if (lane < cout && valid) g = gy[r * ldgy + lane] * act_grad(act, __ldg(y + r * ldy + lane));
+      if (lane < cout && valid) g = gy[r * ldgy + lane] * agrad(__ldg(y + r * ldy + lane));
       const float dot = warp_sum(g * hn);
       float d = (nrm >= kL2NormEps) ? (g - hn * dot) * inv : g * inv;
       if (lane < cout) dh[r * lddh + lane] = d;
@@ -63,6 +64,7 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
            float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
            float* __restrict__ dh, int64_t lddh, int act) {
   extern __shared__ float smem[];
+  const ActGrad agrad(act);
   float* s_w = smem;                                 // [cin][cout]
   float* s_a = s_w + cin * cout;                     // [cin][kEpiRows]  (transposed row tile)
   float* s_red = s_a + cin * kEpiRows;               // [8 warps][kEpiRows]
@@ -154,7 +156,7 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
           if (valid && c < cout) {                    // independent loads (no y -> gy dependency chain)
             const float yv = __ldg(y + r * ldy + c);
             const float gv = gy[r * ldgy + c];
-            g = gv * act_grad(act, yv);
+            g = gv * agrad(yv);
           }
           gm[rr][j] = g;
           s = fmaf(g, acc[rr][j] * inv[rr], s);

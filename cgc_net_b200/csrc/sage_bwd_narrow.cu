@@ -36,6 +36,7 @@ k_sage_bwd_narrow(const float* __restrict__ gy, int64_t ldgy, const float* __res
                   int64_t ldy, const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
                   float* __restrict__ dsa, int64_t lddsa, float* __restrict__ partial, int cinp, int vec, int act) {
   extern __shared__ __align__(16) float smem[];
+  const ActGrad agrad(act);
   const int cin_r = (cin + 3) & ~3;          // W rows staged (zero padded)
   const int cin_e = (cin + 4) & ~3;          // sa columns of the dW contraction: cin, the ones column, zero pad
   const int SA = nb_stride(cin + 1), SD = nb_stride(cout);
@@ -122,16 +123,16 @@ k_sage_bwd_narrow(const float* __restrict__ gy, int64_t ldgy, const float* __res
           if (vec) {
             const float4 yv = __ldg(reinterpret_cast<const float4*>(yrow) + c4);
             const float4 gv = __ldg(reinterpret_cast<const float4*>(grow) + c4);
-            g4.x = gv.x * act_grad(act, yv.x);
-            g4.y = gv.y * act_grad(act, yv.y);
-            g4.z = gv.z * act_grad(act, yv.z);
-            g4.w = gv.w * act_grad(act, yv.w);
+            g4.x = gv.x * agrad(yv.x);
+            g4.y = gv.y * agrad(yv.y);
+            g4.z = gv.z * agrad(yv.z);
+            g4.w = gv.w * agrad(yv.w);
           } else {
             float gs[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int c = 4 * c4 + j;
-              gs[j] = c < cout ? __ldg(grow + c) * act_grad(act, __ldg(yrow + c)) : 0.f;
+              gs[j] = c < cout ? __ldg(grow + c) * agrad(__ldg(yrow + c)) : 0.f;
             }
             g4 = make_float4(gs[0], gs[1], gs[2], gs[3]);
           }
