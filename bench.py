@@ -12,8 +12,9 @@ One JSON line is printed by rank 0:
   value      graphs/s with the batch already resident in HBM (device-timed, max over ranks)
   e2e        the same through the public module call with HOST (pinned) inputs: per-step H2D copy of
              x / edge_index / batch / y and a D2H read of the loss inside the timed region
-  roofline   the SAGE gather kernel (cgc_sage_gather_mean_fwd) alone: algorithmic bytes / launch time
-             vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline   the SAGE gather kernel (cgc_sage_gather_ell_fwd) alone: algorithmic bytes / launch time
+             vs the measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes of one launch
+             from the committed ncu capture (profiles/gather_r1_ncu.txt)
   cpu_baseline  the dense CPU oracle port of the reference path timed on this box's host cores on a
              bounded sample (N = 1, rank 0 only)
 `--impl reference` times that CPU oracle port alone (the reference is pure Python on dense torch ops;
@@ -36,6 +37,10 @@ import torch  # noqa: E402
 MODEL_ARGS = (11404, 16, 20, 20, True, True, 20, 3, 0.10, [50])      # train.py:254-261, setting.py:15
 METRIC = 'graphs/sec (1800-node, deg-8) fwd+bwd'
 FEAT = 16
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_sage_gather_ell launch at B=64 x 1800 x F=16, cold L2
+# (ncu --set full, profiles/gather_r1_ncu.txt): 9.77 MB read (tile 7.37 + uint16 indices 1.84 + scales / map),
+# 0 written inside the launch (the 7.37 MB of outputs are still in L2 when it ends).
+GATHER_NCU_DRAM_BYTES = 9768704
 
 
 def parse():
@@ -325,10 +330,14 @@ def run_ours(args):
         achieved = alg_bytes / (us * 1e-6) / 1e9
         line['roofline'] = {'kernel': 'k_sage_gather_ell (cgc_sage_gather_ell_fwd, F=16, unfused)', 'bound': 'hbm',
                             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                            'traffic': None, 'peak_source': which, 'algorithmic_bytes_per_launch': alg_bytes,
+                            'traffic': GATHER_NCU_DRAM_BYTES if (args.batch_per_gpu, args.nodes, args.degree) == (64, 1800, 8) else None,
+                            'traffic_source': 'profiles/gather_r1_ncu.txt (ncu --set full, one cold launch; '
+                                              'outputs, 7.37 MB, still in L2 at kernel end)',
+                            'peak_source': which, 'algorithmic_bytes_per_launch': alg_bytes,
                             'us_per_launch': us,
                             'timing': 'CUDA-graph replay of %d launches over %d rotating input copies (%.0f MB > L2), '
-                                      'CUDA events on the launching stream' % (copies, copies, copies * alg_bytes / 1e6)}
+                                      'CUDA events on the launching stream, median of 5 blocks of 20 replays'
+                                      % (copies, copies, copies * alg_bytes / 1e6)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, dt, cores, n_graphs = cpu_oracle_rate(args, 3, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'graphs/s', 'cores': cores, 'kind': 'port',
