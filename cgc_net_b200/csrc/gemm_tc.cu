@@ -83,6 +83,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (CTA-scope
+// release) semantics on purpose: `.release.cluster` / `.acquire.cluster` compile to MEMBAR.ALL.GPU + ERRBAR on the
+// arrive and CCTL.IVALL on every wait (measured: the pair kernel 1.5x SLOWER than the single-CTA one); the
+// tensor-memory / shared-memory hand-off is ordered by the tcgen05 fences and fence.proxy.async around it.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// wait on a barrier whose arrivals may come from the peer CTA (same instruction as mbar_wait, own labels)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TCC_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TCC_DONE;\n\t"
+      "bra TCC_WAIT;\n\t"
+      "TCC_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             uint64_t* bar) {
   asm volatile(
@@ -141,6 +180,20 @@ __device__ __forceinline__ void umma_tf32_ts2(uint32_t tmem_d, uint32_t tmem_a, 
       "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// CTA pair: D (256 x N, 128 rows in each CTA's TMEM) += A (each CTA's TMEM) * B (N/2 columns in each CTA's smem)
+__device__ __forceinline__ void umma_tf32_ts2_pair(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo,
+                                                   uint32_t bdesc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], bd, %4, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -167,6 +220,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// commit of cta_group::2 MMAs, arriving on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -204,7 +265,8 @@ __device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float* acc) {
 struct TileCoord {
   int bz, split, m0, n0, kbeg, kend;
 };
-__device__ __forceinline__ TileCoord tile_coord(const Params& p, int t) {
+// bm = rows of one scheduled tile (128, or 256 for a CTA pair); rank = this CTA's half of it
+__device__ __forceinline__ TileCoord tile_coord(const Params& p, int t, int bm = BM, int rank = 0) {
   TileCoord c;
   int nt = t % p.tiles_n;
   int r = t / p.tiles_n;
@@ -212,7 +274,7 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, int t) {
   int z = r / p.tiles_m;                  // bz * ksplit + split
   c.bz = z / p.g.ksplit;
   c.split = z - c.bz * p.g.ksplit;
-  c.m0 = mt * BM;
+  c.m0 = mt * bm + rank * BM;
   c.n0 = nt * p.bn;
   c.kbeg = c.split * p.g.kchunk;
   c.kend = min(p.g.k, c.kbeg + p.g.kchunk);
@@ -268,10 +330,15 @@ __device__ __forceinline__ void store_segment(const Params& p, const TileCoord& 
   }
 }
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages
+// its own 128 rows of A (TMEM) and only BN/2 columns of B (shared memory); the leader (rank 0) issues the MMAs,
+// whose B reads are served half by each CTA's shared memory -- the B share of the shared-memory traffic halves.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-  constexpr int kBBytes = BN * BK * 4;
+  constexpr int kBCols = PAIR ? BN / 2 : BN;          // B columns staged by this CTA
+  constexpr int kBBytes = kBCols * BK * 4;
+  constexpr int kTileM = PAIR ? 2 * BM : BM;
   constexpr int kStageBytes = kOperandBytes + 2 * kBBytes;
   constexpr int kTxBytes = kOperandBytes + kBBytes;
   constexpr int kAccCols = BN;
@@ -287,29 +354,40 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&xfull[s], kSplitThreads);
+      mbar_init(&xfull[s], PAIR ? 2 * (kSplitThreads / 32) : kSplitThreads);   // pair: one arrival per split warp of both CTAs
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], kEpiThreads);
+      mbar_init(&tempty[a], PAIR ? 2 * (kEpiThreads / 32) : kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -318,8 +396,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = tile_coord(p, t);
+      for (int t = tile_first; t < p.total_tiles; t += tile_step) {
+        const TileCoord c = tile_coord(p, t, kTileM, rank);
+        const int bn0 = c.n0 + rank * kBCols;          // pair: this CTA's half of the B columns
         for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], kTxBytes);
@@ -333,9 +412,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           if (p.b_mn_major) {
 #pragma unroll
-            for (int ch = 0; ch < BN / 32; ++ch) tma_load_3d(sb + ch * 4096, &map_b, c.n0 + ch * 32, k0, c.bz, &full[s]);
+            for (int ch = 0; ch < kBCols / 32; ++ch) tma_load_3d(sb + ch * 4096, &map_b, bn0 + ch * 32, k0, c.bz, &full[s]);
           } else {
-            tma_load_3d(sb, &map_b, k0, c.n0, c.bz, &full[s]);
+            tma_load_3d(sb, &map_b, k0, bn0, c.bz, &full[s]);
           }
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
@@ -345,9 +424,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     // ================================ MMA issuer ================================
     // The whole warp runs the loop (so addresses / descriptors stay warp-uniform and cheap to form);
     // one elected lane issues.  A is fed from TMEM (lane = row, column = k), B from shared memory.
-    {
+    // Pair: only the leader CTA issues (for both); its waits see the peer's arrivals (cluster scope).
+    if (!PAIR || rank == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.b_mn_major << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       // B MN-major (SW128 with 32B atoms): 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart
       //           (SBO), one K=8 step = the next 1024 B.
       // B K-major  (SW128): 8-row groups 1024 B apart (SBO), one K=8 step = 32 B inside the 128 B swizzle row.
@@ -362,17 +442,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       uint32_t chunk_it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = tile_coord(p, t);
+      for (int t = tile_first; t < p.total_tiles; t += tile_step) {
+        const TileCoord c = tile_coord(p, t, kTileM, rank);
         int k0 = c.kbeg;
         while (k0 < c.kend) {
           const uint32_t buf = chunk_it & 1u;
-          mbar_wait(&tempty[buf], ((chunk_it >> 1) & 1u) ^ 1u);
+          if (PAIR) mbar_wait_cluster(&tempty[buf], ((chunk_it >> 1) & 1u) ^ 1u);
+          else mbar_wait(&tempty[buf], ((chunk_it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * (uint32_t)kAccCols;
           uint32_t accumulate = 0;
           for (int kb = 0; kb < p.chunk_blocks && k0 < c.kend; ++kb, k0 += BK) {
-            mbar_wait(&xfull[s], ph);
+            if (PAIR) mbar_wait_cluster(&xfull[s], ph);
+            else mbar_wait(&xfull[s], ph);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t bh = desc_lo_base | (smem_base16 + (uint32_t)((s * kStageBytes + kOperandBytes) >> 4));
@@ -381,17 +463,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               const uint32_t a_lo = a_hi + (uint32_t)BK;
 #pragma unroll
               for (int kk = 0; kk < BK / 8; ++kk) {
-                umma_tf32_ts2(d_tmem, a_lo + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
-                umma_tf32_ts2(d_tmem, a_hi + kk * 8, bl + kk * b_kstep16, desc_hi, idesc, 1u);
-                umma_tf32_ts2(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, 1u);
+                if (PAIR) {
+                  umma_tf32_ts2_pair(d_tmem, a_lo + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
+                  umma_tf32_ts2_pair(d_tmem, a_hi + kk * 8, bl + kk * b_kstep16, desc_hi, idesc, 1u);
+                  umma_tf32_ts2_pair(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, 1u);
+                } else {
+                  umma_tf32_ts2(d_tmem, a_lo + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
+                  umma_tf32_ts2(d_tmem, a_hi + kk * 8, bl + kk * b_kstep16, desc_hi, idesc, 1u);
+                  umma_tf32_ts2(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, 1u);
+                }
               }
-              umma_commit(&empty[s]);                   // frees the stage once these MMAs have read it
+              if (PAIR) umma_commit_pair(&empty[s]);    // frees the stage in BOTH CTAs
+              else umma_commit(&empty[s]);              // frees the stage once these MMAs have read it
             }
             __syncwarp();
             accumulate = 1u;
             if (++s == kStages) { s = 0; ph ^= 1; }
           }
-          if (elect_one()) umma_commit(&tfull[buf]);    // chunk complete -> promotion warps
+          if (elect_one()) {                            // chunk complete -> promotion warps (pair: of both CTAs)
+            if (PAIR) umma_commit_pair(&tfull[buf]);
+            else umma_commit(&tfull[buf]);
+          }
           __syncwarp();
           ++chunk_it;
         }
@@ -402,8 +494,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int tid = threadIdx.x - 128;
     int s = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord c = tile_coord(p, t);
+    for (int t = tile_first; t < p.total_tiles; t += tile_step) {
+      const TileCoord c = tile_coord(p, t, kTileM, rank);
       for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + (size_t)s * kStageBytes;
@@ -456,7 +548,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&xfull[s]);
+        if (PAIR) {
+          // one arrival per warp on the LEADER's barrier (remote arrivals are DSMEM transactions: 256 of them
+          // per stage would serialise on the barrier)
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&xfull[s]);
+            else mbar_arrive_cluster(&xfull[s], 0);
+          }
+        } else {
+          mbar_arrive(&xfull[s]);
+        }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
@@ -466,8 +568,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int half = (warp - 8) >> 2;                  // which BN/2 accumulator columns this warp owns
     constexpr int kCols = BN / 2;                      // 64, 32 or 16
     uint32_t chunk_it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord c = tile_coord(p, t);
+    for (int t = tile_first; t < p.total_tiles; t += tile_step) {
+      const TileCoord c = tile_coord(p, t, kTileM, rank);
       float acc[kCols];
 #pragma unroll
       for (int j = 0; j < kCols; ++j) acc[j] = 0.f;
@@ -483,7 +585,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           for (int j = 0; j < kCols; j += 32) tmem_ld32_add(taddr + (uint32_t)j, acc + j);
         }
         tc_fence_before();
-        mbar_arrive(&tempty[buf]);
+        if (PAIR) {
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&tempty[buf]);
+            else mbar_arrive_cluster(&tempty[buf], 0);
+          }
+        } else {
+          mbar_arrive(&tempty[buf]);
+        }
         ++chunk_it;
       }
       const int row = c.m0 + q * 32 + lane;
@@ -498,10 +608,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // no CTA frees tensor memory (or exits) while its peer still uses the pair
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                   : "memory");
   }
 }
 
@@ -583,9 +698,14 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   q.chunk_blocks = chunk_blocks;
   q.a_mn_major = ta ? 1 : 0;          // A stored [k, m]: m contiguous
   q.b_mn_major = tb ? 0 : 1;          // B stored [k, n]: n contiguous
-  q.tiles_m = (int)ceil_div(p.m, BM);
   const int bn = p.n <= 32 ? 32 : (p.n <= 64 ? 64 : 128);      // skinny outputs: narrow MMA tile, same A stream
   q.bn = bn;
+  static const int pair_mode = []() {
+    const char* e = getenv("CGC_TC_PAIR");                     // 0 disables the cta_group::2 kernel
+    return e ? atoi(e) : 1;
+  }();
+  const bool pair = pair_mode != 0 && bn == 128 && p.m > BM;    // 256-row tiles on a CTA pair
+  q.tiles_m = (int)ceil_div(p.m, pair ? 2 * BM : BM);
   q.tiles_n = (int)ceil_div(p.n, bn);
   int64_t tiles = (int64_t)q.tiles_m * q.tiles_n * p.batch;
   p.ksplit = 1;
@@ -620,23 +740,45 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   else ok = make_map(&map_a, p.a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)p.batch, p.lda, p.stride_a, BM, false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for A");
   if (q.b_mn_major) ok = make_map(&map_b, p.b, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.batch, p.ldb, p.stride_b, BK, true);
-  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b, (uint32_t)bn, false);
+  else ok = make_map(&map_b, p.b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)p.batch, p.ldb, p.stride_b,
+                     (uint32_t)(pair ? bn / 2 : bn), false);
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for B");
 
   int grid = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
   const size_t smem = smem_bytes(bn);
-#define CGC_TC_CASE(N)                                                                                   \
-  case N:                                                                                                \
-    CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_gemm_tc<N><<<grid, kThreads, smem, st>>>(map_a, map_b, q);                                         \
+  if (pair) {
+    // one cluster of 2 CTAs (same TPC) per 256-row tile; persistent over the tiles
+    const int clusters = q.total_tiles < kNumSMs / 2 ? q.total_tiles : kNumSMs / 2;
+    auto kern = k_gemm_tc<128, true>;
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CGC_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, q));
+    CGC_CHECK_LAUNCH("k_gemm_tc<pair>");
+  } else {
+#define CGC_TC_CASE(N)                                                                                          \
+  case N:                                                                                                       \
+    CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_gemm_tc<N, false><<<grid, kThreads, smem, st>>>(map_a, map_b, q);                                         \
     break;
-  switch (bn) {
-    CGC_TC_CASE(32)
-    CGC_TC_CASE(64)
-    CGC_TC_CASE(128)
-  }
+    switch (bn) {
+      CGC_TC_CASE(32)
+      CGC_TC_CASE(64)
+      CGC_TC_CASE(128)
+    }
 #undef CGC_TC_CASE
-  CGC_CHECK_LAUNCH("k_gemm_tc");
+    CGC_CHECK_LAUNCH("k_gemm_tc");
+  }
   if (p.ksplit > 1) {
     int64_t total = (int64_t)p.m * p.n * p.batch;
     int64_t blocks = ceil_div(total, 256);
