@@ -711,11 +711,19 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   p.ksplit = 1;
   p.kchunk = p.k;
   p.partial = nullptr;
-  if (tiles < kNumSMs && p.k >= 4096 && work != nullptr) {      // split K to fill the SMs
-    int64_t ks = ceil_div(2 * kNumSMs, tiles);
+  const int units = pair ? kNumSMs / 2 : kNumSMs;               // CTAs (or CTA pairs) that run tiles concurrently
+  if (tiles < units && p.k >= 4096 && work != nullptr) {        // split K to fill the SMs
+    // pick the split whose work items fill whole waves best (items / units close to an integer from below)
     int64_t kmax = p.k / 1024;
-    if (ks > kmax) ks = kmax;
-    while (ks > 1 && ks * p.batch * (int64_t)p.m * p.n * 4 > work_bytes) --ks;
+    if (kmax > 24) kmax = 24;
+    int64_t ks = 1;
+    double best = 0.0;
+    for (int64_t cand = 1; cand <= kmax; ++cand) {
+      if (cand * p.batch * (int64_t)p.m * p.n * 4 > work_bytes) break;
+      const double waves = (double)(tiles * cand) / units;
+      const double eff = waves / (double)ceil_div(tiles * cand, units);
+      if (eff > best + 0.02) { best = eff; ks = cand; }
+    }
     if (ks > 1) {
       int64_t chunk = ceil_div(ceil_div(p.k, ks), chunk_blocks * BK) * (chunk_blocks * BK);
       p.kchunk = (int)chunk;
