@@ -14,24 +14,43 @@ import torch.distributed as dist
 
 
 class FlatGradBucket(object):
-    """All parameter gradients as views of one contiguous buffer."""
+    """One contiguous buffer for every parameter gradient, filled once per step.
+
+    ``zero()`` drops the ``.grad`` tensors, so autograd *assigns* each freshly computed gradient instead of
+    launching one ``grad += new`` kernel per parameter (60 launches per step for the BASELINE model).
+    ``all_reduce_mean()`` packs them into the flat buffer with one multi-tensor copy, all-reduces it once, and
+    leaves every ``.grad`` as a view of the buffer (what the optimiser then reads).  With a single rank nothing
+    is copied at all."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
 
     def zero(self):
-        """Use instead of ``optimizer.zero_grad()`` (keeps the views alive)."""
-        self.flat.zero_()
+        """Use instead of ``optimizer.zero_grad()``."""
+        for p in self.params:
+            p.grad = None
 
     def nbytes(self):
         return self.flat.numel() * self.flat.element_size()
+
+    def pack(self):
+        """Copy the per-parameter gradients into the flat buffer (missing gradients count as zero) and make
+        every ``.grad`` a view of it."""
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad is not v]
+        if len(have) < len(self.params):
+            self.flat.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def all_reduce_mean(self, group=None):
         """Sum over ranks, then 1/R: the mean of per-replica mean losses (train.py:179)."""
@@ -40,6 +59,7 @@ class FlatGradBucket(object):
         world = dist.get_world_size(group)
         if world == 1:
             return
+        self.pack()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.mul_(1.0 / world)
 

@@ -70,6 +70,7 @@ def test_two_rank_gradient_allreduce(tmp_path, torch_backend):
         bucket.zero()
         _, loss = model(graph.Batch.from_data_list(parallel.shard_for_rank(graphs, rank, 2)))
         loss.backward()
+        bucket.pack()
         flats.append(bucket.flat.clone())
     want = (flats[0] + flats[1]) / 2
     assert got['flat'].numel() == sum(p.numel() for p in _make_model().parameters())
@@ -79,11 +80,19 @@ def test_two_rank_gradient_allreduce(tmp_path, torch_backend):
 def test_flat_bucket_views_and_sharding():
     model = _make_model()
     bucket = parallel.FlatGradBucket(model.parameters())
-    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
-    bucket.flat.fill_(2.0)
-    assert all(float(p.grad.min()) == 2.0 for p in model.parameters())
     bucket.zero()
-    assert float(bucket.flat.abs().sum()) == 0.0
+    assert all(p.grad is None for p in model.parameters())      # autograd will assign, not accumulate
+    for i, p in enumerate(model.parameters()):
+        if i % 2 == 0:                                           # half of the gradients present, half missing
+            p.grad = torch.full_like(p, 2.0)
+    bucket.pack()
+    lo = bucket.flat.data_ptr()
+    hi = lo + bucket.nbytes()
+    assert all(lo <= p.grad.data_ptr() < hi for p in model.parameters())        # views of the one buffer
+    for i, p in enumerate(model.parameters()):
+        assert float(p.grad.min()) == float(p.grad.max()) == (2.0 if i % 2 == 0 else 0.0)
+    bucket.flat.fill_(3.0)
+    assert all(float(p.grad.min()) == 3.0 for p in model.parameters())
     bucket.all_reduce_mean()                           # no process group: a no-op
     graphs = _graphs()
     assert sum(len(parallel.shard_for_rank(graphs, r, 2)) for r in range(2)) == len(graphs)
