@@ -38,6 +38,7 @@ _SIGNATURES = {
     'cgc_csr_transpose': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_radius_graph': [_c_vp, _c_vp, _c_i32, _c_i32, _c_f64, _c_i32, _c_int, _c_vp, _c_vp, _c_vp],
     'cgc_knn_to_coo': [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp],
+    'cgc_farthest_point_sample': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_vp, _c_vp],
     'cgc_spmm': [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64,
                  _c_int, _c_vp],
     'cgc_sage_gather_mean_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp,
@@ -207,6 +208,14 @@ class CudaBackend(object):
         self._check(self.lib.cgc_knn_to_coo(_ptr(nbr, torch.int32), _ptr(deg, torch.int32),
                                             _ptr(offsets, torch.int64), deg.numel(), int(k), int(num_edges),
                                             _ptr(edge_index, torch.int64), self._stream()), 'cgc_knn_to_coo')
+
+    def farthest_point_sample(self, pos, start, first, out_start, nmax, out):
+        if not pos.is_contiguous() or pos.dim() != 2 or pos.shape[1] != 2:
+            raise CgcError('cgc_farthest_point_sample needs contiguous [n, 2] positions')
+        self._check(self.lib.cgc_farthest_point_sample(_ptr(pos, torch.float32), _ptr(start, torch.int32),
+                                                       _ptr(first, torch.int32), _ptr(out_start, torch.int32),
+                                                       first.numel(), nmax, _ptr(out, torch.int32),
+                                                       self._stream()), 'cgc_farthest_point_sample')
 
     # -- sparse gather
     def spmm(self, rowptr, col, val, x, src_scale, row_scale, out, accumulate):

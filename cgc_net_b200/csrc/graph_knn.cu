@@ -5,6 +5,8 @@
 // scipy's cKDTree.query(k, distance_upper_bound=r); here one thread owns one centre, scans its graph's positions
 // from shared memory and keeps the k best (distance, index) pairs in registers.  Distances are evaluated in
 // double precision on the float positions (as cKDTree does), ties broken by the lower node index.
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace cgc {
@@ -108,5 +110,85 @@ extern "C" int cgc_knn_to_coo(const int32_t* nbr, const int32_t* deg, const int6
   k_knn_to_coo<<<(unsigned)ceil_div(n_total, 256), 256, 0, as_stream(stream)>>>(nbr, deg, offsets, n_total, k,
                                                                                num_edges, edge_index);
   CGC_CHECK_LAUNCH("k_knn_to_coo");
+  return 0;
+}
+
+// ------------------------------------------------------------------ farthest-point node sampling
+// FarthestSampler.__call__ (reference common/utils.py:187-197) on the distance matrix that
+// construct_feature_graph.py:17-24 stores: d(i, j) = (int16) sqrt((xi-xj)^2 + (yi-yj)^2) (truncation).  The
+// reference walks a [N, N] int16 matrix loaded from disk; here one CTA owns one graph, keeps the running
+// min-distance vector in shared memory and evaluates the distances from the positions on the fly:
+//   sel_0 = first[g];  mind = d(sel_0, .);  sel_i = argmax(mind) (first maximum, like np.argmax);
+//   mind = min(mind, d(sel_i, .)).
+namespace cgc {
+
+constexpr int kFpsThreads = 256;
+
+__device__ __forceinline__ int fps_dist(float2 a, float2 b) {
+  const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
+  return (int)(short)(long long)sqrt(dx * dx + dy * dy);       // astype(np.int16) of the float64 distance
+}
+
+__global__ void __launch_bounds__(kFpsThreads)
+k_farthest_point_sample(const float* __restrict__ pos, const int* __restrict__ start, const int* __restrict__ first,
+                        const int* __restrict__ out_start, int* __restrict__ out) {
+  extern __shared__ unsigned char fps_smem[];
+  const int g = blockIdx.x;
+  const int n0 = __ldg(start + g), n = __ldg(start + g + 1) - n0;
+  const int o0 = __ldg(out_start + g), k = __ldg(out_start + g + 1) - o0;
+  if (n <= 0 || k <= 0) return;
+  float2* s_pos = reinterpret_cast<float2*>(fps_smem);
+  int* s_min = reinterpret_cast<int*>(s_pos + n);
+  __shared__ int s_val[kFpsThreads / 32], s_idx[kFpsThreads / 32], s_sel;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += kFpsThreads)
+    s_pos[i] = make_float2(__ldg(pos + 2 * (int64_t)(n0 + i)), __ldg(pos + 2 * (int64_t)(n0 + i) + 1));
+  int sel = min(max(__ldg(first + g), 0), n - 1);
+  __syncthreads();
+  if (tid == 0) out[o0] = sel;
+  for (int i = tid; i < n; i += kFpsThreads) s_min[i] = fps_dist(s_pos[sel], s_pos[i]);
+  for (int it = 1; it < k; ++it) {
+    __syncthreads();
+    // arg max with the lowest index on ties
+    int bv = INT_MIN, bi = 0x7fffffff;
+    for (int i = tid; i < n; i += kFpsThreads) {
+      const int v = s_min[i];
+      if (v > bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      int v = s_val[0], ix = s_idx[0];
+      for (int w = 1; w < kFpsThreads / 32; ++w)
+        if (s_val[w] > v || (s_val[w] == v && s_idx[w] < ix)) { v = s_val[w]; ix = s_idx[w]; }
+      s_sel = ix;
+      out[o0 + it] = ix;
+    }
+    __syncthreads();
+    sel = s_sel;
+    const float2 ps = s_pos[sel];
+    for (int i = tid; i < n; i += kFpsThreads) s_min[i] = min(s_min[i], fps_dist(ps, s_pos[i]));
+  }
+}
+
+}  // namespace cgc
+
+extern "C" int cgc_farthest_point_sample(const float* pos, const int32_t* start, const int32_t* first,
+                                         const int32_t* out_start, int32_t num_graphs, int32_t nmax, int32_t* out,
+                                         void* stream) {
+  CGC_REQUIRE(pos && start && first && out_start && out && num_graphs > 0 && nmax > 0, CGC_ERR_ARG,
+              "cgc_farthest_point_sample: bad args");
+  const size_t smem = (size_t)nmax * (sizeof(float2) + sizeof(int));
+  CGC_REQUIRE(smem <= 200 * 1024, CGC_ERR_UNSUPPORTED,
+              "cgc_farthest_point_sample: %d nodes per graph do not fit shared memory", nmax);
+  CGC_CUDA(cudaFuncSetAttribute(cgc::k_farthest_point_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cgc::k_farthest_point_sample<<<(unsigned)num_graphs, cgc::kFpsThreads, smem, as_stream(stream)>>>(pos, start, first,
+                                                                                                   out_start, out);
+  CGC_CHECK_LAUNCH("k_farthest_point_sample");
   return 0;
 }

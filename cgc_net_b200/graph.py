@@ -155,3 +155,43 @@ def radius_graph(pos, r, batch=None, loop=False, max_num_neighbors=32, num_nodes
     if num_edges:
         be.knn_to_coo(nbr, deg, offsets, k, num_edges, edge_index)
     return edge_index
+
+
+def sample_nodes(pos, num_nodes_list, ratio, method='fuse', generator=None):
+    """Node subsampling of the reference's loaders (``_sampling``, dataflow/data.py:195-225) on the GPU: per graph
+    ``int(n * ratio)`` node ids by ``method``:
+
+    * ``'random'``   -- ``np.random.choice(n, k, replace=False)`` (data.py:223): a random subset;
+    * ``'farthest'`` -- ``FarthestSampler`` (common/utils.py:187-197) from a random first node: ``cgc_farthest_point_sample``;
+    * ``'fuse'``     -- 70 % farthest-point, 30 % drawn at random from the rest (data.py:210-219).
+
+    Returns a list of int64 tensors of LOCAL node ids (one per graph, farthest-point ids first).  The random
+    draws come from ``generator`` (a CPU ``torch.Generator``), not from numpy's global stream."""
+    from . import _backend
+    be = _backend.get()
+    dev = pos.device
+    counts = [int(n) for n in num_nodes_list]
+    ks = [int(n * ratio) for n in counts]
+    if method == 'random':
+        return [torch.randperm(n, generator=generator)[:k].to(dev) for n, k in zip(counts, ks)]
+    far = ks if method == 'farthest' else [int(0.7 * k) for k in ks]
+    start = torch.tensor([0] + counts, dtype=torch.int64).cumsum(0).to(torch.int32)
+    ostart = torch.tensor([0] + far, dtype=torch.int64).cumsum(0).to(torch.int32)
+    first = torch.tensor([int(torch.randint(0, max(n, 1), (1,), generator=generator)) for n in counts],
+                         dtype=torch.int32)
+    out = torch.zeros(max(int(ostart[-1]), 1), dtype=torch.int32, device=dev)
+    if int(ostart[-1]) > 0:
+        be.farthest_point_sample(pos.contiguous().float(), start.to(dev), first.to(dev), ostart.to(dev),
+                                 max(counts), out)
+    result = []
+    os_ = ostart.tolist()
+    for g, (n, k) in enumerate(zip(counts, ks)):
+        ids = out[os_[g]:os_[g + 1]].long()
+        if method == 'fuse' and k > far[g]:
+            taken = torch.zeros(n, dtype=torch.bool)
+            taken[ids.cpu()] = True
+            rest = (~taken).nonzero().view(-1)
+            extra = rest[torch.randperm(rest.numel(), generator=generator)[:k - far[g]]]
+            ids = torch.cat([ids, extra.to(dev)])
+        result.append(ids)
+    return result

@@ -110,6 +110,15 @@ CGC_API int cgc_radius_graph(const float* pos, const int32_t* start, int32_t num
 CGC_API int cgc_knn_to_coo(const int32_t* nbr, const int32_t* deg, const int64_t* offsets, int64_t n_total,
                    int32_t k, int64_t num_edges, int64_t* edge_index, void* stream);
 
+/* Farthest-point node sampling = FarthestSampler.__call__ (common/utils.py:187-197) over the int16 distance
+ * matrix of construct_feature_graph.py:17-24, d(i,j) = (int16) sqrt(|pos_i - pos_j|^2), evaluated on the fly:
+ * out[out_start[g]] = first[g] (local id; the reference draws it with np.random.randint), then repeatedly the
+ * first arg-max of the running min-distance.  start / out_start: [num_graphs + 1] offsets (nodes / samples);
+ * out: local node ids.  The 'fuse' sampler (dataflow/data.py:210-219) takes 70 % of its nodes from this. */
+CGC_API int cgc_farthest_point_sample(const float* pos, const int32_t* start, const int32_t* first,
+                              const int32_t* out_start, int32_t num_graphs, int32_t nmax, int32_t* out,
+                              void* stream);
+
 /* ------------------------------------------------------------------ sparse neighbour gather
  * out[r,:] (+)= row_scale[r] * sum_{e in row r} val[e] * src_scale[col[e]] * x[col[e], :]
  * = torch.matmul(adj, x) / adj.sum(-1).clamp(min=1) of DenseSAGEConv.forward (forward: CSR +

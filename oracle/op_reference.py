@@ -130,6 +130,27 @@ class TorchBackend(object):
         edge_index[0, :num_edges] = nbr[valid].long()
         edge_index[1, :num_edges] = centre[valid]
 
+    def farthest_point_sample(self, pos, start, first, out_start, nmax, out):
+        """FarthestSampler.__call__ (common/utils.py:187-197) on the int16 distance matrix of
+        construct_feature_graph.py:17-24 (euc_dist: float64 sqrt, astype(int16)), first index given."""
+        import numpy as np
+        st, ost, fi = start.tolist(), out_start.tolist(), first.tolist()
+        for g in range(len(fi)):
+            p = pos[st[g]:st[g + 1]].double().numpy()
+            k = ost[g + 1] - ost[g]
+            if p.shape[0] == 0 or k <= 0:
+                continue
+            ax = (p[:, 0, np.newaxis].T - p[:, 0, np.newaxis]) ** 2
+            ay = (p[:, 1, np.newaxis].T - p[:, 1, np.newaxis]) ** 2
+            arr = np.sqrt(ax + ay).astype(np.int16)
+            far = np.zeros(k, dtype=np.int32)
+            far[0] = fi[g]
+            dist = arr[far[0]]
+            for i in range(1, k):
+                far[i] = np.argmax(dist)
+                dist = np.minimum(dist, arr[far[i]])
+            out[ost[g]:ost[g + 1]] = torch.from_numpy(far)
+
     # ---------------------------------------------------------------- sparse gather
     def spmm(self, rowptr, col, val, x, src_scale, row_scale, out, accumulate):
         rows = rowptr.numel() - 1

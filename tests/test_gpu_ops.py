@@ -557,3 +557,24 @@ def test_radius_graph_matches_ckdtree(cuda_backend, sizes, r, k, loop):
     assert torch.equal(ei[0], nbr[valid].long()) and torch.equal(ei[1], centre[valid])
     if loop:
         assert torch.equal(nbr[:, 0].long(), torch.arange(sum(sizes)))      # the centre itself comes first
+
+
+@pytest.mark.parametrize('sizes,ratio', [([1800, 700, 33], 0.5), ([2999], 0.35), ([64, 1, 5], 1.0)])
+def test_farthest_point_sample_matches_reference_sampler(cuda_backend, sizes, ratio):
+    """cgc_farthest_point_sample == FarthestSampler on the int16 distance matrix (bit-exact index sequences)."""
+    g = torch.Generator().manual_seed(sum(sizes))
+    pos = torch.rand(sum(sizes), 2, generator=g) * 3584.0
+    start = torch.zeros(len(sizes) + 1, dtype=torch.int32)
+    start[1:] = torch.tensor(sizes).cumsum(0).to(torch.int32)
+    ks = [max(1, int(n * ratio)) for n in sizes]
+    ostart = torch.zeros(len(sizes) + 1, dtype=torch.int32)
+    ostart[1:] = torch.tensor(ks).cumsum(0).to(torch.int32)
+    first = torch.tensor([int(torch.randint(0, n, (1,), generator=g)) for n in sizes], dtype=torch.int32)
+    out = torch.zeros(sum(ks), dtype=torch.int32)
+    both(cuda_backend, 'farthest_point_sample', [pos, start, first, ostart, max(sizes), out], [5])
+    for gi, k in enumerate(ks):
+        ids = out[int(ostart[gi]):int(ostart[gi + 1])]
+        assert int(ids[0]) == int(first[gi]) and int(ids.max()) < sizes[gi]
+    picks = graph.sample_nodes(pos.cuda(), sizes, 0.5, 'fuse', generator=torch.Generator().manual_seed(1))
+    for n, ids in zip(sizes, picks):
+        assert ids.numel() == int(n * 0.5) and ids.unique().numel() == ids.numel() and (n == 1 or int(ids.max()) < n)
