@@ -56,6 +56,8 @@ struct Params {
   int write_hi;      // 1: also store the masked hi tile (not needed: kind::tf32 ignores the low 13 bits)
   int chunk_blocks;  // K-blocks per TMEM accumulation chunk (promotion period), CGC_TC_CHUNK overrides
   int bn;            // N tile (= the kernel's BN template argument)
+  int b_warps;       // pair mode: B lo split on warps 2-3 (CGC_TC_BWARPS, lab switch)
+  int a_first;       // split warps stage A before splitting B (CGC_TC_AFIRST, lab switch)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -361,7 +363,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&xfull[s], PAIR ? 2 * (kSplitThreads / 32) : kSplitThreads);   // pair: one arrival per split warp of both CTAs
+      mbar_init(&xfull[s], PAIR ? 2 * (kSplitThreads / 32 + (p.b_warps ? 2 : 0)) : kSplitThreads);   // pair: one arrival per A / B split warp of both CTAs
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -499,11 +501,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + (size_t)s * kStageBytes;
-        // ---- B: lo tile next to the landed tile (element-wise, layout preserving)
+        auto split_b = [&]() {
+        // ---- B: lo tile next to the landed tile (element-wise, layout preserving); pair: done by warps 2-3
         uint4* bhi = reinterpret_cast<uint4*>(sa + kOperandBytes);
         uint4* blo = bhi + kBBytes / 16;
 #pragma unroll 4
-        for (int i = tid; i < kBBytes / 16; i += kSplitThreads) {
+        for (int i = (PAIR && p.b_warps) ? kBBytes / 16 : tid; i < kBBytes / 16; i += kSplitThreads) {
           const uint4 v = bhi[i];
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
@@ -517,6 +520,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           blo[i] = l;
         }
+        };
+        if (!p.a_first) split_b();
         // ---- A: thread `tid` owns row `tid` of the tile: gather its 32 k-values out of the swizzled
         //      shared-memory tile, split, and store hi | lo into this lane's TMEM columns.
         uint32_t ah[BK], al[BK];
@@ -545,6 +550,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kATmemBase + s * kATmemCols);
         tmem_st32(ta, ah);
         tmem_st32(ta + (uint32_t)BK, al);
+        if (p.a_first) split_b();                      // overlaps the latency of the two tensor-memory stores just issued
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -558,6 +564,38 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
         } else {
           mbar_arrive(&xfull[s]);
+        }
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (PAIR && p.b_warps && (warp == 2 || warp == 3)) {
+    // ================================ B lo split (pair mode) ================================
+    // 64 otherwise idle threads take the element-wise B split off the A-staging warps (measured: those were busy
+    // 87 % of the time and paced the MMA).
+    const int tid = threadIdx.x - 64;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = tile_first; t < p.total_tiles; t += tile_step) {
+      const TileCoord c = tile_coord(p, t, kTileM, rank);
+      for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
+        mbar_wait(&full[s], ph);
+        uint4* bhi = reinterpret_cast<uint4*>(smem + (size_t)s * kStageBytes + kOperandBytes);
+        uint4* blo = bhi + kBBytes / 16;
+#pragma unroll
+        for (int i = tid; i < kBBytes / 16; i += 64) {
+          const uint4 v = bhi[i];
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+          blo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&xfull[s]);
+          else mbar_arrive_cluster(&xfull[s], 0);
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
@@ -740,6 +778,10 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
     return e ? atoi(e) : 0;
   }();
   q.write_hi = write_hi;
+  static const int b_warps = []() { const char* e = getenv("CGC_TC_BWARPS"); return e ? atoi(e) : 0; }();
+  static const int a_first = []() { const char* e = getenv("CGC_TC_AFIRST"); return e ? atoi(e) : 0; }();
+  q.b_warps = b_warps;
+  q.a_first = a_first;
   q.g = p;
 
   CUtensorMap map_a, map_b;
