@@ -195,3 +195,63 @@ def sample_nodes(pos, num_nodes_list, ratio, method='fuse', generator=None):
             ids = torch.cat([ids, extra.to(dev)])
         result.append(ids)
     return result
+
+
+class DevicePrefetcher(object):
+    """Wrap an iterable of HOST ``Batch`` objects (pinned memory) and yield them on ``device``, copying batch
+    ``i + 1`` on a side stream while the caller computes on batch ``i`` -- the loader-side counterpart of the
+    reference's ``DataListLoader(num_workers=...)`` + ``.to(device)`` inside ``DataParallel`` (train.py:174-178,
+    dataflow/data.py:52), so the 23 MB host->device copy of a 64-graph batch leaves the critical path.
+
+    Two persistent device slots (grown on demand) are recycled: no allocator traffic per batch, and a slot is
+    overwritten only after the compute stream has passed the point where its previous batch was handed back."""
+
+    def __init__(self, batches, device, slots=2):
+        self.batches, self.device = batches, torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = [dict(bufs={}, free=None) for _ in range(slots)]
+
+    def _buffer(self, slot, name, host):
+        buf = slot['bufs'].get(name)
+        if buf is None or buf.dtype != host.dtype or buf.numel() < host.numel():
+            buf = torch.empty(max(host.numel(), 1), dtype=host.dtype, device=self.device)
+            slot['bufs'][name] = buf
+        return buf[:host.numel()].view(host.shape)
+
+    def _issue(self, host_batch, slot):
+        views = {}
+        for name in ('x', 'edge_index', 'batch', 'y'):
+            t = getattr(host_batch, name)
+            views[name] = None if t is None else self._buffer(slot, name, t)      # allocation on the caller's stream
+        with torch.cuda.stream(self.stream):
+            if slot['free'] is not None:
+                self.stream.wait_event(slot['free'])           # the slot's previous batch has been consumed
+            for name, dst in views.items():
+                if dst is not None:
+                    dst.copy_(getattr(host_batch, name), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return Batch(views['x'], views['edge_index'], views['batch'], views['y'], host_batch.num_nodes_list), done
+
+    def __iter__(self):
+        it = iter(self.batches)
+        compute = torch.cuda.current_stream(self.device)
+        n = len(self.slots)
+        i = 0
+        try:
+            nxt = self._issue(next(it), self.slots[0])
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, done = nxt
+            i += 1
+            try:
+                nxt = self._issue(next(it), self.slots[i % n])
+            except StopIteration:
+                nxt = None
+            compute.wait_event(done)
+            yield cur
+            # the caller is back: everything it enqueued on the compute stream so far used `cur`
+            free = torch.cuda.Event()
+            free.record(compute)
+            self.slots[(i - 1) % n]['free'] = free

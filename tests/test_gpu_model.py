@@ -242,3 +242,17 @@ def test_gin_and_activations_vs_oracle(gemm_mode, gcn_name, activation, norm_adj
     helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()},
                                **_grad_tol(gemm_mode, norm_adj))
     _check_assignments(ours, orc)
+
+
+def test_device_prefetcher_yields_identical_batches(cuda_backend):
+    """graph.DevicePrefetcher: batches copied on the side stream arrive intact and in order."""
+    batches = [graph.Batch.from_data_list(helpers.make_graphs([50 + i, 31], [5, 4], seed=i)).pin_memory()
+               for i in range(4)]
+    seen = 0
+    for host, dev in zip(batches, graph.DevicePrefetcher(batches, 'cuda:0')):
+        assert dev.x.is_cuda and dev.num_nodes_list == host.num_nodes_list
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(dev.x.cpu(), host.x) and torch.equal(dev.edge_index.cpu(), host.edge_index)
+        assert torch.equal(dev.batch.cpu(), host.batch) and torch.equal(dev.y.cpu(), host.y)
+        seen += 1
+    assert seen == 4
