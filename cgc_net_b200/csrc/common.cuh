@@ -46,10 +46,14 @@ constexpr float kL2NormEps = 1e-12f;    // F.normalize eps
 constexpr float kRenormEps = 1e-15f;    // model/network.py:8
 
 // Row mask in the padded node layout: row r is a real node iff r % nmax < num_nodes[r / nmax].
+// Padded row counts fit 32 bits everywhere in the library (the CSR indices are int32), so the division is a
+// 32-bit one (a 64-bit division costs ~3x the instructions) and the function stays branch-free: it is inlined
+// into load loops whose batching a branch would break.
 __device__ __forceinline__ bool row_valid(const int32_t* __restrict__ num_nodes, int nmax, int64_t r) {
   if (num_nodes == nullptr) return true;
-  int64_t g = r / nmax;
-  return (int)(r - g * nmax) < __ldg(num_nodes + g);
+  const uint32_t ru = (uint32_t)r;
+  const uint32_t g = ru / (uint32_t)nmax;
+  return (int)(ru - g * (uint32_t)nmax) < __ldg(num_nodes + g);
 }
 
 // Activation that follows a conv (GNN_Module._activation, network.py:82-90): 0 relu, 1 elu (alpha 1), 2 leaky relu

@@ -58,7 +58,7 @@ constexpr int kEpiThreads = 256;
 constexpr int kEpiRows = 8;
 
 template <int NC, bool BWD>
-__global__ void __launch_bounds__(kEpiThreads)
+__global__ void __launch_bounds__(kEpiThreads, NC == 1 ? 4 : (NC == 2 ? 3 : 2))
 k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
            const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
            float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
@@ -68,6 +68,7 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
   float* s_w = smem;                                 // [cin][cout]
   float* s_a = s_w + cin * cout;                     // [cin][kEpiRows]  (transposed row tile)
   float* s_red = s_a + cin * kEpiRows;               // [8 warps][kEpiRows]
+  int* s_valid = reinterpret_cast<int*>(s_red + (kEpiThreads / 32) * kEpiRows);   // [kEpiRows] row-mask flags of the tile
   for (int i = threadIdx.x; i < cin * cout; i += kEpiThreads) s_w[i] = w[i];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   float bj[NC];
@@ -84,13 +85,18 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
       int rr = i / cin, k = i - rr * cin;
       s_a[k * kEpiRows + rr] = (r0 + rr < rows) ? __ldg(sa + (r0 + rr) * ldsa + k) : 0.f;
     }
+    // the row mask once per tile (a 64-bit division per row: 8 threads do it instead of every thread 8 times)
+    if (t < kEpiRows) s_valid[t] = (r0 + t < rows && row_valid(num_nodes, nmax, r0 + t)) ? 1 : 0;
     __syncthreads();
+    uint32_t vmask = 0;                              // flags in a register: the row loops below stay branch-free
+#pragma unroll
+    for (int rr = 0; rr < kEpiRows; ++rr) vmask |= (uint32_t)s_valid[rr] << rr;
     float acc[kEpiRows][NC];
 #pragma unroll
     for (int rr = 0; rr < kEpiRows; ++rr)
 #pragma unroll
       for (int j = 0; j < NC; ++j) acc[rr][j] = bj[j];
-    for (int k = 0; k < cin; ++k) {
+    auto k_step = [&](int k) {
       float wv[NC];
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
@@ -104,6 +110,13 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
       for (int rr = 0; rr < kEpiRows; ++rr)
 #pragma unroll
         for (int j = 0; j < NC; ++j) acc[rr][j] = fmaf(av[rr], wv[j], acc[rr][j]);
+    };
+    if constexpr (BWD) {
+      // compiler's own unrolling: forcing a factor (1 or 4) on this register-capped instantiation cost 1.4-2x
+      for (int k = 0; k < cin; ++k) k_step(k);
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < cin; ++k) k_step(k);
     }
     // row norms
     float part[kEpiRows];
@@ -134,7 +147,7 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
       for (int rr = 0; rr < kEpiRows; ++rr) {
         const int64_t r = r0 + rr;
         if (r >= rows) break;
-        const bool valid = row_valid(num_nodes, nmax, r);
+        const bool valid = (vmask >> rr) & 1u;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
           int c = t + kEpiThreads * j;
@@ -147,6 +160,8 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
 #pragma unroll
       for (int rr = 0; rr < kEpiRows; ++rr) {
         const int64_t r = r0 + rr;
+        // (backward: per-thread mask evaluation as in round 1a -- routing it through the shared flags made this
+        //  register-capped instantiation 1.4-2x slower)
         const bool valid = (r < rows) && row_valid(num_nodes, nmax, r);
         float s = 0.f;
 #pragma unroll
@@ -209,7 +224,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
   }
   const int nc = (int)ceil_div(cout, kEpiThreads);
   CGC_REQUIRE(nc <= 5, CGC_ERR_UNSUPPORTED, "sage epilogue: cout=%d > 1280", cout);
-  size_t smem = sizeof(float) * (size_t)(cin * cout + cin * kEpiRows + (kEpiThreads / 32) * kEpiRows);
+  size_t smem = sizeof(float) * (size_t)(cin * cout + cin * kEpiRows + (kEpiThreads / 32) * kEpiRows + kEpiRows);
   CGC_REQUIRE(smem <= 200 * 1024, CGC_ERR_UNSUPPORTED, "sage epilogue: W of %dx%d does not fit in shared memory",
               cin, cout);
   int64_t tiles = ceil_div(rows, kEpiRows);
@@ -237,6 +252,72 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
 }
 
 // =================================================================== softmax over clusters
+// 16-byte global loads in program order (asm volatile: the compiler may not sink them behind their first use),
+// so a lane has all its requests in flight before it waits for the first one
+__device__ __forceinline__ float4 ldg_nc_f4_ordered(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// vectorised variant: c % 4 == 0, 16-byte aligned rows; lane owns float4 chunks lane, lane + 32, ... (NV4 of them)
+template <int NV4>
+__global__ void __launch_bounds__(256)
+k_softmax_fwd_v4(const float* __restrict__ z, int64_t rows, int c, const int32_t* __restrict__ num_nodes, int nmax,
+                 float* __restrict__ s, int64_t lds, float* __restrict__ s_full, int32_t* __restrict__ arg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float* zr = z + r * (int64_t)c;
+  const int c4 = c >> 2;
+  float4 v[NV4];
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const int q = lane + 32 * j;
+    v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (q < c4) v[j] = ldg_nc_f4_ordered(zr + 4 * q);
+  }
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const int i = 4 * (lane + 32 * j);
+    if (v[j].x > m) { m = v[j].x; mi = i; }
+    if (v[j].y > m) { m = v[j].y; mi = i + 1; }
+    if (v[j].z > m) { m = v[j].z; mi = i + 2; }
+    if (v[j].w > m) { m = v[j].w; mi = i + 3; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, m, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const bool on = lane + 32 * j < c4;
+    v[j].x = on ? expf(v[j].x - m) : 0.f; v[j].y = on ? expf(v[j].y - m) : 0.f;
+    v[j].z = on ? expf(v[j].z - m) : 0.f; v[j].w = on ? expf(v[j].w - m) : 0.f;
+    sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  const bool valid = row_valid(num_nodes, nmax, r);
+  float* sr = s + r * lds;
+  float* fr = s_full ? s_full + r * (int64_t)c : nullptr;
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const int q = lane + 32 * j;
+    if (q < c4) {
+      const float4 pv = make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+      *reinterpret_cast<float4*>(sr + 4 * q) = valid ? pv : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fr) *reinterpret_cast<float4*>(fr + 4 * q) = pv;
+    }
+  }
+  if (arg && lane == 0) arg[r] = mi;
+}
+
 // one warp per row, row cached in registers (NREG values per lane)
 template <int NREG>
 __global__ void __launch_bounds__(256)
@@ -247,13 +328,18 @@ k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* _
   if (r >= rows) return;
   const float* zr = z + r * (int64_t)c;
   float v[NREG];
-  float m = -INFINITY;
-  int mi = 0x7fffffff;
+  // all loads first (NREG independent requests in flight per lane), then the running max: a compare inside the
+  // load loop chains every load behind the previous one's DRAM latency (measured: 509 us -> see DESIGN.md)
 #pragma unroll
   for (int j = 0; j < NREG; ++j) {
     int i = lane + 32 * j;
     v[j] = (i < c) ? __ldg(zr + i) : -INFINITY;
-    if (v[j] > m) { m = v[j]; mi = i; }
+  }
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) {
+    if (v[j] > m) { m = v[j]; mi = lane + 32 * j; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -285,6 +371,8 @@ k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* _
   if (arg && lane == 0) arg[r] = mi;
 }
 
+// one warp per row; both rows cached in registers (NREG values per lane), every load issued before the first use
+template <int NREG>
 __global__ void __launch_bounds__(256)
 k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t lds, int64_t rows, int c,
               float* __restrict__ gz) {
@@ -293,11 +381,23 @@ k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t
   if (r >= rows) return;
   const float* g = gs + r * lds;
   const float* p = s + r * lds;
+  float gv[NREG], pv[NREG];
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) {
+    const int i = lane + 32 * j;
+    gv[j] = (i < c) ? __ldg(g + i) : 0.f;
+    pv[j] = (i < c) ? __ldg(p + i) : 0.f;
+  }
   float dot = 0.f;
-  for (int i = lane; i < c; i += 32) dot = fmaf(__ldg(g + i), __ldg(p + i), dot);
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) dot = fmaf(gv[j], pv[j], dot);
   dot = warp_sum(dot);
   float* o = gz + r * (int64_t)c;
-  for (int i = lane; i < c; i += 32) o[i] = p[i] * (g[i] - dot);
+#pragma unroll
+  for (int j = 0; j < NREG; ++j) {
+    const int i = lane + 32 * j;
+    if (i < c) o[i] = pv[j] * (gv[j] - dot);
+  }
 }
 
 // =================================================================== small row helpers
@@ -467,7 +567,11 @@ extern "C" int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const in
   CGC_REQUIRE(c <= 32 * 40, CGC_ERR_UNSUPPORTED, "cgc_softmax_fwd: %d clusters > 1280", c);
   cudaStream_t st = as_stream(stream);
   unsigned grid = (unsigned)ceil_div(rows, 8);
-  if (c <= 128)
+  const bool vec = c % 4 == 0 && lds % 4 == 0 && aligned16(z) && aligned16(s) && (s_full == nullptr || aligned16(s_full));
+  if (vec && c > 128) {
+    if (c <= 512) k_softmax_fwd_v4<4><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
+    else k_softmax_fwd_v4<10><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
+  } else if (c <= 128)
     k_softmax_fwd<4><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
   else if (c <= 512)
     k_softmax_fwd<16><<<grid, 256, 0, st>>>(z, rows, c, num_nodes, nmax, s, lds, s_full, arg);
@@ -480,7 +584,12 @@ extern "C" int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const in
 extern "C" int cgc_softmax_bwd(const float* gs, const float* s, int64_t lds, int64_t rows, int32_t c, float* gz,
                                void* stream) {
   CGC_REQUIRE(gs && s && gz && rows > 0 && c > 0 && lds >= c, CGC_ERR_ARG, "cgc_softmax_bwd: bad args");
-  k_softmax_bwd<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(gs, s, lds, rows, c, gz);
+  CGC_REQUIRE(c <= 1280, CGC_ERR_UNSUPPORTED, "cgc_softmax_bwd: c=%d > 1280", c);
+  const unsigned grid = (unsigned)ceil_div(rows, 8);
+  cudaStream_t st = as_stream(stream);
+  if (c <= 128) k_softmax_bwd<4><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz);
+  else if (c <= 512) k_softmax_bwd<16><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz);
+  else k_softmax_bwd<40><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz);
   CGC_CHECK_LAUNCH("k_softmax_bwd");
   return 0;
 }
