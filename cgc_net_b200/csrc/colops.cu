@@ -63,7 +63,8 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 }
 
 // one warp per column: lanes stride over the row-block partials (fixed order -> deterministic)
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nrb, int c, int col,
+template <typename P>
+__device__ __forceinline__ void reduce_partials(const P* __restrict__ partial, int nrb, int c, int col,
                                                 double& t1, double& t2) {
   const int lane = threadIdx.x & 31;
   t1 = 0.0;
@@ -76,8 +77,9 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   t2 = warp_sum_f64(t2);
 }
 
+template <typename P>
 __global__ void __launch_bounds__(256)
-k_bn_finalize(const float* __restrict__ partial, int nrb, int c, int64_t rows, float* __restrict__ running_mean,
+k_bn_finalize(const P* __restrict__ partial, int nrb, int c, int64_t rows, float* __restrict__ running_mean,
               float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
               float* __restrict__ invstd) {
   int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -304,6 +306,94 @@ __global__ void k_colmax_bwd(const float* __restrict__ g, const int32_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------ fused narrow SAGE layer, forward
+// y = act(l2normalize(sa W + b) * mask) for cout <= 32, cin <= 64, PLUS the BatchNorm column sums of y in the same
+// pass: one thread per row (the warp-per-row epilogue spent its time in shuffles: 36 us for a 9 MB tensor), the
+// 256-row tile staged through shared memory so that both the sa reads and the y writes are coalesced, W read as
+// warp-wide broadcasts.  Each CTA leaves sum / sum-of-squares partials in the layout k_bn_finalize reads, so the
+// separate statistics pass over y (k_colreduce<stats>) disappears.
+constexpr int kNfThreads = 256;
+
+__global__ void __launch_bounds__(kNfThreads)
+k_sage_fwd_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
+                  const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout, int act,
+                  float* __restrict__ y, int64_t ldy, double* __restrict__ partial) {
+  extern __shared__ float nf_smem[];
+  const int sa_stride = cin | 1;                         // odd strides: conflict-free row-per-thread access
+  const int sy_stride = cout | 1;
+  float* s_w = nf_smem;                                  // [cin][32]
+  float* s_b = s_w + cin * 32;                           // [32]
+  float* s_a = s_b + 32;                                 // [256][sa_stride]
+  float* s_y = s_a + kNfThreads * sa_stride;             // [256][sy_stride]
+  __shared__ double s_p[(kNfThreads / 32) * 2 * 32];     // [8 warps][2][32] column sums (double: var = E[y^2] - mean^2 cancels)
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < cin * 32; i += kNfThreads) {
+    const int k = i >> 5, c = i & 31;
+    s_w[i] = c < cout ? __ldg(w + k * cout + c) : 0.f;
+  }
+  if (t < 32) s_b[t] = (bias && t < cout) ? __ldg(bias + t) : 0.f;
+  double tot1 = 0.0, tot2 = 0.0;                         // this thread's column (lane < cout) over warp's rows, all tiles
+  const int64_t ntiles = (rows + kNfThreads - 1) / kNfThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kNfThreads;
+    const int nr = (int)min((int64_t)kNfThreads, rows - r0);
+    __syncthreads();                                     // previous tile's s_a / s_y consumed (and s_w staged)
+    for (int i = t; i < nr * cin; i += kNfThreads) {     // coalesced when ldsa == cin (row-major contiguous tile)
+      const int rr = i / cin, k = i - rr * cin;
+      s_a[rr * sa_stride + k] = __ldg(sa + (r0 + rr) * ldsa + k);
+    }
+    __syncthreads();
+    if (t < nr) {
+      float h[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) h[c] = s_b[c];
+      const float* arow = s_a + t * sa_stride;
+      for (int k = 0; k < cin; ++k) {
+        const float a = arow[k];
+        const float4* wr = reinterpret_cast<const float4*>(s_w + k * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wv = wr[c4];
+          h[4 * c4] = fmaf(a, wv.x, h[4 * c4]); h[4 * c4 + 1] = fmaf(a, wv.y, h[4 * c4 + 1]);
+          h[4 * c4 + 2] = fmaf(a, wv.z, h[4 * c4 + 2]); h[4 * c4 + 3] = fmaf(a, wv.w, h[4 * c4 + 3]);
+        }
+      }
+      float n2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) n2 = fmaf(h[c], h[c], n2);          // padded columns are exactly 0
+      const float inv = 1.0f / fmaxf(sqrtf(n2), kL2NormEps);
+      const bool valid = row_valid(num_nodes, nmax, r0 + t);
+      float* yrow = s_y + t * sy_stride;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < cout) yrow[c] = valid ? act_fwd(act, h[c] * inv) : 0.f;
+    }
+    __syncthreads();
+    for (int i = t; i < nr * cout; i += kNfThreads) {    // coalesced write-out
+      const int rr = i / cout, c = i - rr * cout;
+      y[(r0 + rr) * ldy + c] = s_y[rr * sy_stride + c];
+    }
+    if (lane < cout) {                                   // column sums over this warp's 32 rows of the tile
+      const int rbeg = warp * 32, rend = min(nr, rbeg + 32);
+      for (int rr = rbeg; rr < rend; ++rr) {
+        const double v = (double)s_y[rr * sy_stride + lane];
+        tot1 += v;
+        tot2 = fma(v, v, tot2);
+      }
+    }
+  }
+  s_p[(warp * 2 + 0) * 32 + lane] = tot1;
+  s_p[(warp * 2 + 1) * 32 + lane] = tot2;
+  __syncthreads();
+  if (t < 2 * cout) {
+    const int which = t / cout, c = t - which * cout;
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kNfThreads / 32; ++wv) v += s_p[(wv * 2 + which) * 32 + c];
+    partial[((int64_t)blockIdx.x * 2 + which) * cout + c] = v;
+  }
+}
+
 static void reduce_geometry(int64_t rows, int c, int& nrb, int64_t& rows_per_block, dim3& grid) {
   int colblocks = (int)ceil_div(c, kRedX);
   int64_t want = ceil_div((int64_t)kNumSMs * 6, colblocks);
@@ -334,7 +424,7 @@ extern "C" int cgc_bn_stats(const float* y, int64_t ldy, int64_t rows, int32_t c
   k_colreduce<RED_STATS><<<grid, dim3(kRedX, kRedY), 0, st>>>(y, ldy, nullptr, 0, nullptr, nullptr, nullptr, 0, rows,
                                                               c, rpb, partial);
   CGC_CHECK_LAUNCH("k_colreduce<stats>");
-  k_bn_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, rows, running_mean, running_var,
+  k_bn_finalize<float><<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, rows, running_mean, running_var,
                                                             momentum, eps, mean, invstd);
   CGC_CHECK_LAUNCH("k_bn_finalize");
   return 0;
@@ -463,5 +553,34 @@ extern "C" int cgc_colmax_bwd(const float* g, const int32_t* arg, int32_t num_gr
   k_colmax_bwd<<<(unsigned)ceil_div((int64_t)num_graphs * c, 256), 256, 0, as_stream(stream)>>>(g, arg, num_graphs,
                                                                                                nmax, c, gx);
   CGC_CHECK_LAUNCH("k_colmax_bwd");
+  return 0;
+}
+
+extern "C" int cgc_sage_layer_fwd_narrow(const float* sa, int64_t ldsa, const float* w, const float* b,
+                                         const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
+                                         int32_t cout, int act, float* y, int64_t ldy, float* running_mean,
+                                         float* running_var, float momentum, float eps, float* mean, float* invstd,
+                                         void* work, int64_t work_bytes, void* stream) {
+  CGC_REQUIRE(sa && w && y && mean && invstd && work && rows > 0 && cin > 0 && cout > 0 && ldsa >= cin && ldy >= cout,
+              CGC_ERR_ARG, "cgc_sage_layer_fwd_narrow: bad args");
+  CGC_REQUIRE(cout <= 32 && cin <= 64, CGC_ERR_UNSUPPORTED,
+              "cgc_sage_layer_fwd_narrow: needs cout <= 32 and cin <= 64 (got %d, %d)", cout, cin);
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_layer_fwd_narrow: mask without nmax");
+  CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG,
+              "cgc_sage_layer_fwd_narrow: unknown activation %d", act);
+  const size_t smem = sizeof(float) * ((size_t)cin * 32 + 32 + (size_t)kNfThreads * ((cin | 1) + (cout | 1)));
+  int64_t blocks = ceil_div(rows, kNfThreads);
+  const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((200 * 1024) / (smem + 1024));
+  if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;
+  CGC_REQUIRE(blocks * 2 * cout * 8 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_sage_layer_fwd_narrow: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  double* partial = reinterpret_cast<double*>(work);
+  CGC_CUDA(cudaFuncSetAttribute(k_sage_fwd_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sage_fwd_narrow<<<(unsigned)blocks, kNfThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, act, y,
+                                                               ldy, partial);
+  CGC_CHECK_LAUNCH("k_sage_fwd_narrow");
+  k_bn_finalize<double><<<(unsigned)ceil_div(cout, 8), 256, 0, st>>>(partial, (int)blocks, cout, rows, running_mean, running_var,
+                                                               momentum, eps, mean, invstd);
+  CGC_CHECK_LAUNCH("k_bn_finalize");
   return 0;
 }

@@ -210,16 +210,20 @@ class GnnModuleFunction(Function):
             a = _f32(m, w.shape[0], device=dev)          # sa = rs * (A x)
             _agg(be, cfg, adj, rs, x_prev, a)
             y = _f32(m, couts[k], device=dev)
-            be.sage_epilogue_fwd(a, w, b, cfg.mask, y, cfg.act)
             dst = cat[:, off: off + couts[k]]
             mean = invstd = None
             if cfg.has_bn:
                 mean = _f32(couts[k], device=dev)
                 invstd = _f32(couts[k], device=dev)
                 rmean, rvar = cfg.bn_buffers[k]
-                if cfg.training:
+            if cfg.has_bn and cfg.training and couts[k] <= 32 and w.shape[0] <= 64:
+                # narrow layer: epilogue and BatchNorm batch statistics in ONE pass over the rows
+                be.sage_layer_fwd_narrow(a, w, b, cfg.mask, y, cfg.act, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
+            else:
+                be.sage_epilogue_fwd(a, w, b, cfg.mask, y, cfg.act)
+                if cfg.has_bn and cfg.training:
                     be.bn_stats(y, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
-                else:
+                elif cfg.has_bn:
                     be.bn_eval_stats(rmean, rvar, BN_EPS, mean, invstd)
             be.bn_apply(y, mean, invstd, gamma if cfg.has_bn else None,
                         beta if cfg.has_bn else None, cfg.mask, dst)

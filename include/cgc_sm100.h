@@ -182,6 +182,16 @@ CGC_API int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w,
                           const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
                           int32_t cout, int act, float* y, int64_t ldy, void* stream);
 
+/* Fused narrow layer forward (cout <= 32, cin <= 64, training mode): cgc_sage_epilogue_fwd AND cgc_bn_stats of
+ * its output in one pass over the rows (thread per row, coalesced tile staging, per-CTA column-sum partials in
+ * `work`, the same deterministic double-precision finalize): y as above; mean / invstd / running stats as
+ * cgc_bn_stats(y). */
+CGC_API int cgc_sage_layer_fwd_narrow(const float* sa, int64_t ldsa, const float* w, const float* b,
+                              const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
+                              int32_t cout, int act, float* y, int64_t ldy, float* running_mean,
+                              float* running_var, float momentum, float eps, float* mean, float* invstd,
+                              void* work, int64_t work_bytes, void* stream);
+
 /* dh = d loss / d (sa @ W + b) given gy = d loss / d y.  dh may alias gy. */
 CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,
                 const float* b, const float* y, int64_t ldy, const int32_t* num_nodes,

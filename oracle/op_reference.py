@@ -308,6 +308,10 @@ class TorchBackend(object):
         h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
         y.copy_(self._act(act, h * inv * valid))
 
+    def sage_layer_fwd_narrow(self, sa, w, b, mask, y, act, rmean, rvar, momentum, eps, mean, invstd):
+        self.sage_epilogue_fwd(sa, w, b, mask, y, act)
+        self.bn_stats(y, rmean, rvar, momentum, eps, mean, invstd)
+
     def sage_dh(self, gy, sa, w, b, y, mask, dh, act=0):
         h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
         hn = h * inv

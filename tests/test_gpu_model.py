@@ -43,7 +43,9 @@ def gemm_mode(request, cuda_backend):
 def _grad_tol(mode, norm_adj=False):
     if mode == 'tcgen05':
         return dict(tol=3e-3, slack=20.0)
-    return dict(tol=1e-3, slack=10.0) if norm_adj else dict(tol=3e-4, slack=10.0)
+    # floor: tensors whose largest gradient is below 2e-3 (tiny pool stages) are residues of cancellation; their
+    # absolute fp32 rounding noise is ~5e-7 whatever the summation order (measured: 3.6e-7 on GCN_pool_2.gcn2.bias)
+    return dict(tol=1e-3, slack=10.0, floor=2e-3) if norm_adj else dict(tol=3e-4, slack=10.0, floor=2e-3)
 
 
 def _run_pair(ours, orc, batch, dense=None):

@@ -578,3 +578,24 @@ def test_farthest_point_sample_matches_reference_sampler(cuda_backend, sizes, ra
     picks = graph.sample_nodes(pos.cuda(), sizes, 0.5, 'fuse', generator=torch.Generator().manual_seed(1))
     for n, ids in zip(sizes, picks):
         assert ids.numel() == int(n * 0.5) and ids.unique().numel() == ids.numel() and (n == 1 or int(ids.max()) < n)
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 20), (20, 20), (60, 20), (33, 32), (5, 3)])
+@pytest.mark.parametrize('act', [0, 1])
+def test_sage_layer_fwd_narrow(cuda_backend, cin, cout, act):
+    """Fused narrow forward (epilogue + BatchNorm statistics in one pass) == epilogue followed by bn_stats;
+    strided sa / y (column slices), ragged row mask, several tiles per CTA."""
+    b, nmax = 5, 1237
+    rows = b * nmax
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    saw = torch.randn(rows, cin + 8, generator=g)
+    sa = saw[:, 4:4 + cin]
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax)
+    yw = torch.zeros(rows, cout + 4)
+    y = yw[:, 0:cout]
+    rmean, rvar = torch.randn(cout, generator=g), torch.rand(cout, generator=g) + 0.5
+    mean, invstd = torch.zeros(cout), torch.zeros(cout)
+    both(cuda_backend, 'sage_layer_fwd_narrow', [sa, w, bias, mask, y, act, rmean, rvar, 0.1, 1e-5, mean, invstd],
+         [4, 6, 7, 10, 11], rtol=1e-5, atol=1e-6)
