@@ -394,6 +394,53 @@ k_sage_fwd_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __res
   }
 }
 
+// BatchNorm-backward column sums for narrow matrices (c <= 32): sum_r g and sum_r g * xhat with g = gx * mask.
+// The generic k_colreduce gives 32 lanes to the columns of ONE row (20 of them busy, 80-byte requests); here a
+// CTA stages a 256-row tile of gx and y with coalesced loads and each warp reduces its 32 rows per column.
+__global__ void __launch_bounds__(kNfThreads)
+k_bn_bwd_sums_narrow(const float* __restrict__ gx, int64_t ldgx, const float* __restrict__ y, int64_t ldy,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int c,
+                     float* __restrict__ partial) {
+  constexpr int kRows = 128;                       // rows per tile (2 x 128 x 33 floats of static shared memory)
+  __shared__ float s_g[kRows * 33], s_x[kRows * 33];
+  __shared__ float s_p[(kNfThreads / 32) * 2 * 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float mu = lane < c ? __ldg(mean + lane) : 0.f, is = lane < c ? __ldg(invstd + lane) : 0.f;
+  float tot1 = 0.f, tot2 = 0.f;
+  const int64_t ntiles = (rows + kRows - 1) / kRows;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kRows;
+    const int nr = (int)min((int64_t)kRows, rows - r0);
+    __syncthreads();
+    for (int i = t; i < nr * c; i += kNfThreads) {
+      const int rr = i / c, k = i - rr * c;
+      const int64_t r = r0 + rr;
+      s_g[rr * 33 + k] = __ldg(gx + r * ldgx + k);
+      s_x[rr * 33 + k] = __ldg(y + r * ldy + k);
+    }
+    __syncthreads();
+    if (lane < c) {
+      const int rbeg = warp * (kRows / 8), rend = min(nr, rbeg + kRows / 8);
+      for (int rr = rbeg; rr < rend; ++rr) {
+        const float g = row_valid(num_nodes, nmax, r0 + rr) ? s_g[rr * 33 + lane] : 0.f;
+        tot1 += g;
+        tot2 = fmaf(g, (s_x[rr * 33 + lane] - mu) * is, tot2);
+      }
+    }
+  }
+  s_p[(warp * 2 + 0) * 32 + lane] = tot1;
+  s_p[(warp * 2 + 1) * 32 + lane] = tot2;
+  __syncthreads();
+  if (t < 2 * c) {
+    const int which = t / c, col = t - which * c;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kNfThreads / 32; ++wv) v += s_p[(wv * 2 + which) * 32 + col];
+    partial[((int64_t)blockIdx.x * 2 + which) * c + col] = v;
+  }
+}
+
 static void reduce_geometry(int64_t rows, int c, int& nrb, int64_t& rows_per_block, dim3& grid) {
   int colblocks = (int)ceil_div(c, kRedX);
   int64_t want = ceil_div((int64_t)kNumSMs * 6, colblocks);
@@ -490,12 +537,22 @@ extern "C" int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t
   int64_t rpb;
   dim3 grid;
   reduce_geometry(rows, c, nrb, rpb, grid);
-  CGC_REQUIRE((int64_t)nrb * 2 * c * 4 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_bn_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   float* partial = reinterpret_cast<float*>(work);
-  k_colreduce<RED_BN_BWD><<<grid, dim3(kRedX, kRedY), 0, st>>>(gx, ldgx, y, ldy, mean, invstd, num_nodes, nmax, rows,
-                                                               c, rpb, partial);
-  CGC_CHECK_LAUNCH("k_colreduce<bn_bwd>");
+  if (c <= 32) {
+    int64_t blocks = ceil_div(rows, 128);
+    if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
+    nrb = (int)blocks;
+    CGC_REQUIRE((int64_t)nrb * 2 * c * 4 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_bn_bwd: workspace too small");
+    k_bn_bwd_sums_narrow<<<(unsigned)blocks, kNfThreads, 0, st>>>(gx, ldgx, y, ldy, mean, invstd, num_nodes, nmax, rows,
+                                                                 c, partial);
+    CGC_CHECK_LAUNCH("k_bn_bwd_sums_narrow");
+  } else {
+    CGC_REQUIRE((int64_t)nrb * 2 * c * 4 <= work_bytes, CGC_ERR_WORKSPACE, "cgc_bn_bwd: workspace too small");
+    k_colreduce<RED_BN_BWD><<<grid, dim3(kRedX, kRedY), 0, st>>>(gx, ldgx, y, ldy, mean, invstd, num_nodes, nmax, rows,
+                                                                 c, rpb, partial);
+    CGC_CHECK_LAUNCH("k_colreduce<bn_bwd>");
+  }
   k_sum_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, d_beta, d_gamma);
   CGC_CHECK_LAUNCH("k_sum_finalize");
   const bool vec = c >= 64 && c % 4 == 0 && ldgx % 4 == 0 && ldy % 4 == 0 && ldgy % 4 == 0 && aligned16(gx) &&
