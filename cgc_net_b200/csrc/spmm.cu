@@ -626,15 +626,15 @@ static int launch_ell(const uint16_t* ell, const float* ellw, const float* ell_s
   const size_t smem = ((size_t)nmax + 2) * feat * 4;
   CGC_REQUIRE(smem + 1024 <= 227 * 1024, CGC_ERR_UNSUPPORTED,
               "cgc_sage_gather_ell_fwd: feature tile of %lld B does not fit in shared memory", (long long)smem);
-  int parts = kNumSMs / num_graphs;
-  if (const char* e = getenv("CGC_GATHER_PARTS")) parts = atoi(e);
+  static const int parts_override = []() { const char* e = getenv("CGC_GATHER_PARTS"); return e ? atoi(e) : 0; }();
+  static const int chunk_override = []() { const char* e = getenv("CGC_GATHER_CHUNK"); return e ? atoi(e) : 0; }();
+  int parts = parts_override > 0 ? parts_override : kNumSMs / num_graphs;       // lab switches, read once
   if (parts < 1) parts = 1;
   const int nrow8 = (nmax + 7) & ~7;
   int rpp = (int)ceil_div(nrow8, parts);
   rpp = (rpp + 7) & ~7;                                 // CTAs own whole 8-row blocks of the table
   parts = (int)ceil_div(nrow8, rpp);
-  uint32_t chunk = kBulkChunk;
-  if (const char* e = getenv("CGC_GATHER_CHUNK")) chunk = (uint32_t)atoi(e);
+  const uint32_t chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
   auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS>;
   CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<num_graphs * parts, THREADS, smem, st>>>(ell, ellw, ell_scale, perm, rowptr, col, val, x, nmax, feat, parts, rpp,

@@ -259,3 +259,73 @@ def test_radius_graph_wrapper_feeds_the_encoder(torch_backend):
     ours.eval(), orc.eval()
     with torch.no_grad():
         assert helpers.rel_err(ours(batch), orc(batch)) < 1e-4
+
+
+def test_compat_data_containers_and_loaders():
+    """cgc_net_b200.compat: the torch_geometric 1.2.1 surface the reference's loaders use (dataflow/data.py:4-11)."""
+    from cgc_net_b200 import compat
+    d = compat.Data(x=torch.randn(5, 3), edge_index=torch.tensor([[0, 1], [1, 2]]), y=torch.tensor([1]),
+                    pos=torch.rand(5, 2), patch_idx=torch.tensor([7]))
+    assert d.num_nodes == 5 and set(k for k, _ in d) >= {'x', 'edge_index', 'y', 'pos', 'patch_idx'}
+    choice = torch.tensor([4, 0, 2])
+    for key, item in d:                                   # the reference's node subsampling idiom (data.py:241-243)
+        if torch.is_tensor(item) and item.size(0) == 5:
+            d[key] = item[choice]
+    assert d.x.shape == (3, 3) and d.pos.shape == (3, 2)
+
+    class DS(compat.Dataset):
+        def __init__(self):
+            super(DS, self).__init__(root=None)
+
+        def __len__(self):
+            return 4
+
+        def get(self, idx):
+            g = graph.synthetic_cell_graph(6 + idx, 3, 4, seed=idx)
+            return compat.Data(x=g.x, edge_index=g.edge_index, y=g.y, pos=g.pos, patch_idx=torch.tensor([idx]))
+
+    lists = list(compat.DataListLoader(DS(), batch_size=2))
+    assert len(lists) == 2 and isinstance(lists[0], list) and lists[0][1].num_nodes == 7
+    batches = list(compat.DataLoader(DS(), batch_size=4))
+    b = batches[0]
+    assert b.num_graphs == 4 and b.x.shape[0] == 6 + 7 + 8 + 9 and b.patch_idx.tolist() == [0, 1, 2, 3]
+    assert int(b.edge_index.max()) < b.x.shape[0] and b.batch.tolist() == sorted(b.batch.tolist())
+    # utils
+    ei = torch.tensor([[0, 2, 2], [1, 0, 2]])
+    adj = compat.sparse_to_dense(ei)
+    assert adj.tolist() == [[0, 1, 0], [0, 0, 0], [1, 0, 1]]
+    back, _ = compat.dense_to_sparse(adj)
+    assert sorted(map(tuple, back.t().tolist())) == sorted(map(tuple, ei.t().tolist()))
+    dense, counts = compat.to_dense_batch(torch.arange(5.0).view(5, 1), torch.tensor([0, 0, 1, 1, 1]))
+    assert counts.tolist() == [2, 3] and dense.shape == (2, 3, 1) and float(dense[0, 2, 0]) == 0.0
+
+
+def test_compat_radius_graph_cpu_matches_kernel_semantics(torch_backend):
+    """CPU path of compat.radius_graph (cKDTree, as torch_cluster does) == the per-operator formula of the GPU
+    kernel; flow argument; loop=False drops the centre."""
+    from cgc_net_b200 import compat
+    g = torch.Generator().manual_seed(3)
+    pos = torch.rand(50, 2, generator=g) * 200.0
+    batch = torch.cat([torch.zeros(30, dtype=torch.long), torch.ones(20, dtype=torch.long)])
+    a = compat.radius_graph(pos, 60.0, batch, True, 5)
+    b = graph.radius_graph(pos, 60.0, batch, True, 5)                 # library path (CPU formulas injected)
+    assert torch.equal(a, b)
+    t2s = compat.radius_graph(pos, 60.0, batch, True, 5, flow='target_to_source')
+    assert torch.equal(t2s, a.flip(0))
+    noloop = compat.radius_graph(pos, 60.0, batch, False, 5)
+    assert bool((noloop[0] != noloop[1]).all())
+
+
+@pytest.mark.parametrize('method', ['random', 'farthest', 'fuse'])
+def test_sample_nodes_counts_and_uniqueness(torch_backend, method):
+    """graph.sample_nodes (dataflow/data.py:195-225): int(n * ratio) distinct local ids per graph; the farthest-point
+    prefix is reproducible from the generator seed."""
+    g = torch.Generator().manual_seed(11)
+    sizes = [40, 25, 3]
+    pos = torch.rand(sum(sizes), 2, generator=g) * 500.0
+    picks = graph.sample_nodes(pos, sizes, 0.5, method, generator=torch.Generator().manual_seed(5))
+    again = graph.sample_nodes(pos, sizes, 0.5, method, generator=torch.Generator().manual_seed(5))
+    for n, ids, ids2 in zip(sizes, picks, again):
+        assert ids.numel() == int(n * 0.5) and ids.unique().numel() == ids.numel()
+        assert ids.numel() == 0 or (int(ids.min()) >= 0 and int(ids.max()) < n)
+        assert torch.equal(ids, ids2)
