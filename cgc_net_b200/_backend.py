@@ -48,6 +48,8 @@ _SIGNATURES = {
                          _c_vp],
     'cgc_sage_gather_ell_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32,
                                 _c_i32, _c_vp, _c_vp],
+    'cgc_gather_wide_ell': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32,
+                            _c_i32, _c_vp, _c_i64, _c_int, _c_vp],
     'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_sage_layer_fwd_narrow': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp,
                                   _c_i64, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
@@ -265,6 +267,16 @@ class CudaBackend(object):
                                                      _ptr(x, torch.float32), num_graphs, nmax, x.shape[1],
                                                      _ptr(out, torch.float32), self._stream()),
                     'cgc_sage_gather_ell_fwd')
+
+    def gather_wide_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
+                        accumulate):
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        self._check(self.lib.cgc_gather_wide_ell(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32),
+                                                 _ptr(ell_scale, torch.float32), _ptr(perm, torch.int32), width,
+                                                 _ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                                 _ptr(val, torch.float32), xp, ldx, num_graphs, nmax, x.shape[1],
+                                                 op, ldo, int(accumulate), self._stream()), 'cgc_gather_wide_ell')
 
     # -- SAGE epilogue
     def sage_epilogue_fwd(self, sa, w, b, mask, y, act=0):

@@ -8,6 +8,7 @@
 //
 // Reference arithmetic: torch.matmul(adj, x) / adj.sum(-1).clamp(min=1) of PyG 1.2.1
 // DenseSAGEConv.forward (call sites model/network.py:114-116) and adj @ s of _diff_pool (:207).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -502,6 +503,162 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
   }
 }
 
+
+// ------------------------------------------------------------------ wide gather over the ELL16 table
+// out[r, :] (+)= scale[r] * sum_e val[e] * x[col[e], :] for wide feature matrices (A*S of _diff_pool, F = 1140, and
+// its transpose in the backward).  The generic k_spmm reads every x row once per referencing edge through L2
+// (8x 525 MB at the BASELINE shape: L2-bandwidth bound, 425 us); here a work item is (graph, 16-column slice): the
+// slice of the graph's rows -- a strided [nmax, 16] tile -- is brought into shared memory ONCE by 2-D TMA
+// (cp.async.bulk.tensor, boxes of 16 columns x `box_rows` rows), the rows are gathered from shared memory exactly
+// like in k_sage_gather_ell, and the CTA (persistent, one per SM) double-buffers: the tile of item i+1 lands
+// while item i is gathered.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+constexpr int kWideThreads = 1024;
+constexpr int kWideCols = 16;                // columns per slice (64-byte shared-memory rows, as in the F = 16 gather)
+
+template <int W, bool WEIGHTED, int RB>                  // RB = rows per thread and batch
+__global__ void __launch_bounds__(kWideThreads, 1)
+k_gather_wide_ell(const __grid_constant__ CUtensorMap map_x, const uint16_t* __restrict__ ell,
+                  const float* __restrict__ ellw, const float* __restrict__ ell_scale,
+                  const uint32_t* __restrict__ perm, const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const float* __restrict__ val, int num_graphs, int nmax, int feat, int box_rows, int nbuf,
+                  float* __restrict__ out, int64_t ldo, int accumulate) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int G = kWideThreads / 4;
+  constexpr int NW = W / 2;
+  const int nrow8 = (nmax + 7) & ~7;
+  const int nboxes = (nmax + box_rows - 1) / box_rows;
+  const uint32_t buf_rows = (uint32_t)max(nboxes * box_rows, nmax + 2);          // tile (+ TMA overhang), >= 2 zero rows
+  const uint32_t buf_bytes = buf_rows * 64u;
+  const uint32_t tile_tx = (uint32_t)nboxes * (uint32_t)box_rows * 64u;
+  const int nslices = (feat + kWideCols - 1) / kWideCols;
+  const int64_t nitems = (int64_t)num_graphs * nslices;
+  __shared__ __align__(8) uint64_t full[2];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t item, int b) {                 // thread 0: all boxes of one tile onto full[b]
+    const int g = (int)(item / nslices), sidx = (int)(item - (int64_t)g * nslices);
+    mbar_expect_tx(&full[b], tile_tx);
+    for (int bx = 0; bx < nboxes; ++bx)
+      tma_load_2d(smem_raw + (size_t)b * buf_bytes + (size_t)bx * box_rows * 64, &map_x, sidx * kWideCols,
+                  g * nmax + bx * box_rows, &full[b]);
+  };
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  if (tid == 0) {
+    if (first < nitems) issue(first, 0);
+    if (nbuf > 1 && first + step < nitems) issue(first + step, 1);
+  }
+  const int sl = tid & 3, grp = tid >> 2;
+  const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
+  const uint32_t ovf_mark = (uint32_t)nmax + 1u;
+  uint32_t ph0 = 0u, ph1 = 0u;                            // barrier parities (scalars: no local-memory array)
+  int it = 0;
+  for (int64_t item = first; item < nitems; item += step, ++it) {
+    const int b = nbuf > 1 ? (it & 1) : 0;
+    const int g = (int)(item / nslices), sidx = (int)(item - (int64_t)g * nslices);
+    const int c0 = sidx * kWideCols + sl * 4;             // first output column of this lane
+    const bool lane_on = c0 < feat;
+    const int64_t grow0 = (int64_t)g * nmax;
+    const int64_t trow0 = (int64_t)g * nrow8;
+    const uint32_t tile_base = smem_u32(smem_raw) + (uint32_t)b * buf_bytes;
+    const uint32_t lane_base = tile_base + (uint32_t)sl * 16u;
+    if (b == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1u; }
+    else { mbar_wait(&full[1], ph1); ph1 ^= 1u; }
+    // zero rows for empty slots / overflow marks (the TMA overhang may have landed there)
+    if (tid < 32) reinterpret_cast<float*>(smem_raw + (size_t)b * buf_bytes)[(size_t)nmax * 16 + tid] = 0.f;
+    __syncthreads();
+    for (int i0 = 0; i0 * G < nrow8; i0 += RB) {
+      uint32_t idx[RB][NW];
+      float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
+      float rsc[RB];
+      uint32_t pw[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int t = (i0 + i) * G + grp;
+        const bool on = t < nrow8;
+        const int64_t trow = trow0 + (on ? t : 0);
+        pw[i] = on ? __ldg(perm + (trow >> 3)) : 0xFFFFFFFFu;
+        rsc[i] = (on && ell_scale != nullptr) ? __ldg(ell_scale + trow) : 1.0f;
+#pragma unroll
+        for (int q = 0; q < NW / 4; ++q) {
+          uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
+          if (on) v = ldg_u4(ell + trow * W + q * 8);
+          idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
+        }
+        if (WEIGHTED) {
+#pragma unroll
+          for (int q = 0; q < W / 4; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on) v = ldg_f4(ellw + trow * W + q * 4);
+            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
+            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
+            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
+            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int t = (i0 + i) * G + grp;
+        if (t >= nrow8) continue;
+        const int lrow = (t & ~7) + (int)((pw[i] >> (3 * (t & 7))) & 7u);
+        if (lrow >= nmax) continue;
+        const int64_t row = grow0 + lrow;
+        float4 o;
+        if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
+          F32x4 acc;
+          acc.lo = 0ull; acc.hi = 0ull;
+#pragma unroll
+          for (int u = 0; u < W; ++u) {
+            const uint32_t j = ell_slot(idx[i], u);
+            const F32x4 v = lds_x4(lane_base + j * 64u);
+            if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
+            else add_x4(acc, v);
+          }
+          o = unpack_x4(acc);
+        } else {
+          const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+          o = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = e0; k < e1; ++k) {
+            const uint32_t j = (uint32_t)(__ldg(col + k) - (int)grow0);
+            const float w = WEIGHTED ? __ldg(val + k) : 1.0f;
+            const float4 v = lds_f4(lane_base + j * 64u);
+            o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y); o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
+          }
+        }
+        if (lane_on) {
+          const float s = rsc[i];
+          o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+          float4* dst = reinterpret_cast<float4*>(out + row * ldo + c0);
+          if (accumulate) {
+            const float4 old = *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *dst = o;
+        }
+      }
+    }
+    __syncthreads();                                      // everyone is done with buffer b
+    if (tid == 0) {
+      const int64_t nxt = item + (nbuf > 1 ? 2 : 1) * step;
+      if (nxt < nitems) issue(nxt, b);
+    }
+  }
+}
+
 }  // namespace cgc
 
 using namespace cgc;
@@ -675,4 +832,77 @@ extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val
     else            { if (wt) CGC_ELL(16, 8, true, 1, 512); else CGC_ELL(16, 8, false, 4, 512); }
   }
 #undef CGC_ELL
+}
+
+// 2-D tensor map {feat, rows} over a row-major fp32 matrix, box = {16 columns, box_rows rows}, no swizzle
+static bool make_slice_map(CUtensorMap* map, const float* base, uint64_t feat, uint64_t rows, int64_t ld,
+                           uint32_t box_rows) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(sym);
+    return nullptr;
+  }();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {feat, rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kWideCols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+extern "C" int cgc_gather_wide_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                                   const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                                   const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
+                                   int32_t feat, float* out, int64_t ldo, int accumulate, void* stream) {
+  CGC_REQUIRE(ell && perm && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
+              "cgc_gather_wide_ell: bad args");
+  CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_gather_wide_ell: width must be 8 or 16");
+  CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
+              "cgc_gather_wide_ell: val and ell_val must be given together");
+  CGC_REQUIRE(feat % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ldx >= feat && ldo >= feat && aligned16(x) &&
+                  aligned16(out) && aligned16(ell) && (ell_val == nullptr || aligned16(ell_val)),
+              CGC_ERR_UNSUPPORTED, "cgc_gather_wide_ell: needs feat, ldx, ldo multiples of 4 and 16B-aligned pointers");
+  // box rows: as large as possible (<= 256) with the smallest overhang past nmax; two buffers if they fit
+  const int64_t budget = 227 * 1024 - 256;
+  int best_box = 0, nbuf = 0;
+  for (int want = 2; want >= 1 && best_box == 0; --want) {
+    int64_t best_rows = -1;
+    for (int box = 256; box >= 8; box -= 8) {
+      const int64_t rows_alloc = ceil_div(nmax, box) * box;
+      const int64_t rows_buf = rows_alloc > nmax + 2 ? rows_alloc : nmax + 2;
+      if (rows_buf * 64 * want > budget) continue;
+      if (best_rows < 0 || rows_alloc < best_rows) { best_rows = rows_alloc; best_box = box; }
+    }
+    if (best_box) nbuf = want;
+  }
+  CGC_REQUIRE(best_box > 0, CGC_ERR_UNSUPPORTED, "cgc_gather_wide_ell: %d rows per graph do not fit shared memory", nmax);
+  CUtensorMap map;
+  CGC_REQUIRE(make_slice_map(&map, x, (uint64_t)feat, (uint64_t)num_graphs * nmax, ldx, (uint32_t)best_box),
+              CGC_ERR_UNSUPPORTED, "cgc_gather_wide_ell: cuTensorMapEncodeTiled failed");
+  const int64_t rows_alloc = ceil_div(nmax, best_box) * best_box;
+  const int64_t rows_buf = rows_alloc > nmax + 2 ? rows_alloc : nmax + 2;
+  const size_t smem = (size_t)(rows_buf * 64 * nbuf);
+  const int64_t nitems = (int64_t)num_graphs * ceil_div(feat, kWideCols);
+  const int grid = (int)(nitems < kNumSMs ? nitems : kNumSMs);
+  cudaStream_t st = as_stream(stream);
+#define CGC_WIDE(W_, WT_)                                                                                          \
+  do {                                                                                                             \
+    auto kern = k_gather_wide_ell<W_, WT_, ((W_) == 8 && !(WT_)) ? 4 : 2>;                                                                  \
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+    kern<<<grid, kWideThreads, smem, st>>>(map, ell, ell_val, ell_scale, perm, rowptr, col, val, num_graphs, nmax,  \
+                                          feat, best_box, nbuf, out, ldo, accumulate);                             \
+  } while (0)
+  if (width == 8) { if (ell_val) CGC_WIDE(8, true); else CGC_WIDE(8, false); }
+  else            { if (ell_val) CGC_WIDE(16, true); else CGC_WIDE(16, false); }
+#undef CGC_WIDE
+  CGC_CHECK_LAUNCH("k_gather_wide_ell");
+  return 0;
 }

@@ -28,6 +28,7 @@ from torch.autograd import Function
 from . import _backend
 
 RENORM_P = 0.4       # model/network.py:260,271,280
+BUILD_TRANSPOSED_ELL = False     # see build_sparse_graph
 ACTIVATIONS = {'relu': 0, 'elu': 1, 'leakyrelu': 2}     # GNN_Module._activation (network.py:82-90) -> CGC_ACT_*
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -68,6 +69,8 @@ class SparseGraph(object):
         self.rs = None
         self.mask = None
         self.ell = self.ell_val = self.ell_scale = self.ell_perm = None   # row-padded CSR (cgc_csr_to_ell16)
+        self.ell_t = self.ell_t_val = self.ell_t_scale = self.ell_t_perm = None   # the same for A^T (from the CSC)
+        self.ell_t_width = 0
         self.ell_width = 0
 
 
@@ -129,6 +132,17 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
         g.ell_perm = torch.empty(trows // 8, dtype=torch.int32, device=dev)
         be.csr_to_ell16(g.rowptr, g.col, g.val, g.rs, num_graphs, nmax, g.ell_width, feat == 16, g.ell, g.ell_val,
                         g.ell_scale, g.ell_perm)
+        if BUILD_TRANSPOSED_ELL:
+            # table of the transposed adjacency (wide gather of the DiffPool backward, A^T gP).  In-degrees vary more
+            # than out-degrees, the pitch has to be 16 and half of the slots are padding: measured 620 us vs 425 us
+            # for the generic CSC gather at the BASELINE shape, so it is off by default.
+            g.ell_t_width = 8 if 2 * cap <= 8 * real_rows else 16
+            g.ell_t = torch.empty(trows * g.ell_t_width, dtype=torch.int16, device=dev)
+            g.ell_t_val = _f32(trows * g.ell_t_width, device=dev) if norm_adj else None
+            g.ell_t_scale = _f32(trows, device=dev)
+            g.ell_t_perm = torch.empty(trows // 8, dtype=torch.int32, device=dev)
+            be.csr_to_ell16(g.colptr, g.row, g.val_t, None, num_graphs, nmax, g.ell_t_width, True, g.ell_t,
+                            g.ell_t_val, g.ell_t_scale, g.ell_t_perm)
     return xp, g
 
 
@@ -520,6 +534,12 @@ class DenseJKFunction(Function):
         return (g_feats, None, None, d_att_w, d_att_b) + tuple(grads)
 
 
+def _wide_ell_ok(g, table, x, out):
+    """The shared-memory wide gather needs an ELL16 table, 16-byte aligned rows and a slice tile that fits."""
+    return (table is not None and x.shape[1] >= 64 and x.shape[1] % 4 == 0 and x.stride(0) % 4 == 0
+            and out.stride(0) % 4 == 0 and (g.nmax + 2) * 64 <= 226 * 1024)
+
+
 # ----------------------------------------------------------------------------- diff-pool
 class DiffPoolFunction(Function):
     """``_diff_pool`` (network.py:194-208): ``S = softmax(Z) * mask``; ``X' = S^T X``; ``A' = S^T (A S)``.
@@ -544,7 +564,11 @@ class DiffPoolFunction(Function):
         p = _mat(m, c, dev)
         if cfg.graph is not None:
             g = cfg.graph
-            be.spmm(g.rowptr, g.col, g.val, s, None, None, p, False)
+            if _wide_ell_ok(g, g.ell, s, p):
+                be.gather_wide_ell(g.ell, g.ell_val, None, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val, s,
+                                   g.num_graphs, g.nmax, p, False)
+            else:
+                be.spmm(g.rowptr, g.col, g.val, s, None, None, p, False)
         else:
             be.gemm(adj, _as3d(s, b, n), _as3d(p, b, n), False, False)
         ap = _f32(b, c, c, device=dev)
@@ -572,7 +596,11 @@ class DiffPoolFunction(Function):
         g_adj = None
         if cfg.graph is not None:
             g = cfg.graph
-            be.spmm(g.colptr, g.row, g.val_t, g_p, None, None, g_s, True)              # + A^T gP
+            if _wide_ell_ok(g, g.ell_t, g_p, g_s):
+                be.gather_wide_ell(g.ell_t, g.ell_t_val, None, g.ell_t_perm, g.ell_t_width, g.colptr, g.row,
+                                   g.val_t, g_p, g.num_graphs, g.nmax, g_s, True)         # + A^T gP
+            else:
+                be.spmm(g.colptr, g.row, g.val_t, g_p, None, None, g_s, True)              # + A^T gP
         else:
             be.gemm(adj, _as3d(g_p, b, n), _as3d(g_s, b, n), True, False, beta=1.0)
             if ctx.want_adj:

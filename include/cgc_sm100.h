@@ -173,6 +173,16 @@ CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, c
                             const int32_t* col, const float* val, const float* x, int32_t num_graphs,
                             int32_t nmax, int32_t feat, float* out, void* stream);
 
+/* Wide gather over the same ELL16 table: out[r, :feat] (+)= scale[r] * sum_e val[e] * x[col[e], :feat] for wide
+ * feature matrices -- A*S of _diff_pool (network.py:207, feat = 1140) and, with the table of the transposed
+ * adjacency, its backward.  A work item is (graph, 16-column slice): the strided [nmax, 16] slice is staged in
+ * shared memory once by 2-D TMA and gathered there (double-buffered, persistent CTAs), instead of fetching every
+ * x row once per referencing edge through L2.  ell_scale nullable (= 1).  feat, ldx, ldo multiples of 4. */
+CGC_API int cgc_gather_wide_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                        const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                        const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
+                        int32_t feat, float* out, int64_t ldo, int accumulate, void* stream);
+
 /* ------------------------------------------------------------------ SAGE layer epilogue
  * y = act( l2normalize(sa @ W + b) * mask )      [rows, cout]
  * DenseSAGEConv.forward lines matmul(out, weight) / + bias / F.normalize(p=2, eps=1e-12) /

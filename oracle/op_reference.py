@@ -273,6 +273,19 @@ class TorchBackend(object):
             self.spmm(rowptr, col, val, x, None, None, full, False)
             out[grow[over]] = full[grow[over]] * scale[over][:, None]
 
+    def gather_wide_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
+                        accumulate):
+        """Same sums as sage_gather_ell_fwd on a wide (possibly strided) matrix, optional scale, optional +=."""
+        trows = num_graphs * ((nmax + 7) // 8 * 8)
+        scale = ell_scale if ell_scale is not None else torch.ones(trows)
+        res = torch.zeros(num_graphs * nmax, x.shape[1], dtype=x.dtype)
+        self.sage_gather_ell_fwd(ell, ell_val, scale, perm, width, rowptr, col, val, x.contiguous(), num_graphs, nmax,
+                                 res)
+        if accumulate:
+            out += res
+        else:
+            out.copy_(res)
+
     @staticmethod
     def _act(act, v):
         if act == 0:
