@@ -520,7 +520,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-constexpr int kWideThreads = 1024;
+constexpr int kWideThreads = 512;
 constexpr int kWideCols = 16;                // columns per slice (64-byte shared-memory rows, as in the F = 16 gather)
 
 template <int W, bool WEIGHTED, int RB>                  // RB = rows per thread and batch
@@ -540,6 +540,7 @@ k_gather_wide_ell(const __grid_constant__ CUtensorMap map_x, const uint16_t* __r
   const uint32_t tile_tx = (uint32_t)nboxes * (uint32_t)box_rows * 64u;
   const int nslices = (feat + kWideCols - 1) / kWideCols;
   const int64_t nitems = (int64_t)num_graphs * nslices;
+  const int nbatch = (nrow8 + G * RB - 1) / (G * RB);      // batches per item
   __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -564,68 +565,81 @@ k_gather_wide_ell(const __grid_constant__ CUtensorMap map_x, const uint16_t* __r
   const int sl = tid & 3, grp = tid >> 2;
   const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
   const uint32_t ovf_mark = (uint32_t)nmax + 1u;
+
+  // Index vectors (weights, scale, position map) of one batch of RB rows.  They are loaded one batch AHEAD of
+  // their use -- across item boundaries too -- so that their L2 latency hides behind the previous batch's gather.
+  struct Batch {
+    uint32_t idx[RB][NW];
+    float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
+    float rsc[RB];
+    uint32_t pw[RB];
+  };
+  auto load_batch = [&](Batch& bt, int64_t item, int bi) {
+    const int g = (int)(item / nslices);
+    const int64_t trow0 = (int64_t)g * nrow8;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int t = (bi * RB + i) * G + grp;
+      const bool on = item < nitems && t < nrow8;
+      const int64_t trow = trow0 + (on ? t : 0);
+      bt.pw[i] = on ? __ldg(perm + (trow >> 3)) : 0xFFFFFFFFu;
+      bt.rsc[i] = (on && ell_scale != nullptr) ? __ldg(ell_scale + trow) : 1.0f;
+#pragma unroll
+      for (int q = 0; q < NW / 4; ++q) {
+        uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
+        if (on) v = ldg_u4(ell + trow * W + q * 8);
+        bt.idx[i][4 * q] = v.x; bt.idx[i][4 * q + 1] = v.y; bt.idx[i][4 * q + 2] = v.z; bt.idx[i][4 * q + 3] = v.w;
+      }
+      if (WEIGHTED) {
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on) v = ldg_f4(ellw + trow * W + q * 4);
+          bt.wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
+          bt.wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
+          bt.wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
+          bt.wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
+        }
+      }
+    }
+  };
+
   uint32_t ph0 = 0u, ph1 = 0u;                            // barrier parities (scalars: no local-memory array)
   int it = 0;
+  Batch cur, nxt;
+  load_batch(cur, first, 0);
   for (int64_t item = first; item < nitems; item += step, ++it) {
     const int b = nbuf > 1 ? (it & 1) : 0;
     const int g = (int)(item / nslices), sidx = (int)(item - (int64_t)g * nslices);
     const int c0 = sidx * kWideCols + sl * 4;             // first output column of this lane
     const bool lane_on = c0 < feat;
     const int64_t grow0 = (int64_t)g * nmax;
-    const int64_t trow0 = (int64_t)g * nrow8;
-    const uint32_t tile_base = smem_u32(smem_raw) + (uint32_t)b * buf_bytes;
-    const uint32_t lane_base = tile_base + (uint32_t)sl * 16u;
+    const uint32_t lane_base = smem_u32(smem_raw) + (uint32_t)b * buf_bytes + (uint32_t)sl * 16u;
     if (b == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1u; }
     else { mbar_wait(&full[1], ph1); ph1 ^= 1u; }
     // zero rows for empty slots / overflow marks (the TMA overhang may have landed there)
     if (tid < 32) reinterpret_cast<float*>(smem_raw + (size_t)b * buf_bytes)[(size_t)nmax * 16 + tid] = 0.f;
     __syncthreads();
-    for (int i0 = 0; i0 * G < nrow8; i0 += RB) {
-      uint32_t idx[RB][NW];
-      float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
-      float rsc[RB];
-      uint32_t pw[RB];
+    for (int bi = 0; bi < nbatch; ++bi) {
+      // prefetch the next batch (of this item, or the first one of the CTA's next item)
+      if (bi + 1 < nbatch) load_batch(nxt, item, bi + 1);
+      else load_batch(nxt, item + step, 0);
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        const int t = (i0 + i) * G + grp;
-        const bool on = t < nrow8;
-        const int64_t trow = trow0 + (on ? t : 0);
-        pw[i] = on ? __ldg(perm + (trow >> 3)) : 0xFFFFFFFFu;
-        rsc[i] = (on && ell_scale != nullptr) ? __ldg(ell_scale + trow) : 1.0f;
-#pragma unroll
-        for (int q = 0; q < NW / 4; ++q) {
-          uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
-          if (on) v = ldg_u4(ell + trow * W + q * 8);
-          idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
-        }
-        if (WEIGHTED) {
-#pragma unroll
-          for (int q = 0; q < W / 4; ++q) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (on) v = ldg_f4(ellw + trow * W + q * 4);
-            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
-            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
-            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
-            wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const int t = (i0 + i) * G + grp;
+        const int t = (bi * RB + i) * G + grp;
         if (t >= nrow8) continue;
-        const int lrow = (t & ~7) + (int)((pw[i] >> (3 * (t & 7))) & 7u);
+        const int lrow = (t & ~7) + (int)((cur.pw[i] >> (3 * (t & 7))) & 7u);
         if (lrow >= nmax) continue;
         const int64_t row = grow0 + lrow;
         float4 o;
-        if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
+        if ((cur.idx[i][0] & 0xFFFFu) != ovf_mark) {
           F32x4 acc;
           acc.lo = 0ull; acc.hi = 0ull;
 #pragma unroll
           for (int u = 0; u < W; ++u) {
-            const uint32_t j = ell_slot(idx[i], u);
+            const uint32_t j = ell_slot(cur.idx[i], u);
             const F32x4 v = lds_x4(lane_base + j * 64u);
-            if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
+            if (WEIGHTED) fma_x4(acc, cur.wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
             else add_x4(acc, v);
           }
           o = unpack_x4(acc);
@@ -640,7 +654,7 @@ k_gather_wide_ell(const __grid_constant__ CUtensorMap map_x, const uint16_t* __r
           }
         }
         if (lane_on) {
-          const float s = rsc[i];
+          const float s = cur.rsc[i];
           o.x *= s; o.y *= s; o.z *= s; o.w *= s;
           float4* dst = reinterpret_cast<float4*>(out + row * ldo + c0);
           if (accumulate) {
@@ -650,11 +664,12 @@ k_gather_wide_ell(const __grid_constant__ CUtensorMap map_x, const uint16_t* __r
           *dst = o;
         }
       }
+      cur = nxt;
     }
     __syncthreads();                                      // everyone is done with buffer b
     if (tid == 0) {
-      const int64_t nxt = item + (nbuf > 1 ? 2 : 1) * step;
-      if (nxt < nitems) issue(nxt, b);
+      const int64_t nx = item + (nbuf > 1 ? 2 : 1) * step;
+      if (nx < nitems) issue(nx, b);
     }
   }
 }
@@ -895,7 +910,7 @@ extern "C" int cgc_gather_wide_ell(const uint16_t* ell, const float* ell_val, co
   cudaStream_t st = as_stream(stream);
 #define CGC_WIDE(W_, WT_)                                                                                          \
   do {                                                                                                             \
-    auto kern = k_gather_wide_ell<W_, WT_, ((W_) == 8 && !(WT_)) ? 4 : 2>;                                                                  \
+    auto kern = k_gather_wide_ell<W_, WT_, ((W_) == 8 ? 8 : 4) / ((WT_) ? 2 : 1)>;                                                                  \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
     kern<<<grid, kWideThreads, smem, st>>>(map, ell, ell_val, ell_scale, perm, rowptr, col, val, num_graphs, nmax,  \
                                           feat, best_box, nbuf, out, ldo, accumulate);                             \
