@@ -6,7 +6,7 @@ OUT=gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
 nproc > $OUT/host_cores.txt; lscpu | grep "Model name" >> $OUT/host_cores.txt
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || echo BUILD_FAILED
-GROUPS_=${GROUPS_:-"tcgen05 tf32_operand graph_build spmm sage_gather ell sage_epilogue act_fwd sage_layer scale_rows batchnorm softmax colmax dense_adjacency gemm_fp32 gemm_epilogue jk radius farthest"}
+GROUPS_=${GROUPS_:-"tcgen05 tf32_operand graph_build spmm sage_gather ell sage_epilogue act_fwd sage_layer scale_rows batchnorm softmax colmax dense_adjacency gemm_fp32 gemm_epilogue jk radius farthest gather_wide fwd_narrow"}
 for grp in $GROUPS_; do
   timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q --tb=short -k "$grp" > $OUT/ops_$grp.log 2>&1
   rc=$?
