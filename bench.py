@@ -16,6 +16,8 @@ One JSON line is printed by rank 0:
   roofline   the SAGE gather kernel (cgc_sage_gather_ell_fwd) alone: algorithmic bytes / launch time
              vs the measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes of one launch
              from the committed ncu capture (profiles/gather_r1_ncu.txt)
+  roofline_tensor  the kernel with the largest share of the step (tcgen05 3xTF32 GEMM, CTA pairs): algorithmic
+             fp32 FLOPs / launch time vs half the measured bf16 peak, and the same counting the 3 MMA passes
   cpu_baseline  the dense CPU oracle port of the reference path timed on this box's host cores on a
              bounded sample (N = 1, rank 0 only)
 `--impl reference` times that CPU oracle port alone (the reference is pure Python on dense torch ops;
@@ -239,6 +241,30 @@ def gather_roofline(args, device, variant='ell', parity=True, scale=True):
     return alg_bytes, samples[len(samples) // 2], copies       # median of 5 blocks of 20 x `copies` launches
 
 
+def gemm_roofline(device):
+    """The kernel with the largest share of the step (k_gemm_tc, 53 %): the `lin` contraction of GCN_pool_1
+    (115200 x 1140 x 1180, network.py:121-124) alone, CUDA events around 5 launches after 3 warm-ups; the three
+    operands (1.6 GB) exceed L2.  Algorithmic FLOPs = 2 M N K (what the reference's fp32 matmul computes); the
+    kernel spends 3 tf32 MMA passes on them (3xTF32)."""
+    from cgc_net_b200 import _backend
+    be = _backend.get()
+    m, n, k = 115200, 1140, 1180
+    a = torch.randn(m, k, device=device)
+    b = torch.randn(n, k, device=device)
+    c = torch.empty(m, n, device=device)
+    for _ in range(3):
+        be.gemm(a, b, c, False, True, precision=1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        be.gemm(a, b, c, False, True, precision=1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    return 2.0 * m * n * k, ms
+
+
 # ----------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
@@ -357,6 +383,21 @@ def run_ours(args):
                             'timing': 'CUDA-graph replay of %d launches over %d rotating input copies (%.0f MB > L2), '
                                       'CUDA events on the launching stream, median of 5 blocks of 20 replays'
                                       % (copies, copies, copies * alg_bytes / 1e6)}
+    if rank == 0 and not args.no_roofline:
+        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.isfile(peaks_path):
+            tpeak, twhich = float(json.load(open(peaks_path))['bf16_tflops']) / 2.0, \
+                'measured (MEASURED_PEAKS.json bf16_tflops / 2: tf32 runs at half the bf16 rate)'
+        else:
+            tpeak, twhich = 1590.0 / 2.0, 'fallback (B200_PROFILING.md 1.59 PFLOP/s bf16 / 2)'
+        flops, ms = gemm_roofline(device)
+        line['roofline_tensor'] = {
+            'kernel': 'k_gemm_tc<128, pair> (cgc_gemm, tcgen05 3xTF32, cta_group::2) on lin 115200x1140x1180',
+            'bound': 'tensor', 'achieved': flops / ms / 1e9, 'peak': tpeak, 'unit': 'TFLOP/s',
+            'frac': flops / ms / 1e9 / tpeak, 'mma_passes': 3, 'mma_work_frac': 3.0 * flops / ms / 1e9 / tpeak,
+            'peak_source': twhich, 'ms_per_launch': ms, 'step_share': 0.53,
+            'note': 'achieved = algorithmic fp32 FLOPs (2MNK) per second; the kernel issues 3 tf32 MMA passes per '
+                    'product to stay within fp32 parity, mma_work_frac counts those'}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, dt, cores, n_graphs = cpu_oracle_rate(args, 3, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'graphs/s', 'cores': cores, 'kind': 'port',
