@@ -166,7 +166,7 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- gather roofline
-def gather_roofline(args, device, variant='ell', parity=True, scale=True):
+def gather_roofline(args, device, variant='ell', parity=True):
     """The SAGE gather kernel alone (F = 16, unfused): CUDA-graph replay over rotating input copies whose
     total footprint exceeds L2, timed with CUDA events on the launching stream.
     variant 'ell' = cgc_sage_gather_ell_fwd (fixed-pitch index table), 'csr' = cgc_sage_gather_mean_fwd."""

@@ -17,8 +17,8 @@ args = argparse.Namespace(batch_per_gpu=64, nodes=1800, degree=8)
 dev = torch.device('cuda', 0)
 torch.cuda.set_device(0)
 for v in a.variants.split(','):
-    variant, parity = ('ell', False) if v == 'ell-noparity' else (v.split('-')[0], True)
-    alg, us, copies = bench.gather_roofline(args, dev, variant, parity, scale=not v.endswith('-noscale'))
+    variant, parity = ('ell', False) if v == 'ell-noparity' else (v, True)
+    alg, us, copies = bench.gather_roofline(args, dev, variant, parity)
     print('%-14s stage=%s  %.2f us/launch  %.0f GB/s algorithmic  samples %s' % (
         v, os.environ.get('CGC_GATHER_STAGE', '0'), us, alg / us / 1e3,
         ' '.join('%.2f' % t for t in bench.gather_roofline.samples)))
