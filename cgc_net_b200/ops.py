@@ -118,19 +118,19 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
     g.row = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
     g.val_t = _f32(max(cap, 1), device=dev) if norm_adj else None
     be.csr_transpose(g.rowptr, g.col, g.val, g.colptr, g.row, g.val_t, work)
-    # Fixed-pitch index table of the shared-memory gather: pitch 8 when the mean row degree allows it, else 16;
-    # rows above the pitch are flagged and walk the CSR.  The slot-parity order pays off for 64-byte rows.
-    feat = x.shape[1]
+    # Fixed-pitch index table of the shared-memory gathers (layer-1 SAGE gather when the feature width allows it,
+    # wide A*S of the DiffPool forward always): pitch 8 when the mean row degree allows it, else 16; rows above the
+    # pitch are flagged and walk the CSR.  The slot-parity / row-pairing order serves the 64-byte shared-memory rows
+    # both kernels use.
     real_rows = max(n_total, 1)
-    if nmax < 0xFFFF and cap <= 16 * real_rows and feat % 4 == 0 and feat <= 32 \
-            and (nmax + 2) * feat * 4 + 1024 <= 227 * 1024:
+    if nmax + 1 <= 0xFFFF and cap <= 16 * real_rows and (nmax + 2) * 64 + 1024 <= 227 * 1024:
         g.ell_width = 8 if cap <= 8 * real_rows else 16
         trows = be.ell16_rows(num_graphs, nmax)
         g.ell = torch.empty(trows * g.ell_width, dtype=torch.int16, device=dev)
         g.ell_val = _f32(trows * g.ell_width, device=dev) if norm_adj else None
         g.ell_scale = _f32(trows, device=dev)
         g.ell_perm = torch.empty(trows // 8, dtype=torch.int32, device=dev)
-        be.csr_to_ell16(g.rowptr, g.col, g.val, g.rs, num_graphs, nmax, g.ell_width, feat == 16, g.ell, g.ell_val,
+        be.csr_to_ell16(g.rowptr, g.col, g.val, g.rs, num_graphs, nmax, g.ell_width, True, g.ell, g.ell_val,
                         g.ell_scale, g.ell_perm)
         if BUILD_TRANSPOSED_ELL:
             # table of the transposed adjacency (wide gather of the DiffPool backward, A^T gP).  In-degrees vary more

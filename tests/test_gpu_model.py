@@ -258,3 +258,16 @@ def test_device_prefetcher_yields_identical_batches(cuda_backend):
         assert torch.equal(dev.batch.cpu(), host.batch) and torch.equal(dev.y.cpu(), host.y)
         seen += 1
     assert seen == 4
+
+
+def test_eighteen_feature_input_vs_oracle(gemm_mode):
+    """18 input features (the reference's real width): generic layer-1 gather + ELL16 wide gather for A*S."""
+    graphs = helpers.make_graphs([333, 801, 57, 640], [5, 8, 12, 6], feat=18, seed=17)
+    batch = graph.Batch.from_data_list(graphs)
+    ours, orc = helpers.build_pair((2000, 18, 20, 20, True, True, 20, 3, 0.1, [50]), load_data_sparse=True,
+                                   collect_assign=True)
+    lo, losso, lr, lossr = _run_pair(ours, orc, batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    _, _, truth = helpers.oracle_fp64(orc, batch)
+    helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()}, **_grad_tol(gemm_mode))
+    _check_assignments(ours, orc)

@@ -329,3 +329,18 @@ def test_sample_nodes_counts_and_uniqueness(torch_backend, method):
         assert ids.numel() == int(n * 0.5) and ids.unique().numel() == ids.numel()
         assert ids.numel() == 0 or (int(ids.min()) >= 0 and int(ids.max()) < n)
         assert torch.equal(ids, ids2)
+
+
+def test_eighteen_feature_input(torch_backend):
+    """The reference's own feature width (16 appearance + 2 coordinate features, dataflow/data.py:22-53): not a
+    multiple of 4, so layer 1 takes the generic gather while the ELL16 table still serves the wide A*S."""
+    graphs = helpers.make_graphs([41, 67, 30], [5, 8, 6], feat=18, seed=31)
+    batch = graph.Batch.from_data_list(graphs)
+    args = (300, 18, 20, 20, True, True, 20, 3, 0.1, [50])
+    ours, orc = helpers.build_pair(args, load_data_sparse=True)
+    ours.train(), orc.train()
+    lo, losso = ours(batch)
+    lr, lossr = orc(batch)
+    assert helpers.rel_err(lo, lr) < 1e-4
+    losso.backward(), lossr.backward()
+    _grad_check(ours, orc, batch)
