@@ -271,3 +271,26 @@ def test_eighteen_feature_input_vs_oracle(gemm_mode):
     _, _, truth = helpers.oracle_fp64(orc, batch)
     helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()}, **_grad_tol(gemm_mode))
     _check_assignments(ours, orc)
+
+
+def test_full_size_jumping_knowledge_properties(cuda_backend):
+    """The published configuration (--jk, parallel_train.sh:3) at BASELINE size (64 x 1800 nodes): the fused DenseJK
+    kernels at M = 115 200 rows.  The JK output is a convex combination of the three layer outputs of every node
+    (alpha = softmax over layers), so it lies between their element-wise min and max; gradients are finite."""
+    graphs = graph.synthetic_batch(8, 1800, 8, 16, seed=6) * 8
+    batch = graph.Batch.from_data_list(graphs).to('cuda')
+    torch.manual_seed(0)
+    m = network.SoftPoolingGcnEncoder(11404, 16, 20, 20, True, True, 20, 3, 0.1, [50], concat=True,
+                                      load_data_sparse=True, jk=True).cuda().train()
+    xp, g = ops.build_sparse_graph(batch.x, batch.edge_index, batch.batch, batch.num_nodes_list, False)
+    feat = m.GCN_embed_1(xp, None, g.mask, graph=g)
+    out = m.jk1(feat, 64, 1800)
+    layers = feat.view(-1, 3, 20)
+    lo, hi = layers.min(1).values, layers.max(1).values
+    assert out.shape == (64 * 1800, 20)
+    assert bool((out >= lo - 1e-5).all()) and bool((out <= hi + 1e-5).all())
+    logits, loss = m(batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(logits).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    assert float(m.jk1.lstm.weight_ih_l0.grad.abs().max()) > 0 and float(m.jk1.att.weight.grad.abs().max()) > 0
