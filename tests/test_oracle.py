@@ -176,3 +176,57 @@ def test_jk_reference_formulas_match_autograd():
     d_aw = torch.cat([sum(hs[d, t] @ dsc[t] for t in range(layers)) for d in range(2)])
     assert float((d_aw - att.weight.grad.view(-1)).abs().max()) < 1e-12
     assert float((dsc.sum() - att.bias.grad).abs().max()) < 1e-12
+
+
+def test_ell16_reference_table_invariants():
+    """Property test (hypothesis) of the ELL16 restatement the GPU builder is compared with bit-exactly: for random
+    CSRs the table is a re-ordering of every row's entries (weights stay attached to their columns), pad slots
+    follow the valid ones, overflow rows are flagged, and the position map permutes each block of 8 rows."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import op_reference
+    ref = op_reference.TorchBackend()
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.integers(1, 3), st.integers(1, 41), st.sampled_from([8, 16]), st.integers(0, 20), st.integers(0, 1),
+           st.integers(0, 2 ** 31 - 1))
+    def check(b, nmax, width, maxdeg, pair, seed):
+        g = torch.Generator().manual_seed(seed)
+        rows = b * nmax
+        deg = torch.randint(0, min(maxdeg, nmax) + 1, (rows,), generator=g)
+        rowptr = torch.zeros(rows + 1, dtype=torch.int32)
+        rowptr[1:] = deg.cumsum(0).to(torch.int32)
+        cols = [torch.randperm(nmax, generator=g)[:int(deg[r])].sort().values + (r // nmax) * nmax for r in range(rows)]
+        col = torch.cat(cols + [torch.zeros(1, dtype=torch.long)]).to(torch.int32)
+        val = torch.rand(int(rowptr[-1]) + 1, generator=g)
+        trows = ref.ell16_rows(b, nmax)
+        ell = torch.zeros(trows * width, dtype=torch.int16)
+        ellw, ells = torch.zeros(trows * width), torch.zeros(trows)
+        perm = torch.zeros(trows // 8, dtype=torch.int32)
+        ref.csr_to_ell16(rowptr, col, val, None, b, nmax, width, pair, ell, ellw, ells, perm)
+        table = ell.view(trows, width).long() & 0xFFFF
+        wt = ellw.view(trows, width)
+        nrow8 = trows // b
+        seen = set()
+        for t in range(trows):
+            gidx, p = divmod(t, nrow8)
+            pw = int(perm[t // 8]) & 0xFFFFFF
+            lrow = p // 8 * 8 + ((pw >> (3 * (p % 8))) & 7)
+            seen.add((gidx, lrow))
+            if lrow >= nmax:
+                assert bool((table[t] == nmax).all())
+                continue
+            r = gidx * nmax + lrow
+            lo, hi = int(rowptr[r]), int(rowptr[r + 1])
+            if hi - lo > width:
+                assert int(table[t, 0]) == nmax + 1
+                continue
+            n = hi - lo
+            assert bool((table[t, n:] == nmax).all()) and bool((wt[t, n:] == 0).all())       # pads last, weight 0
+            got = sorted(zip(table[t, :n].tolist(), wt[t, :n].tolist()))
+            want = sorted(zip((col[lo:hi].long() - gidx * nmax).tolist(), val[lo:hi].tolist()))
+            assert got == want
+            if not pair:
+                assert table[t, :n].tolist() == (col[lo:hi].long() - gidx * nmax).tolist() and lrow == p
+        assert len(seen) == trows                                                            # a permutation per block
+
+    check()
