@@ -56,12 +56,12 @@ def golden_sage_conv():
                         adj_rowsum=_np(adj.sum(-1)[0]), out=_np(out[0]))
 
 
-def _encoder_case(name, norm_adj, sizes, degrees, max_nodes, ratio, seed):
+def _encoder_case(name, norm_adj, sizes, degrees, max_nodes, ratio, seed, gcn_name='SAGE', activation='relu', jk=False):
     graphs = _messy_graphs(sizes, degrees, 16, seed)
     batch = graph.Batch.from_data_list(graphs)
     args = (max_nodes, 16, 20, 20, True, True, 20, 3, ratio, [50])
-    kw = dict(concat=True, gcn_name='SAGE', collect_assign=True, load_data_sparse=True,
-              norm_adj=norm_adj)
+    kw = dict(concat=True, gcn_name=gcn_name, collect_assign=True, load_data_sparse=True,
+              norm_adj=norm_adj, activation=activation, jk=jk)
     torch.manual_seed(seed)
     model = reference_loader.build_reference_encoder(*args, **kw)
     model.train()
@@ -70,7 +70,8 @@ def _encoder_case(name, norm_adj, sizes, degrees, max_nodes, ratio, seed):
     loss.backward()
     rec = dict(x=_np(batch.x), edge_index=_np(batch.edge_index), batch=_np(batch.batch), y=_np(batch.y),
                num_nodes=np.asarray(batch.num_nodes_list), max_nodes=max_nodes, ratio=ratio,
-               norm_adj=int(norm_adj), logits=_np(logits), loss=_np(loss))
+               norm_adj=int(norm_adj), logits=_np(logits), loss=_np(loss), gcn_name=np.asarray(gcn_name),
+               activation=np.asarray(activation), jk=int(jk))
     for k, v in state.items():
         rec['param/' + k] = v
     for k, p in model.named_parameters():
@@ -119,6 +120,10 @@ def main():
     golden_pool_stage1()
     _encoder_case('encoder_small_plain', False, [150, 97, 181, 64], [8, 5, 8, 6], 500, 0.1, seed=21)
     _encoder_case('encoder_small_normadj', True, [150, 97, 181, 64], [8, 5, 8, 6], 500, 0.1, seed=22)
+    # variants of the reference (network.py:82-99, 11-55): DenseGINConv + elu, and the published --jk configuration
+    _encoder_case('encoder_small_gin_elu', True, [120, 97, 64], [8, 5, 6], 400, 0.1, seed=23, gcn_name='GIN',
+                  activation='elu')
+    _encoder_case('encoder_small_jk', False, [120, 97, 64], [8, 5, 6], 400, 0.1, seed=24, jk=True)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -25,7 +25,7 @@ import torch
 import helpers
 from cgc_net_b200 import graph, network, ops
 from oracle import restatement
-from test_oracle import _batch_from, _load
+from test_oracle import GOLDEN_ENCODERS, _batch_from, _load, _variant_kwargs
 
 pytestmark = pytest.mark.gpu
 
@@ -71,14 +71,14 @@ def _check_assignments(ours, orc):
     return exempt
 
 
-@pytest.mark.parametrize('name', ['encoder_small_plain', 'encoder_small_normadj'])
+@pytest.mark.parametrize('name', GOLDEN_ENCODERS)
 def test_golden_vectors(cuda_backend, name):
     """Known answers minted from the verbatim reference (oracle/make_golden.py); these shapes are small
     enough that every contraction runs on the fp32 FMA kernel."""
     g = _load(name)
     args = (int(g['max_nodes']), 16, 20, 20, True, True, 20, 3, float(g['ratio']), [50])
-    m = network.SoftPoolingGcnEncoder(*args, concat=True, gcn_name='SAGE', collect_assign=True,
-                                      load_data_sparse=True, norm_adj=bool(int(g['norm_adj'])))
+    m = network.SoftPoolingGcnEncoder(*args, concat=True, collect_assign=True, load_data_sparse=True,
+                                      **_variant_kwargs(g))
     m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
     m = m.cuda().train()
     batch = _batch_from(g).to('cuda')

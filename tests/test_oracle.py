@@ -21,10 +21,19 @@ def _batch_from(g):
                        [int(n) for n in g['num_nodes']])
 
 
+GOLDEN_ENCODERS = ['encoder_small_plain', 'encoder_small_normadj', 'encoder_small_gin_elu', 'encoder_small_jk']
+
+
+def _variant_kwargs(g):
+    """Constructor keywords recorded with a golden encoder case (oracle/make_golden.py)."""
+    return dict(gcn_name=str(g['gcn_name']) if 'gcn_name' in g.files else 'SAGE',
+                activation=str(g['activation']) if 'activation' in g.files else 'relu',
+                jk=bool(int(g['jk'])) if 'jk' in g.files else False, norm_adj=bool(int(g['norm_adj'])))
+
+
 def _oracle_from(g, **kw):
     args = (int(g['max_nodes']), 16, 20, 20, True, True, 20, 3, float(g['ratio']), [50])
-    m = restatement.OracleEncoder(*args, concat=True, gcn_name='SAGE', load_data_sparse=True,
-                                  norm_adj=bool(int(g['norm_adj'])), **kw)
+    m = restatement.OracleEncoder(*args, concat=True, load_data_sparse=True, **_variant_kwargs(g), **kw)
     m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
     return m
 
@@ -41,7 +50,7 @@ def test_sage_conv_golden():
     np.testing.assert_allclose(out[0].detach().numpy(), g['out'], rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize('name', ['encoder_small_plain', 'encoder_small_normadj'])
+@pytest.mark.parametrize('name', GOLDEN_ENCODERS)
 def test_encoder_golden(name):
     g = _load(name)
     m = _oracle_from(g, collect_assign=True)

@@ -9,7 +9,7 @@ import torch
 import helpers
 from cgc_net_b200 import _backend, graph, network, ops
 from oracle import restatement
-from test_oracle import _batch_from, _load
+from test_oracle import GOLDEN_ENCODERS, _batch_from, _load, _variant_kwargs
 
 
 def _grad_check(ours, orc, batch):
@@ -18,12 +18,12 @@ def _grad_check(ours, orc, batch):
     helpers.assert_grads_close(ours, truth, {k: p.grad for k, p in orc.named_parameters()})
 
 
-@pytest.mark.parametrize('name', ['encoder_small_plain', 'encoder_small_normadj'])
+@pytest.mark.parametrize('name', GOLDEN_ENCODERS)
 def test_module_matches_golden(torch_backend, name):
     g = _load(name)
     args = (int(g['max_nodes']), 16, 20, 20, True, True, 20, 3, float(g['ratio']), [50])
-    m = network.SoftPoolingGcnEncoder(*args, concat=True, gcn_name='SAGE', collect_assign=True,
-                                      load_data_sparse=True, norm_adj=bool(int(g['norm_adj'])))
+    m = network.SoftPoolingGcnEncoder(*args, concat=True, collect_assign=True, load_data_sparse=True,
+                                      **_variant_kwargs(g))
     m.load_state_dict({k[len('param/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('param/')})
     m.train()
     logits, loss = m(_batch_from(g))
