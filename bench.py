@@ -56,7 +56,7 @@ def parse():
     ap.add_argument('--nodes', type=int, default=1800)
     ap.add_argument('--degree', type=int, default=8)
     ap.add_argument('--norm-adj', action='store_true')
-    ap.add_argument('--cpu-sample-graphs', type=int, default=8)
+    ap.add_argument('--cpu-sample-graphs', type=int, default=16)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     return ap.parse_args()
@@ -149,7 +149,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))      # ~10 s of CPU work on 16 cores
     rate, dt, cores, n_graphs = cpu_oracle_rate(args, steps, warmup)
     sample = '%d of the %d graphs per step (dense CPU oracle port, fwd+bwd+Adam), %d steps' % (
         n_graphs, args.batch_per_gpu, steps)
@@ -399,10 +399,10 @@ def run_ours(args):
             'note': 'achieved = algorithmic fp32 FLOPs (2MNK) per second; the kernel issues 3 tf32 MMA passes per '
                     'product to stay within fp32 parity, mma_work_frac counts those'}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, dt, cores, n_graphs = cpu_oracle_rate(args, 3, 1)
+        rate, dt, cores, n_graphs = cpu_oracle_rate(args, 8, 1)                     # ~8 s of CPU work on 16 cores
         line['cpu_baseline'] = {'value': rate, 'unit': 'graphs/s', 'cores': cores, 'kind': 'port',
                                 'sample': '%d of the %d graphs per step (dense CPU oracle port of the reference '
-                                          'path, fwd+bwd+Adam), 3 timed steps after 1 warm-up' % (n_graphs, b)}
+                                          'path, fwd+bwd+Adam), 8 timed steps after 1 warm-up' % (n_graphs, b)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
