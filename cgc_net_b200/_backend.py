@@ -110,6 +110,9 @@ def _ptr(t, dtype=None):
         return None
     if not t.is_cuda:
         raise CgcError('libcgc_sm100 needs CUDA tensors (got a %s tensor); no CPU fallback' % t.device)
+    if t.device.index != torch.cuda.current_device():
+        raise CgcError('tensor on %s but the current CUDA device is cuda:%d: the library enqueues on the current '
+                       'device (use `with torch.cuda.device(t.device):`)' % (t.device, torch.cuda.current_device()))
     if dtype is not None and t.dtype != dtype:
         raise CgcError('expected %s, got %s' % (dtype, t.dtype))
     return t.data_ptr()
@@ -137,7 +140,10 @@ class CudaBackend(object):
         self._work = {}
         self.work_bytes = int(self.lib.cgc_workspace_bytes())
         self.launches = 0           # C-ABI calls issued (bench.py reports it as gpu_launches)
-        self.gemm_precision = int(os.environ.get('CGC_GEMM_PRECISION', '-1'))
+        # GEMM mode of calls that do not name one: -1 = library's choice (tcgen05 3xTF32 where the shape allows),
+        # 0 = exact-fp32 FMA everywhere, 1 = tcgen05 forced.  A Python attribute only (tests flip it); the
+        # library itself reads no environment variable.
+        self.gemm_precision = -1
 
     def kernel_launches(self):
         """CUDA kernels launched by the library so far (process-wide)."""
@@ -145,6 +151,10 @@ class CudaBackend(object):
 
     # -- helpers
     def _stream(self):
+        """Stream the kernels are enqueued on.  The C entry points use the calling thread's CURRENT device
+        (include/cgc_sm100.h, "Threading"), so every tensor of a call must live on it: ``_ptr`` checks that and
+        raises instead of launching on foreign pointers (e.g. a model on cuda:1 while cuda:0 is current --
+        wrap the call in ``torch.cuda.device(...)`` as ``compat.DataParallel`` and ``bench.py`` do)."""
         return torch.cuda.current_stream().cuda_stream
 
     def _workspace(self, device):

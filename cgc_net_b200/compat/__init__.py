@@ -150,6 +150,8 @@ class DataParallel(torch.nn.Module):
         p = next(self.module.parameters(), None)
         if p is not None and p.is_cuda:
             batch = batch.to(p.device, non_blocking=True)
+            with torch.cuda.device(p.device):        # the library enqueues on the CURRENT device (see _backend._stream)
+                return self.module(batch)
         return self.module(batch)
 
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/cgc_sm100.h"
 
@@ -89,6 +90,17 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Tuning / profiling switches read from the environment exist only in lab builds (make LAB=1 -> -DCGC_LAB): the
+// release library never lets an environment variable change its numerics or skip work.
+#ifdef CGC_LAB
+inline int lab_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+inline int lab_env(const char*, int dflt) { return dflt; }
+#endif
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

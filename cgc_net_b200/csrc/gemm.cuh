@@ -35,6 +35,7 @@ int gemm_simt(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cuda
 
 // tcgen05 3xTF32 path.  Returns 1 ("not taken") when the shape / alignment is unsupported.
 bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced);
-int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaStream_t st);
+// passes: 3 = 3xTF32 (fp32-grade products), 1 = one TF32 pass on round-to-nearest operands
+int gemm_tc(GemmParams p, int ta, int tb, int passes, void* work, int64_t work_bytes, cudaStream_t st);
 
 }  // namespace cgc

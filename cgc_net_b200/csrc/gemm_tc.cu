@@ -53,12 +53,17 @@ struct Params {
   int a_mn_major, b_mn_major;
   int tiles_m, tiles_n, total_tiles;       // total = tiles_m * tiles_n * batch * ksplit
   int c_vec;
-  int write_hi;      // 1: also store the masked hi tile (not needed: kind::tf32 ignores the low 13 bits)
-  int chunk_blocks;  // K-blocks per TMEM accumulation chunk (promotion period), CGC_TC_CHUNK overrides
+  int passes;        // 3: 3xTF32 (lo*hi + hi*lo + hi*hi, fp32-grade products); 1: single TF32 pass on operands
+                     //    rounded to nearest (10-bit mantissa products, unbiased)
+  int chunk_blocks;  // K-blocks per TMEM accumulation chunk (promotion period): 24 MMA adds per chunk either way
   int bn;            // N tile (= the kernel's BN template argument)
-  int b_warps;       // pair mode: B lo split on warps 2-3 (CGC_TC_BWARPS, lab switch)
-  int a_first;       // split warps stage A before splitting B (CGC_TC_AFIRST, lab switch)
+  int b_warps;       // pair mode: B lo split on warps 2-3 (lab switch CGC_TC_BWARPS, CGC_LAB builds only)
+  int a_first;       // split warps stage A before splitting B (lab switch CGC_TC_AFIRST, CGC_LAB builds only)
 };
+
+// fp32 -> tf32 (10-bit mantissa), round to nearest (ties away from zero): what a single-pass contraction feeds the
+// tensor core instead of the hardware's truncation, so that sign-definite operands (softmax rows) carry no bias
+__device__ __forceinline__ uint32_t tf32_rn(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -464,6 +469,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               const uint32_t a_hi = tmem_base + (uint32_t)(kATmemBase + s * kATmemCols);
               const uint32_t a_lo = a_hi + (uint32_t)BK;
 #pragma unroll
+              if (p.passes == 1) {
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                  if (PAIR) umma_tf32_ts2_pair(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
+                  else umma_tf32_ts2(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
+                }
+              } else {
+#pragma unroll
               for (int kk = 0; kk < BK / 8; ++kk) {
                 if (PAIR) {
                   umma_tf32_ts2_pair(d_tmem, a_lo + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, kk == 0 ? accumulate : 1u);
@@ -474,6 +487,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                   umma_tf32_ts2(d_tmem, a_hi + kk * 8, bl + kk * b_kstep16, desc_hi, idesc, 1u);
                   umma_tf32_ts2(d_tmem, a_hi + kk * 8, bh + kk * b_kstep16, desc_hi, idesc, 1u);
                 }
+              }
               }
               if (PAIR) umma_commit_pair(&empty[s]);    // frees the stage in BOTH CTAs
               else umma_commit(&empty[s]);              // frees the stage once these MMAs have read it
@@ -508,16 +522,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll 4
         for (int i = (PAIR && p.b_warps) ? kBBytes / 16 : tid; i < kBBytes / 16; i += kSplitThreads) {
           const uint4 v = bhi[i];
+          if (p.passes == 1) {                         // single pass: the landed tile is rounded in place, no lo tile
+            uint4 h;
+            h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+            bhi[i] = h;
+            continue;
+          }
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
           l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
           l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
           l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
-          if (p.write_hi) {
-            uint4 h;
-            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-            bhi[i] = h;
-          }
           blo[i] = l;
         }
         };
@@ -541,15 +556,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             ah[4 * ch + 0] = v.x; ah[4 * ch + 1] = v.y; ah[4 * ch + 2] = v.z; ah[4 * ch + 3] = v.w;
           }
         }
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-          const uint32_t h = ah[k] & 0xFFFFE000u;
-          al[k] = __float_as_uint(__uint_as_float(ah[k]) - __uint_as_float(h));
-          ah[k] = h;
-        }
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kATmemBase + s * kATmemCols);
-        tmem_st32(ta, ah);
-        tmem_st32(ta + (uint32_t)BK, al);
+        if (p.passes == 1) {
+#pragma unroll
+          for (int k = 0; k < BK; ++k) ah[k] = tf32_rn(ah[k]);
+          tmem_st32(ta, ah);
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK; ++k) {
+            const uint32_t h = ah[k] & 0xFFFFE000u;
+            al[k] = __float_as_uint(__uint_as_float(ah[k]) - __uint_as_float(h));
+            ah[k] = h;
+          }
+          tmem_st32(ta, ah);
+          tmem_st32(ta + (uint32_t)BK, al);
+        }
         if (p.a_first) split_b();                      // overlaps the latency of the two tensor-memory stores just issued
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
@@ -584,6 +605,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int i = tid; i < kBBytes / 16; i += 64) {
           const uint4 v = bhi[i];
+          if (p.passes == 1) {
+            uint4 h;
+            h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+            bhi[i] = h;
+            continue;
+          }
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
           l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
@@ -725,23 +752,20 @@ bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
   return tc::get_encode_fn() != nullptr;
 }
 
-int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaStream_t st) {
+int gemm_tc(GemmParams p, int ta, int tb, int passes, void* work, int64_t work_bytes, cudaStream_t st) {
   using namespace tc;
-  static const int chunk_blocks = []() {
-    const char* e = getenv("CGC_TC_CHUNK");
-    int v = e ? atoi(e) : kDefaultChunkBlocks;
-    return v < 1 ? 1 : (v > 64 ? 64 : v);
-  }();
+  // promotion period: 24 tensor-core adds per TMEM chunk in both modes (2 K-blocks x 12 MMAs, or 6 x 4)
+  static const int chunk_override = lab_env("CGC_TC_CHUNK", 0);
+  int chunk_blocks = passes == 1 ? 3 * kDefaultChunkBlocks : kDefaultChunkBlocks;
+  if (chunk_override > 0) chunk_blocks = chunk_override > 64 ? 64 : chunk_override;
   Params q;
+  q.passes = passes == 1 ? 1 : 3;
   q.chunk_blocks = chunk_blocks;
   q.a_mn_major = ta ? 1 : 0;          // A stored [k, m]: m contiguous
   q.b_mn_major = tb ? 0 : 1;          // B stored [k, n]: n contiguous
   const int bn = p.n <= 32 ? 32 : (p.n <= 64 ? 64 : 128);      // skinny outputs: narrow MMA tile, same A stream
   q.bn = bn;
-  static const int pair_mode = []() {
-    const char* e = getenv("CGC_TC_PAIR");                     // 0 disables the cta_group::2 kernel
-    return e ? atoi(e) : 1;
-  }();
+  static const int pair_mode = lab_env("CGC_TC_PAIR", 1);        // 0 disables the cta_group::2 kernel (CGC_LAB builds)
   const bool pair = pair_mode != 0 && bn == 128 && p.m > BM;    // 256-row tiles on a CTA pair
   q.tiles_m = (int)ceil_div(p.m, pair ? 2 * BM : BM);
   q.tiles_n = (int)ceil_div(p.n, bn);
@@ -773,13 +797,8 @@ int gemm_tc(GemmParams p, int ta, int tb, void* work, int64_t work_bytes, cudaSt
   CGC_REQUIRE(tiles < (1ll << 31), CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): too many tiles");
   q.total_tiles = (int)tiles;
   q.c_vec = (aligned16(p.c) && p.ldc % 4 == 0 && p.stride_c % 4 == 0) ? 1 : 0;
-  static const int write_hi = []() {
-    const char* e = getenv("CGC_TC_WRITE_HI");
-    return e ? atoi(e) : 0;
-  }();
-  q.write_hi = write_hi;
-  static const int b_warps = []() { const char* e = getenv("CGC_TC_BWARPS"); return e ? atoi(e) : 0; }();
-  static const int a_first = []() { const char* e = getenv("CGC_TC_AFIRST"); return e ? atoi(e) : 0; }();
+  static const int b_warps = lab_env("CGC_TC_BWARPS", 0);
+  static const int a_first = lab_env("CGC_TC_AFIRST", 0);
   q.b_warps = b_warps;
   q.a_first = a_first;
   q.g = p;

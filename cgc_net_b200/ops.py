@@ -33,6 +33,23 @@ ACTIVATIONS = {'relu': 0, 'elu': 1, 'leakyrelu': 2}     # GNN_Module._activation
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
+# Pass budget of the large tensor-core contractions: site -> ``precision`` argument of
+# ``cgc_gemm`` (None = the backend's default, 3xTF32; 2 = one TF32 pass on round-to-nearest operands).  Only
+# consulted when the backend is in its default mode: ``gemm_precision = 0`` (exact-fp32 test mode) overrides it.
+PASS_BUDGET = {
+    'lin_fwd': None,        # lin of GNN_Module: feeds softmax / arg-max(S) -> must stay fp32-grade
+    'lin_dw': None, 'lin_dx': None,
+    'pool_stx': None, 'pool_stas': None,
+    'pool_gs': None, 'pool_gp': None, 'pool_gx': None, 'pool_gadj': None,
+    'dense_agg': None, 'dense_agg_t': None, 'dense_dadj': None,
+}
+
+
+def _prec(be, site):
+    if getattr(be, 'gemm_precision', -1) != -1:
+        return None
+    return PASS_BUDGET.get(site)
+
 
 def _f32(*shape, device):
     return torch.empty(*shape, dtype=torch.float32, device=device)
@@ -178,7 +195,8 @@ def _agg(be, cfg, adj, rs, x_prev, out):
             be.spmm(g.rowptr, g.col, g.val, x_prev, None, rs, out, False)
     else:
         b, n = cfg.num_graphs, cfg.nmax
-        be.gemm(adj, _as3d(x_prev, b, n), out.view(b, n, -1), False, False, row_scale=rs)
+        be.gemm(adj, _as3d(x_prev, b, n), out.view(b, n, -1), False, False, row_scale=rs,
+                precision=_prec(be, 'dense_agg'))
 
 
 def _agg_t(be, cfg, adj, g_a, src_scale, out, accumulate):
@@ -189,7 +207,7 @@ def _agg_t(be, cfg, adj, g_a, src_scale, out, accumulate):
     else:
         b, n = cfg.num_graphs, cfg.nmax
         be.gemm(adj, _as3d(g_a, b, n), _as3d(out, b, n), True, False,
-                beta=1.0 if accumulate else 0.0)
+                beta=1.0 if accumulate else 0.0, precision=_prec(be, 'dense_agg_t'))
 
 
 def _as3d(t, b, n):
@@ -245,7 +263,7 @@ class GnnModuleFunction(Function):
             x_prev, off = dst, off + couts[k]
         if cfg.has_lin:
             out = _f32(m, w_lin.shape[0], device=dev)
-            be.gemm(cat, w_lin, out, False, True, bias=b_lin, rowmask=cfg.mask)
+            be.gemm(cat, w_lin, out, False, True, bias=b_lin, rowmask=cfg.mask, precision=_prec(be, 'lin_fwd'))
         else:
             out = cat
         ctx.cfg, ctx.couts = cfg, couts
@@ -267,14 +285,14 @@ class GnnModuleFunction(Function):
         grads = [None] * 14
         if cfg.has_lin:
             d_wl = torch.empty_like(w_lin)
-            be.gemm(g_out, cat, d_wl, True, False)            # dY^T X (K = M; padded rows of X are 0)
+            be.gemm(g_out, cat, d_wl, True, False, precision=_prec(be, 'lin_dw'))     # dY^T X (K = M; padded rows of X are 0)
             grads[12] = d_wl
             if b_lin is not None:
                 d_bl = torch.empty_like(b_lin)
                 be.colsum(g_out, cfg.mask, d_bl)
                 grads[13] = d_bl
             g_cat = _f32(m, cat.shape[1], device=dev)
-            be.gemm(g_out, w_lin, g_cat, False, False, rowmask=cfg.mask)   # (dY * mask) W
+            be.gemm(g_out, w_lin, g_cat, False, False, rowmask=cfg.mask, precision=_prec(be, 'lin_dx'))   # (dY * mask) W
         else:
             g_cat = g_out.clone()                              # accumulated into below
         dense = cfg.graph is None
@@ -336,7 +354,8 @@ class GnnModuleFunction(Function):
                 _agg_t(be, cfg, adj, ga, src_scale, g_x0, False)
         if want_adj:
             b_, n_ = cfg.num_graphs, cfg.nmax
-            be.gemm(ga_all.view(b_, n_, -1), xc_all.view(b_, n_, -1), d_adj, False, True)   # dA = gA x^T
+            be.gemm(ga_all.view(b_, n_, -1), xc_all.view(b_, n_, -1), d_adj, False, True,
+                    precision=_prec(be, 'dense_dadj'))                                       # dA = gA x^T
             # rs_i = 1 / clamp(rsum_i, 1)  ->  dA_ij += -[rsum_i >= 1] d_rs_i / rsum_i^2   (all j)
             be.add_rs_grad(d_adj, rsum, d_rs)
         return (None, g_x0, d_adj, None, None) + tuple(grads)
@@ -560,7 +579,7 @@ class DiffPoolFunction(Function):
         be.softmax_fwd(z.contiguous(), cfg.mask, s, s_full, arg)
         x = x.contiguous()
         xp = _f32(b, c, x.shape[1], device=dev)
-        be.gemm(_as3d(s, b, n), x.view(b, n, -1), xp, True, False)
+        be.gemm(_as3d(s, b, n), x.view(b, n, -1), xp, True, False, precision=_prec(be, 'pool_stx'))
         p = _mat(m, c, dev)
         if cfg.graph is not None:
             g = cfg.graph
@@ -572,8 +591,12 @@ class DiffPoolFunction(Function):
         else:
             be.gemm(adj, _as3d(s, b, n), _as3d(p, b, n), False, False)
         ap = _f32(b, c, c, device=dev)
-        be.gemm(_as3d(s, b, n), _as3d(p, b, n), ap, True, False)
-        ctx.cfg, ctx.s, ctx.p, ctx.x, ctx.adj = cfg, s, p, x, adj
+        be.gemm(_as3d(s, b, n), _as3d(p, b, n), ap, True, False, precision=_prec(be, 'pool_stas'))
+        ctx.cfg = cfg
+        ctx.has_adj = adj is not None
+        # s / p are intermediates (never returned), x / adj inputs: saved through autograd so that in-place edits
+        # are caught and nothing forms a tensor -> grad_fn -> ctx -> tensor cycle
+        ctx.save_for_backward(s, p, x, *([adj] if adj is not None else []))
         ctx.want_adj = adj is not None and ctx.needs_input_grad[3]
         outs = (xp, ap, s_full, arg)
         ctx.mark_non_differentiable(*[t for t in (s_full, arg) if t is not None])
@@ -582,17 +605,20 @@ class DiffPoolFunction(Function):
     @staticmethod
     def backward(ctx, g_xp, g_ap, _gs_full, _garg):
         be = _backend.get()
-        cfg, s, p, x, adj = ctx.cfg, ctx.s, ctx.p, ctx.x, ctx.adj
+        cfg = ctx.cfg
+        s, p, x = ctx.saved_tensors[:3]
+        adj = ctx.saved_tensors[3] if ctx.has_adj else None
         dev = s.device
         m, c = s.shape
         b, n = cfg.num_graphs, cfg.nmax
         g_ap = g_ap.contiguous() if g_ap is not None else torch.zeros(b, c, c, device=dev)
         g_xp = g_xp.contiguous() if g_xp is not None else torch.zeros(b, c, x.shape[1], device=dev)
         g_s = _mat(m, c, dev)
-        be.gemm(_as3d(p, b, n), g_ap, _as3d(g_s, b, n), False, True)                   # P gA'^T
-        be.gemm(x.view(b, n, -1), g_xp, _as3d(g_s, b, n), False, True, beta=1.0)       # + X gX'^T
+        be.gemm(_as3d(p, b, n), g_ap, _as3d(g_s, b, n), False, True, precision=_prec(be, 'pool_gs'))     # P gA'^T
+        be.gemm(x.view(b, n, -1), g_xp, _as3d(g_s, b, n), False, True, beta=1.0,
+                precision=_prec(be, 'pool_gs'))                                          # + X gX'^T
         g_p = _mat(m, c, dev)
-        be.gemm(_as3d(s, b, n), g_ap, _as3d(g_p, b, n), False, False)                  # S gA'
+        be.gemm(_as3d(s, b, n), g_ap, _as3d(g_p, b, n), False, False, precision=_prec(be, 'pool_gp'))    # S gA'
         g_adj = None
         if cfg.graph is not None:
             g = cfg.graph
@@ -605,9 +631,10 @@ class DiffPoolFunction(Function):
             be.gemm(adj, _as3d(g_p, b, n), _as3d(g_s, b, n), True, False, beta=1.0)
             if ctx.want_adj:
                 g_adj = torch.empty_like(adj)
-                be.gemm(_as3d(g_p, b, n), _as3d(s, b, n), g_adj, False, True)          # gP S^T
+                be.gemm(_as3d(g_p, b, n), _as3d(s, b, n), g_adj, False, True,
+                        precision=_prec(be, 'pool_gadj'))                                # gP S^T
         g_x = _f32(m, x.shape[1], device=dev)
-        be.gemm(_as3d(s, b, n), g_xp, g_x.view(b, n, -1), False, False)                # S gX'
+        be.gemm(_as3d(s, b, n), g_xp, g_x.view(b, n, -1), False, False, precision=_prec(be, 'pool_gx'))  # S gX'
         g_z = _f32(m, c, device=dev)
         be.softmax_bwd(g_s, s, g_z)
         return None, g_z, g_x, g_adj, None
@@ -648,14 +675,16 @@ class DenseRenormFunction(Function):
         out = torch.empty_like(adj)
         rho = _f32(adj.shape[0] * adj.shape[1], device=adj.device)   # off-diagonal row sums + EPS
         be.dense_renorm_fwd(adj, p, mask, out, rho)
-        ctx.p, ctx.mask, ctx.out, ctx.rho = p, mask, out, rho
+        ctx.p, ctx.mask = p, mask
+        ctx.save_for_backward(out, rho)       # `out` is this node's own output: saved through autograd (no cycle)
         return out
 
     @staticmethod
     def backward(ctx, g):
         be = _backend.get()
-        g_adj = torch.empty_like(ctx.out)
-        be.dense_renorm_bwd(g.contiguous(), ctx.out, ctx.rho, ctx.p, ctx.mask, g_adj)
+        out, rho = ctx.saved_tensors
+        g_adj = torch.empty_like(out)
+        be.dense_renorm_bwd(g.contiguous(), out, rho, ctx.p, ctx.mask, g_adj)
         return g_adj, None, None
 
 

@@ -43,10 +43,14 @@ class FlatGradBucket(object):
 
     def pack(self):
         """Copy the per-parameter gradients into the flat buffer (missing gradients count as zero) and make
-        every ``.grad`` a view of it."""
-        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad is not v]
-        if len(have) < len(self.params):
-            self.flat.zero_()
+        every ``.grad`` a view of it.  Idempotent: gradients that already ARE the views (a second ``pack()``,
+        ``pack()`` followed by ``all_reduce_mean()``, gradient accumulation without ``zero()``) stay untouched."""
+        have = []
+        for v, p in zip(self.views, self.params):
+            if p.grad is None:
+                v.zero_()                       # only a MISSING gradient is zeroed; a live view keeps its content
+            elif p.grad.data_ptr() != v.data_ptr() or p.grad.shape != v.shape:
+                have.append((v, p.grad))
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         for p, v in zip(self.params, self.views):

@@ -98,3 +98,29 @@ def test_flat_bucket_views_and_sharding():
     assert sum(len(parallel.shard_for_rank(graphs, r, 2)) for r in range(2)) == len(graphs)
     by_nodes = [parallel.shard_for_rank(graphs, r, 2, by_nodes=True) for r in range(2)]
     assert sum(len(s) for s in by_nodes) == len(graphs)
+
+
+def test_flat_bucket_pack_is_idempotent():
+    """pack() twice, pack() + all_reduce_mean(), and accumulation into the live views must keep the gradients
+    (the second pack() used to zero the whole buffer)."""
+    model = _make_model()
+    bucket = parallel.FlatGradBucket(model.parameters())
+    bucket.zero()
+    for i, p in enumerate(model.parameters()):
+        p.grad = torch.full_like(p, float(i + 1))
+    bucket.pack()
+    first = bucket.flat.clone()
+    assert float(first.abs().min()) > 0
+    bucket.pack()                                       # every .grad already is its view
+    assert torch.equal(bucket.flat, first)
+    bucket.all_reduce_mean()                            # no process group: no-op, still intact
+    assert torch.equal(bucket.flat, first)
+    for p in model.parameters():                        # gradient accumulation without zero(): grads live in the views
+        p.grad += 1.0
+    bucket.pack()
+    assert torch.equal(bucket.flat, first + 1.0)
+    params = list(model.parameters())
+    params[0].grad = None                               # one gradient missing -> only ITS view is zeroed
+    bucket.pack()
+    assert float(params[0].grad.abs().max()) == 0.0
+    assert torch.equal(params[1].grad, torch.full_like(params[1], 3.0))
