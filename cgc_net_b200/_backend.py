@@ -48,6 +48,12 @@ _SIGNATURES = {
                          _c_vp],
     'cgc_sage_gather_ell_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i32,
                                 _c_i32, _c_vp, _c_vp],
+    'cgc_sage_gather_ell': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32,
+                            _c_i32, _c_vp, _c_i64, _c_int, _c_vp],
+    'cgc_sage_layer_ell_supported': [_c_i32, _c_i32, _c_i32],
+    'cgc_sage_layer_ell_fwd': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32,
+                               _c_i32, _c_vp, _c_vp, _c_vp, _c_i32, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
+                               _c_f32, _c_f32, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp],
     'cgc_gather_wide_ell': [_c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32,
                             _c_i32, _c_vp, _c_i64, _c_int, _c_vp],
     'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
@@ -86,6 +92,9 @@ _SIGNATURES = {
 _RESTYPES = {'cgc_last_error': ctypes.c_char_p, 'cgc_workspace_bytes': _c_i64, 'cgc_launch_count': _c_i64,
              'cgc_coo_to_csr_workspace': _c_i64, 'cgc_ell16_rows': _c_i64, 'cgc_jk_tape_floats': _c_i64}
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+
+GATHER_ACCUMULATE, GATHER_TABLES_READY, GATHER_NO_PDL = 1, 2, 4        # CGC_GATHER_* flags of include/cgc_sm100.h
 
 
 class CgcError(RuntimeError):
@@ -277,6 +286,46 @@ class CudaBackend(object):
                                                      _ptr(x, torch.float32), num_graphs, nmax, x.shape[1],
                                                      _ptr(out, torch.float32), self._stream()),
                     'cgc_sage_gather_ell_fwd')
+
+    def sage_gather_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
+                        accumulate=False, tables_ready=False, pdl=True):
+        """General ELL16 gather: x / out may be column slices (leading dimensions); ``accumulate`` adds into out;
+        ``tables_ready`` = the tables were not written by the kernel enqueued right before (PDL prologue)."""
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        flags = (GATHER_ACCUMULATE if accumulate else 0) | (GATHER_TABLES_READY if tables_ready else 0) | \
+                (0 if pdl else GATHER_NO_PDL)
+        self._check(self.lib.cgc_sage_gather_ell(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32),
+                                                 _ptr(ell_scale, torch.float32), _ptr(perm, torch.int32), width,
+                                                 _ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                                 _ptr(val, torch.float32), xp, ldx, num_graphs, nmax, x.shape[1],
+                                                 op, ldo, flags, self._stream()), 'cgc_sage_gather_ell')
+
+    def sage_layer_ell_supported(self, cin, cout, nmax):
+        return bool(self.lib.cgc_sage_layer_ell_supported(int(cin), int(cout), int(nmax)))
+
+    def sage_layer_ell_fwd(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, w, b,
+                           mask, act, sa, y, rmean, rvar, momentum, eps, mean, invstd, tables_ready=False, pdl=True):
+        """Fused narrow SAGE layer (gather + W + bias + L2 norm + mask + act + BatchNorm statistics); ``mean`` None =
+        no statistics (eval mode / no BatchNorm)."""
+        xp, ldx = _mat(x)
+        yp, ldy = _mat(y)
+        if not sa.is_contiguous():
+            raise CgcError('cgc_sage_layer_ell_fwd needs a contiguous sa')
+        nn, _ = _mask(mask)
+        wp, wb = self._workspace(x.device)
+        self._check(self.lib.cgc_sage_layer_ell_fwd(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32),
+                                                    _ptr(ell_scale, torch.float32), _ptr(perm, torch.int32), width,
+                                                    _ptr(rowptr, torch.int32), _ptr(col, torch.int32),
+                                                    _ptr(val, torch.float32), xp, ldx, num_graphs, nmax, x.shape[1],
+                                                    _ptr(w.contiguous(), torch.float32), _ptr(b, torch.float32), nn,
+                                                    w.shape[1], int(act), _ptr(sa, torch.float32), yp, ldy,
+                                                    _ptr(rmean, torch.float32), _ptr(rvar, torch.float32),
+                                                    float(momentum), float(eps), _ptr(mean, torch.float32),
+                                                    _ptr(invstd, torch.float32), wp, wb,
+                                                    (GATHER_TABLES_READY if tables_ready else 0) |
+                                                    (0 if pdl else GATHER_NO_PDL), self._stream()),
+                    'cgc_sage_layer_ell_fwd')
 
     def gather_wide_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
                         accumulate):

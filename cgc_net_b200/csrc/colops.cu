@@ -455,6 +455,17 @@ static void reduce_geometry(int64_t rows, int c, int& nrb, int64_t& rows_per_blo
 
 }  // namespace cgc
 
+namespace cgc {
+// shared with sage_layer.cu: finalize of per-block [2][c] double partial sums
+int bn_finalize_partials(const double* partial, int blocks, int c, int64_t rows, float* running_mean,
+                         float* running_var, float momentum, float eps, float* mean, float* invstd, cudaStream_t st) {
+  k_bn_finalize<double><<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, blocks, c, rows, running_mean, running_var,
+                                                                 momentum, eps, mean, invstd);
+  CGC_CHECK_LAUNCH("k_bn_finalize");
+  return 0;
+}
+}  // namespace cgc
+
 using namespace cgc;
 
 extern "C" int cgc_bn_stats(const float* y, int64_t ldy, int64_t rows, int32_t c, float* running_mean,

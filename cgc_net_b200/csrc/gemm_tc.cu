@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include "ell_gather.cuh"
 #include "gemm.cuh"
 
 namespace cgc {
@@ -700,38 +701,10 @@ __global__ void __launch_bounds__(256) k_tc_splitk_reduce(GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// 3-D tensor map {inner, rows, batch} over a row-major fp32 operand.
+// 3-D tensor map {inner, rows, batch} over a row-major fp32 operand (encoded once per distinct view, api.cu)
 static bool make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t batch, int64_t ld,
                      int64_t batch_stride, uint32_t box_rows, bool mn_major) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[3] = {inner, rows, batch};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : (int64_t)rows * ld) * 4};
-  cuuint32_t box[3] = {32, box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  return tensor_map_3d(map, base, inner, rows, batch, ld, batch_stride, box_rows, mn_major);
 }
 
 }  // namespace tc
@@ -749,7 +722,7 @@ bool gemm_tc_supported(const GemmParams& p, int ta, int tb, bool forced) {
     if ((double)hi * (lo < 96 ? 128 : lo) * p.k * p.batch < 6.7e7) return false;
   }
   if (p.lda * 4 >= (1ll << 40) || p.ldb * 4 >= (1ll << 40)) return false;
-  return tc::get_encode_fn() != nullptr;
+  return tensor_map_available();
 }
 
 int gemm_tc(GemmParams p, int ta, int tb, int passes, void* work, int64_t work_bytes, cudaStream_t st) {

@@ -1,0 +1,382 @@
+// One narrow SAGE layer in one kernel: neighbour gather (ELL16 table, TMA-staged feature tile) -> W -> bias ->
+// L2-normalise -> mask -> activation -> BatchNorm column partial sums.
+//
+// Reference arithmetic (model/network.py:114-116 with PyG 1.2.1 DenseSAGEConv.forward inlined):
+//   out = matmul(adj, x) / adj.sum(-1).clamp(min=1);  out = matmul(out, weight) + bias;
+//   out = F.normalize(out, p=2, dim=-1) * mask;  x_k = bn_k(act(out))      (this kernel stops at the batch sums)
+//
+// Layout of the work: CTA (g, p) owns a contiguous range of graph g's table rows and stages the graph's whole
+// [nmax, CIN] input tile in shared memory (1-D bulk copies, or 2-D TMA boxes when x is a column slice of the
+// concat buffer).  LPR = CIN / 4 lanes serve one row: each lane gathers one float4 of the row's neighbour sum
+// exactly like k_sage_gather_ell.  Then the LPR lanes exchange their float4s (warp shuffles), so every lane holds
+// the whole aggregated row, and each lane produces the output columns it owns with W kept in REGISTERS for the
+// whole kernel (CIN x 4 or 5 values per lane; W never goes through shared memory, which is the saturated unit):
+//   CIN = 16 (4 lanes): lane sl owns columns 4sl..4sl+3 and 16+sl;   CIN = 20 (5 lanes): columns 4sl..4sl+3.
+// The squared norm is reduced over the LPR lanes, the row is scaled, masked, activated and stored, and the lane
+// keeps running sums of y and y^2 of its columns; at the end they are reduced over the CTA (shuffles, then one
+// shared-memory pass in double precision) into `partial[cta][2][20]` for the fixed-order finalize kernel.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ell_gather.cuh"
+
+namespace cgc {
+
+constexpr int kLayerCout = 20;
+constexpr int kLayerThreads = 384;
+
+struct SageLayerArgs {
+  const uint16_t* ell;
+  const float* ellw;
+  const float* ell_scale;
+  const uint32_t* perm;
+  const int* rowptr;
+  const int* col;
+  const float* val;
+  const float* x;
+  const float* w;            // [CIN, 20] row-major
+  const float* b;            // [20] or null
+  const int32_t* num_nodes;  // row mask, or null
+  float* sa;                 // [rows, CIN]
+  float* y;                  // [rows, ldy]
+  int64_t ldy;
+  double* partial;           // [grid][2][20] column sums of y and y^2, or null
+  int nmax, parts, rpp, box_rows, early, act;
+};
+
+template <int CIN, int W, bool WEIGHTED, bool STRIDED>
+__global__ void __launch_bounds__(kLayerThreads, 1)
+k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int COUT = kLayerCout;
+  constexpr int LPR = CIN / 4;                         // lanes per row: 4 or 5
+  constexpr int GPW = 32 / LPR;                        // row groups per warp: 8 or 6
+  constexpr int NWARPS = kLayerThreads / 32;
+  constexpr int G = NWARPS * GPW;                      // rows in flight per pass of the CTA
+  constexpr int NW = W / 2;
+  constexpr int RB = (W == 16 && WEIGHTED) ? 1 : 2;
+  constexpr int NOWN = COUT / LPR;                     // output columns per lane: 5 or 4
+  constexpr bool EXTRA = NOWN == 5;                    // 4 lanes: the fifth column is 16 + sl
+  static_assert(CIN == 16 || CIN == 20, "instantiated for 16 or 20 input channels");
+  constexpr uint32_t row_bytes = CIN * 4u;
+
+  const int nmax = a.nmax, parts = a.parts;
+  const int nrow8 = (nmax + 7) & ~7;
+  const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
+  const int r0 = p * a.rpp;
+  const int nrows = min(a.rpp, nrow8 - r0);
+  pdl_launch_dependents();
+  const int64_t grow0 = (int64_t)g * nmax;
+  const int64_t trow0 = (int64_t)g * nrow8 + r0;
+  float* s_x = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_red[NWARPS][2][COUT];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gw = lane / LPR, sl = lane - gw * LPR;
+  const bool active = gw < GPW;                        // CIN = 20: lanes 30, 31 idle
+  const int grp = warp * GPW + (active ? gw : 0);
+  const int lbase = lane - sl;                         // first lane of this row group
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (STRIDED) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (!STRIDED && tid < 2 * CIN) s_x[(size_t)nmax * CIN + tid] = 0.f;
+
+  const uint32_t lane_base = smem_u32(smem_raw) + (uint32_t)sl * 16u;
+  const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
+  const uint32_t ovf_mark = (uint32_t)nmax + 1u;
+
+  uint32_t idx[RB][NW];
+  float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
+  float rsc[RB];
+  uint32_t pw[RB];
+  auto load_batch = [&](int i0) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int t = (i0 + i) * G + grp;
+      const bool on = active && t < nrows;
+      const int64_t trow = trow0 + (on ? t : 0);
+      pw[i] = on ? __ldg(a.perm + (trow >> 3)) : 0xFFFFFFFFu;
+      rsc[i] = on ? __ldg(a.ell_scale + trow) : 1.0f;
+#pragma unroll
+      for (int q = 0; q < NW / 4; ++q) {
+        uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
+        if (on) v = ldg_u4(a.ell + trow * W + q * 8);
+        idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
+      }
+      if (WEIGHTED) {
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on) v = ldg_f4(a.ellw + trow * W + q * 4);
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
+          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
+        }
+      }
+    }
+  };
+  // W columns of this lane, in registers for the whole kernel: wr[k][0..3] = W[k][4sl..4sl+3], wr[k][4] = W[k][16+sl]
+  float wr[CIN][NOWN];
+  float br[NOWN];
+  auto load_weights = [&]() {
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+      const float4 v = ldg_f4(a.w + k * COUT + 4 * sl);
+      wr[k][0] = v.x; wr[k][1] = v.y; wr[k][2] = v.z; wr[k][3] = v.w;
+      if (EXTRA) wr[k][NOWN - 1] = __ldg(a.w + k * COUT + 16 + sl);
+    }
+    if (a.b != nullptr) {
+      const float4 v = ldg_f4(a.b + 4 * sl);
+      br[0] = v.x; br[1] = v.y; br[2] = v.z; br[3] = v.w;
+      if (EXTRA) br[NOWN - 1] = __ldg(a.b + 16 + sl);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) br[j] = 0.f;
+    }
+  };
+
+  if (a.early) { load_batch(0); load_weights(); }
+  pdl_wait();
+  if (tid == 0 && nrows > 0) {
+    if (STRIDED) {
+      const int nboxes = (nmax + a.box_rows - 1) / a.box_rows;
+      mbar_expect_tx(&bar, (uint32_t)nboxes * (uint32_t)a.box_rows * row_bytes);
+      for (int bx = 0; bx < nboxes; ++bx)
+        tma_load_2d(smem_raw + (size_t)bx * a.box_rows * row_bytes, &map_x, 0, (int)grow0 + bx * a.box_rows, &bar);
+    } else {
+      const uint32_t tile_bytes = (uint32_t)nmax * row_bytes;
+      mbar_expect_tx(&bar, tile_bytes);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + grow0 * CIN);
+      for (uint32_t off = 0; off < tile_bytes; off += 32768u) {
+        const uint32_t n = min(32768u, tile_bytes - off);
+        bulk_g2s(smem_raw + off, src + off, n, &bar);
+      }
+    }
+  }
+  if (!a.early) { load_batch(0); load_weights(); }
+  const int nn = a.num_nodes ? __ldg(a.num_nodes + g) : nmax;   // real nodes of this graph
+  __syncthreads();
+  if (nrows > 0) mbar_wait(&bar, 0);
+  if (STRIDED) {
+    if (tid < 2 * CIN) s_x[(size_t)nmax * CIN + tid] = 0.f;
+    __syncthreads();
+  }
+
+  float s1[NOWN], s2[NOWN];
+#pragma unroll
+  for (int j = 0; j < NOWN; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+
+  for (int i0 = 0; i0 * G < nrows; i0 += RB) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int t = (i0 + i) * G + grp;
+      // rows are handed out warp-uniformly in t's high part only: the shuffles below need every lane of the warp,
+      // so no early `continue`; inactive lanes / rows compute on zeros and skip the stores
+      const int lrow = ((r0 + t) & ~7) + (int)((pw[i] >> (3 * (t & 7))) & 7u);
+      const bool row_on = active && t < nrows && lrow < nmax;
+      const int64_t row = grow0 + (row_on ? lrow : 0);
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_on) {
+        if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
+          F32x4 acc;
+          acc.lo = 0ull; acc.hi = 0ull;
+#pragma unroll
+          for (int u = 0; u < W; ++u) {
+            const uint32_t j = ell_slot(idx[i], u);
+            const F32x4 v = lds_x4(lane_base + j * row_bytes);
+            if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
+            else add_x4(acc, v);
+          }
+          o = unpack_x4(acc);
+        } else {
+          const int eb = __ldg(a.rowptr + row), ee = __ldg(a.rowptr + row + 1);
+          for (int k = eb; k < ee; ++k) {
+            const uint32_t j = (uint32_t)(__ldg(a.col + k) - (int)grow0);
+            const float wv = WEIGHTED ? __ldg(a.val + k) : 1.0f;
+            const float4 v = lds_f4(lane_base + j * row_bytes);
+            o.x = fmaf(wv, v.x, o.x); o.y = fmaf(wv, v.y, o.y); o.z = fmaf(wv, v.z, o.z); o.w = fmaf(wv, v.w, o.w);
+          }
+        }
+        const float s = rsc[i];
+        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+        *reinterpret_cast<float4*>(a.sa + row * CIN + sl * 4) = o;
+      }
+      // all-gather of the aggregated row over its LPR lanes
+      float full[CIN];
+#pragma unroll
+      for (int d = 0; d < LPR; ++d) {
+        full[4 * d + 0] = __shfl_sync(0xffffffffu, o.x, lbase + d);
+        full[4 * d + 1] = __shfl_sync(0xffffffffu, o.y, lbase + d);
+        full[4 * d + 2] = __shfl_sync(0xffffffffu, o.z, lbase + d);
+        full[4 * d + 3] = __shfl_sync(0xffffffffu, o.w, lbase + d);
+      }
+      float z[NOWN];
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) z[j] = br[j];
+#pragma unroll
+      for (int k = 0; k < CIN; ++k)
+#pragma unroll
+        for (int j = 0; j < NOWN; ++j) z[j] = fmaf(full[k], wr[k][j], z[j]);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) ss = fmaf(z[j], z[j], ss);
+      float tot = 0.f;
+#pragma unroll
+      for (int d = 0; d < LPR; ++d) tot += __shfl_sync(0xffffffffu, ss, lbase + d);
+      const float inv = 1.0f / fmaxf(sqrtf(tot), kL2NormEps);
+      const bool valid = lrow < nn;
+      float yv[NOWN];
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) yv[j] = valid ? act_fwd(a.act, z[j] * inv) : 0.f;
+      if (row_on) {
+        float* yrow = a.y + row * a.ldy;
+        *reinterpret_cast<float4*>(yrow + 4 * sl) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        if (EXTRA) yrow[16 + sl] = yv[NOWN - 1];
+#pragma unroll
+        for (int j = 0; j < NOWN; ++j) { s1[j] += yv[j]; s2[j] = fmaf(yv[j], yv[j], s2[j]); }
+      }
+    }
+    if ((i0 + RB) * G < nrows) load_batch(i0 + RB);
+  }
+
+  if (a.partial == nullptr) return;
+  // column sums: over the warp's row groups (lanes with equal sl), then over the warps in double precision
+#pragma unroll
+  for (int j = 0; j < NOWN; ++j) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < GPW; ++d) {
+      t1 += __shfl_sync(0xffffffffu, s1[j], sl + d * LPR);
+      t2 += __shfl_sync(0xffffffffu, s2[j], sl + d * LPR);
+    }
+    if (gw == 0) {
+      const int c = (EXTRA && j == NOWN - 1) ? 16 + sl : 4 * sl + j;
+      s_red[warp][0][c] = t1;
+      s_red[warp][1][c] = t2;
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * COUT) {
+    const int which = tid / COUT, c = tid - which * COUT;
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < NWARPS; ++wv) v += (double)s_red[wv][which][c];
+    a.partial[((int64_t)blockIdx.x * 2 + which) * COUT + c] = v;
+  }
+}
+
+// colops.cu: mean / invstd / running statistics from per-block [2][c] double partial sums (fixed order)
+int bn_finalize_partials(const double* partial, int blocks, int c, int64_t rows, float* running_mean,
+                         float* running_var, float momentum, float eps, float* mean, float* invstd, cudaStream_t st);
+
+template <int CIN, int W, bool WEIGHTED, bool STRIDED>
+static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, int64_t work_bytes, float* running_mean,
+                        float* running_var, float momentum, float eps, float* mean, float* invstd, cudaStream_t st) {
+  const int nmax = a.nmax;
+  size_t smem = ((size_t)nmax + 2) * CIN * 4;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (STRIDED) {
+    int64_t rows_buf = 0;
+    a.box_rows = pick_box_rows(nmax, CIN * 4, 1, 227 * 1024 - 2048, &rows_buf);
+    CGC_REQUIRE(a.box_rows > 0, CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: %d rows do not fit in shared memory", nmax);
+    smem = (size_t)rows_buf * CIN * 4;
+    CGC_REQUIRE(tensor_map_2d(&map, a.x, (uint64_t)CIN, (uint64_t)num_graphs * nmax, ldx, (uint32_t)CIN,
+                              (uint32_t)a.box_rows),
+                CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: cuTensorMapEncodeTiled failed");
+  }
+  int parts = kNumSMs / num_graphs;
+  if (parts < 1) parts = 1;
+  const int nrow8 = (nmax + 7) & ~7;
+  int rpp = (int)ceil_div(nrow8, parts);
+  rpp = (rpp + 7) & ~7;
+  parts = (int)ceil_div(nrow8, rpp);
+  a.parts = parts;
+  a.rpp = rpp;
+  const int grid = num_graphs * parts;
+  if (a.partial != nullptr)
+    CGC_REQUIRE((int64_t)grid * 2 * kLayerCout * 8 <= work_bytes, CGC_ERR_WORKSPACE,
+                "cgc_sage_layer_ell_fwd: workspace too small");
+  auto kern = k_sage_layer_ell<CIN, W, WEIGHTED, STRIDED>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  PdlLaunch L(dim3((unsigned)grid), dim3(kLayerThreads), smem, st, pdl);
+  CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, a));
+  CGC_CHECK_LAUNCH("k_sage_layer_ell");
+  if (a.partial != nullptr)
+    return bn_finalize_partials(a.partial, grid, kLayerCout, (int64_t)num_graphs * nmax, running_mean, running_var,
+                                momentum, eps, mean, invstd, st);
+  return 0;
+}
+
+}  // namespace cgc
+
+using namespace cgc;
+
+extern "C" int cgc_sage_layer_ell_supported(int32_t cin, int32_t cout, int32_t nmax) {
+  if (cout != kLayerCout || (cin != 16 && cin != 20) || nmax <= 0 || nmax + 1 > 0xFFFF) return 0;
+  int64_t rows_buf = 0;
+  // the strided variant needs the larger buffer (box overhang); require it so both input layouts are served
+  return pick_box_rows(nmax, cin * 4, 1, 227 * 1024 - 2048, &rows_buf) > 0 ? 1 : 0;
+}
+
+extern "C" int cgc_sage_layer_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                                      const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                                      const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
+                                      int32_t cin, const float* w, const float* b, const int32_t* num_nodes,
+                                      int32_t cout, int act, float* sa, float* y, int64_t ldy, float* running_mean,
+                                      float* running_var, float momentum, float eps, float* mean, float* invstd,
+                                      void* work, int64_t work_bytes, int flags, void* stream) {
+  CGC_REQUIRE(ell && ell_scale && perm && rowptr && col && x && w && sa && y && num_graphs > 0 && nmax > 0, CGC_ERR_ARG,
+              "cgc_sage_layer_ell_fwd: bad args");
+  CGC_REQUIRE(cgc_sage_layer_ell_supported(cin, cout, nmax), CGC_ERR_UNSUPPORTED,
+              "cgc_sage_layer_ell_fwd: instantiated for cin 16 / 20 and cout 20 with the tile in shared memory "
+              "(got cin %d cout %d nmax %d)", cin, cout, nmax);
+  CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: width must be 8 or 16");
+  CGC_REQUIRE(ldx >= cin && ldx % 4 == 0 && ldy >= cout && ldy % 4 == 0 && aligned16(x) && aligned16(y) &&
+                  aligned16(sa) && aligned16(ell) && aligned16(w) && (b == nullptr || aligned16(b)),
+              CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: ldx / ldy multiples of 4 and 16B-aligned pointers needed");
+  CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
+              "cgc_sage_layer_ell_fwd: val and ell_val must be given together");
+  CGC_REQUIRE(ell_val == nullptr || aligned16(ell_val), CGC_ERR_UNSUPPORTED,
+              "cgc_sage_layer_ell_fwd: ell_val must be 16B-aligned");
+  CGC_REQUIRE((flags & CGC_GATHER_ACCUMULATE) == 0, CGC_ERR_ARG, "cgc_sage_layer_ell_fwd: ACCUMULATE is not a layer flag");
+  CGC_REQUIRE(mean == nullptr || (invstd != nullptr && work != nullptr), CGC_ERR_ARG,
+              "cgc_sage_layer_ell_fwd: statistics need invstd and a workspace");
+  SageLayerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ell = ell; a.ellw = ell_val; a.ell_scale = ell_scale; a.perm = perm; a.rowptr = rowptr; a.col = col; a.val = val;
+  a.x = x; a.w = w; a.b = b; a.num_nodes = num_nodes; a.sa = sa; a.y = y; a.ldy = ldy;
+  a.partial = mean ? reinterpret_cast<double*>(work) : nullptr;
+  a.nmax = nmax; a.act = act;
+  a.early = (flags & CGC_GATHER_TABLES_READY) ? 1 : 0;
+  cudaStream_t st = as_stream(stream);
+  const bool wt = ell_val != nullptr, strided = ldx != cin;
+  const bool pdl = (flags & CGC_GATHER_NO_PDL) == 0;
+  if (!pdl) a.early = 0;
+#define CGC_LAYER(CIN_, W_, WT_)                                                                                   \
+  do {                                                                                                             \
+    if (strided)                                                                                                   \
+      return launch_layer<CIN_, W_, WT_, true>(a, num_graphs, ldx, pdl, work_bytes, running_mean, running_var, momentum, \
+                                               eps, mean, invstd, st);                                             \
+    return launch_layer<CIN_, W_, WT_, false>(a, num_graphs, ldx, pdl, work_bytes, running_mean, running_var, momentum,  \
+                                              eps, mean, invstd, st);                                              \
+  } while (0)
+  if (cin == 16) {
+    if (width == 8) { if (wt) CGC_LAYER(16, 8, true); else CGC_LAYER(16, 8, false); }
+    else            { if (wt) CGC_LAYER(16, 16, true); else CGC_LAYER(16, 16, false); }
+  } else {
+    if (width == 8) { if (wt) CGC_LAYER(20, 8, true); else CGC_LAYER(20, 8, false); }
+    else            { if (wt) CGC_LAYER(20, 16, true); else CGC_LAYER(20, 16, false); }
+  }
+#undef CGC_LAYER
+}

@@ -10,8 +10,10 @@
 // DenseSAGEConv.forward (call sites model/network.py:114-116) and adj @ s of _diff_pool (:207).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "ell_gather.cuh"
 
 namespace cgc {
 
@@ -88,36 +90,6 @@ __global__ void __launch_bounds__(256) k_spmm(const int* __restrict__ rowptr, co
 }
 
 // ------------------------------------------------------------------ TMA-staged SAGE gather
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 constexpr int kGatherThreads = 512;
 constexpr int kGatherMaxRows = 1024;        // rows of one CTA (rowptr staging buffer)
 constexpr int kStageUnroll = 16;            // independent loads in flight per thread while staging
@@ -331,66 +303,55 @@ __global__ void __launch_bounds__(128) k_csr_to_ell16(const int* __restrict__ ro
   perm[blk] = pw;
 }
 
-__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ float4 ldg_f4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-// 16 bytes of shared memory as two packed f32x2 registers (operands of FADD2 / FFMA2)
-struct F32x4 {
-  unsigned long long lo, hi;
-};
-__device__ __forceinline__ F32x4 lds_x4(uint32_t addr) {
-  F32x4 v;
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void add_x4(F32x4& acc, const F32x4& v) {
-  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.lo) : "l"(v.lo));
-  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.hi) : "l"(v.hi));
-}
-__device__ __forceinline__ void fma_x4(F32x4& acc, float w, const F32x4& v) {
-  unsigned long long ww;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.lo) : "l"(v.lo), "l"(ww));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.hi) : "l"(v.hi), "l"(ww));
-}
-__device__ __forceinline__ float4 unpack_x4(const F32x4& v) {
-  float4 o;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(v.lo));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.z), "=f"(o.w) : "l"(v.hi));
-  return o;
-}
-
-// slot t (compile-time after unrolling) of a row's packed uint16 index words
-__device__ __forceinline__ uint32_t ell_slot(const uint32_t* words, int t) {
-  const uint32_t w = words[t >> 1];
-  return (t & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
-
 // grid = num_graphs * parts; CTA (g, p) owns table rows [p*rpp, min((p+1)*rpp, nrow8)) of graph g (rpp % 8 == 0).
 // LPR lanes per row, one float4 of the feature row per lane; group grp = tid / LPR serves table rows grp, grp+G, ...
 // Before the tile barrier every thread loads the index vectors (weights, row scales) of its RB rows (next batch:
 // prefetched); after it the slot loop is pure LDS.128 + packed FADD2 / FFMA2 on registers.
 // Everything a thread reads before the barrier (indices, weights, scale, position map) is addressed by the table
 // row alone: no load depends on another.
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
+//
+// STRIDED: x has a leading dimension > feat (a column slice of the concat buffer, layers 2-3 of a GNN_Module): the
+// tile is staged by 2-D TMA boxes {feat, box_rows} described by map_x instead of 1-D bulk copies; out always
+// takes ldo.  ACC: out += result (the CSC gathers of the backward accumulate into slices of the gradient buffer).
+//
+// Programmatic dependent launch: the kernel is launched with programmatic stream serialization, so its prologue
+// (barrier init, zero rows and -- when the caller says the tables were not written by the kernel right before it,
+// `early_tables` -- all index / scale / position-map loads) runs under the tail of the previous kernel;
+// pdl_wait() then orders the tile copy (x is the previous kernel's output) and every store after it.
+struct EllGatherArgs {
+  const uint16_t* ell;
+  const float* ellw;
+  const float* ell_scale;
+  const uint32_t* perm;
+  const int* rowptr;
+  const int* col;
+  const float* val;
+  const float* x;
+  float* out;
+  int64_t ldo;
+  int nmax, feat, parts, rpp;
+  int box_rows;          // STRIDED: rows per TMA box
+  int early_tables;      // index tables may be read before pdl_wait()
+  int lab_stage;         // CGC_LAB builds: 1 = exit at entry, 2 = exit after the tile copy (timeline measurements)
+  uint32_t chunk;        // bytes per 1-D bulk copy
+};
+
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
 __global__ void __launch_bounds__(THREADS, 1)
-k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ ellw,
-                  const float* __restrict__ ell_scale, const uint32_t* __restrict__ perm,
-                  const int* __restrict__ rowptr,
-                  const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ x,
-                  int nmax, int feat, int parts, int rpp, float* __restrict__ out, int stage_limit, uint32_t chunk) {
+k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int G = THREADS / LPR;
   constexpr int NW = W / 2;                            // 32-bit index words per row
+  const int nmax = a.nmax, feat = a.feat, parts = a.parts;
   const int nrow8 = (nmax + 7) & ~7;
   const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
-  const int r0 = p * rpp;
-  const int nrows = min(rpp, nrow8 - r0);
-  if (nrows <= 0 || stage_limit == 1) return;
+  const int r0 = p * a.rpp;
+  const int nrows = min(a.rpp, nrow8 - r0);
+  pdl_launch_dependents();                             // the next PDL kernel may start its prologue
+#ifdef CGC_LAB
+  if (a.lab_stage == 1) return;
+#endif
+  if (nrows <= 0) return;
   const int64_t grow0 = (int64_t)g * nmax;             // first padded row of the graph (x / out / rowptr)
   const int64_t trow0 = (int64_t)g * nrow8 + r0;       // first table row of this CTA
   const uint32_t row_bytes = (uint32_t)feat * 4u;
@@ -401,22 +362,11 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    uint32_t lo = 0, hi = tile_bytes;
-    if (stage_limit == 3) {                            // lab: each CTA copies only its share of the tile
-      const uint32_t share = (tile_bytes / parts) & ~15u;
-      lo = p * share; hi = lo + share;
-    } else if (stage_limit >= 4) {                     // lab: every CTA copies the first 1/(stage-2) of the tile
-      hi = (tile_bytes / (stage_limit - 2)) & ~15u;
-    }
-    mbar_expect_tx(&bar, hi - lo);
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + grow0 * feat);
-    for (uint32_t off = lo; off < hi; off += chunk) {
-      uint32_t n = min(chunk, hi - off);
-      bulk_g2s(smem_raw + off, src + off, n, &bar);
-    }
+    if (STRIDED) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
   }
-  // two zero rows behind the tile: index nmax = empty slot, nmax + 1 = overflow mark
-  if (threadIdx.x < 2 * feat) s_x[(size_t)nmax * feat + threadIdx.x] = 0.f;
+  // two zero rows behind the tile: index nmax = empty slot, nmax + 1 = overflow mark (STRIDED: the overhang of the
+  // last TMA box lands there, so they are written after the barrier instead)
+  if (!STRIDED && threadIdx.x < 2 * feat) s_x[(size_t)nmax * feat + threadIdx.x] = 0.f;
 
   const int sl = threadIdx.x % LPR;
   const int grp = threadIdx.x / LPR;
@@ -435,19 +385,19 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
       const int t = (i0 + i) * G + grp;                // table row inside the CTA
       const bool on = t < nrows;
       const int64_t trow = trow0 + (on ? t : 0);
-      pw[i] = on ? __ldg(perm + (trow >> 3)) : 0xFFFFFFFFu;
-      rsc[i] = on ? __ldg(ell_scale + trow) : 1.0f;
+      pw[i] = on ? __ldg(a.perm + (trow >> 3)) : 0xFFFFFFFFu;
+      rsc[i] = on ? __ldg(a.ell_scale + trow) : 1.0f;
 #pragma unroll
       for (int q = 0; q < NW / 4; ++q) {
         uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
-        if (on) v = ldg_u4(ell + trow * W + q * 8);
+        if (on) v = ldg_u4(a.ell + trow * W + q * 8);
         idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
       }
       if (WEIGHTED) {
 #pragma unroll
         for (int q = 0; q < W / 4; ++q) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on) v = ldg_f4(ellw + trow * W + q * 4);
+          if (on) v = ldg_f4(a.ellw + trow * W + q * 4);
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
           wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
@@ -457,10 +407,42 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
     }
   };
 
-  load_batch(0);
+  if (a.early_tables) load_batch(0);                   // flies under the previous kernel's tail
+  pdl_wait();                                          // x (and, without early_tables, the tables) are now final
+  if (threadIdx.x == 0) {
+    if (STRIDED) {
+      const int nboxes = (nmax + a.box_rows - 1) / a.box_rows;
+      mbar_expect_tx(&bar, (uint32_t)nboxes * (uint32_t)a.box_rows * row_bytes);
+      for (int bx = 0; bx < nboxes; ++bx)
+        tma_load_2d(smem_raw + (size_t)bx * a.box_rows * row_bytes, &map_x, 0, (int)grow0 + bx * a.box_rows, &bar);
+    } else {
+      uint32_t lo = 0, hi = tile_bytes;
+#ifdef CGC_LAB
+      if (a.lab_stage == 3) {                          // lab: each CTA copies only its share of the tile
+        const uint32_t share = (tile_bytes / parts) & ~15u;
+        lo = p * share; hi = lo + share;
+      } else if (a.lab_stage >= 4) {                   // lab: every CTA copies the first 1/(stage-2) of the tile
+        hi = (tile_bytes / (a.lab_stage - 2)) & ~15u;
+      }
+#endif
+      mbar_expect_tx(&bar, hi - lo);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + grow0 * feat);
+      for (uint32_t off = lo; off < hi; off += a.chunk) {
+        uint32_t n = min(a.chunk, hi - off);
+        bulk_g2s(smem_raw + off, src + off, n, &bar);
+      }
+    }
+  }
+  if (!a.early_tables) load_batch(0);
   __syncthreads();                                     // zero rows visible, barrier initialised
   mbar_wait(&bar, 0);
-  if (stage_limit >= 2) return;
+  if (STRIDED) {
+    if (threadIdx.x < 2 * feat) s_x[(size_t)nmax * feat + threadIdx.x] = 0.f;
+    __syncthreads();
+  }
+#ifdef CGC_LAB
+  if (a.lab_stage >= 2) return;
+#endif
 
   for (int i0 = 0; i0 * G < nrows; i0 += RB) {
 #pragma unroll
@@ -485,18 +467,23 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
         o = unpack_x4(acc);
       } else {
         // degree > W: walk the CSR (column ids are global padded rows)
-        const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+        const int b = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
         o = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = b; k < e; ++k) {
-          const uint32_t j = (uint32_t)(__ldg(col + k) - (int)grow0);
-          const float w = WEIGHTED ? __ldg(val + k) : 1.0f;
+          const uint32_t j = (uint32_t)(__ldg(a.col + k) - (int)grow0);
+          const float w = WEIGHTED ? __ldg(a.val + k) : 1.0f;
           const float4 v = lds_f4(lane_base + j * row_bytes);
           o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y); o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
         }
       }
       if (lane_on) {
         o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-        *reinterpret_cast<float4*>(out + row * feat + sl * 4) = o;
+        float4* dst = reinterpret_cast<float4*>(a.out + row * a.ldo + sl * 4);
+        if (ACC) {
+          const float4 old = *dst;
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *dst = o;
       }
     }
     if ((i0 + RB) * G < nrows) load_batch(i0 + RB);
@@ -512,14 +499,6 @@ k_sage_gather_ell(const uint16_t* __restrict__ ell, const float* __restrict__ el
 // (cp.async.bulk.tensor, boxes of 16 columns x `box_rows` rows), the rows are gathered from shared memory exactly
 // like in k_sage_gather_ell, and the CTA (persistent, one per SM) double-buffers: the tile of item i+1 lands
 // while item i is gathered.
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-
 constexpr int kWideThreads = 512;
 constexpr int kWideCols = 16;                // columns per slice (64-byte shared-memory rows, as in the F = 16 gather)
 
@@ -772,73 +751,78 @@ extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const
   return 0;
 }
 
-static int ell_stage_limit() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CGC_GATHER_STAGE");      // profiling aid: 1 = exit at entry, 2 = exit after the tile copy
-    v = e ? atoi(e) : 0;
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
+static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cudaStream_t st) {
+  const int nmax = a.nmax, feat = a.feat;
+  size_t smem = ((size_t)nmax + 2) * feat * 4;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (STRIDED) {
+    int64_t rows_buf = 0;
+    a.box_rows = pick_box_rows(nmax, feat * 4, 1, 227 * 1024 - 1024, &rows_buf);
+    CGC_REQUIRE(a.box_rows > 0, CGC_ERR_UNSUPPORTED,
+                "cgc_sage_gather_ell: %d rows x %d features do not fit in shared memory", nmax, feat);
+    smem = (size_t)rows_buf * feat * 4;
+    CGC_REQUIRE(tensor_map_2d(&map, a.x, (uint64_t)feat, (uint64_t)num_graphs * nmax, ldx, (uint32_t)feat,
+                              (uint32_t)a.box_rows),
+                CGC_ERR_UNSUPPORTED, "cgc_sage_gather_ell: cuTensorMapEncodeTiled failed");
   }
-  return v;
-}
-
-static int ell_threads() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CGC_GATHER_THREADS");    // tuning aid: 512 or 1024 threads per CTA
-    v = e ? atoi(e) : 1024;
-  }
-  return v;
-}
-
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS>
-static int launch_ell(const uint16_t* ell, const float* ellw, const float* ell_scale, const uint32_t* perm,
-                      const int32_t* rowptr,
-                      const int32_t* col, const float* val, const float* x, int num_graphs, int nmax, int feat,
-                      float* out, cudaStream_t st) {
-  const size_t smem = ((size_t)nmax + 2) * feat * 4;
   CGC_REQUIRE(smem + 1024 <= 227 * 1024, CGC_ERR_UNSUPPORTED,
-              "cgc_sage_gather_ell_fwd: feature tile of %lld B does not fit in shared memory", (long long)smem);
-  static const int parts_override = []() { const char* e = getenv("CGC_GATHER_PARTS"); return e ? atoi(e) : 0; }();
-  static const int chunk_override = []() { const char* e = getenv("CGC_GATHER_CHUNK"); return e ? atoi(e) : 0; }();
-  int parts = parts_override > 0 ? parts_override : kNumSMs / num_graphs;       // lab switches, read once
+              "cgc_sage_gather_ell: feature tile of %lld B does not fit in shared memory", (long long)smem);
+  static const int parts_override = lab_env("CGC_GATHER_PARTS", 0);      // lab switches: CGC_LAB builds only
+  static const int chunk_override = lab_env("CGC_GATHER_CHUNK", 0);
+  static const int stage = lab_env("CGC_GATHER_STAGE", 0);
+  int parts = parts_override > 0 ? parts_override : kNumSMs / num_graphs;
   if (parts < 1) parts = 1;
   const int nrow8 = (nmax + 7) & ~7;
   int rpp = (int)ceil_div(nrow8, parts);
   rpp = (rpp + 7) & ~7;                                 // CTAs own whole 8-row blocks of the table
   parts = (int)ceil_div(nrow8, rpp);
-  const uint32_t chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
-  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS>;
-  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<num_graphs * parts, THREADS, smem, st>>>(ell, ellw, ell_scale, perm, rowptr, col, val, x, nmax, feat, parts, rpp,
-                                                  out, ell_stage_limit(), chunk);
+  a.parts = parts;
+  a.rpp = rpp;
+  a.lab_stage = stage;
+  a.chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
+  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC>;
+  static size_t smem_set = 0;                           // per instantiation: raise the limit only when it grows
+  if (smem > smem_set) {
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  PdlLaunch L(dim3((unsigned)(num_graphs * parts)), dim3(THREADS), smem, st, pdl);
+  CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, a));
   CGC_CHECK_LAUNCH("k_sage_gather_ell");
   return 0;
 }
 
-extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
-                                       const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
-                                       const float* val, const float* x, int32_t num_graphs, int32_t nmax,
-                                       int32_t feat, float* out, void* stream) {
-  CGC_REQUIRE(ell && ell_scale && perm && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
-              "cgc_sage_gather_ell_fwd: bad args");
-  CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_sage_gather_ell_fwd: width must be 8 or 16");
-  CGC_REQUIRE(feat % 4 == 0 && feat <= 32 && aligned16(x) && aligned16(out) && aligned16(ell), CGC_ERR_UNSUPPORTED,
-              "cgc_sage_gather_ell_fwd: feat must be a multiple of 4 and <= 32 (got %d), 16B-aligned x/out/ell", feat);
-  CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
-              "cgc_sage_gather_ell_fwd: val and ell_val must be given together");
-  CGC_REQUIRE(ell_val == nullptr || aligned16(ell_val), CGC_ERR_UNSUPPORTED,
-              "cgc_sage_gather_ell_fwd: ell_val must be 16B-aligned");
-  cudaStream_t st = as_stream(stream);
+// flags of cgc_sage_gather_ell (include/cgc_sm100.h)
+static int ell_gather_dispatch(const uint16_t* ell, const float* ell_val, const float* ell_scale, const uint32_t* perm,
+                               int32_t width, const int32_t* rowptr, const int32_t* col, const float* val,
+                               const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax, int32_t feat, float* out,
+                               int64_t ldo, int flags, cudaStream_t st) {
+  EllGatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ell = ell; a.ellw = ell_val; a.ell_scale = ell_scale; a.perm = perm;
+  a.rowptr = rowptr; a.col = col; a.val = val; a.x = x; a.out = out; a.ldo = ldo;
+  a.nmax = nmax; a.feat = feat;
+  a.early_tables = (flags & CGC_GATHER_TABLES_READY) ? 1 : 0;
   const bool wt = ell_val != nullptr;
-  const bool big = ell_threads() >= 1024;
-#define CGC_ELL(W_, LPR_, WT_, RB_, TH_)                                                                             \
-  return launch_ell<W_, LPR_, WT_, RB_, TH_>(ell, ell_val, ell_scale, perm, rowptr, col, val, x, num_graphs, nmax,   \
-                                            feat, out, st)
+  const bool strided = ldx != feat;
+  const bool acc = (flags & CGC_GATHER_ACCUMULATE) != 0;
+  const bool pdl = (flags & CGC_GATHER_NO_PDL) == 0;
+  if (!pdl) a.early_tables = 0;
+#define CGC_ELL(W_, LPR_, WT_, RB_, TH_)                                                                  \
+  do {                                                                                                    \
+    if (strided) {                                                                                        \
+      if (acc) return launch_ell<W_, LPR_, WT_, RB_, TH_, true, true>(a, num_graphs, ldx, pdl, st);            \
+      return launch_ell<W_, LPR_, WT_, RB_, TH_, true, false>(a, num_graphs, ldx, pdl, st);                    \
+    }                                                                                                     \
+    if (acc) return launch_ell<W_, LPR_, WT_, RB_, TH_, false, true>(a, num_graphs, ldx, pdl, st);             \
+    return launch_ell<W_, LPR_, WT_, RB_, TH_, false, false>(a, num_graphs, ldx, pdl, st);                     \
+  } while (0)
   if (feat <= 16) {
     if (width == 8) {
       if (wt) CGC_ELL(8, 4, true, 2, 512);
-      else if (big) CGC_ELL(8, 4, false, 4, 1024);
-      else CGC_ELL(8, 4, false, 8, 512);
+      else CGC_ELL(8, 4, false, 4, 1024);
     } else {
       if (wt) CGC_ELL(16, 4, true, 1, 512); else CGC_ELL(16, 4, false, 4, 512);
     }
@@ -847,6 +831,35 @@ extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val
     else            { if (wt) CGC_ELL(16, 8, true, 1, 512); else CGC_ELL(16, 8, false, 4, 512); }
   }
 #undef CGC_ELL
+}
+
+extern "C" int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                                   const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                                   const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
+                                   int32_t feat, float* out, int64_t ldo, int flags, void* stream) {
+  CGC_REQUIRE(ell && ell_scale && perm && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
+              "cgc_sage_gather_ell: bad args");
+  CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_sage_gather_ell: width must be 8 or 16");
+  CGC_REQUIRE(feat % 4 == 0 && feat <= 32 && ldx >= feat && ldo >= feat && ldx % 4 == 0 && ldo % 4 == 0 &&
+                  aligned16(x) && aligned16(out) && aligned16(ell),
+              CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_ell: feat must be a multiple of 4 and <= 32 (got %d), ldx / ldo multiples of 4, "
+              "16B-aligned x/out/ell", feat);
+  CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
+              "cgc_sage_gather_ell: val and ell_val must be given together");
+  CGC_REQUIRE(ell_val == nullptr || aligned16(ell_val), CGC_ERR_UNSUPPORTED,
+              "cgc_sage_gather_ell: ell_val must be 16B-aligned");
+  return ell_gather_dispatch(ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, ldx, num_graphs, nmax, feat,
+                             out, ldo, flags, as_stream(stream));
+}
+
+// contiguous x / out, plain store, tables possibly fresh: the round-1 entry point, kept for callers of that ABI
+extern "C" int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                                       const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                                       const float* val, const float* x, int32_t num_graphs, int32_t nmax,
+                                       int32_t feat, float* out, void* stream) {
+  return cgc_sage_gather_ell(ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, feat, num_graphs, nmax, feat,
+                             out, feat, 0, stream);
 }
 
 // 2-D tensor map {feat, rows} over a row-major fp32 matrix, box = {16 columns, box_rows rows}, no swizzle

@@ -89,6 +89,14 @@ class SparseGraph(object):
         self.ell_t = self.ell_t_val = self.ell_t_scale = self.ell_t_perm = None   # the same for A^T (from the CSC)
         self.ell_t_width = 0
         self.ell_width = 0
+        # True until the first kernel that reads the ELL16 tables has been enqueued: that consumer directly follows
+        # the table builder in the stream, so it must not read the tables in its programmatic-launch prologue
+        self.tables_fresh = True
+
+    def tables_ready(self):
+        """For the ``tables_ready`` flag of the ELL16 kernels: False exactly once after the build."""
+        fresh, self.tables_fresh = self.tables_fresh, False
+        return not fresh
 
 
 def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False):
@@ -184,10 +192,11 @@ def _agg(be, cfg, adj, rs, x_prev, out):
         g = cfg.graph
         feat = x_prev.shape[1]
         dense_io = x_prev.is_contiguous() and out.is_contiguous() and feat % 4 == 0 and feat <= 32
-        if dense_io and g.ell is not None and rs is g.rs and (g.nmax + 2) * feat * 4 + 1024 <= 227 * 1024:
-            # fixed-pitch index table (rs baked in) + TMA-staged feature tile (the roofline kernel)
-            be.sage_gather_ell_fwd(g.ell, g.ell_val, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val,
-                                   x_prev, g.num_graphs, g.nmax, out)
+        if _ell_ok(g, x_prev, out) and rs is g.rs:
+            # fixed-pitch index table (rs baked in) + TMA-staged feature tile (the roofline kernel); column slices
+            # of the concat buffer (layers 2-3) are staged by 2-D TMA boxes
+            be.sage_gather_ell(g.ell, g.ell_val, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val,
+                               x_prev, g.num_graphs, g.nmax, out, tables_ready=g.tables_ready())
         elif dense_io and g.nmax * feat * 4 + 12288 <= 220 * 1024:
             # whole-graph feature tile fits in shared memory: TMA-staged gather (the roofline kernel)
             be.sage_gather_mean_fwd(g.rowptr, g.col, g.val, rs, x_prev, g.num_graphs, g.nmax, out)
@@ -197,6 +206,15 @@ def _agg(be, cfg, adj, rs, x_prev, out):
         b, n = cfg.num_graphs, cfg.nmax
         be.gemm(adj, _as3d(x_prev, b, n), out.view(b, n, -1), False, False, row_scale=rs,
                 precision=_prec(be, 'dense_agg'))
+
+
+def _ell_ok(g, x, out):
+    """The shared-memory ELL16 gather serves feature widths that are multiples of 4 up to 32, 16-byte aligned rows
+    (leading dimensions multiples of 4 floats) and tiles that fit: (round_up(nmax, box) rows) * feat * 4 <= 225 KB."""
+    feat = x.shape[1]
+    return (g.ell is not None and feat % 4 == 0 and feat <= 32 and x.stride(1) == 1 and out.stride(1) == 1
+            and x.stride(0) % 4 == 0 and out.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+            and out.data_ptr() % 16 == 0 and (g.nmax + 256) * feat * 4 <= 225 * 1024)
 
 
 def _agg_t(be, cfg, adj, g_a, src_scale, out, accumulate):
@@ -240,7 +258,6 @@ class GnnModuleFunction(Function):
         for k in range(3):
             w, b, gamma, beta = conv[k]
             a = _f32(m, w.shape[0], device=dev)          # sa = rs * (A x)
-            _agg(be, cfg, adj, rs, x_prev, a)
             y = _f32(m, couts[k], device=dev)
             dst = cat[:, off: off + couts[k]]
             mean = invstd = None
@@ -248,6 +265,25 @@ class GnnModuleFunction(Function):
                 mean = _f32(couts[k], device=dev)
                 invstd = _f32(couts[k], device=dev)
                 rmean, rvar = cfg.bn_buffers[k]
+            g = cfg.graph
+            if (g is not None and rs is g.rs and _ell_ok(g, x_prev, a)
+                    and be.sage_layer_ell_supported(w.shape[0], couts[k], g.nmax)):
+                # the whole layer up to the BatchNorm statistics in ONE kernel (gather + W + bias + L2 norm + mask
+                # + activation + column partial sums)
+                stats = cfg.has_bn and cfg.training
+                be.sage_layer_ell_fwd(g.ell, g.ell_val, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val,
+                                      x_prev, g.num_graphs, g.nmax, w, b, cfg.mask, cfg.act, a, y,
+                                      rmean if stats else None, rvar if stats else None, BN_MOMENTUM, BN_EPS,
+                                      mean if stats else None, invstd if stats else None,
+                                      tables_ready=g.tables_ready())
+                if cfg.has_bn and not cfg.training:
+                    be.bn_eval_stats(rmean, rvar, BN_EPS, mean, invstd)
+                be.bn_apply(y, mean, invstd, gamma if cfg.has_bn else None,
+                            beta if cfg.has_bn else None, cfg.mask, dst)
+                saved += [a, y, mean, invstd]
+                x_prev, off = dst, off + couts[k]
+                continue
+            _agg(be, cfg, adj, rs, x_prev, a)
             if cfg.has_bn and cfg.training and couts[k] <= 32 and w.shape[0] <= 64:
                 # narrow layer: epilogue and BatchNorm batch statistics in ONE pass over the rows
                 be.sage_layer_fwd_narrow(a, w, b, cfg.mask, y, cfg.act, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)

@@ -173,6 +173,41 @@ CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, c
                             const int32_t* col, const float* val, const float* x, int32_t num_graphs,
                             int32_t nmax, int32_t feat, float* out, void* stream);
 
+/* General form of the ELL16 gather: x and out may be column slices of wider matrices (leading dimensions ldx, ldo:
+ * the layer-2/3 inputs of a GNN_Module live in the concat buffer, network.py:118; the CSC gathers of the backward
+ * add into slices of the gradient buffer).  A strided x tile is staged by 2-D TMA boxes instead of 1-D bulk copies.
+ * flags:
+ *   CGC_GATHER_ACCUMULATE    out += result (default: out = result)
+ *   CGC_GATHER_TABLES_READY  the index tables were NOT written by the kernel enqueued right before this call:
+ *                            the kernel is launched with programmatic stream serialization and may then load its
+ *                            indices / scales while the previous kernel drains (x is always read after it).
+ *   CGC_GATHER_NO_PDL        launch without programmatic stream serialization. */
+#define CGC_GATHER_ACCUMULATE 1
+#define CGC_GATHER_TABLES_READY 2
+#define CGC_GATHER_NO_PDL 4      /* plain stream-ordered launch (A/B measurements of the programmatic launch) */
+CGC_API int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                        const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                        const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
+                        int32_t feat, float* out, int64_t ldo, int flags, void* stream);
+
+/* One whole narrow SAGE layer up to the BatchNorm statistics in ONE kernel (SURVEY K3+K4(+K5 partial sums);
+ * reference lines network.py:114-116 = DenseSAGEConv.forward + activation, and the batch statistics of bn_k):
+ *   sa = scale * sum_e val[e] * x[col[e], :]          (the ELL16 gather above, tile staged by TMA)
+ *   y  = act( l2normalize(sa @ W + b) * mask )         (cgc_sage_epilogue_fwd)
+ *   mean / invstd / running stats of y over all `num_graphs * nmax` rows (cgc_bn_stats), when mean != NULL:
+ *   per-CTA column partial sums in `work`, finalised in fixed order in double precision by a second tiny kernel.
+ * sa [rows, cin] (contiguous) is written as well: the backward needs it (dW = sa^T dh).
+ * Instantiated for (cin, cout) in {(16, 20), (20, 20)}: cgc_sage_layer_ell_supported(); other shapes take
+ * cgc_sage_gather_ell + cgc_sage_layer_fwd_narrow.  flags as for cgc_sage_gather_ell (ACCUMULATE not allowed). */
+CGC_API int cgc_sage_layer_ell_supported(int32_t cin, int32_t cout, int32_t nmax);
+CGC_API int cgc_sage_layer_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
+                           const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
+                           const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
+                           int32_t cin, const float* w, const float* b, const int32_t* num_nodes, int32_t cout,
+                           int act, float* sa, float* y, int64_t ldy, float* running_mean, float* running_var,
+                           float momentum, float eps, float* mean, float* invstd, void* work,
+                           int64_t work_bytes, int flags, void* stream);
+
 /* Wide gather over the same ELL16 table: out[r, :feat] (+)= scale[r] * sum_e val[e] * x[col[e], :feat] for wide
  * feature matrices -- A*S of _diff_pool (network.py:207, feat = 1140) and, with the table of the transposed
  * adjacency, its backward.  A work item is (graph, 16-column slice): the strided [nmax, 16] slice is staged in

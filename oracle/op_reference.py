@@ -273,6 +273,29 @@ class TorchBackend(object):
             self.spmm(rowptr, col, val, x, None, None, full, False)
             out[grow[over]] = full[grow[over]] * scale[over][:, None]
 
+    def sage_gather_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
+                        accumulate=False, tables_ready=False, pdl=True):
+        """cgc_sage_gather_ell: strided x / out, optional +=."""
+        res = torch.zeros(num_graphs * nmax, x.shape[1], dtype=x.dtype)
+        self.sage_gather_ell_fwd(ell, ell_val, ell_scale, perm, width, rowptr, col, val, x.contiguous(), num_graphs,
+                                 nmax, res)
+        if accumulate:
+            out += res
+        else:
+            out.copy_(res)
+
+    @staticmethod
+    def sage_layer_ell_supported(cin, cout, nmax):
+        return cout == 20 and cin in (16, 20) and 0 < nmax < 0xFFFF and ((nmax + 255) // 8 * 8) * cin * 4 <= 227 * 1024 - 2048
+
+    def sage_layer_ell_fwd(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, w, b,
+                           mask, act, sa, y, rmean, rvar, momentum, eps, mean, invstd, tables_ready=False, pdl=True):
+        """cgc_sage_layer_ell_fwd = the ELL16 gather, then the SAGE epilogue, then the batch statistics."""
+        self.sage_gather_ell(ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, sa)
+        self.sage_epilogue_fwd(sa, w, b, mask, y, act)
+        if mean is not None:
+            self.bn_stats(y, rmean, rvar, momentum, eps, mean, invstd)
+
     def gather_wide_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
                         accumulate):
         """Same sums as sage_gather_ell_fwd on a wide (possibly strided) matrix, optional scale, optional +=."""

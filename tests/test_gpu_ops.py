@@ -628,3 +628,132 @@ def test_gather_wide_ell(cuda_backend, feat, b, nmax, width, maxdeg, weighted, a
                 [ell, ellw, scale, perm, width, rowptr, col, val, x, b, nmax, out, accumulate], [11],
                 rtol=1e-5, atol=1e-5)
     assert torch.equal(args[11]._base[:, feat:].cpu(), ow[:, feat:])            # nothing outside the slice touched
+
+
+def _ell_tables(rowptr, col, val, rsc, b, nmax, width, pair):
+    trows = REF.ell16_rows(b, nmax)
+    ell = torch.zeros(trows * width, dtype=torch.int16)
+    ellw = torch.zeros(trows * width) if val is not None else None
+    ells = torch.zeros(trows)
+    perm = torch.zeros(trows // 8, dtype=torch.int32)
+    REF.csr_to_ell16(rowptr, col, val, rsc, b, nmax, width, pair, ell, ellw, ells, perm)
+    return ell, ellw, ells, perm
+
+
+@pytest.mark.parametrize('feat,b,nmax,width,maxdeg', [(16, 3, 70, 8, 8), (20, 5, 333, 8, 10), (16, 64, 1800, 8, 8),
+                                                      (20, 64, 1800, 8, 8), (8, 9, 40, 16, 16), (32, 2, 1500, 16, 18)])
+@pytest.mark.parametrize('weighted,accumulate,ready', [(False, False, True), (True, True, False), (False, True, True)])
+def test_sage_gather_ell_strided(cuda_backend, feat, b, nmax, width, maxdeg, weighted, accumulate, ready):
+    """General ELL16 gather: x / out as column slices of wider matrices (2-D TMA staging), += mode, and the
+    programmatic-launch prologue with and without early table loads; nothing outside the slices is touched."""
+    rows = b * nmax
+    rowptr, col = _random_csr(rows, maxdeg, seed=nmax + feat, block=nmax) if rows < 5000 else _knn_csr(b, nmax)
+    nnz = int(rowptr[-1])
+    g = torch.Generator().manual_seed(21)
+    val = torch.rand(nnz + 3, generator=g) if weighted else None
+    rsc = torch.rand(rows, generator=g) if weighted else None
+    ell, ellw, ells, perm = _ell_tables(rowptr, col, val, rsc, b, nmax, width, int(feat == 16))
+    xw = torch.randn(rows, feat + 44, generator=g)
+    x = xw[:, 20:20 + feat]
+    ow = torch.randn(rows, feat + 12, generator=g)
+    out = ow[:, 4:4 + feat]
+    want = out.clone() if accumulate else torch.zeros(rows, feat)
+    ref = torch.zeros(rows, feat)
+    REF.sage_gather_mean_fwd(rowptr, col, val, rsc, x.contiguous(), b, nmax, ref)
+    want = want + ref if accumulate else ref
+    args = both(cuda_backend, 'sage_gather_ell',
+                [ell, ellw, ells, perm, width, rowptr, col, val, x, b, nmax, out, accumulate, ready], [11],
+                rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    base = args[11]._base.cpu()
+    assert torch.equal(base[:, :4], ow[:, :4]) and torch.equal(base[:, 4 + feat:], ow[:, 4 + feat:])
+    # contiguous operands through the same entry point (1-D bulk-copy staging)
+    xc, oc = x.contiguous(), (out.clone() if accumulate else torch.zeros(rows, feat))
+    both(cuda_backend, 'sage_gather_ell', [ell, ellw, ells, perm, width, rowptr, col, val, xc, b, nmax, oc,
+                                           accumulate, ready], [11], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('cin,b,nmax,width,maxdeg', [(16, 3, 70, 8, 8), (20, 5, 333, 8, 10), (16, 64, 1800, 8, 8),
+                                                     (20, 64, 1800, 8, 8), (16, 7, 1237, 16, 18), (20, 2, 2100, 16, 12)])
+@pytest.mark.parametrize('weighted,strided,stats,act', [(False, False, True, 0), (True, True, True, 1),
+                                                        (False, True, False, 2)])
+def test_sage_layer_ell_fwd(cuda_backend, cin, b, nmax, width, maxdeg, weighted, strided, stats, act):
+    """Fused narrow layer (gather + W + bias + L2 norm + mask + activation + BatchNorm statistics) == ELL16 gather
+    followed by the epilogue and bn_stats: aggregate sa, output y (strided), mean / invstd, running statistics;
+    ragged row mask, overflow rows (width 16 with degree up to 18), both tile-staging paths, eval mode (no stats)."""
+    rows = b * nmax
+    rowptr, col = _random_csr(rows, maxdeg, seed=nmax + cin, block=nmax) if rows < 5000 else _knn_csr(b, nmax)
+    nnz = int(rowptr[-1])
+    g = torch.Generator().manual_seed(cin + nmax)
+    val = torch.rand(nnz + 3, generator=g) if weighted else None
+    rsc = torch.rand(rows, generator=g) if weighted else None
+    ell, ellw, ells, perm = _ell_tables(rowptr, col, val, rsc, b, nmax, width, int(cin == 16))
+    xw = torch.randn(rows, cin + 40, generator=g)
+    x = xw[:, 20:20 + cin] if strided else xw[:, :cin].contiguous()
+    w = torch.randn(cin, 20, generator=g) / cin ** 0.5
+    bias = torch.randn(20, generator=g) * 0.1
+    mask = _mask(b, nmax, seed=3)
+    sa = torch.zeros(rows, cin)
+    yw = torch.zeros(rows, 24)
+    y = yw[:, :20]
+    rmean, rvar = torch.randn(20, generator=g), torch.rand(20, generator=g) + 0.5
+    mean, invstd = (torch.zeros(20), torch.zeros(20)) if stats else (None, None)
+    outs = [15, 16] + ([17, 18, 21, 22] if stats else [])
+    both(cuda_backend, 'sage_layer_ell_fwd',
+         [ell, ellw, ells, perm, width, rowptr, col, val, x, b, nmax, w, bias, mask, act, sa, y,
+          rmean if stats else None, rvar if stats else None, 0.1, 1e-5, mean, invstd, True], outs,
+         rtol=2e-5, atol=2e-6)
+    # no bias, tables flagged as fresh (no early loads)
+    y2 = torch.zeros(rows, 20)
+    both(cuda_backend, 'sage_layer_ell_fwd',
+         [ell, ellw, ells, perm, width, rowptr, col, val, x, b, nmax, w, None, mask, act, sa, y2,
+          None, None, 0.1, 1e-5, None, None, False], [15, 16], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize('case', ['lin', 'splitk', 'batched_pair', 'single_pass'])
+def test_gemm_tcgen05_bitwise_determinism(cuda_backend, case):
+    """The CTA-pair kernel hands tensor / shared memory between the two CTAs with CTA-scope arrives ordered by
+    tcgen05 fences.  A race there would show up as run-to-run differences: 100 repeats of
+    the same contraction must be BITWISE identical -- persistent tile loop (lin), split-K with its fixed-order
+    reduction, the batched pair layout of the pooled adjacency, and the single-pass mode."""
+    g = torch.Generator().manual_seed(3)
+    prec = 1
+    if case == 'lin':
+        a, b, c = torch.randn(9000, 1180, generator=g), torch.randn(1140, 1180, generator=g), torch.empty(9000, 1140)
+        ta, tb = False, True
+    elif case == 'splitk':                     # dW of lin: K = rows, few output tiles -> split-K partials
+        a, b, c = torch.randn(20000, 1140, generator=g), torch.randn(20000, 1180, generator=g), torch.empty(1140, 1180)
+        ta, tb = True, False
+    elif case == 'batched_pair':               # S^T (A S): batch of [1140, 1800] x [1800, 1140]
+        a, b = torch.rand(3, 1800, 1140, generator=g), torch.rand(3, 1800, 1140, generator=g)
+        c, ta, tb = torch.empty(3, 1140, 1140), True, False
+    else:
+        a, b, c = torch.randn(9000, 1140, generator=g), torch.randn(1140, 1180, generator=g), torch.empty(9000, 1180)
+        ta, tb, prec = False, False, 2
+    a, b, c = a.cuda(), b.cuda(), c.cuda()
+    cuda_backend.gemm(a, b, c, ta, tb, precision=prec)
+    first = c.clone()
+    for _ in range(100):
+        c.zero_()
+        cuda_backend.gemm(a, b, c, ta, tb, precision=prec)
+        assert torch.equal(c, first), 'tcgen05 GEMM (%s) is not run-to-run deterministic' % case
+    ref = (a.transpose(-1, -2) if ta else a).double() @ (b.transpose(-1, -2) if tb else b).double()
+    tol = 2e-3 if prec == 2 else 5e-6
+    assert float((first.double() - ref).abs().max() / ref.abs().max()) < tol
+
+
+def test_gemm_single_pass_tf32(cuda_backend):
+    """precision = 2: one TF32 pass on round-to-nearest operands.  Unbiased (sign-definite operands show no drift:
+    relative error of a sum of positive products << 2^-11) and ~1e-4-grade on random data, all operand layouts."""
+    g = torch.Generator().manual_seed(5)
+    for ta in (False, True):
+        for tb in (False, True):
+            m, n, k = 700, 1140, 1800
+            a = torch.rand(k, m, generator=g) if ta else torch.rand(m, k, generator=g)
+            b = torch.rand(n, k, generator=g) if tb else torch.rand(k, n, generator=g)
+            c = torch.empty(m, n).cuda()
+            cuda_backend.gemm(a.cuda(), b.cuda(), c, ta, tb, precision=2)
+            ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+            rel = (c.cpu().double() - ref) / ref
+            assert float(rel.abs().max()) < 1e-4, (ta, tb, float(rel.abs().max()))      # K = 1800 averages the rounding
+            assert abs(float(rel.mean())) < 3e-6, (ta, tb, float(rel.mean()))            # no truncation bias (2^-12 = 2.4e-4)

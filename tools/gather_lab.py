@@ -1,5 +1,5 @@
-"""Gather-kernel lab: microseconds per launch of the roofline kernel variants at the BASELINE shape
-(same harness as bench.py's roofline leg).  CGC_GATHER_STAGE=1|2 in the environment truncates the ELL kernel
+"""Gather-kernel lab: microseconds per launch of the roofline kernel family at the BASELINE shape (same harness as
+bench.py's roofline leg).  With a LAB build (make LAB=1) CGC_GATHER_STAGE=1|2 truncates the ELL kernel
 (1 = exit at entry: launch floor; 2 = exit after the TMA tile copy)."""
 import argparse
 import os
@@ -10,15 +10,25 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 
+VARIANTS = {
+    'ell': dict(),
+    'ell-nopdl': dict(pdl=False),
+    'ell-vardeg': dict(row_is_centre=False),
+    'ell-weighted': dict(norm_adj=True),
+    'layer': dict(kind='layer'),
+    'layer-nopdl': dict(kind='layer', pdl=False),
+    'layer-weighted': dict(kind='layer', norm_adj=True),
+    'csr': dict(kind='csr'),
+}
 ap = argparse.ArgumentParser()
-ap.add_argument('--variants', default='ell,ell-noparity,csr')
+ap.add_argument('--variants', default='ell,ell-nopdl,ell-vardeg,ell-weighted,layer,layer-nopdl,csr')
 a = ap.parse_args()
 args = argparse.Namespace(batch_per_gpu=64, nodes=1800, degree=8)
 dev = torch.device('cuda', 0)
 torch.cuda.set_device(0)
+lab = bool(os.environ.get('CGC_GATHER_STAGE'))
 for v in a.variants.split(','):
-    variant, parity = ('ell', False) if v == 'ell-noparity' else (v, True)
-    alg, us, copies = bench.gather_roofline(args, dev, variant, parity)
-    print('%-14s stage=%s  %.2f us/launch  %.0f GB/s algorithmic  samples %s' % (
-        v, os.environ.get('CGC_GATHER_STAGE', '0'), us, alg / us / 1e3,
+    alg, us, copies = bench.gather_roofline(args, dev, check=not lab, **VARIANTS[v])
+    print('%-16s stage=%s  %.2f us/launch  %.0f GB/s algorithmic (%.3f of 6530.6)  samples %s' % (
+        v, os.environ.get('CGC_GATHER_STAGE', '0'), us, alg / us / 1e3, alg / us / 1e3 / 6530.6,
         ' '.join('%.2f' % t for t in bench.gather_roofline.samples)))
