@@ -112,7 +112,7 @@ extern "C" int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t 
               "cgc_gemm: leading dimension too small (lda=%lld ldb=%lld ldc=%lld)", (long long)lda,
               (long long)ldb, (long long)ldc);
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_gemm: mask without nmax");
-  CGC_REQUIRE(precision >= -1 && precision <= 2, CGC_ERR_ARG, "cgc_gemm: precision must be -1, 0, 1 or 2");
+  CGC_REQUIRE(precision >= -1 && precision <= 3, CGC_ERR_ARG, "cgc_gemm: precision must be -1, 0, 1, 2 or 3");
   GemmParams p;
   p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
   p.a = a; p.lda = lda; p.stride_a = stride_a;
@@ -123,9 +123,10 @@ extern "C" int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t 
   p.a_vec = aligned16(a) && lda % 4 == 0 && stride_a % 4 == 0;
   p.b_vec = aligned16(b) && ldb % 4 == 0 && stride_b % 4 == 0;
   cudaStream_t st = as_stream(stream);
-  if (precision != 0 && gemm_tc_supported(p, trans_a, trans_b, precision == 1))
-    return gemm_tc(p, trans_a, trans_b, precision == 2 ? 1 : 3, work, work_bytes, st);
-  CGC_REQUIRE(precision != 1, CGC_ERR_UNSUPPORTED,
+  const bool forced = precision == 1 || precision == 3;
+  if (precision != 0 && gemm_tc_supported(p, trans_a, trans_b, forced))
+    return gemm_tc(p, trans_a, trans_b, precision >= 2 ? 1 : 3, work, work_bytes, st);
+  CGC_REQUIRE(!forced, CGC_ERR_UNSUPPORTED,
               "cgc_gemm: tcgen05 path does not support this shape/alignment (m=%d n=%d k=%d)", m, n, k);
   return gemm_simt(p, trans_a, trans_b, work, work_bytes, st);
 }

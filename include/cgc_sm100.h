@@ -354,7 +354,8 @@ CGC_API int cgc_dense_renorm_bwd(const float* g, const float* out, const float* 
  *            -1 = library's choice (tcgen05 3xTF32 when the shape/alignment allows, else fp32 FMA),
  *            2 = like -1, but a contraction taken by the tensor-core path runs ONE TF32 pass on operands
  *                rounded to nearest (10-bit mantissa products, ~2e-4 relative per product, unbiased): for
- *                contractions whose consumers tolerate it (pass budget). */
+ *                contractions whose consumers tolerate it (pass budget),
+ *            3 = single TF32 pass on the tensor-core path or CGC_ERR_UNSUPPORTED (as 1 is to -1). */
 CGC_API int cgc_gemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t k, float alpha,
              const float* a, int64_t lda, int64_t stride_a, const float* b, int64_t ldb,
              int64_t stride_b, float beta, float* c, int64_t ldc, int64_t stride_c,

@@ -24,7 +24,7 @@ def check(name, got, want, tol):
 # tcgen05 GEMM
 for ta in (False, True):
     for tb in (False, True):
-        for prec in (1, 2):
+        for prec in (1, 3):
             m, n, k = 384, 256, 160
             a = torch.randn((k, m) if ta else (m, k), generator=g)
             b = torch.randn((n, k) if tb else (k, n), generator=g)
