@@ -295,8 +295,9 @@ def gather_roofline(args, device, kind='gather', row_is_centre=True, norm_adj=Fa
         scs = [g.ell_scale.clone() for _ in range(copies)]
     if kind == 'gather':
         def launch(i):
-            be.sage_gather_ell(ells[i], vals[i], scs[i], perms[i], g.ell_width, g.rowptr, g.col, g.val, xs[i], b, n,
-                               outs[i], tables_ready=True, pdl=pdl)
+            # binary adjacency: no scale vector (mean derived from the row's slots), as ops._agg calls it
+            be.sage_gather_ell(ells[i], vals[i], scs[i] if vals[i] is not None else None, perms[i], g.ell_width,
+                               g.rowptr, g.col, g.val, xs[i], b, n, outs[i], tables_ready=True, pdl=pdl)
     elif kind == 'layer':
         torch.manual_seed(3)
         w = (torch.rand(FEAT, 20, device=device) - 0.5) * 0.5
@@ -306,7 +307,8 @@ def gather_roofline(args, device, kind='gather', row_is_centre=True, norm_adj=Fa
         mean, invstd = torch.empty(20, device=device), torch.empty(20, device=device)
 
         def launch(i):
-            be.sage_layer_ell_fwd(ells[i], vals[i], scs[i], perms[i], g.ell_width, g.rowptr, g.col, g.val, xs[i], b, n,
+            be.sage_layer_ell_fwd(ells[i], vals[i], scs[i] if vals[i] is not None else None, perms[i], g.ell_width,
+                                  g.rowptr, g.col, g.val, xs[i], b, n,
                                   w, bias, g.mask, 0, outs[i], ys[i], rm, rv, 0.1, 1e-5, mean, invstd,
                                   tables_ready=True, pdl=pdl)
     else:

@@ -87,11 +87,17 @@ __device__ __forceinline__ float4 unpack_x4(const F32x4& v) {
   return o;
 }
 
+// ELL16 table: 12-bit local column ids; slot 0 carries the served local row (3 bits) above them
+constexpr uint32_t kEllColMask = 0x0FFFu;
+constexpr int kEllRowShift = 12;
 // slot t (compile-time after unrolling) of a row's packed uint16 index words
 __device__ __forceinline__ uint32_t ell_slot(const uint32_t* words, int t) {
   const uint32_t w = words[t >> 1];
+  if (t == 0) return w & kEllColMask;
   return (t & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
+// local row (0..7 within the 8-row block) served by the table row whose first index word is w0
+__device__ __forceinline__ int ell_served_row(uint32_t w0) { return (int)((w0 >> kEllRowShift) & 7u); }
 
 // ---- host side
 // 2-D tensor map {cols, rows} over a row-major fp32 matrix with leading dimension ld (floats), box = {box_cols,

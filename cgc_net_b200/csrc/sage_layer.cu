@@ -43,6 +43,7 @@ struct SageLayerArgs {
   int64_t ldy;
   double* partial;           // [grid][2][20] column sums of y and y^2, or null
   int nmax, parts, rpp, box_rows, early, act;
+  int tile_smem;             // bytes of the feature tile buffer (the table slice follows it)
 };
 
 template <int CIN, int W, bool WEIGHTED, bool STRIDED>
@@ -55,7 +56,6 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
   constexpr int NWARPS = kLayerThreads / 32;
   constexpr int G = NWARPS * GPW;                      // rows in flight per pass of the CTA
   constexpr int NW = W / 2;
-  constexpr int RB = (W == 16 && WEIGHTED) ? 1 : 2;
   constexpr int NOWN = COUT / LPR;                     // output columns per lane: 5 or 4
   constexpr bool EXTRA = NOWN == 5;                    // 4 lanes: the fifth column is 16 + sl
   static_assert(CIN == 16 || CIN == 20, "instantiated for 16 or 20 input channels");
@@ -65,12 +65,17 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
   const int nrow8 = (nmax + 7) & ~7;
   const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
   const int r0 = p * a.rpp;
-  const int nrows = min(a.rpp, nrow8 - r0);
+  const int nrows = min(a.rpp, nrow8 - r0);            // > 0 by construction of parts, multiple of 8
   pdl_launch_dependents();
   const int64_t grow0 = (int64_t)g * nmax;
   const int64_t trow0 = (int64_t)g * nrow8 + r0;
   float* s_x = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bar;
+  // the CTA's slice of the index table (and weights / scales) behind the feature tile: brought in by bulk copies
+  // at kernel start, so no global load sits between two rows of the gather loop
+  unsigned char* s_idx = smem_raw + a.tile_smem;
+  float* s_scale = reinterpret_cast<float*>(s_idx + (size_t)a.rpp * W * 2);
+  float* s_wgt = s_scale + a.rpp;
+  __shared__ __align__(8) uint64_t bar, bar_t;
   __shared__ float s_red[NWARPS][2][COUT];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -78,48 +83,23 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
   const bool active = gw < GPW;                        // CIN = 20: lanes 30, 31 idle
   const int grp = warp * GPW + (active ? gw : 0);
   const int lbase = lane - sl;                         // first lane of this row group
+  const bool has_scale = a.ell_scale != nullptr;
 
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar_t, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (STRIDED) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
   }
   if (!STRIDED && tid < 2 * CIN) s_x[(size_t)nmax * CIN + tid] = 0.f;
 
-  const uint32_t lane_base = smem_u32(smem_raw) + (uint32_t)sl * 16u;
-  const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
-  const uint32_t ovf_mark = (uint32_t)nmax + 1u;
-
-  uint32_t idx[RB][NW];
-  float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
-  float rsc[RB];
-  uint32_t pw[RB];
-  auto load_batch = [&](int i0) {
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int t = (i0 + i) * G + grp;
-      const bool on = active && t < nrows;
-      const int64_t trow = trow0 + (on ? t : 0);
-      pw[i] = on ? __ldg(a.perm + (trow >> 3)) : 0xFFFFFFFFu;
-      rsc[i] = on ? __ldg(a.ell_scale + trow) : 1.0f;
-#pragma unroll
-      for (int q = 0; q < NW / 4; ++q) {
-        uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
-        if (on) v = ldg_u4(a.ell + trow * W + q * 8);
-        idx[i][4 * q] = v.x; idx[i][4 * q + 1] = v.y; idx[i][4 * q + 2] = v.z; idx[i][4 * q + 3] = v.w;
-      }
-      if (WEIGHTED) {
-#pragma unroll
-        for (int q = 0; q < W / 4; ++q) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on) v = ldg_f4(a.ellw + trow * W + q * 4);
-          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q : 0] = v.x;
-          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 1 : 0] = v.y;
-          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 2 : 0] = v.z;
-          wgt[WEIGHTED ? i : 0][WEIGHTED ? 4 * q + 3 : 0] = v.w;
-        }
-      }
-    }
+  auto issue_tables = [&]() {                          // thread 0
+    const uint32_t ib = (uint32_t)nrows * W * 2u, sb = has_scale ? (uint32_t)nrows * 4u : 0u;
+    const uint32_t wb = WEIGHTED ? (uint32_t)nrows * W * 4u : 0u;
+    mbar_expect_tx(&bar_t, ib + sb + wb);
+    bulk_g2s(s_idx, a.ell + trow0 * W, ib, &bar_t);
+    if (has_scale) bulk_g2s(s_scale, a.ell_scale + trow0, sb, &bar_t);
+    if (WEIGHTED) bulk_g2s(s_wgt, a.ellw + trow0 * W, wb, &bar_t);
   };
   // W columns of this lane, in registers for the whole kernel: wr[k][0..3] = W[k][4sl..4sl+3], wr[k][4] = W[k][16+sl]
   float wr[CIN][NOWN];
@@ -141,9 +121,13 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
     }
   };
 
-  if (a.early) { load_batch(0); load_weights(); }
+  __syncthreads();                                     // barriers initialised before anything is issued on them
+  if (a.early) {
+    if (tid == 0) issue_tables();
+    load_weights();
+  }
   pdl_wait();
-  if (tid == 0 && nrows > 0) {
+  if (tid == 0) {
     if (STRIDED) {
       const int nboxes = (nmax + a.box_rows - 1) / a.box_rows;
       mbar_expect_tx(&bar, (uint32_t)nboxes * (uint32_t)a.box_rows * row_bytes);
@@ -158,91 +142,117 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
         bulk_g2s(smem_raw + off, src + off, n, &bar);
       }
     }
+    if (!a.early) issue_tables();
   }
-  if (!a.early) { load_batch(0); load_weights(); }
+  if (!a.early) load_weights();
   const int nn = a.num_nodes ? __ldg(a.num_nodes + g) : nmax;   // real nodes of this graph
-  __syncthreads();
-  if (nrows > 0) mbar_wait(&bar, 0);
+  mbar_wait(&bar_t, 0);
+  mbar_wait(&bar, 0);
   if (STRIDED) {
     if (tid < 2 * CIN) s_x[(size_t)nmax * CIN + tid] = 0.f;
     __syncthreads();
   }
 
+  const uint32_t lane_base = smem_u32(smem_raw) + (uint32_t)sl * 16u;
+  const uint32_t idx_base = smem_u32(s_idx);
+  const uint32_t ovf_mark = (uint32_t)nmax + 1u;
   float s1[NOWN], s2[NOWN];
 #pragma unroll
   for (int j = 0; j < NOWN; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
 
-  for (int i0 = 0; i0 * G < nrows; i0 += RB) {
+  auto load_idx = [&](uint32_t* dst, int t) {          // the row's W slots: 16 or 32 bytes, broadcast to its lanes
+    const bool on = active && t < nrows;
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int t = (i0 + i) * G + grp;
-      // rows are handed out warp-uniformly in t's high part only: the shuffles below need every lane of the warp,
-      // so no early `continue`; inactive lanes / rows compute on zeros and skip the stores
-      const int lrow = ((r0 + t) & ~7) + (int)((pw[i] >> (3 * (t & 7))) & 7u);
-      const bool row_on = active && t < nrows && lrow < nmax;
-      const int64_t row = grow0 + (row_on ? lrow : 0);
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row_on) {
-        if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
-          F32x4 acc;
-          acc.lo = 0ull; acc.hi = 0ull;
+    for (int q = 0; q < NW / 4; ++q) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (on) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(idx_base + (uint32_t)t * (W * 2u) + q * 16u));
+      dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
+    }
+  };
+  uint32_t cur[NW], nxt[NW];
+  load_idx(cur, grp);
+  for (int t0 = 0; t0 < nrows; t0 += G) {              // warp-uniform trip count: the shuffles need every lane
+    const int t = t0 + grp;
+    load_idx(nxt, t + G);
+    const int lrow = ((r0 + t) & ~7) + ell_served_row(cur[0]);
+    const bool row_on = active && t < nrows && lrow < nmax;
+    const int64_t row = grow0 + (row_on ? lrow : 0);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_on) {
+      float s = has_scale ? s_scale[t] : 1.0f;
+      if ((cur[0] & kEllColMask) != ovf_mark) {
+        float wg[WEIGHTED ? W : 1];
+        if (WEIGHTED) {
 #pragma unroll
-          for (int u = 0; u < W; ++u) {
-            const uint32_t j = ell_slot(idx[i], u);
-            const F32x4 v = lds_x4(lane_base + j * row_bytes);
-            if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
-            else add_x4(acc, v);
-          }
-          o = unpack_x4(acc);
-        } else {
-          const int eb = __ldg(a.rowptr + row), ee = __ldg(a.rowptr + row + 1);
-          for (int k = eb; k < ee; ++k) {
-            const uint32_t j = (uint32_t)(__ldg(a.col + k) - (int)grow0);
-            const float wv = WEIGHTED ? __ldg(a.val + k) : 1.0f;
-            const float4 v = lds_f4(lane_base + j * row_bytes);
-            o.x = fmaf(wv, v.x, o.x); o.y = fmaf(wv, v.y, o.y); o.z = fmaf(wv, v.z, o.z); o.w = fmaf(wv, v.w, o.w);
+          for (int q = 0; q < W / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(s_wgt + (size_t)t * W + 4 * q);
+            wg[WEIGHTED ? 4 * q : 0] = v.x; wg[WEIGHTED ? 4 * q + 1 : 0] = v.y;
+            wg[WEIGHTED ? 4 * q + 2 : 0] = v.z; wg[WEIGHTED ? 4 * q + 3 : 0] = v.w;
           }
         }
-        const float s = rsc[i];
-        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-        *reinterpret_cast<float4*>(a.sa + row * CIN + sl * 4) = o;
+        F32x4 acc;
+        acc.lo = 0ull; acc.hi = 0ull;
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          const uint32_t j = ell_slot(cur, u);
+          if (!WEIGHTED) cnt += (j != (uint32_t)nmax) ? 1 : 0;
+          const F32x4 v = lds_x4(lane_base + j * row_bytes);
+          if (WEIGHTED) fma_x4(acc, wg[WEIGHTED ? u : 0], v);
+          else add_x4(acc, v);
+        }
+        if (!WEIGHTED && !has_scale) s = 1.0f / fmaxf((float)cnt, 1.0f);      // the DenseSAGEConv mean
+        o = unpack_x4(acc);
+      } else {
+        const int eb = __ldg(a.rowptr + row), ee = __ldg(a.rowptr + row + 1);
+        if (!WEIGHTED && !has_scale) s = 1.0f / fmaxf((float)(ee - eb), 1.0f);
+        for (int k = eb; k < ee; ++k) {
+          const uint32_t j = (uint32_t)(__ldg(a.col + k) - (int)grow0);
+          const float wv = WEIGHTED ? __ldg(a.val + k) : 1.0f;
+          const float4 v = lds_f4(lane_base + j * row_bytes);
+          o.x = fmaf(wv, v.x, o.x); o.y = fmaf(wv, v.y, o.y); o.z = fmaf(wv, v.z, o.z); o.w = fmaf(wv, v.w, o.w);
+        }
       }
-      // all-gather of the aggregated row over its LPR lanes
-      float full[CIN];
-#pragma unroll
-      for (int d = 0; d < LPR; ++d) {
-        full[4 * d + 0] = __shfl_sync(0xffffffffu, o.x, lbase + d);
-        full[4 * d + 1] = __shfl_sync(0xffffffffu, o.y, lbase + d);
-        full[4 * d + 2] = __shfl_sync(0xffffffffu, o.z, lbase + d);
-        full[4 * d + 3] = __shfl_sync(0xffffffffu, o.w, lbase + d);
-      }
-      float z[NOWN];
-#pragma unroll
-      for (int j = 0; j < NOWN; ++j) z[j] = br[j];
-#pragma unroll
-      for (int k = 0; k < CIN; ++k)
-#pragma unroll
-        for (int j = 0; j < NOWN; ++j) z[j] = fmaf(full[k], wr[k][j], z[j]);
-      float ss = 0.f;
-#pragma unroll
-      for (int j = 0; j < NOWN; ++j) ss = fmaf(z[j], z[j], ss);
-      float tot = 0.f;
-#pragma unroll
-      for (int d = 0; d < LPR; ++d) tot += __shfl_sync(0xffffffffu, ss, lbase + d);
-      const float inv = 1.0f / fmaxf(sqrtf(tot), kL2NormEps);
-      const bool valid = lrow < nn;
-      float yv[NOWN];
-#pragma unroll
-      for (int j = 0; j < NOWN; ++j) yv[j] = valid ? act_fwd(a.act, z[j] * inv) : 0.f;
-      if (row_on) {
-        float* yrow = a.y + row * a.ldy;
-        *reinterpret_cast<float4*>(yrow + 4 * sl) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-        if (EXTRA) yrow[16 + sl] = yv[NOWN - 1];
-#pragma unroll
-        for (int j = 0; j < NOWN; ++j) { s1[j] += yv[j]; s2[j] = fmaf(yv[j], yv[j], s2[j]); }
-      }
+      o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+      *reinterpret_cast<float4*>(a.sa + row * CIN + sl * 4) = o;
     }
-    if ((i0 + RB) * G < nrows) load_batch(i0 + RB);
+    // all-gather of the aggregated row over its LPR lanes
+    float full[CIN];
+#pragma unroll
+    for (int d = 0; d < LPR; ++d) {
+      full[4 * d + 0] = __shfl_sync(0xffffffffu, o.x, lbase + d);
+      full[4 * d + 1] = __shfl_sync(0xffffffffu, o.y, lbase + d);
+      full[4 * d + 2] = __shfl_sync(0xffffffffu, o.z, lbase + d);
+      full[4 * d + 3] = __shfl_sync(0xffffffffu, o.w, lbase + d);
+    }
+    float z[NOWN];
+#pragma unroll
+    for (int j = 0; j < NOWN; ++j) z[j] = br[j];
+#pragma unroll
+    for (int k = 0; k < CIN; ++k)
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) z[j] = fmaf(full[k], wr[k][j], z[j]);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NOWN; ++j) ss = fmaf(z[j], z[j], ss);
+    float tot = 0.f;
+#pragma unroll
+    for (int d = 0; d < LPR; ++d) tot += __shfl_sync(0xffffffffu, ss, lbase + d);
+    const float inv = 1.0f / fmaxf(sqrtf(tot), kL2NormEps);
+    const bool valid = lrow < nn;
+    float yv[NOWN];
+#pragma unroll
+    for (int j = 0; j < NOWN; ++j) yv[j] = valid ? act_fwd(a.act, z[j] * inv) : 0.f;
+    if (row_on) {
+      float* yrow = a.y + row * a.ldy;
+      *reinterpret_cast<float4*>(yrow + 4 * sl) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+      if (EXTRA) yrow[16 + sl] = yv[NOWN - 1];
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) { s1[j] += yv[j]; s2[j] = fmaf(yv[j], yv[j], s2[j]); }
+    }
+#pragma unroll
+    for (int q = 0; q < NW; ++q) cur[q] = nxt[q];
   }
 
   if (a.partial == nullptr) return;
@@ -296,9 +306,16 @@ static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, 
   const int nrow8 = (nmax + 7) & ~7;
   int rpp = (int)ceil_div(nrow8, parts);
   rpp = (rpp + 7) & ~7;
+  // the table slice of the CTA's rows (indices, scales, weights) sits behind the tile: split finer if it does not fit
+  a.tile_smem = (int)((smem + 127) & ~(size_t)127);
+  const size_t per_row = (size_t)W * 2 + 4 + (WEIGHTED ? (size_t)W * 4 : 0);
+  const size_t room = 227 * 1024 - 2048 - 128 - (size_t)a.tile_smem;
+  if ((size_t)rpp * per_row > room) rpp = (int)(room / per_row) & ~7;
+  CGC_REQUIRE(rpp >= 8, CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: no shared memory left for the index table (nmax %d)", nmax);
   parts = (int)ceil_div(nrow8, rpp);
   a.parts = parts;
   a.rpp = rpp;
+  smem = (size_t)a.tile_smem + (size_t)rpp * per_row;
   const int grid = num_graphs * parts;
   if (a.partial != nullptr)
     CGC_REQUIRE((int64_t)grid * 2 * kLayerCout * 8 <= work_bytes, CGC_ERR_WORKSPACE,
@@ -323,7 +340,7 @@ static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, 
 using namespace cgc;
 
 extern "C" int cgc_sage_layer_ell_supported(int32_t cin, int32_t cout, int32_t nmax) {
-  if (cout != kLayerCout || (cin != 16 && cin != 20) || nmax <= 0 || nmax + 1 > 0xFFFF) return 0;
+  if (cout != kLayerCout || (cin != 16 && cin != 20) || nmax <= 0 || nmax + 1 > (int)kEllColMask) return 0;
   int64_t rows_buf = 0;
   // the strided variant needs the larger buffer (box overhang); require it so both input layouts are served
   return pick_box_rows(nmax, cin * 4, 1, 227 * 1024 - 2048, &rows_buf) > 0 ? 1 : 0;

@@ -223,6 +223,9 @@ k_sage_gather_tile(const int* __restrict__ rowptr, const int* __restrict__ col, 
 // dependent 64-byte reads go to DRAM at random and delay the tile barrier by 2 us.)
 // Only the summation order inside a row changes; the adjacency is exactly that of to_dense_adj (utils.py:29-33).
 constexpr int kEllMaxW = 16;
+// Slot 0 of every table row also carries, in bits 12-14, the local row q (within the 8-row block) the table row
+// serves -- the same information as the `perm` words, readable without a second load.  Column ids therefore use 12
+// bits: nmax + 1 <= 0xFFF (every kernel that gathers from a shared-memory tile needs nmax <= ~3600 anyway).
 
 __global__ void __launch_bounds__(128) k_csr_to_ell16(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                       const float* __restrict__ val,
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(128) k_csr_to_ell16(const int* __restrict__ ro
       o[pos] = (uint16_t)nmax;
       if (ow) ow[pos] = 0.f;
     }
+    o[0] = (uint16_t)(o[0] | (q << kEllRowShift));     // the local row (within its 8-row block) this table row serves
   }
   perm[blk] = pw;
 }
@@ -336,8 +340,13 @@ struct EllGatherArgs {
   uint32_t chunk;        // bytes per 1-D bulk copy
 };
 
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
-__global__ void __launch_bounds__(THREADS, 1)
+// LEAN (unweighted tables, ell_scale == NULL): the row's scale is the DenseSAGEConv mean 1 / max(deg, 1) with deg
+// counted from the row's own slots, and the served row comes from the slot-0 tag, so a row costs 4 index registers
+// and nothing else.  With 512 threads x 8 rows this fits 64 registers and two CTAs share an SM (2 x 113.6 KB of
+// shared memory): under programmatic dependent launch the NEXT launch's CTAs are already resident, with their index
+// vectors loaded, when this launch's CTAs finish.
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC, bool LEAN>
+__global__ void __launch_bounds__(THREADS, LEAN ? 2 : 1)
 k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int G = THREADS / LPR;
@@ -375,18 +384,17 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
   const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
   const uint32_t ovf_mark = (uint32_t)nmax + 1u;
 
+  static_assert(!(LEAN && WEIGHTED), "the lean variant serves unweighted tables");
   uint32_t idx[RB][NW];
   float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
-  float rsc[RB];
-  uint32_t pw[RB];                                     // position map word of the row's block
+  float rsc[LEAN ? 1 : RB];
   auto load_batch = [&](int i0) {
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
       const int t = (i0 + i) * G + grp;                // table row inside the CTA
       const bool on = t < nrows;
       const int64_t trow = trow0 + (on ? t : 0);
-      pw[i] = on ? __ldg(a.perm + (trow >> 3)) : 0xFFFFFFFFu;
-      rsc[i] = on ? __ldg(a.ell_scale + trow) : 1.0f;
+      if (!LEAN) rsc[LEAN ? 0 : i] = (on && a.ell_scale != nullptr) ? __ldg(a.ell_scale + trow) : 1.0f;
 #pragma unroll
       for (int q = 0; q < NW / 4; ++q) {
         uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
@@ -449,25 +457,30 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
     for (int i = 0; i < RB; ++i) {
       const int t = (i0 + i) * G + grp;
       if (t >= nrows) continue;                        // whole quarter-warps at a time
-      const int lrow = ((r0 + t) & ~7) + (int)((pw[i] >> (3 * (t & 7))) & 7u);
+      const int lrow = ((r0 + t) & ~7) + ell_served_row(idx[i][0]);
       if (lrow >= nmax) continue;                      // padding of the graph's last 8-row block
       const int64_t row = grow0 + lrow;
       float4 o;
-      const float s = rsc[i];
-      if ((idx[i][0] & 0xFFFFu) != ovf_mark) {
+      float s = LEAN ? 1.0f : rsc[LEAN ? 0 : i];
+      const bool mean_scale = LEAN || (!WEIGHTED && a.ell_scale == nullptr);   // scale = 1 / max(deg, 1)
+      if ((idx[i][0] & kEllColMask) != ovf_mark) {
         F32x4 acc;
         acc.lo = 0ull; acc.hi = 0ull;
+        int cnt = 0;
 #pragma unroll
         for (int u = 0; u < W; ++u) {
           const uint32_t j = ell_slot(idx[i], u);
+          if (!WEIGHTED) cnt += (j != (uint32_t)nmax) ? 1 : 0;
           const F32x4 v = lds_x4(lane_base + j * row_bytes);
           if (WEIGHTED) fma_x4(acc, wgt[WEIGHTED ? i : 0][WEIGHTED ? u : 0], v);
           else add_x4(acc, v);
         }
+        if (mean_scale) s = 1.0f / fmaxf((float)cnt, 1.0f);
         o = unpack_x4(acc);
       } else {
         // degree > W: walk the CSR (column ids are global padded rows)
         const int b = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
+        if (mean_scale) s = 1.0f / fmaxf((float)(e - b), 1.0f);
         o = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = b; k < e; ++k) {
           const uint32_t j = (uint32_t)(__ldg(a.col + k) - (int)grow0);
@@ -611,7 +624,7 @@ k_gather_wide_ell(const __grid_constant__ CUtensorMap map_x, const uint16_t* __r
         if (lrow >= nmax) continue;
         const int64_t row = grow0 + lrow;
         float4 o;
-        if ((cur.idx[i][0] & 0xFFFFu) != ovf_mark) {
+        if ((cur.idx[i][0] & kEllColMask) != ovf_mark) {
           F32x4 acc;
           acc.lo = 0ull; acc.hi = 0ull;
 #pragma unroll
@@ -740,7 +753,7 @@ extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const
               "cgc_csr_to_ell16: bad args");
   CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: width must be 8 or 16 (got %d)",
               width);
-  CGC_REQUIRE(nmax + 1 <= 0xFFFF, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: nmax %d does not fit uint16 local ids", nmax);
+  CGC_REQUIRE(nmax + 1 <= kEllColMask, CGC_ERR_UNSUPPORTED, "cgc_csr_to_ell16: nmax %d does not fit 12-bit local ids", nmax);
   CGC_REQUIRE((ell_val == nullptr) == (val == nullptr), CGC_ERR_ARG,
               "cgc_csr_to_ell16: val and ell_val must be given together");
   const int64_t blocks8 = cgc_ell16_rows(num_graphs, nmax) / 8;
@@ -751,7 +764,7 @@ extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const
   return 0;
 }
 
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC, bool LEAN = false>
 static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cudaStream_t st) {
   const int nmax = a.nmax, feat = a.feat;
   size_t smem = ((size_t)nmax + 2) * feat * 4;
@@ -782,10 +795,13 @@ static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cu
   a.rpp = rpp;
   a.lab_stage = stage;
   a.chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
-  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC>;
+  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC, LEAN>;
   static size_t smem_set = 0;                           // per instantiation: raise the limit only when it grows
   if (smem > smem_set) {
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (LEAN)                                           // two CTAs per SM need the whole 228 KB as shared memory
+      CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
     smem_set = smem;
   }
   PdlLaunch L(dim3((unsigned)(num_graphs * parts)), dim3(THREADS), smem, st, pdl);
@@ -822,6 +838,8 @@ static int ell_gather_dispatch(const uint16_t* ell, const float* ell_val, const 
   if (feat <= 16) {
     if (width == 8) {
       if (wt) CGC_ELL(8, 4, true, 2, 512);
+      else if (ell_scale == nullptr && !strided && !acc)       // the roofline configuration: two CTAs per SM
+        return launch_ell<8, 4, false, 8, 512, false, false, true>(a, num_graphs, ldx, pdl, st);
       else CGC_ELL(8, 4, false, 4, 1024);
     } else {
       if (wt) CGC_ELL(16, 4, true, 1, 512); else CGC_ELL(16, 4, false, 4, 512);
@@ -837,8 +855,10 @@ extern "C" int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, co
                                    const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
                                    const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
                                    int32_t feat, float* out, int64_t ldo, int flags, void* stream) {
-  CGC_REQUIRE(ell && ell_scale && perm && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
+  CGC_REQUIRE(ell && perm && rowptr && col && x && out && num_graphs > 0 && nmax > 0 && feat > 0, CGC_ERR_ARG,
               "cgc_sage_gather_ell: bad args");
+  CGC_REQUIRE(ell_scale != nullptr || ell_val == nullptr, CGC_ERR_ARG,
+              "cgc_sage_gather_ell: ell_scale may be NULL (= the mean 1 / max(deg, 1)) only for unweighted tables");
   CGC_REQUIRE(width == 8 || width == 16, CGC_ERR_UNSUPPORTED, "cgc_sage_gather_ell: width must be 8 or 16");
   CGC_REQUIRE(feat % 4 == 0 && feat <= 32 && ldx >= feat && ldo >= feat && ldx % 4 == 0 && ldo % 4 == 0 &&
                   aligned16(x) && aligned16(out) && aligned16(ell),

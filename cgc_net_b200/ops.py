@@ -29,6 +29,7 @@ from . import _backend
 
 RENORM_P = 0.4       # model/network.py:260,271,280
 BUILD_TRANSPOSED_ELL = False     # see build_sparse_graph
+BUILD_BACKWARD_ELL = True        # ELL16 table of A^T for the narrow CSC gathers of the backward
 ACTIVATIONS = {'relu': 0, 'elu': 1, 'leakyrelu': 2}     # GNN_Module._activation (network.py:82-90) -> CGC_ACT_*
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -89,6 +90,10 @@ class SparseGraph(object):
         self.ell_t = self.ell_t_val = self.ell_t_scale = self.ell_t_perm = None   # the same for A^T (from the CSC)
         self.ell_t_width = 0
         self.ell_width = 0
+        # table of A^T with the mean normaliser of the SOURCE row folded into the edge weights (rs[i] * A[i, j] at
+        # table row j): the CSC gathers of the narrow-layer backward, dX = A^T (rs * dsa)
+        self.ell_b = self.ell_b_val = self.ell_b_scale = self.ell_b_perm = self.val_b = None
+        self.ell_b_width = 0
         # True until the first kernel that reads the ELL16 tables has been enqueued: that consumer directly follows
         # the table builder in the stream, so it must not read the tables in its programmatic-launch prologue
         self.tables_fresh = True
@@ -140,7 +145,7 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
     else:
         be.row_inv_degree(g.rowptr, g.rs)
     g.colptr = torch.empty(rows + 1, dtype=torch.int32, device=dev)
-    g.row = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    g.row = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
     g.val_t = _f32(max(cap, 1), device=dev) if norm_adj else None
     be.csr_transpose(g.rowptr, g.col, g.val, g.colptr, g.row, g.val_t, work)
     # Fixed-pitch index table of the shared-memory gathers (layer-1 SAGE gather when the feature width allows it,
@@ -148,7 +153,7 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
     # pitch are flagged and walk the CSR.  The slot-parity / row-pairing order serves the 64-byte shared-memory rows
     # both kernels use.
     real_rows = max(n_total, 1)
-    if nmax + 1 <= 0xFFFF and cap <= 16 * real_rows and (nmax + 2) * 64 + 1024 <= 227 * 1024:
+    if nmax + 1 <= 0xFFF and cap <= 16 * real_rows and (nmax + 2) * 64 + 1024 <= 227 * 1024:
         g.ell_width = 8 if cap <= 8 * real_rows else 16
         trows = be.ell16_rows(num_graphs, nmax)
         g.ell = torch.empty(trows * g.ell_width, dtype=torch.int16, device=dev)
@@ -157,6 +162,19 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
         g.ell_perm = torch.empty(trows // 8, dtype=torch.int32, device=dev)
         be.csr_to_ell16(g.rowptr, g.col, g.val, g.rs, num_graphs, nmax, g.ell_width, True, g.ell, g.ell_val,
                         g.ell_scale, g.ell_perm)
+        if BUILD_BACKWARD_ELL and torch.is_grad_enabled():
+            # weights of the transposed edges: rs of the edge's source row (times the renormalised value); the unused
+            # tail of g.row is zero-filled (valid indices)
+            g.val_b = torch.index_select(g.rs, 0, g.row)
+            if norm_adj:
+                g.val_b = g.val_b * g.val_t
+            g.ell_b_width = 16                      # in-degrees spread around the mean: pitch 16, the rest walks the CSC
+            g.ell_b = torch.empty(trows * 16, dtype=torch.int16, device=dev)
+            g.ell_b_val = _f32(trows * 16, device=dev)
+            g.ell_b_scale = _f32(trows, device=dev)
+            g.ell_b_perm = torch.empty(trows // 8, dtype=torch.int32, device=dev)
+            be.csr_to_ell16(g.colptr, g.row, g.val_b, None, num_graphs, nmax, 16, True, g.ell_b, g.ell_b_val,
+                            g.ell_b_scale, g.ell_b_perm)
         if BUILD_TRANSPOSED_ELL:
             # table of the transposed adjacency (wide gather of the DiffPool backward, A^T gP).  In-degrees vary more
             # than out-degrees, the pitch has to be 16 and half of the slots are padding: measured 620 us vs 425 us
@@ -195,8 +213,10 @@ def _agg(be, cfg, adj, rs, x_prev, out):
         if _ell_ok(g, x_prev, out) and rs is g.rs:
             # fixed-pitch index table (rs baked in) + TMA-staged feature tile (the roofline kernel); column slices
             # of the concat buffer (layers 2-3) are staged by 2-D TMA boxes
-            be.sage_gather_ell(g.ell, g.ell_val, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val,
-                               x_prev, g.num_graphs, g.nmax, out, tables_ready=g.tables_ready())
+            # binary adjacency: no scale vector (the kernel derives the mean 1 / max(deg, 1) from the row's slots)
+            be.sage_gather_ell(g.ell, g.ell_val, g.ell_scale if g.ell_val is not None else None, g.ell_perm,
+                               g.ell_width, g.rowptr, g.col, g.val, x_prev, g.num_graphs, g.nmax, out,
+                               tables_ready=g.tables_ready())
         elif dense_io and g.nmax * feat * 4 + 12288 <= 220 * 1024:
             # whole-graph feature tile fits in shared memory: TMA-staged gather (the roofline kernel)
             be.sage_gather_mean_fwd(g.rowptr, g.col, g.val, rs, x_prev, g.num_graphs, g.nmax, out)
@@ -221,7 +241,12 @@ def _agg_t(be, cfg, adj, g_a, src_scale, out, accumulate):
     """``A^T (src_scale * g)`` into ``out`` (``+=`` when ``accumulate``)."""
     if cfg.graph is not None:
         g = cfg.graph
-        be.spmm(g.colptr, g.row, g.val_t, g_a, src_scale, None, out, accumulate)
+        if g.ell_b is not None and src_scale is g.rs and _ell_ok(g, g_a, out):
+            # rs is folded into the table's edge weights; a column slice of the gradient buffer is a strided out
+            be.sage_gather_ell(g.ell_b, g.ell_b_val, g.ell_b_scale, g.ell_b_perm, g.ell_b_width, g.colptr, g.row,
+                               g.val_b, g_a, g.num_graphs, g.nmax, out, accumulate=accumulate, tables_ready=True)
+        else:
+            be.spmm(g.colptr, g.row, g.val_t, g_a, src_scale, None, out, accumulate)
     else:
         b, n = cfg.num_graphs, cfg.nmax
         be.gemm(adj, _as3d(g_a, b, n), _as3d(out, b, n), True, False,
@@ -271,8 +296,8 @@ class GnnModuleFunction(Function):
                 # the whole layer up to the BatchNorm statistics in ONE kernel (gather + W + bias + L2 norm + mask
                 # + activation + column partial sums)
                 stats = cfg.has_bn and cfg.training
-                be.sage_layer_ell_fwd(g.ell, g.ell_val, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, g.val,
-                                      x_prev, g.num_graphs, g.nmax, w, b, cfg.mask, cfg.act, a, y,
+                be.sage_layer_ell_fwd(g.ell, g.ell_val, g.ell_scale if g.ell_val is not None else None, g.ell_perm,
+                                      g.ell_width, g.rowptr, g.col, g.val, x_prev, g.num_graphs, g.nmax, w, b, cfg.mask, cfg.act, a, y,
                                       rmean if stats else None, rvar if stats else None, BN_MOMENTUM, BN_EPS,
                                       mean if stats else None, invstd if stats else None,
                                       tables_ready=g.tables_ready())

@@ -238,6 +238,8 @@ class TorchBackend(object):
                         if vl is not None:
                             wtab[trow, t] = vl[i]
             pw_all.append(pw)
+            for p in range(8):                      # slot 0 also carries the served local row (bits 12-14)
+                table[blk * 8 + p, 0] |= ((pw >> (3 * p)) & 7) << 12
         table = torch.where(table >= 32768, table - 65536, table).to(torch.int16)
         ell.view(-1)[:table.numel()].copy_(table.view(-1))
         if ell_val is not None:
@@ -251,9 +253,12 @@ class TorchBackend(object):
         nrow8 = (nmax + 7) // 8 * 8
         trows = num_graphs * nrow8
         idx = ell.view(-1)[:trows * width].view(trows, width).long() & 0xFFFF
+        served = (idx[:, 0] >> 12) & 7
+        idx[:, 0] &= 0xFFF
         pw = perm.view(-1)[:trows // 8].long() & 0xFFFFFF
         pos = torch.arange(trows)
         lrow = (pos % nrow8) // 8 * 8 + ((pw[pos // 8] >> (3 * (pos % 8))) & 7)             # local row per table row
+        assert bool((served == ((pw[pos // 8] >> (3 * (pos % 8))) & 7)).all()), 'slot-0 row tag disagrees with perm'
         gid = pos // nrow8
         real = lrow < nmax
         xz = torch.cat([x.view(num_graphs, nmax, -1),
@@ -264,7 +269,11 @@ class TorchBackend(object):
         else:
             res = src.sum(1)
         grow = gid * nmax + lrow.clamp(max=nmax - 1)
-        scale = ell_scale.view(-1)[:trows]
+        if ell_scale is None:                   # unweighted table: the mean 1 / max(deg, 1), deg from the row itself
+            deg = (rowptr[1:] - rowptr[:-1]).float()[grow]
+            scale = 1.0 / torch.where(real, deg, torch.ones_like(deg)).clamp(min=1)
+        else:
+            scale = ell_scale.view(-1)[:trows]
         res = res * scale[:, None]
         out[grow[real]] = res[real]
         over = real & (idx[:, 0] == nmax + 1)
@@ -286,7 +295,7 @@ class TorchBackend(object):
 
     @staticmethod
     def sage_layer_ell_supported(cin, cout, nmax):
-        return cout == 20 and cin in (16, 20) and 0 < nmax < 0xFFFF and ((nmax + 255) // 8 * 8) * cin * 4 <= 227 * 1024 - 2048
+        return cout == 20 and cin in (16, 20) and 0 < nmax < 0xFFF and ((nmax + 255) // 8 * 8) * cin * 4 <= 227 * 1024 - 2048
 
     def sage_layer_ell_fwd(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, w, b,
                            mask, act, sa, y, rmean, rvar, momentum, eps, mean, invstd, tables_ready=False, pdl=True):

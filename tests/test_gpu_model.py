@@ -10,9 +10,9 @@ Tolerances
     - ``fp32``    mode (every contraction on the exact-fp32 FMA kernel): tol 3e-4 (the fp32 reference's own
       distance to float64 on these tensors, measured with tools/grad_diag.py), slack 10 -- i.e. "as exact
       as the reference's own arithmetic": same rounding class, different summation order;
-    - ``tcgen05`` mode (the default product path: 3xTF32 tensor-core contractions whose TMEM accumulation
-      rounds toward zero, promoted to fp32 every K = 64; ~1e-6 relative per contraction instead of ~1e-7):
-      tol 3e-3 -- stated, measured ~1e-3 on the worst tensors;
+    - ``tcgen05`` mode (the default product path: tensor-core contractions with the shipped pass budget, TMEM
+      accumulation rounding toward zero promoted to fp32 every 24 MMA adds; ~1e-6 relative per 3xTF32 contraction
+      instead of ~1e-7): tol 1e-3, slack 5 (round 1: 3e-3 / 20);
     - ``norm_adj``: row sums are 1 +- 1 ulp, so DenseSAGEConv's clamp(min=1) gates its gradient by
       summation order; every fp32 evaluation (the reference's included) moves by a few 1e-4: tol 1e-3.
 """
@@ -42,7 +42,7 @@ def gemm_mode(request, cuda_backend):
 
 def _grad_tol(mode, norm_adj=False):
     if mode == 'tcgen05':
-        return dict(tol=3e-3, slack=20.0)
+        return dict(tol=1e-3, slack=5.0, floor=2e-3)
     # floor: tensors whose largest gradient is below 2e-3 (tiny pool stages) are residues of cancellation; their
     # absolute fp32 rounding noise is ~5e-7 whatever the summation order (measured: 3.6e-7 on GCN_pool_2.gcn2.bias)
     return dict(tol=1e-3, slack=10.0, floor=2e-3) if norm_adj else dict(tol=3e-4, slack=10.0, floor=2e-3)

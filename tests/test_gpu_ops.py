@@ -175,6 +175,8 @@ def test_csr_to_ell16_bit_exact(cuda_backend, width, maxdeg, pair, weighted):
          [8, 9, 10, 11] if weighted else [8, 10, 11], exact=(8, 9, 10, 11))
     # every row's entry set survives the re-ordering
     table = (ell.view(trows, width).long() & 0xFFFF)
+    assert torch.equal((table[:, 0] >> 12) & 7, (perm.long()[torch.arange(trows) // 8] >> (3 * (torch.arange(trows) % 8))) & 7)
+    table[:, 0] &= 0xFFF                                  # slot 0 carries the served local row in bits 12-14
     pos = torch.arange(trows)
     lrow = (pos % 64) // 8 * 8 + ((perm.long()[pos // 8] >> (3 * (pos % 8))) & 7)
     deg = (rowptr[1:] - rowptr[:-1]).long()
@@ -671,6 +673,19 @@ def test_sage_gather_ell_strided(cuda_backend, feat, b, nmax, width, maxdeg, wei
     xc, oc = x.contiguous(), (out.clone() if accumulate else torch.zeros(rows, feat))
     both(cuda_backend, 'sage_gather_ell', [ell, ellw, ells, perm, width, rowptr, col, val, xc, b, nmax, oc,
                                            accumulate, ready], [11], rtol=1e-5, atol=1e-5)
+    if not weighted:
+        # unweighted table without a scale vector: the DenseSAGEConv mean 1 / max(deg, 1) from the row's own slots
+        # (feat 16, width 8, contiguous, plain store = the two-CTAs-per-SM roofline variant)
+        ell, ellw, _, perm = _ell_tables(rowptr, col, None, None, b, nmax, width, int(feat == 16))
+        for xa, oa in ((xc, torch.zeros(rows, feat)), (x, ow.clone()[:, 4:4 + feat])):
+            if accumulate:
+                oa.zero_()
+            both(cuda_backend, 'sage_gather_ell', [ell, None, None, perm, width, rowptr, col, None, xa, b, nmax, oa,
+                                                   False, ready], [11], rtol=1e-5, atol=1e-5)
+            deg = (rowptr[1:] - rowptr[:-1]).float().clamp(min=1)
+            mean = torch.zeros(rows, feat)
+            REF.spmm(rowptr, col, None, xc, None, 1.0 / deg, mean, False)
+            torch.testing.assert_close(oa, mean, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize('cin,b,nmax,width,maxdeg', [(16, 3, 70, 8, 8), (20, 5, 333, 8, 10), (16, 64, 1800, 8, 8),
@@ -703,8 +718,11 @@ def test_sage_layer_ell_fwd(cuda_backend, cin, b, nmax, width, maxdeg, weighted,
          [ell, ellw, ells, perm, width, rowptr, col, val, x, b, nmax, w, bias, mask, act, sa, y,
           rmean if stats else None, rvar if stats else None, 0.1, 1e-5, mean, invstd, True], outs,
          rtol=2e-5, atol=2e-6)
-    # no bias, tables flagged as fresh (no early loads)
+    # no bias, tables flagged as fresh (no early loads); unweighted tables: no scale vector (mean from the slots)
     y2 = torch.zeros(rows, 20)
+    if not weighted:
+        ell, ellw, ells, perm = _ell_tables(rowptr, col, None, None, b, nmax, width, int(cin == 16))
+        ells = None
     both(cuda_backend, 'sage_layer_ell_fwd',
          [ell, ellw, ells, perm, width, rowptr, col, val, x, b, nmax, w, None, mask, act, sa, y2,
           None, None, 0.1, 1e-5, None, None, False], [15, 16], rtol=2e-5, atol=2e-6)

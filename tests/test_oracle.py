@@ -213,6 +213,8 @@ def test_ell16_reference_table_invariants():
         perm = torch.zeros(trows // 8, dtype=torch.int32)
         ref.csr_to_ell16(rowptr, col, val, None, b, nmax, width, pair, ell, ellw, ells, perm)
         table = ell.view(trows, width).long() & 0xFFFF
+        tags = (table[:, 0] >> 12) & 7                    # slot 0 carries the served local row in bits 12-14
+        table[:, 0] &= 0xFFF
         wt = ellw.view(trows, width)
         nrow8 = trows // b
         seen = set()
@@ -220,6 +222,7 @@ def test_ell16_reference_table_invariants():
             gidx, p = divmod(t, nrow8)
             pw = int(perm[t // 8]) & 0xFFFFFF
             lrow = p // 8 * 8 + ((pw >> (3 * (p % 8))) & 7)
+            assert int(tags[t]) == (pw >> (3 * (p % 8))) & 7
             seen.add((gidx, lrow))
             if lrow >= nmax:
                 assert bool((table[t] == nmax).all())

@@ -22,7 +22,7 @@ variant = os.environ.get('VARIANT', 'ell')
 for _ in range(3):
     flush.zero_()
     if variant == 'ell':
-        be.sage_gather_ell(g.ell, None, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, None, xp, b, n, out,
+        be.sage_gather_ell(g.ell, None, None, g.ell_perm, g.ell_width, g.rowptr, g.col, None, xp, b, n, out,
                            tables_ready=True)
     elif variant == 'layer':
         be.sage_layer_ell_fwd(g.ell, None, g.ell_scale, g.ell_perm, g.ell_width, g.rowptr, g.col, None, xp, b, n, w,
