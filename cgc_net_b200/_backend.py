@@ -59,6 +59,8 @@ _SIGNATURES = {
     'cgc_sage_epilogue_fwd': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_sage_layer_fwd_narrow': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp,
                                   _c_i64, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    'cgc_sage_layer_fwd_wide': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp,
+                                _c_i64, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_act_fwd': [_c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
@@ -358,6 +360,18 @@ class CudaBackend(object):
                                                        _ptr(rvar, torch.float32), float(momentum), float(eps),
                                                        _ptr(mean, torch.float32), _ptr(invstd, torch.float32),
                                                        wp, wb, self._stream()), 'cgc_sage_layer_fwd_narrow')
+
+    def sage_layer_fwd_wide(self, sa, w, b, mask, y, act, rmean, rvar, momentum, eps, mean, invstd):
+        sp, lds = _mat(sa)
+        yp, ldy = _mat(y)
+        nn, nmax = _mask(mask)
+        wp, wb = self._workspace(sa.device)
+        self._check(self.lib.cgc_sage_layer_fwd_wide(sp, lds, _ptr(w.contiguous(), torch.float32),
+                                                     _ptr(b, torch.float32), nn, nmax, sa.shape[0], w.shape[0],
+                                                     w.shape[1], int(act), yp, ldy, _ptr(rmean, torch.float32),
+                                                     _ptr(rvar, torch.float32), float(momentum), float(eps),
+                                                     _ptr(mean, torch.float32), _ptr(invstd, torch.float32),
+                                                     wp, wb, self._stream()), 'cgc_sage_layer_fwd_wide')
 
     def sage_dh(self, gy, sa, w, b, y, mask, dh, act=0):
         gp, ldg = _mat(gy)

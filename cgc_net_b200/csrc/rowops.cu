@@ -62,9 +62,14 @@ __global__ void __launch_bounds__(kEpiThreads, NC == 1 ? 4 : (NC == 2 ? 3 : 2))
 k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
            const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
            float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
-           float* __restrict__ dh, int64_t lddh, int act) {
+           float* __restrict__ dh, int64_t lddh, int act, double* __restrict__ partial) {
   extern __shared__ float smem[];
   const ActGrad agrad(act);
+  // forward with BatchNorm statistics (partial != null): every thread owns its columns in the CTA, so the column
+  // sums of y and y^2 over the CTA's tiles accumulate in registers and leave as one [2][cout] partial per CTA
+  float st1[NC], st2[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) { st1[j] = 0.f; st2[j] = 0.f; }
   float* s_w = smem;                                 // [cin][cout]
   float* s_a = s_w + cin * cout;                     // [cin][kEpiRows]  (transposed row tile)
   float* s_red = s_a + cin * kEpiRows;               // [8 warps][kEpiRows]
@@ -151,7 +156,12 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
           int c = t + kEpiThreads * j;
-          if (c < cout) y[r * ldy + c] = valid ? act_fwd(act, acc[rr][j] * inv[rr]) : 0.f;
+          if (c < cout) {
+            const float v = valid ? act_fwd(act, acc[rr][j] * inv[rr]) : 0.f;
+            y[r * ldy + c] = v;
+            st1[j] += v;
+            st2[j] = fmaf(v, v, st2[j]);
+          }
         }
       }
     } else {
@@ -203,13 +213,23 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
       }
     }
   }
+  if (!BWD && partial != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = t + kEpiThreads * j;
+      if (c < cout) {
+        partial[((int64_t)blockIdx.x * 2 + 0) * cout + c] = (double)st1[j];
+        partial[((int64_t)blockIdx.x * 2 + 1) * cout + c] = (double)st2[j];
+      }
+    }
+  }
 }
 
 template <bool BWD>
 static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const float* b,
                            const int32_t* num_nodes, int nmax, int64_t rows, int cin, int cout, float* y,
                            int64_t ldy, const float* gy, int64_t ldgy, float* dh, int64_t lddh, int act,
-                           cudaStream_t st) {
+                           cudaStream_t st, double* partial = nullptr, int64_t work_bytes = 0, int* blocks_out = nullptr) {
   CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG, "sage epilogue: unknown activation %d", act);
   if (cout <= 32) {
     CGC_REQUIRE(cin <= 64, CGC_ERR_UNSUPPORTED, "sage epilogue: cin=%d > 64", cin);
@@ -232,12 +252,16 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
   int64_t blocks = tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm;
+  if (partial != nullptr) {
+    CGC_REQUIRE(blocks * 2 * cout * 8 <= work_bytes, CGC_ERR_WORKSPACE, "sage epilogue: workspace too small");
+    *blocks_out = (int)blocks;
+  }
 #define CGC_EPI_CASE(N)                                                                                       \
   case N: {                                                                                                   \
     auto kern = k_epi_wide<N, BWD>;                                                                           \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     kern<<<(unsigned)blocks, kEpiThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, \
-                                                      gy, ldgy, dh, lddh, act);                               \
+                                                      gy, ldgy, dh, lddh, act, partial);                      \
   } break;
   switch (nc) {
     CGC_EPI_CASE(1)
@@ -540,6 +564,30 @@ extern "C" int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float*
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_epilogue_fwd: mask without nmax");
   return launch_epilogue<false>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, nullptr, 0, nullptr, 0,
                                 act, as_stream(stream));
+}
+
+namespace cgc {
+int bn_finalize_partials(const double* partial, int blocks, int c, int64_t rows, float* running_mean,
+                         float* running_var, float momentum, float eps, float* mean, float* invstd, cudaStream_t st);
+}
+
+extern "C" int cgc_sage_layer_fwd_wide(const float* sa, int64_t ldsa, const float* w, const float* b,
+                                       const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
+                                       int32_t cout, int act, float* y, int64_t ldy, float* running_mean,
+                                       float* running_var, float momentum, float eps, float* mean, float* invstd,
+                                       void* work, int64_t work_bytes, void* stream) {
+  CGC_REQUIRE(sa && w && y && mean && invstd && work && rows > 0 && cin > 0 && cout > 0 && ldsa >= cin && ldy >= cout,
+              CGC_ERR_ARG, "cgc_sage_layer_fwd_wide: bad args");
+  CGC_REQUIRE(cout > 32 && cout <= 1280, CGC_ERR_UNSUPPORTED,
+              "cgc_sage_layer_fwd_wide: needs 32 < cout <= 1280 (got %d); narrow layers take cgc_sage_layer_fwd_narrow", cout);
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_layer_fwd_wide: mask without nmax");
+  int blocks = 0;
+  cudaStream_t st = as_stream(stream);
+  int rc = launch_epilogue<false>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, nullptr, 0, nullptr, 0, act,
+                                  st, reinterpret_cast<double*>(work), work_bytes, &blocks);
+  if (rc != 0) return rc;
+  return bn_finalize_partials(reinterpret_cast<const double*>(work), blocks, cout, rows, running_mean, running_var,
+                              momentum, eps, mean, invstd, st);
 }
 
 extern "C" int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t ldsa, const float* w,

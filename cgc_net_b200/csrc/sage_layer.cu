@@ -353,8 +353,10 @@ extern "C" int cgc_sage_layer_ell_fwd(const uint16_t* ell, const float* ell_val,
                                       int32_t cout, int act, float* sa, float* y, int64_t ldy, float* running_mean,
                                       float* running_var, float momentum, float eps, float* mean, float* invstd,
                                       void* work, int64_t work_bytes, int flags, void* stream) {
-  CGC_REQUIRE(ell && ell_scale && perm && rowptr && col && x && w && sa && y && num_graphs > 0 && nmax > 0, CGC_ERR_ARG,
+  CGC_REQUIRE(ell && perm && rowptr && col && x && w && sa && y && num_graphs > 0 && nmax > 0, CGC_ERR_ARG,
               "cgc_sage_layer_ell_fwd: bad args");
+  CGC_REQUIRE(ell_scale != nullptr || ell_val == nullptr, CGC_ERR_ARG,
+              "cgc_sage_layer_ell_fwd: ell_scale may be NULL (= the mean 1 / max(deg, 1)) only for unweighted tables");
   CGC_REQUIRE(cgc_sage_layer_ell_supported(cin, cout, nmax), CGC_ERR_UNSUPPORTED,
               "cgc_sage_layer_ell_fwd: instantiated for cin 16 / 20 and cout 20 with the tile in shared memory "
               "(got cin %d cout %d nmax %d)", cin, cout, nmax);

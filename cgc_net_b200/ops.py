@@ -312,6 +312,9 @@ class GnnModuleFunction(Function):
             if cfg.has_bn and cfg.training and couts[k] <= 32 and w.shape[0] <= 64:
                 # narrow layer: epilogue and BatchNorm batch statistics in ONE pass over the rows
                 be.sage_layer_fwd_narrow(a, w, b, cfg.mask, y, cfg.act, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
+            elif cfg.has_bn and cfg.training and 32 < couts[k] <= 1280 and w.shape[0] <= 64:
+                # wide layer (20 -> 1140): the statistics ride on the epilogue, no separate pass over y
+                be.sage_layer_fwd_wide(a, w, b, cfg.mask, y, cfg.act, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
             else:
                 be.sage_epilogue_fwd(a, w, b, cfg.mask, y, cfg.act)
                 if cfg.has_bn and cfg.training:

@@ -227,6 +227,16 @@ CGC_API int cgc_sage_epilogue_fwd(const float* sa, int64_t ldsa, const float* w,
                           const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
                           int32_t cout, int act, float* y, int64_t ldy, void* stream);
 
+/* Wide counterpart (32 < cout <= 1280: the 20 -> 1140 assignment layer of GCN_pool_1, network.py:146-148): the same
+ * epilogue with the BatchNorm column sums of y accumulated in the registers of the threads that own the columns,
+ * one [2][cout] double partial per CTA in `work`, then the fixed-order finalize -- the separate 525 MB statistics
+ * pass over y disappears. */
+CGC_API int cgc_sage_layer_fwd_wide(const float* sa, int64_t ldsa, const float* w, const float* b,
+                            const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin,
+                            int32_t cout, int act, float* y, int64_t ldy, float* running_mean,
+                            float* running_var, float momentum, float eps, float* mean, float* invstd,
+                            void* work, int64_t work_bytes, void* stream);
+
 /* Fused narrow layer forward (cout <= 32, cin <= 64, training mode): cgc_sage_epilogue_fwd AND cgc_bn_stats of
  * its output in one pass over the rows (thread per row, coalesced tile staging, per-CTA column-sum partials in
  * `work`, the same deterministic double-precision finalize): y as above; mean / invstd / running stats as

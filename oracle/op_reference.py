@@ -357,6 +357,8 @@ class TorchBackend(object):
         self.sage_epilogue_fwd(sa, w, b, mask, y, act)
         self.bn_stats(y, rmean, rvar, momentum, eps, mean, invstd)
 
+    sage_layer_fwd_wide = sage_layer_fwd_narrow      # same formulas; the library splits them by output width
+
     def sage_dh(self, gy, sa, w, b, y, mask, dh, act=0):
         h, nrm, inv, valid = self._epilogue(sa, w, b, mask)
         hn = h * inv

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Only usable where the read-only
 reference checkout exists (the build container); the GPU box has no ``/root/reference``,
-so nothing executed there may call this -- ``available()`` lets tests skip.
+unless a copy has been staged under ``baseline/_ref`` (``oracle/stage_reference.py``) -- ``available()`` lets callers
+skip or fall back to the restatement.
 
 The only patch applied to the imported module is ``construct_mask``: the reference
 hard-codes ``.cuda()`` at ``model/network.py:180``; on a CPU-only host the tensor stays
@@ -17,7 +18,19 @@ import torch
 
 from . import pyg_shim
 
-REFERENCE_ROOT = os.environ.get('CGC_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """CGC_REFERENCE_ROOT, the read-only checkout of the build container, or the staged copy that travels to the
+    GPU box (oracle/stage_reference.py -> baseline/_ref, git-ignored)."""
+    for cand in (os.environ.get('CGC_REFERENCE_ROOT'), '/root/reference', os.path.join(_REPO, 'baseline', '_ref')):
+        if cand and os.path.isfile(os.path.join(cand, 'model', 'network.py')):
+            return cand
+    return '/root/reference'
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

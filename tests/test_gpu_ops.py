@@ -775,3 +775,23 @@ def test_gemm_single_pass_tf32(cuda_backend):
             rel = (c.cpu().double() - ref) / ref
             assert float(rel.abs().max()) < 1e-4, (ta, tb, float(rel.abs().max()))      # K = 1800 averages the rounding
             assert abs(float(rel.mean())) < 3e-6, (ta, tb, float(rel.mean()))            # no truncation bias (2^-12 = 2.4e-4)
+
+
+@pytest.mark.parametrize('cin,cout', [(20, 1140), (20, 114), (60, 300), (16, 33)])
+@pytest.mark.parametrize('act', [0, 1])
+def test_sage_layer_fwd_wide(cuda_backend, cin, cout, act):
+    """Wide epilogue with the BatchNorm statistics accumulated in the column-owning threads == epilogue followed by
+    bn_stats (many tiles per CTA, ragged mask, strided y)."""
+    b, nmax = 7, 1237
+    rows = b * nmax
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    sa = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax)
+    yw = torch.zeros(rows, cout + 4)
+    y = yw[:, 0:cout]
+    rmean, rvar = torch.randn(cout, generator=g), torch.rand(cout, generator=g) + 0.5
+    mean, invstd = torch.zeros(cout), torch.zeros(cout)
+    both(cuda_backend, 'sage_layer_fwd_wide', [sa, w, bias, mask, y, act, rmean, rvar, 0.1, 1e-5, mean, invstd],
+         [4, 6, 7, 10, 11], rtol=2e-5, atol=1e-6)

@@ -1,0 +1,109 @@
+"""The reference's own ``train.train()`` loop (train.py:138-244) running UNCHANGED on the GPU through
+``libcgc_sm100.so`` (VERDICT r1 item 6 / SURVEY 8(f) row 3).
+
+Needs a reference checkout: ``/root/reference`` (the build container) or ``baseline/_ref`` (a staged copy that
+travels to the GPU box: ``oracle/stage_reference.py``); skips cleanly otherwise.  ``cgc_net_b200.compat`` stands in
+for torch_geometric / tensorboardX and maps ``from model import network`` (train.py:16) to the B200 module; the model
+is wrapped and moved exactly as train.py:285 does (``DataParallel(model).cuda()``).  The loss of every iteration
+is then compared with the same loop driven by the per-operator CPU formulas of the oracle."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from cgc_net_b200 import _backend, compat, graph
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = next((p for p in (os.environ.get('CGC_REFERENCE_ROOT'), '/root/reference', os.path.join(ROOT, 'baseline', '_ref'))
+            if p and os.path.isfile(os.path.join(p, 'train.py'))), None)
+MODS = ('torch_geometric', 'tensorboardX', 'model', 'train', 'common', 'dataflow', 'setting')
+
+
+class _FakeLoader(object):
+    """What prepare_train_val_loader returns, reduced to what train() touches."""
+
+    def __init__(self, batches):
+        self.batches = batches
+        self.dataset = types.SimpleNamespace(set_epoch=lambda e: None, set_val_epoch=lambda e: None)
+
+    def __iter__(self):
+        return iter(self.batches)
+
+    def __len__(self):
+        return len(self.batches)
+
+
+def _data_list(sizes, seed):
+    out = []
+    for i, n in enumerate(sizes):
+        d = graph.synthetic_cell_graph(n, 6, 16, seed=seed * 10 + i, row_is_centre=False)
+        out.append(compat.Data(x=d.x, edge_index=d.edge_index, y=d.y, pos=d.pos, patch_idx=torch.tensor([i])))
+    return out
+
+
+def _run_reference_train(tmp_path, on_gpu):
+    """Import the reference train.py fresh and run two epochs of its train() over two batches; returns the
+    per-iteration losses and the final state_dict."""
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split('.')[0] in MODS}
+    for k in saved:
+        sys.modules.pop(k, None)
+    compat.install(replace_model=True, force=True)
+    sys.path.insert(0, REF)
+    argv = sys.argv
+    sys.argv = ['train.py', '--load_data_list', '--input_feature_dim', '16', '--assign-ratio', '0.1', '--step_size', '1']
+    try:
+        import train as ref_train                                # the reference file, unmodified
+        from model import network                                # train.py:16 -> cgc_net_b200.network
+        from torch_geometric.nn import DataParallel              # train.py:17
+        import cgc_net_b200.network as ours
+        assert network is ours
+        args = ref_train.arg_parse()
+        args.num_epochs, args.resultdir, args.num_classes = 2, str(tmp_path), 3
+        torch.manual_seed(0)
+        # constructor call of train.py:254-261; max_num_nodes 3000 -> 300 / 30 clusters (wide gather + tcgen05 lin)
+        model = network.SoftPoolingGcnEncoder(3000, args.input_feature_dim, args.hidden_dim, args.output_dim, True,
+                                              True, args.hidden_dim, args.num_classes, args.assign_ratio, [50],
+                                              concat=True, gcn_name=args.gcn_name, collect_assign=args.visualization,
+                                              load_data_sparse=(args.load_data_list and not args.visualization),
+                                              norm_adj=args.norm_adj, activation=args.activation,
+                                              drop_out=args.drop_out, jk=args.jump_knowledge)
+        model = DataParallel(model)
+        if on_gpu:
+            model = model.cuda()                                 # train.py:285
+        losses = []
+        model.module.register_forward_hook(lambda m, i, o: losses.append(float(o[1].detach())) if m.training else None)
+        loader = _FakeLoader([_data_list([500, 640, 380], 1), _data_list([700, 450], 2)])
+        trained, val_accs = ref_train.train(loader, model, args, val_dataset=None, test_dataset=None, writer=None)
+        return losses, {k: v.detach().cpu() for k, v in trained.module.state_dict().items()}
+    finally:
+        sys.argv = argv
+        sys.path.remove(REF)
+        for k in list(sys.modules):
+            if k.split('.')[0] in MODS:
+                sys.modules.pop(k, None)
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+@pytest.mark.skipif(REF is None, reason='no reference checkout (/root/reference or baseline/_ref)')
+def test_reference_train_loop_on_gpu(cuda_backend, tmp_path):
+    before = cuda_backend.kernel_launches()
+    gpu_losses, gpu_state = _run_reference_train(tmp_path / 'gpu', on_gpu=True)
+    assert cuda_backend.kernel_launches() - before > 500, 'the reference loop did not run on libcgc_sm100'
+    assert len(gpu_losses) == 4 and all(v == v and abs(v) < 1e3 for v in gpu_losses)
+    assert int(gpu_state['GCN_embed_1.bn1.num_batches_tracked']) == 4
+    # the same loop on the per-operator CPU formulas of the oracle (the checker)
+    from oracle import op_reference
+    _backend.use_backend_for_testing(op_reference.TorchBackend())
+    try:
+        cpu_losses, cpu_state = _run_reference_train(tmp_path / 'cpu', on_gpu=False)
+    finally:
+        _backend.use_backend_for_testing(None)
+    print('losses gpu %s\n       cpu %s' % (gpu_losses, cpu_losses))
+    assert abs(gpu_losses[0] - cpu_losses[0]) <= 1e-5 * max(1.0, abs(cpu_losses[0]))     # same init, same data
+    for a, b in zip(gpu_losses, cpu_losses):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b))             # Adam (lr 1e-3) amplifies rounding between steps
+    for k in ('GCN_embed_1.bn1.running_mean', 'GCN_pool_1.bn3.running_var'):
+        assert float((gpu_state[k] - cpu_state[k]).abs().max()) <= 1e-3 * float(cpu_state[k].abs().max())
