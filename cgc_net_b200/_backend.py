@@ -172,6 +172,7 @@ class CudaBackend(object):
         w = self._work.get(device)
         if w is None:
             w = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
+            w[-256:].zero_()            # completion counters live in the tail (include/cgc_sm100.h, "workspace")
             self._work[device] = w
         return w.data_ptr(), self.work_bytes
 

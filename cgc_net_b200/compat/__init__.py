@@ -77,7 +77,7 @@ class Batch(_graph.Batch):
     @staticmethod
     def from_data_list(data_list):
         base = _graph.Batch.from_data_list(data_list)
-        out = Batch(base.x, base.edge_index, base.batch, base.y, base.num_nodes_list)
+        out = Batch(base.x, base.edge_index, base.batch, base.y, base.num_nodes_list, base.max_degree, base.self_loops)
         for key in ('pos', 'patch_idx'):
             vals = [getattr(d, key, None) for d in data_list]
             if all(torch.is_tensor(v) for v in vals):
@@ -86,7 +86,7 @@ class Batch(_graph.Batch):
 
     def _map(self, fn):
         m = _graph.Batch._map(self, fn)
-        out = Batch(m.x, m.edge_index, m.batch, m.y, m.num_nodes_list)
+        out = Batch(m.x, m.edge_index, m.batch, m.y, m.num_nodes_list, m.max_degree, m.self_loops)
         for key in ('pos', 'patch_idx'):
             if hasattr(self, key):
                 setattr(out, key, fn(getattr(self, key)))
@@ -155,9 +155,22 @@ class DataParallel(torch.nn.Module):
         return self.module(batch)
 
 
+EXTRA_SELF_SLOT = False      # see radius_graph
+
+
 def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, flow='source_to_target'):
     """``torch_cluster.radius_graph`` @1.4.2.  CUDA positions run the library kernel (``graph.radius_graph``);
-    CPU positions (loader workers) use scipy's cKDTree exactly like torch_cluster's CPU path."""
+    CPU positions (loader workers) use scipy's cKDTree exactly like torch_cluster's CPU path.
+
+    KNOWN UNCERTAINTY: with ``loop=True`` this returns at most
+    ``max_num_neighbors`` in-edges per centre INCLUDING the self loop.  torch_cluster 1.4.x may instead query
+    ``max_num_neighbors + 1`` candidates regardless of ``loop`` and only drop self pairs when ``loop=False``, which
+    would give up to 9 in-edges (8 neighbours + self) for the reference's ``radius_graph(pos, 100, None, True, 8)``
+    (dataflow/data.py:348).  The 1.4.2 source is neither vendored nor installable here, so it could not be
+    checked; set ``EXTRA_SELF_SLOT = True`` to reproduce the k + 1 reading on both the CPU and the GPU path.  The
+    model path is indifferent: it consumes whatever ``edge_index`` the loader produced."""
+    if loop and EXTRA_SELF_SLOT:
+        max_num_neighbors = int(max_num_neighbors) + 1
     assert flow in ('source_to_target', 'target_to_source')
     if x.is_cuda:
         ei = _graph.radius_graph(x, r, batch, loop, max_num_neighbors)

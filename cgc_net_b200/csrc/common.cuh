@@ -107,5 +107,8 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // Scratch layout: every entry point that needs scratch uses the front of the shared buffer.
 constexpr int64_t kWorkspaceBytes = 256ll << 20;   // 256 MiB (split-K partials dominate)
+// The LAST kCounterBytes of the workspace hold self-resetting completion counters ("the last CTA finalises"): zero
+// when the buffer is first handed to the library, zero again after every call that used them.
+constexpr int64_t kCounterBytes = 256;
 
 }  // namespace cgc

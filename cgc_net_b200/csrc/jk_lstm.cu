@@ -292,7 +292,18 @@ k_jk_bwd(const float* __restrict__ g_out, int64_t ldg, const float* __restrict__
 
 using namespace cgc;
 
-static bool jk_supported(int channels, int layers) { return channels == 20 && layers == 3; }
+// Instantiated shapes: `--hidden-dim` values (train.py:393) whose LSTM weights fit in shared memory next to the
+// thread-private state columns: C = 16 / 20 / 32 (hidden 24 / 30 / 48), 3 layers.  C = 64 would need 491 KB of
+// weights (W_ih 2 x 384 x 64, W_hh 2 x 384 x 96) and stays on the library LSTM.
+static bool jk_supported(int channels, int layers) {
+  return layers == 3 && (channels == 16 || channels == 20 || channels == 32);
+}
+#define CGC_JK_DISPATCH(channels, CALL)       \
+  switch (channels) {                         \
+    case 16: { CALL(16, 24) } break;          \
+    case 20: { CALL(20, 30) } break;          \
+    default: { CALL(32, 48) } break;          \
+  }
 
 extern "C" int cgc_jk_supported(int32_t channels, int32_t layers) { return jk_supported(channels, layers) ? 1 : 0; }
 
@@ -322,14 +333,17 @@ extern "C" int cgc_jk_lstm_fwd(const float* feats, int64_t ld, int64_t rows, int
                   att_b && out && rows > 0,
               CGC_ERR_ARG, "cgc_jk_lstm_fwd: bad args");
   CGC_REQUIRE(jk_supported(channels, layers), CGC_ERR_UNSUPPORTED,
-              "cgc_jk_lstm_fwd: instantiated for channels=20, layers=3 (got %d, %d)", channels, layers);
+              "cgc_jk_lstm_fwd: instantiated for channels 16 / 20 / 32, layers=3 (got %d, %d)", channels, layers);
   CGC_REQUIRE(ld >= (int64_t)channels * layers && ldo >= channels, CGC_ERR_ARG, "cgc_jk_lstm_fwd: leading dims");
-  using S = JkShape<20, 30, 3>;
-  auto kern = k_jk_fwd<20, 30, 3>;
-  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmemBytes));
-  kern<<<(unsigned)ceil_div(rows, kJkThreads), kJkThreads, S::kSmemBytes, as_stream(stream)>>>(
-      feats, ld, rows, jk_weights(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b, att_w, att_b), out,
-      ldo, tape);
+  const JkWeights wts = jk_weights(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b, att_w, att_b);
+#define CGC_JK_FWD(C_, H_)                                                                                         \
+  using S = JkShape<C_, H_, 3>;                                                                                    \
+  auto kern = k_jk_fwd<C_, H_, 3>;                                                                                 \
+  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmemBytes));          \
+  kern<<<(unsigned)ceil_div(rows, kJkThreads), kJkThreads, S::kSmemBytes, as_stream(stream)>>>(feats, ld, rows, wts, \
+                                                                                               out, ldo, tape);
+  CGC_JK_DISPATCH(channels, CGC_JK_FWD)
+#undef CGC_JK_FWD
   CGC_CHECK_LAUNCH("k_jk_fwd");
   return 0;
 }
@@ -342,16 +356,18 @@ extern "C" int cgc_jk_lstm_bwd(const float* g_out, int64_t ldg, const float* fea
                   dscore && rows > 0,
               CGC_ERR_ARG, "cgc_jk_lstm_bwd: bad args");
   CGC_REQUIRE(jk_supported(channels, layers), CGC_ERR_UNSUPPORTED,
-              "cgc_jk_lstm_bwd: instantiated for channels=20, layers=3 (got %d, %d)", channels, layers);
+              "cgc_jk_lstm_bwd: instantiated for channels 16 / 20 / 32, layers=3 (got %d, %d)", channels, layers);
   CGC_REQUIRE(ld >= (int64_t)channels * layers && ldgf >= (int64_t)channels * layers && ldg >= channels, CGC_ERR_ARG,
               "cgc_jk_lstm_bwd: leading dims");
-  using S = JkShape<20, 30, 3>;
-  auto kern = k_jk_bwd<20, 30, 3>;
-  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmemBytes));
-  kern<<<(unsigned)ceil_div(rows, kJkThreads), kJkThreads, S::kSmemBytes, as_stream(stream)>>>(
-      g_out, ldg, feats, ld, rows,
-      jk_weights(w_ih_f, w_hh_f, nullptr, nullptr, w_ih_b, w_hh_b, nullptr, nullptr, att_w, nullptr), tape, g_feats,
-      ldgf, dgates, dscore);
+  const JkWeights wts = jk_weights(w_ih_f, w_hh_f, nullptr, nullptr, w_ih_b, w_hh_b, nullptr, nullptr, att_w, nullptr);
+#define CGC_JK_BWD(C_, H_)                                                                                         \
+  using S = JkShape<C_, H_, 3>;                                                                                    \
+  auto kern = k_jk_bwd<C_, H_, 3>;                                                                                 \
+  CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmemBytes));          \
+  kern<<<(unsigned)ceil_div(rows, kJkThreads), kJkThreads, S::kSmemBytes, as_stream(stream)>>>(                    \
+      g_out, ldg, feats, ld, rows, wts, tape, g_feats, ldgf, dgates, dscore);
+  CGC_JK_DISPATCH(channels, CGC_JK_BWD)
+#undef CGC_JK_BWD
   CGC_CHECK_LAUNCH("k_jk_bwd");
   return 0;
 }

@@ -42,6 +42,12 @@ struct SageLayerArgs {
   float* y;                  // [rows, ldy]
   int64_t ldy;
   double* partial;           // [grid][2][20] column sums of y and y^2, or null
+  unsigned int* counter;     // completion counter of the statistics (zero on entry, reset to zero by the last CTA)
+  float* running_mean;       // BatchNorm outputs written by the last CTA
+  float* running_var;
+  float* mean;
+  float* invstd;
+  float momentum, eps;
   int nmax, parts, rpp, box_rows, early, act;
   int tile_smem;             // bytes of the feature tile buffer (the table slice follows it)
 };
@@ -279,22 +285,53 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
     for (int wv = 0; wv < NWARPS; ++wv) v += (double)s_red[wv][which][c];
     a.partial[((int64_t)blockIdx.x * 2 + which) * COUT + c] = v;
   }
+  // The CTA that finishes last turns the partials into mean / invstd / running statistics (fixed summation order:
+  // the result does not depend on which CTA that is), so the layer needs no separate finalize launch.
+  __shared__ int s_last;
+  __shared__ double s_tot[2][COUT];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 2 * COUT * 8) {                            // 8 threads per (sum kind, column): 320 threads = 10 warps
+    const int col = tid >> 3, sub = tid & 7;
+    const int which = col / COUT, c = col - which * COUT;
+    double v = 0.0;
+    for (int bk = sub; bk < (int)gridDim.x; bk += 8) v += __ldcg(a.partial + ((int64_t)bk * 2 + which) * COUT + c);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (sub == 0) s_tot[which][c] = v;
+  }
+  __syncthreads();
+  if (tid < COUT) {                                    // same arithmetic as k_bn_finalize (colops.cu)
+    const double rows = (double)gridDim.x / parts * nmax;
+    const double mu = s_tot[0][tid] / rows;
+    double var = s_tot[1][tid] / rows - mu * mu;
+    if (var < 0.0) var = 0.0;
+    a.mean[tid] = (float)mu;
+    a.invstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+    if (a.running_mean) a.running_mean[tid] = (1.0f - a.momentum) * a.running_mean[tid] + a.momentum * (float)mu;
+    if (a.running_var) {
+      const double unbiased = rows > 1.0 ? var * rows / (rows - 1.0) : var;
+      a.running_var[tid] = (1.0f - a.momentum) * a.running_var[tid] + a.momentum * (float)unbiased;
+    }
+  }
+  if (tid == 0) *a.counter = 0u;
 }
 
-// colops.cu: mean / invstd / running statistics from per-block [2][c] double partial sums (fixed order)
-int bn_finalize_partials(const double* partial, int blocks, int c, int64_t rows, float* running_mean,
-                         float* running_var, float momentum, float eps, float* mean, float* invstd, cudaStream_t st);
-
 template <int CIN, int W, bool WEIGHTED, bool STRIDED>
-static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, int64_t work_bytes, float* running_mean,
-                        float* running_var, float momentum, float eps, float* mean, float* invstd, cudaStream_t st) {
+static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, void* work, int64_t work_bytes,
+                        cudaStream_t st) {
   const int nmax = a.nmax;
   size_t smem = ((size_t)nmax + 2) * CIN * 4;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (STRIDED) {
     int64_t rows_buf = 0;
-    a.box_rows = pick_box_rows(nmax, CIN * 4, 1, 227 * 1024 - 2048, &rows_buf);
+    a.box_rows = pick_box_rows(nmax, CIN * 4, 1, 227 * 1024 - 4096, &rows_buf);
     CGC_REQUIRE(a.box_rows > 0, CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: %d rows do not fit in shared memory", nmax);
     smem = (size_t)rows_buf * CIN * 4;
     CGC_REQUIRE(tensor_map_2d(&map, a.x, (uint64_t)CIN, (uint64_t)num_graphs * nmax, ldx, (uint32_t)CIN,
@@ -309,7 +346,7 @@ static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, 
   // the table slice of the CTA's rows (indices, scales, weights) sits behind the tile: split finer if it does not fit
   a.tile_smem = (int)((smem + 127) & ~(size_t)127);
   const size_t per_row = (size_t)W * 2 + 4 + (WEIGHTED ? (size_t)W * 4 : 0);
-  const size_t room = 227 * 1024 - 2048 - 128 - (size_t)a.tile_smem;
+  const size_t room = 227 * 1024 - 3072 - 128 - (size_t)a.tile_smem;      // 3 KB: static shared memory + slack
   if ((size_t)rpp * per_row > room) rpp = (int)(room / per_row) & ~7;
   CGC_REQUIRE(rpp >= 8, CGC_ERR_UNSUPPORTED, "cgc_sage_layer_ell_fwd: no shared memory left for the index table (nmax %d)", nmax);
   parts = (int)ceil_div(nrow8, rpp);
@@ -317,9 +354,11 @@ static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, 
   a.rpp = rpp;
   smem = (size_t)a.tile_smem + (size_t)rpp * per_row;
   const int grid = num_graphs * parts;
-  if (a.partial != nullptr)
-    CGC_REQUIRE((int64_t)grid * 2 * kLayerCout * 8 <= work_bytes, CGC_ERR_WORKSPACE,
+  if (a.partial != nullptr) {
+    CGC_REQUIRE((int64_t)grid * 2 * kLayerCout * 8 + kCounterBytes <= work_bytes, CGC_ERR_WORKSPACE,
                 "cgc_sage_layer_ell_fwd: workspace too small");
+    a.counter = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(work) + work_bytes - kCounterBytes);
+  }
   auto kern = k_sage_layer_ell<CIN, W, WEIGHTED, STRIDED>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -329,9 +368,6 @@ static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, 
   PdlLaunch L(dim3((unsigned)grid), dim3(kLayerThreads), smem, st, pdl);
   CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, a));
   CGC_CHECK_LAUNCH("k_sage_layer_ell");
-  if (a.partial != nullptr)
-    return bn_finalize_partials(a.partial, grid, kLayerCout, (int64_t)num_graphs * nmax, running_mean, running_var,
-                                momentum, eps, mean, invstd, st);
   return 0;
 }
 
@@ -343,7 +379,7 @@ extern "C" int cgc_sage_layer_ell_supported(int32_t cin, int32_t cout, int32_t n
   if (cout != kLayerCout || (cin != 16 && cin != 20) || nmax <= 0 || nmax + 1 > (int)kEllColMask) return 0;
   int64_t rows_buf = 0;
   // the strided variant needs the larger buffer (box overhang); require it so both input layouts are served
-  return pick_box_rows(nmax, cin * 4, 1, 227 * 1024 - 2048, &rows_buf) > 0 ? 1 : 0;
+  return pick_box_rows(nmax, cin * 4, 1, 227 * 1024 - 4096 - 8 * 104, &rows_buf) > 0 ? 1 : 0;   // tile + >= 8 table rows
 }
 
 extern "C" int cgc_sage_layer_ell_fwd(const uint16_t* ell, const float* ell_val, const float* ell_scale,
@@ -376,6 +412,8 @@ extern "C" int cgc_sage_layer_ell_fwd(const uint16_t* ell, const float* ell_val,
   a.ell = ell; a.ellw = ell_val; a.ell_scale = ell_scale; a.perm = perm; a.rowptr = rowptr; a.col = col; a.val = val;
   a.x = x; a.w = w; a.b = b; a.num_nodes = num_nodes; a.sa = sa; a.y = y; a.ldy = ldy;
   a.partial = mean ? reinterpret_cast<double*>(work) : nullptr;
+  a.running_mean = running_mean; a.running_var = running_var; a.mean = mean; a.invstd = invstd;
+  a.momentum = momentum; a.eps = eps;
   a.nmax = nmax; a.act = act;
   a.early = (flags & CGC_GATHER_TABLES_READY) ? 1 : 0;
   cudaStream_t st = as_stream(stream);
@@ -385,10 +423,8 @@ extern "C" int cgc_sage_layer_ell_fwd(const uint16_t* ell, const float* ell_val,
 #define CGC_LAYER(CIN_, W_, WT_)                                                                                   \
   do {                                                                                                             \
     if (strided)                                                                                                   \
-      return launch_layer<CIN_, W_, WT_, true>(a, num_graphs, ldx, pdl, work_bytes, running_mean, running_var, momentum, \
-                                               eps, mean, invstd, st);                                             \
-    return launch_layer<CIN_, W_, WT_, false>(a, num_graphs, ldx, pdl, work_bytes, running_mean, running_var, momentum,  \
-                                              eps, mean, invstd, st);                                              \
+      return launch_layer<CIN_, W_, WT_, true>(a, num_graphs, ldx, pdl, work, work_bytes, st);                        \
+    return launch_layer<CIN_, W_, WT_, false>(a, num_graphs, ldx, pdl, work, work_bytes, st);                         \
   } while (0)
   if (cin == 16) {
     if (width == 8) { if (wt) CGC_LAYER(16, 8, true); else CGC_LAYER(16, 8, false); }

@@ -340,13 +340,13 @@ struct EllGatherArgs {
   uint32_t chunk;        // bytes per 1-D bulk copy
 };
 
-// LEAN (unweighted tables, ell_scale == NULL): the row's scale is the DenseSAGEConv mean 1 / max(deg, 1) with deg
-// counted from the row's own slots, and the served row comes from the slot-0 tag, so a row costs 4 index registers
-// and nothing else.  With 512 threads x 8 rows this fits 64 registers and two CTAs share an SM (2 x 113.6 KB of
-// shared memory): under programmatic dependent launch the NEXT launch's CTAs are already resident, with their index
-// vectors loaded, when this launch's CTAs finish.
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC, bool LEAN>
-__global__ void __launch_bounds__(THREADS, LEAN ? 2 : 1)
+// Unweighted tables may come without a scale vector (ell_scale == NULL): the row's scale is then the DenseSAGEConv
+// mean 1 / max(deg, 1) with deg counted from the row's own slots; the served row comes from the slot-0 tag.
+// (Measured and dropped: a 512-thread / 64-register variant that lets two CTAs share an SM, so that under
+// programmatic launch the next launch's CTAs are resident early -- the block scheduler then doubles CTAs up on the
+// 20 SMs the 128-CTA grid leaves idle and the launch waits for those: 8.7 us instead of 6.3 us.)
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
+__global__ void __launch_bounds__(THREADS, 1)
 k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int G = THREADS / LPR;
@@ -384,17 +384,16 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
   const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
   const uint32_t ovf_mark = (uint32_t)nmax + 1u;
 
-  static_assert(!(LEAN && WEIGHTED), "the lean variant serves unweighted tables");
   uint32_t idx[RB][NW];
   float wgt[WEIGHTED ? RB : 1][WEIGHTED ? W : 1];
-  float rsc[LEAN ? 1 : RB];
+  float rsc[RB];
   auto load_batch = [&](int i0) {
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
       const int t = (i0 + i) * G + grp;                // table row inside the CTA
       const bool on = t < nrows;
       const int64_t trow = trow0 + (on ? t : 0);
-      if (!LEAN) rsc[LEAN ? 0 : i] = (on && a.ell_scale != nullptr) ? __ldg(a.ell_scale + trow) : 1.0f;
+      rsc[i] = (on && a.ell_scale != nullptr) ? __ldg(a.ell_scale + trow) : 1.0f;
 #pragma unroll
       for (int q = 0; q < NW / 4; ++q) {
         uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
@@ -461,8 +460,8 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
       if (lrow >= nmax) continue;                      // padding of the graph's last 8-row block
       const int64_t row = grow0 + lrow;
       float4 o;
-      float s = LEAN ? 1.0f : rsc[LEAN ? 0 : i];
-      const bool mean_scale = LEAN || (!WEIGHTED && a.ell_scale == nullptr);   // scale = 1 / max(deg, 1)
+      float s = rsc[i];
+      const bool mean_scale = !WEIGHTED && a.ell_scale == nullptr;            // scale = 1 / max(deg, 1)
       if ((idx[i][0] & kEllColMask) != ovf_mark) {
         F32x4 acc;
         acc.lo = 0ull; acc.hi = 0ull;
@@ -764,7 +763,7 @@ extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const
   return 0;
 }
 
-template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC, bool LEAN = false>
+template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
 static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cudaStream_t st) {
   const int nmax = a.nmax, feat = a.feat;
   size_t smem = ((size_t)nmax + 2) * feat * 4;
@@ -795,13 +794,10 @@ static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cu
   a.rpp = rpp;
   a.lab_stage = stage;
   a.chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
-  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC, LEAN>;
+  auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC>;
   static size_t smem_set = 0;                           // per instantiation: raise the limit only when it grows
   if (smem > smem_set) {
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (LEAN)                                           // two CTAs per SM need the whole 228 KB as shared memory
-      CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared));
     smem_set = smem;
   }
   PdlLaunch L(dim3((unsigned)(num_graphs * parts)), dim3(THREADS), smem, st, pdl);
@@ -838,8 +834,6 @@ static int ell_gather_dispatch(const uint16_t* ell, const float* ell_val, const 
   if (feat <= 16) {
     if (width == 8) {
       if (wt) CGC_ELL(8, 4, true, 2, 512);
-      else if (ell_scale == nullptr && !strided && !acc)       // the roofline configuration: two CTAs per SM
-        return launch_ell<8, 4, false, 8, 512, false, false, true>(a, num_graphs, ldx, pdl, st);
       else CGC_ELL(8, 4, false, 4, 1024);
     } else {
       if (wt) CGC_ELL(16, 4, true, 1, 512); else CGC_ELL(16, 4, false, 4, 512);

@@ -30,9 +30,13 @@ class Data(object):
 class Batch(object):
     """Concatenation of ``Data`` objects (PyG ``Batch`` fields used by network.py:239-240)."""
 
-    def __init__(self, x, edge_index, batch, y=None, num_nodes_list=None):
+    def __init__(self, x, edge_index, batch, y=None, num_nodes_list=None, max_degree=None, self_loops=None):
         self.x, self.edge_index, self.batch, self.y = x, edge_index, batch, y
         self.num_nodes_list = None if num_nodes_list is None else [int(n) for n in num_nodes_list]
+        # host-side facts about the adjacency, so that the index-table pitch can be chosen without a device sync:
+        # largest number of COO entries of one source row, and whether every node carries a self loop
+        self.max_degree = None if max_degree is None else int(max_degree)
+        self.self_loops = None if self_loops is None else bool(self_loops)
 
     @property
     def num_graphs(self):
@@ -44,9 +48,17 @@ class Batch(object):
     def from_data_list(data_list):
         xs, eis, bs, ys, counts = [], [], [], [], []
         offset = 0
+        max_degree, self_loops = 0, True
         for g, d in enumerate(data_list):
             n = d.x.shape[0]
             xs.append(d.x)
+            if max_degree is not None and not d.edge_index.is_cuda:
+                if d.edge_index.shape[1]:
+                    max_degree = max(max_degree, int(torch.bincount(d.edge_index[0], minlength=1).max()))
+                loops = d.edge_index[0][d.edge_index[0] == d.edge_index[1]]
+                self_loops = self_loops and int(torch.unique(loops).numel()) == n
+            else:
+                max_degree = self_loops = None          # device-resident edge lists: not inspected (no sync)
             eis.append(d.edge_index + offset)
             bs.append(torch.full((n,), g, dtype=torch.long))
             if d.y is not None:
@@ -54,11 +66,12 @@ class Batch(object):
             counts.append(n)
             offset += n
         y = torch.cat(ys) if ys else None
-        return Batch(torch.cat(xs), torch.cat(eis, dim=1), torch.cat(bs), y, counts)
+        return Batch(torch.cat(xs), torch.cat(eis, dim=1), torch.cat(bs), y, counts, max_degree, self_loops)
 
     def _map(self, fn):
         y = None if self.y is None else fn(self.y)
-        return Batch(fn(self.x), fn(self.edge_index), fn(self.batch), y, self.num_nodes_list)
+        return Batch(fn(self.x), fn(self.edge_index), fn(self.batch), y, self.num_nodes_list, self.max_degree,
+                     self.self_loops)
 
     def to(self, device, non_blocking=False):
         return self._map(lambda t: t.to(device, non_blocking=non_blocking))
@@ -216,6 +229,7 @@ class DevicePrefetcher(object):
         if buf is None or buf.dtype != host.dtype or buf.numel() < host.numel():
             buf = torch.empty(max(host.numel(), 1), dtype=host.dtype, device=self.device)
             slot['bufs'][name] = buf
+            slot['grown'] = True        # fresh block of the caching allocator: see _issue
         return buf[:host.numel()].view(host.shape)
 
     def _issue(self, host_batch, slot):
@@ -224,6 +238,10 @@ class DevicePrefetcher(object):
             t = getattr(host_batch, name)
             views[name] = None if t is None else self._buffer(slot, name, t)      # allocation on the caller's stream
         with torch.cuda.stream(self.stream):
+            if slot.pop('grown', False):
+                # a buffer was (re)allocated on the caller's stream: the caching allocator may have handed out a
+                # block whose previous user still has kernels pending there, so the copy waits for that stream
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
             if slot['free'] is not None:
                 self.stream.wait_event(slot['free'])           # the slot's previous batch has been consumed
             for name, dst in views.items():
@@ -231,7 +249,8 @@ class DevicePrefetcher(object):
                     dst.copy_(getattr(host_batch, name), non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.stream)
-        return Batch(views['x'], views['edge_index'], views['batch'], views['y'], host_batch.num_nodes_list), done
+        return Batch(views['x'], views['edge_index'], views['batch'], views['y'], host_batch.num_nodes_list,
+                     getattr(host_batch, 'max_degree', None), getattr(host_batch, 'self_loops', None)), done
 
     def __iter__(self):
         it = iter(self.batches)

@@ -166,9 +166,10 @@ class DenseJK(nn.Module):
     network.py:11-55): a bi-LSTM over the 3-step "sequence" of per-layer features of every node scores the
     layers, the scores are soft-maxed and the layers summed with those weights.
 
-    SURVEY 8(f) rank-1 row: for the reference's shape (20 channels x 3 layers) the whole aggregation is ONE
-    hand-written kernel per direction of autograd (``ops.DenseJKFunction`` -> ``cgc_jk_lstm_fwd / bwd``); other
-    shapes keep torch's LSTM (cuDNN, TF32 off).  Parameter names (``lstm.*``, ``att.*``) match the reference for
+    SURVEY 8(f) rank-1 row: for 3 layers of 16 / 20 / 32 channels (``--hidden-dim``, train.py:393; 20 is the
+    reference's default) the whole aggregation is ONE hand-written kernel per direction of autograd
+    (``ops.DenseJKFunction`` -> ``cgc_jk_lstm_fwd / bwd``); wider shapes, whose LSTM weights do not fit in shared
+    memory (64 channels: 491 KB), keep torch's LSTM (cuDNN, TF32 off).  Parameter names (``lstm.*``, ``att.*``) match the reference for
     checkpoint compatibility (the ``nn.LSTM`` / ``nn.Linear`` modules are kept as parameter holders).
     """
 
@@ -261,7 +262,9 @@ class SoftPoolingGcnEncoder(nn.Module):
     def _sparse_input(self, data):
         """network.py:237-243 without the dense adjacency."""
         counts = getattr(data, 'num_nodes_list', None)
-        xp, graph = ops.build_sparse_graph(data.x, data.edge_index, data.batch, counts, self.norm_adj)
+        xp, graph = ops.build_sparse_graph(data.x, data.edge_index, data.batch, counts, self.norm_adj,
+                                           max_degree=getattr(data, 'max_degree', None),
+                                           self_loops=getattr(data, 'self_loops', None))
         return xp, graph, data.y
 
     # ------------------------------------------------------------------ forward

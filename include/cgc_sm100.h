@@ -24,7 +24,8 @@
  *     Never throws, never exits.
  *   - workspace: functions that take (work, work_bytes) need at least
  *     cgc_workspace_bytes() bytes, 256-byte aligned; one buffer may be shared by all calls
- *     on the same stream.
+ *     on the same stream.  Its LAST 256 bytes hold self-resetting completion counters: they must be
+ *     zero when the buffer is first handed to the library (the library leaves them zero).
  */
 #ifndef CGC_SM100_H_
 #define CGC_SM100_H_
@@ -195,7 +196,8 @@ CGC_API int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, const
  *   sa = scale * sum_e val[e] * x[col[e], :]          (the ELL16 gather above, tile staged by TMA)
  *   y  = act( l2normalize(sa @ W + b) * mask )         (cgc_sage_epilogue_fwd)
  *   mean / invstd / running stats of y over all `num_graphs * nmax` rows (cgc_bn_stats), when mean != NULL:
- *   per-CTA column partial sums in `work`, finalised in fixed order in double precision by a second tiny kernel.
+ *   per-CTA column partial sums in `work`, finalised in fixed order in double precision by whichever CTA
+ *   finishes last (completion counter in the tail of `work`): no second launch.
  * sa [rows, cin] (contiguous) is written as well: the backward needs it (dW = sa^T dh).
  * Instantiated for (cin, cout) in {(16, 20), (20, 20)}: cgc_sage_layer_ell_supported(); other shapes take
  * cgc_sage_gather_ell + cgc_sage_layer_fwd_narrow.  flags as for cgc_sage_gather_ell (ACCUMULATE not allowed). */

@@ -502,13 +502,15 @@ def test_tf32_operand_truncation_probe(cuda_backend):
 
 
 # ------------------------------------------------------------------------------- DenseJK (fused bi-LSTM attention)
-@pytest.mark.parametrize('rows', [1, 200, 1000])
-def test_jk_lstm_fwd_bwd(cuda_backend, rows):
+@pytest.mark.parametrize('rows,c', [(1, 20), (200, 20), (1000, 20), (333, 16), (333, 32)])
+def test_jk_lstm_fwd_bwd(cuda_backend, rows, c):
     """cgc_jk_lstm_fwd / bwd against the CPU formulas (themselves pinned to torch.nn.LSTM autograd, see
-    test_oracle.py::test_jk_reference_formulas_match_autograd); strided feats (a slice of a wider buffer)."""
-    c, layers = 20, 3
+    test_oracle.py::test_jk_reference_formulas_match_autograd); strided feats (a slice of a wider buffer); the
+    channel widths the fused kernels are instantiated for (--hidden-dim 16 / 20 / 32)."""
+    layers = 3
     hid = c * layers // 2
-    assert cuda_backend.jk_supported(c, layers) and not cuda_backend.jk_supported(16, 3)
+    assert cuda_backend.jk_supported(c, layers) and not cuda_backend.jk_supported(64, 3)
+    assert not cuda_backend.jk_supported(20, 2)
     torch.manual_seed(rows)
     lstm = torch.nn.LSTM(c, hid, bidirectional=True, batch_first=True)
     att = torch.nn.Linear(2 * hid, 1)

@@ -242,3 +242,43 @@ def test_ell16_reference_table_invariants():
         assert len(seen) == trows                                                            # a permutation per block
 
     check()
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/common/utils.py'), reason='reference checkout not mounted')
+def test_farthest_sampler_restatement_matches_reference_source():
+    """The oracle's farthest-point sampler (op_reference.farthest_point_sample) against FarthestSampler of the
+    reference itself (common/utils.py:187-197), EXECUTED from the reference source (imported behind the
+    torch_geometric stand-ins) on the int16 distance matrix of construct_feature_graph.py:17-24."""
+    import sys
+    import numpy as np
+    from cgc_net_b200 import compat
+    from oracle import op_reference
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split('.')[0] in ('torch_geometric', 'common')}
+    for k in saved:
+        sys.modules.pop(k, None)
+    compat.install(force=True)
+    sys.path.insert(0, '/root/reference')
+    try:
+        from common.utils import FarthestSampler            # the reference class, unmodified
+        ref = op_reference.TorchBackend()
+        g = torch.Generator().manual_seed(3)
+        for n, k in ((57, 20), (400, 280), (1, 1), (33, 33)):
+            pos = torch.rand(n, 2, generator=g) * 900.0
+            p = pos.double().numpy()
+            arr = np.sqrt((p[:, 0, np.newaxis].T - p[:, 0, np.newaxis]) ** 2 +
+                          (p[:, 1, np.newaxis].T - p[:, 1, np.newaxis]) ** 2).astype(np.int16)
+            np.random.seed(n)
+            want = FarthestSampler()(arr, k)                 # draws its first index from numpy's global stream
+            np.random.seed(n)
+            first = np.random.randint(arr.shape[0])
+            assert int(want[0]) == first
+            out = torch.zeros(k, dtype=torch.int32)
+            ref.farthest_point_sample(pos, torch.tensor([0, n], dtype=torch.int32), torch.tensor([first], dtype=torch.int32),
+                                      torch.tensor([0, k], dtype=torch.int32), n, out)
+            assert out.tolist() == want.tolist()
+    finally:
+        sys.path.remove('/root/reference')
+        for k in list(sys.modules):
+            if k.split('.')[0] in ('torch_geometric', 'common'):
+                sys.modules.pop(k, None)
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
