@@ -202,7 +202,7 @@ def cpu_reference_rate(args, steps, warmup, n_graphs):
         os.environ['CGC_REFERENCE_ROOT'] = root
         from oracle import reference_loader
         reference_loader.REFERENCE_ROOT = root
-        model = reference_loader.build_reference_encoder(*MODEL_ARGS, **kw).train()
+        model = reference_loader.build_reference_encoder(*MODEL_ARGS, cpu=True, **kw).train()
         kind = 'reference'
         forward = lambda: reference_loader.run_reference(model, batch)      # noqa: E731
     else:

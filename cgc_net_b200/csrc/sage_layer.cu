@@ -299,7 +299,14 @@ k_sage_layer_ell(const __grid_constant__ CUtensorMap map_x, const SageLayerArgs 
     const int col = tid >> 3, sub = tid & 7;
     const int which = col / COUT, c = col - which * COUT;
     double v = 0.0;
-    for (int bk = sub; bk < (int)gridDim.x; bk += 8) v += __ldcg(a.partial + ((int64_t)bk * 2 + which) * COUT + c);
+    const double* src = a.partial + (int64_t)which * COUT + c;
+    for (int bk = sub; bk < (int)gridDim.x; bk += 64) {        // 8 independent loads in flight, summed in order
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = (bk + 8 * u < (int)gridDim.x) ? __ldcg(src + (int64_t)(bk + 8 * u) * 2 * COUT) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += t[u];
+    }
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 4);

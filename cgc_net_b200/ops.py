@@ -29,7 +29,9 @@ from . import _backend
 
 RENORM_P = 0.4       # model/network.py:260,271,280
 BUILD_TRANSPOSED_ELL = False     # see build_sparse_graph
-BUILD_BACKWARD_ELL = True        # ELL16 table of A^T for the narrow CSC gathers of the backward
+BUILD_BACKWARD_ELL = False       # ELL16 table of A^T for the narrow CSC gathers of the backward: measured 26.6 us per
+                                 # gather (pitch 16, weighted, 7 index batches per thread) + 65 us to build the table vs
+                                 # 24.9 us for the generic CSC gather -> off
 ACTIVATIONS = {'relu': 0, 'elu': 1, 'leakyrelu': 2}     # GNN_Module._activation (network.py:82-90) -> CGC_ACT_*
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -44,7 +46,8 @@ PASS_BUDGET = {
     'lin_dw': 2,            # dW of lin: 5.6e-5
     'lin_dx': 2,            # dX of lin: 6.8e-5
     'pool_stx': None,       # X' = S^T X: logits move 4.5e-3 on one pass
-    'pool_stas': 2,         # A' = S^T (A S): logits 5e-7, gradients 6.4e-5, no index flips
+    'pool_stas': None,      # A' = S^T (A S): fine at full size (logits 5e-7, gradients 6.4e-5, no index flips) but at
+                            # small batches the perturbed A' moves stage-2 gradients past 1e-3 (smoke: 1.4e-3)
     'pool_gs': None,        # dS = P gA'^T + X gX'^T: 1.6e-3 on the small pool-2 tensors
     'pool_gp': 2,           # dP = S gA': 1.5e-5
     'pool_gx': None, 'pool_gadj': None,     # skinny / output-bound: nothing to gain

@@ -40,8 +40,10 @@ def available():
 _network = None
 
 
-def load_network_module():
-    """Return the verbatim ``model.network`` module of the reference."""
+def load_network_module(cpu=False):
+    """Return the verbatim ``model.network`` module of the reference.  ``cpu=True``: the model will run on host
+    tensors although a GPU is present (the CPU arm of bench.py on the GPU box), so ``construct_mask`` must not
+    move its result to the device either."""
     global _network
     if _network is not None:
         return _network
@@ -52,7 +54,7 @@ def load_network_module():
         sys.path.insert(0, REFERENCE_ROOT)
     mod = importlib.import_module('model.network')
 
-    if not torch.cuda.is_available():
+    if cpu or not torch.cuda.is_available():
         orig = mod.SoftPoolingGcnEncoder.construct_mask
 
         def construct_mask_cpu(max_nodes, batch_num_nodes):
@@ -68,9 +70,9 @@ def load_network_module():
     return mod
 
 
-def build_reference_encoder(*args, **kwargs):
+def build_reference_encoder(*args, cpu=False, **kwargs):
     """``model.network.SoftPoolingGcnEncoder(*args, **kwargs)`` of the verbatim reference."""
-    mod = load_network_module()
+    mod = load_network_module(cpu=cpu)
     return mod.SoftPoolingGcnEncoder(*args, **kwargs)
 
 

@@ -21,6 +21,13 @@ if has full; then
   timeout 1500 python -m pytest tests/test_gpu_full_size.py -m gpu -q --tb=short -s > $OUT/full.log 2>&1; echo "full exit=$? $(tail -1 $OUT/full.log)"
   grep -E "rel err|cluster indices|worst gradient|^E  |FAILED" $OUT/full.log | head -40
 fi
+if has dropin; then
+  timeout 900 python -m pytest tests/test_gpu_train_dropin.py -m gpu -q --tb=short -s > $OUT/dropin.log 2>&1; echo "dropin exit=$? $(tail -1 $OUT/dropin.log)"
+  grep -E "losses|cpu \[|^E  |SKIP|skipped" $OUT/dropin.log | head -10
+fi
+if has refarm; then
+  timeout 900 python bench.py --impl reference --steps ${REF_STEPS:-3} --warmup 1 > $OUT/bench_ref.log 2>$OUT/bench_ref.err; echo "refarm exit=$?"; tail -1 $OUT/bench_ref.log | cut -c1-600
+fi
 if has budget; then
   timeout 900 python tools/pass_budget.py > $OUT/pass_budget.log 2>&1; echo "budget exit=$?"; cat $OUT/pass_budget.log | tail -30
 fi
