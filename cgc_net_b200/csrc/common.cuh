@@ -105,6 +105,21 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: raise it only when a launch
+// needs more than what has been set on the CURRENT device so far (`state` = one static array per kernel
+// instantiation), instead of paying the driver call on every launch.
+constexpr int kMaxDevices = 64;
+template <typename Kern>
+inline cudaError_t ensure_dynamic_smem(Kern kern, size_t smem, size_t* state) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < kMaxDevices && smem <= state[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) state[dev] = smem;
+  return e;
+}
+
 // Scratch layout: every entry point that needs scratch uses the front of the shared buffer.
 constexpr int64_t kWorkspaceBytes = 256ll << 20;   // 256 MiB (split-K partials dominate)
 // The LAST kCounterBytes of the workspace hold self-resetting completion counters ("the last CTA finalises"): zero

@@ -792,7 +792,8 @@ int gemm_tc(GemmParams p, int ta, int tb, int passes, void* work, int64_t work_b
     // one cluster of 2 CTAs (same TPC) per 256-row tile; persistent over the tiles
     const int clusters = q.total_tiles < kNumSMs / 2 ? q.total_tiles : kNumSMs / 2;
     auto kern = k_gemm_tc<128, true>;
-    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set[kMaxDevices] = {};           // the size depends on the instantiation only: set once per device
+    CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
     cfg.blockDim = dim3(kThreads);
@@ -809,10 +810,11 @@ int gemm_tc(GemmParams p, int ta, int tb, int passes, void* work, int64_t work_b
     CGC_CHECK_LAUNCH("k_gemm_tc<pair>");
   } else {
 #define CGC_TC_CASE(N)                                                                                          \
-  case N:                                                                                                       \
-    CGC_CUDA(cudaFuncSetAttribute(k_gemm_tc<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  case N: {                                                                                                     \
+    static size_t smem_set[kMaxDevices] = {};                                                                   \
+    CGC_CUDA(ensure_dynamic_smem(k_gemm_tc<N, false>, smem, smem_set));                                         \
     k_gemm_tc<N, false><<<grid, kThreads, smem, st>>>(map_a, map_b, q);                                         \
-    break;
+  } break;
     switch (bn) {
       CGC_TC_CASE(32)
       CGC_TC_CASE(64)

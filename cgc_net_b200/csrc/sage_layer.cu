@@ -367,11 +367,8 @@ static int launch_layer(SageLayerArgs a, int num_graphs, int64_t ldx, bool pdl, 
     a.counter = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(work) + work_bytes - kCounterBytes);
   }
   auto kern = k_sage_layer_ell<CIN, W, WEIGHTED, STRIDED>;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static size_t smem_set[kMaxDevices] = {};             // per instantiation and device
+  CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
   PdlLaunch L(dim3((unsigned)grid), dim3(kLayerThreads), smem, st, pdl);
   CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, a));
   CGC_CHECK_LAUNCH("k_sage_layer_ell");

@@ -946,11 +946,8 @@ static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cu
   a.lab_stage = stage;
   a.chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
   auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC>;
-  static size_t smem_set = 0;                           // per instantiation: raise the limit only when it grows
-  if (smem > smem_set) {
-    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static size_t smem_set[kMaxDevices] = {};             // per instantiation and device
+  CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
   PdlLaunch L(dim3((unsigned)(num_graphs * parts)), dim3(THREADS), smem, st, pdl);
   CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, a));
   CGC_CHECK_LAUNCH("k_sage_gather_ell");
@@ -989,11 +986,8 @@ static int launch_ell_staged(EllGatherArgs a, int num_graphs, int64_t ldx, bool 
   a.chunk = kBulkChunk;
   sa.g = a;
   auto kern = k_sage_gather_ell_staged<W, LPR, WEIGHTED, THREADS, STRIDED, ACC>;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static size_t smem_set[kMaxDevices] = {};             // per instantiation and device
+  CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
   PdlLaunch L(dim3((unsigned)(num_graphs * a.parts)), dim3(THREADS), smem, st, pdl);
   CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, sa));
   CGC_CHECK_LAUNCH("k_sage_gather_ell_staged");

@@ -44,9 +44,10 @@ def _data_list(sizes, seed):
     return out
 
 
-def _run_reference_train(tmp_path, on_gpu):
+def _run_reference_train(tmp_path, on_gpu, optim='adam', lr=None):
     """Import the reference train.py fresh and run two epochs of its train() over two batches; returns the
-    per-iteration losses and the final state_dict."""
+    per-iteration losses and the final state_dict.  ``optim`` / ``lr`` are the reference's own flags
+    (train.py:142,319, common/utils.py:118-126)."""
     saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split('.')[0] in MODS}
     for k in saved:
         sys.modules.pop(k, None)
@@ -62,6 +63,9 @@ def _run_reference_train(tmp_path, on_gpu):
         assert network is ours
         args = ref_train.arg_parse()
         args.num_epochs, args.resultdir, args.num_classes = 2, str(tmp_path), 3
+        args.optim = optim
+        if lr is not None:
+            args.lr = lr
         torch.manual_seed(0)
         # constructor call of train.py:254-261; max_num_nodes 3000 -> 300 / 30 clusters (wide gather + tcgen05 lin)
         model = network.SoftPoolingGcnEncoder(3000, args.input_feature_dim, args.hidden_dim, args.output_dim, True,
@@ -89,21 +93,28 @@ def _run_reference_train(tmp_path, on_gpu):
 
 @pytest.mark.skipif(REF is None, reason='no reference checkout (/root/reference or baseline/_ref)')
 def test_reference_train_loop_on_gpu(cuda_backend, tmp_path):
+    # 1. the reference's default optimiser (Adam, lr 1e-3): the loop runs on the library, the first iteration equals
+    #    the oracle-backed one, everything stays finite.  (Later Adam iterations are not compared tightly: Adam
+    #    divides by sqrt(v), so parameters whose true gradient is ~0 take +-lr steps whose sign is rounding noise,
+    #    and two fp32 implementations -- any two -- drift apart within a few steps.)
     before = cuda_backend.kernel_launches()
     gpu_losses, gpu_state = _run_reference_train(tmp_path / 'gpu', on_gpu=True)
     assert cuda_backend.kernel_launches() - before > 500, 'the reference loop did not run on libcgc_sm100'
     assert len(gpu_losses) == 4 and all(v == v and abs(v) < 1e3 for v in gpu_losses)
     assert int(gpu_state['GCN_embed_1.bn1.num_batches_tracked']) == 4
-    # the same loop on the per-operator CPU formulas of the oracle (the checker)
+    assert all(torch.isfinite(v).all() for v in gpu_state.values() if v.is_floating_point())
+    # 2. the same loop with --optim sgd (update linear in the gradient): the whole loss trajectory and the BatchNorm
+    #    running statistics agree with the loop driven by the per-operator CPU formulas of the oracle (the checker)
+    sgd_losses, sgd_state = _run_reference_train(tmp_path / 'gpu_sgd', on_gpu=True, optim='sgd', lr=0.01)
     from oracle import op_reference
     _backend.use_backend_for_testing(op_reference.TorchBackend())
     try:
-        cpu_losses, cpu_state = _run_reference_train(tmp_path / 'cpu', on_gpu=False)
+        cpu_losses, cpu_state = _run_reference_train(tmp_path / 'cpu_sgd', on_gpu=False, optim='sgd', lr=0.01)
     finally:
         _backend.use_backend_for_testing(None)
-    print('losses gpu %s\n       cpu %s' % (gpu_losses, cpu_losses))
+    print('adam losses gpu %s\nsgd  losses gpu %s\n            cpu %s' % (gpu_losses, sgd_losses, cpu_losses))
     assert abs(gpu_losses[0] - cpu_losses[0]) <= 1e-5 * max(1.0, abs(cpu_losses[0]))     # same init, same data
-    for a, b in zip(gpu_losses, cpu_losses):
-        assert abs(a - b) <= 2e-3 * max(1.0, abs(b))             # Adam (lr 1e-3) amplifies rounding between steps
+    for a, b in zip(sgd_losses, cpu_losses):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b))
     for k in ('GCN_embed_1.bn1.running_mean', 'GCN_pool_1.bn3.running_var'):
-        assert float((gpu_state[k] - cpu_state[k]).abs().max()) <= 1e-3 * float(cpu_state[k].abs().max())
+        assert float((sgd_state[k] - cpu_state[k]).abs().max()) <= 1e-3 * float(cpu_state[k].abs().max())

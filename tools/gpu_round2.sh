@@ -37,6 +37,12 @@ fi
 if has bench; then
   timeout 900 python bench.py --steps ${BENCH_STEPS:-10} --warmup 3 ${BENCH_ARGS} > $OUT/bench.log 2>$OUT/bench.err; echo "bench exit=$?"; tail -1 $OUT/bench.log; tail -5 $OUT/bench.err
 fi
+if has configs; then
+  for c in ${CONFIGS:-4 5}; do
+    timeout 900 python bench.py --config $c --steps ${BENCH_STEPS:-5} --warmup 3 --no-roofline --no-cpu-baseline \
+      > $OUT/bench_c${c}_n1.json 2>$OUT/bench_c${c}_n1.err; echo "config $c exit=$?"; tail -1 $OUT/bench_c${c}_n1.json | cut -c1-900; tail -3 $OUT/bench_c${c}_n1.err
+  done
+fi
 if has launches; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/launches_r2.csv python tools/profile_step.py > $OUT/prof_step.log 2>&1; echo "launches exit=$?"
@@ -49,6 +55,19 @@ fi
 if has ncu_layer; then
   VARIANT=layer timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sage_layer_ell -s 2 -c 1 -f \
     -o $OUT/prof_layer_r2 python tools/profile_gather.py > $OUT/prof_layer.log 2>&1; echo "ncu_layer exit=$?"
+fi
+if has gemmlab; then
+  # A/B of the GEMM lab switches: needs a LAB build (overwrites the release objects ON THE BOX only)
+  make -C cgc_net_b200/csrc clean > /dev/null; make -C cgc_net_b200/csrc LAB=1 -j > $OUT/build_lab.log 2>&1
+  : > $OUT/gemm_lab.log
+  for cfg in "" "CGC_TC_BWARPS=1" "CGC_TC_AFIRST=1" "CGC_TC_BWARPS=1 CGC_TC_AFIRST=1" "CGC_TC_CHUNK=4" "CGC_TC_PAIR=0"; do
+    for prec in 1 3; do
+      env $cfg PREC=$prec timeout 120 python tools/profile_gemm.py >> $OUT/gemm_lab.log 2>&1
+    done
+  done
+  env TA=1 TB=0 M=1140 N=1180 K=115200 timeout 120 python tools/profile_gemm.py >> $OUT/gemm_lab.log 2>&1
+  env TA=1 TB=0 M=1140 N=1180 K=115200 CGC_TC_BWARPS=1 timeout 120 python tools/profile_gemm.py >> $OUT/gemm_lab.log 2>&1
+  cat $OUT/gemm_lab.log
 fi
 if has sanitizer; then
   for tool in memcheck racecheck synccheck; do

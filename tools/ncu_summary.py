@@ -1,4 +1,7 @@
-"""Key metrics of an .ncu-rep (first kernel instance) as a small text table."""
+"""Key metrics of an .ncu-rep (first kernel instance) as a small text table.
+    python tools/ncu_summary.py <file.ncu-rep> [--traffic-json profiles/gather_traffic.json]
+With --traffic-json the DRAM bytes of the launch (read + written) are also written to that file, which bench.py
+reads for `roofline.traffic` (so the figure always comes from a committed capture, never from a constant)."""
 import csv
 import subprocess
 import sys
@@ -18,9 +21,25 @@ out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], captu
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 print('# %s' % sys.argv[1])
+def _bytes(r, key):
+    i = hdr.index(key)
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[units[i]]
+    return float(r[i].replace(',', '')) * scale
+
+
 for r in rows[2:]:
     print('kernel:', r[hdr.index('Kernel Name')][:100])
     for k in KEYS:
         if k in hdr:
             i = hdr.index(k)
             print('  %-95s %s %s' % (k, r[i], units[i]))
+if '--traffic-json' in sys.argv:
+    import json
+    import os
+    r = rows[2]
+    rd, wr = _bytes(r, 'dram__bytes_read.sum'), _bytes(r, 'dram__bytes_write.sum')
+    out = {'kernel': r[hdr.index('Kernel Name')], 'dram_bytes': int(rd + wr), 'dram_bytes_read': int(rd),
+           'dram_bytes_write': int(wr), 'duration_us_under_ncu': float(r[hdr.index('gpu__time_duration.sum')].replace(',', '')),
+           'source': '%s (ncu --set full, one cold launch after an L2 flush; outputs still in L2 at kernel end count as '
+                     '0 bytes written)' % os.path.basename(sys.argv[1])}
+    json.dump(out, open(sys.argv[sys.argv.index('--traffic-json') + 1], 'w'), indent=1)

@@ -1,4 +1,6 @@
-"""Launch the tcgen05 GEMM a few times on the `lin` contraction shape (for ncu --set full)."""
+"""Launch the tcgen05 GEMM a few times on the `lin` contraction shape (for ncu --set full and for A/B timing of
+the lab switches of a LAB build).  Environment: M, N, K, PREC (1 = 3xTF32, 3 = single pass), TA / TB (operand
+layouts: A stored [k, m] / B stored [n, k])."""
 import os
 import sys
 
@@ -9,17 +11,21 @@ from cgc_net_b200 import _backend  # noqa: E402
 
 be = _backend.get()
 m, n, k = int(os.environ.get('M', 115200)), int(os.environ.get('N', 1140)), int(os.environ.get('K', 1180))
-a = torch.randn(m, k, device='cuda')
-b = torch.randn(n, k, device='cuda')
+prec = int(os.environ.get('PREC', 1))
+ta, tb = bool(int(os.environ.get('TA', 0))), bool(int(os.environ.get('TB', 1)))
+a = torch.randn((k, m) if ta else (m, k), device='cuda')
+b = torch.randn((n, k) if tb else (k, n), device='cuda')
 c = torch.empty(m, n, device='cuda')
 for _ in range(3):
-    be.gemm(a, b, c, False, True, precision=1)
+    be.gemm(a, b, c, ta, tb, precision=prec)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5):
-    be.gemm(a, b, c, False, True, precision=1)
+    be.gemm(a, b, c, ta, tb, precision=prec)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print('gemm %dx%dx%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent)' % (m, n, k, ms, 2.0 * m * n * k / ms / 1e9))
+lab = ' '.join('%s=%s' % (k_, v) for k_, v in sorted(os.environ.items()) if k_.startswith('CGC_TC_'))
+print('gemm %dx%dx%d prec %d ta %d tb %d %s: %.3f ms  %.1f TFLOP/s (fp32-equivalent)'
+      % (m, n, k, prec, ta, tb, lab, ms, 2.0 * m * n * k / ms / 1e9))
