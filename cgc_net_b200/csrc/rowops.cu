@@ -96,25 +96,32 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
     uint32_t vmask = 0;                              // flags in a register: the row loops below stay branch-free
 #pragma unroll
     for (int rr = 0; rr < kEpiRows; ++rr) vmask |= (uint32_t)s_valid[rr] << rr;
-    float acc[kEpiRows][NC];
+    // h = a W + b in packed f32x2 arithmetic: one register pair holds the accumulators of two ROWS of the tile for one
+    // column (the transposed row tile delivers a[k][2q], a[k][2q+1] as one 64-bit shared-memory word), W is
+    // duplicated into both halves -- half the FMA issue slots of the scalar loop
+    unsigned long long acc2[kEpiRows / 2][NC];
 #pragma unroll
-    for (int rr = 0; rr < kEpiRows; ++rr)
+    for (int j = 0; j < NC; ++j) {
+      unsigned long long bb;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(bj[j]));
 #pragma unroll
-      for (int j = 0; j < NC; ++j) acc[rr][j] = bj[j];
+      for (int q = 0; q < kEpiRows / 2; ++q) acc2[q][j] = bb;
+    }
     auto k_step = [&](int k) {
-      float wv[NC];
+      unsigned long long wv[NC];
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         int c = t + kEpiThreads * j;
-        wv[j] = (c < cout) ? s_w[k * cout + c] : 0.f;
+        const float w1 = (c < cout) ? s_w[k * cout + c] : 0.f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(wv[j]) : "f"(w1));
       }
-      const float4 a_lo = *reinterpret_cast<const float4*>(s_a + k * kEpiRows);
-      const float4 a_hi = *reinterpret_cast<const float4*>(s_a + k * kEpiRows + 4);
-      const float av[kEpiRows] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(s_a + k * kEpiRows);       // rows (0,1), (2,3)
+      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(s_a + k * kEpiRows + 4);   // rows (4,5), (6,7)
+      const unsigned long long av[kEpiRows / 2] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
-      for (int rr = 0; rr < kEpiRows; ++rr)
+      for (int q = 0; q < kEpiRows / 2; ++q)
 #pragma unroll
-        for (int j = 0; j < NC; ++j) acc[rr][j] = fmaf(av[rr], wv[j], acc[rr][j]);
+        for (int j = 0; j < NC; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[q][j]) : "l"(av[q]), "l"(wv[j]));
     };
     if constexpr (BWD) {
       // compiler's own unrolling: forcing a factor (1 or 4) on this register-capped instantiation cost 1.4-2x
@@ -123,6 +130,12 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
 #pragma unroll 4
       for (int k = 0; k < cin; ++k) k_step(k);
     }
+    float acc[kEpiRows][NC];
+#pragma unroll
+    for (int q = 0; q < kEpiRows / 2; ++q)
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * q][j]), "=f"(acc[2 * q + 1][j]) : "l"(acc2[q][j]));
     // row norms
     float part[kEpiRows];
 #pragma unroll

@@ -103,13 +103,13 @@ def test_reference_train_loop_on_gpu(cuda_backend, tmp_path):
     assert len(gpu_losses) == 4 and all(v == v and abs(v) < 1e3 for v in gpu_losses)
     assert int(gpu_state['GCN_embed_1.bn1.num_batches_tracked']) == 4
     assert all(torch.isfinite(v).all() for v in gpu_state.values() if v.is_floating_point())
-    # 2. the same loop with --optim sgd (update linear in the gradient): the whole loss trajectory and the BatchNorm
+    # 2. the same loop with --optim sgd --lr 0.001 (update linear in the gradient): the whole loss trajectory and the BatchNorm
     #    running statistics agree with the loop driven by the per-operator CPU formulas of the oracle (the checker)
-    sgd_losses, sgd_state = _run_reference_train(tmp_path / 'gpu_sgd', on_gpu=True, optim='sgd', lr=0.01)
+    sgd_losses, sgd_state = _run_reference_train(tmp_path / 'gpu_sgd', on_gpu=True, optim='sgd', lr=0.001)
     from oracle import op_reference
     _backend.use_backend_for_testing(op_reference.TorchBackend())
     try:
-        cpu_losses, cpu_state = _run_reference_train(tmp_path / 'cpu_sgd', on_gpu=False, optim='sgd', lr=0.01)
+        cpu_losses, cpu_state = _run_reference_train(tmp_path / 'cpu_sgd', on_gpu=False, optim='sgd', lr=0.001)
     finally:
         _backend.use_backend_for_testing(None)
     print('adam losses gpu %s\nsgd  losses gpu %s\n            cpu %s' % (gpu_losses, sgd_losses, cpu_losses))

@@ -48,6 +48,10 @@ if has launches; then
     --log-file $OUT/launches_r2.csv python tools/profile_step.py > $OUT/prof_step.log 2>&1; echo "launches exit=$?"
   python tools/summarize_launches.py $OUT/launches_r2.csv > $OUT/launches_r2_summary.txt 2>&1; head -40 $OUT/launches_r2_summary.txt
 fi
+if has ncu_step; then
+  timeout 1500 ncu --section SpeedOfLight --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
+    --clock-control none --profile-from-start off -f -o $OUT/step_r2 python tools/profile_step.py > $OUT/prof_step_full.log 2>&1; echo "ncu_step exit=$?"
+fi
 if has ncu_gather; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sage_gather_ell -s 2 -c 1 -f \
     -o $OUT/prof_gather_r2 python tools/profile_gather.py > $OUT/prof_gather.log 2>&1; echo "ncu_gather exit=$?"

@@ -73,8 +73,8 @@ for norm_adj in (False, True):
     be.sage_epilogue_fwd(ref, w, bias, sg.mask, yref, 0)
     torch.cuda.synchronize()
     check('fused layer na=%d' % norm_adj, y, yref.cpu(), 1e-4)
-    s = torch.rand(xp.shape[0], 116, device=dev)[:, :114]
-    p1, p2 = torch.empty(xp.shape[0], 116, device=dev)[:, :114], torch.empty(xp.shape[0], 116, device=dev)[:, :114]
+    s = torch.rand(xp.shape[0], 120, device=dev)[:, :116]
+    p1, p2 = torch.empty(xp.shape[0], 120, device=dev)[:, :116], torch.empty(xp.shape[0], 120, device=dev)[:, :116]
     be.gather_wide_ell(sg.ell, sg.ell_val, None, sg.ell_perm, sg.ell_width, sg.rowptr, sg.col, sg.val, s,
                        sg.num_graphs, sg.nmax, p1, False)
     be.spmm(sg.rowptr, sg.col, sg.val, s, None, None, p2, False)
