@@ -39,8 +39,9 @@ namespace tc {
 constexpr int BM = 128, BK = 32;                      // BN is a template parameter: 128, 64 or 32
 constexpr int kStages = 4;
 constexpr int kOperandBytes = BM * BK * 4;            // A tile: 16 KB.  Stage = A (as landed) | B (as landed = B_hi) | B_lo
-constexpr int kThreads = 512;
-constexpr int kSplitThreads = 128;
+constexpr int kThreads = 640;                          // warps 0-3 control, 4-7 split group 0, 8-15 promotion, 16-19 split group 1
+constexpr int kSplitThreads = 128;                    // threads of ONE split group (= rows of the A tile)
+constexpr int kSplitGroups = 2;                       // the groups take alternate stages of the ring
 constexpr int kEpiThreads = 256;
 constexpr int kDefaultChunkBlocks = 2;               // K-blocks accumulated in TMEM before promotion to fp32 registers
 constexpr int kATmemBase = 256;                       // accumulators: 2 buffers x BN columns in [0, 256); then the A operand
@@ -506,14 +507,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 16) {
     // ================================ hi / lo split ================================
-    const int tid = threadIdx.x - 128;
+    // Two groups of four warps (4-7 and 16-19; a warp reaches the TMEM lane quarter warp % 4, so each group covers
+    // the 128 rows) take ALTERNATE stages: one group alone spent ~800 cycles per stage in this dependent chain
+    // (LDS of its row -> split -> tcgen05.st -> wait::st -> fences -> arrive) and was busy 86 % of the time while
+    // the tensor pipe idled -- the contraction ran at the split rate whatever the number of MMA passes.
+    const int group = warp >= 16 ? 1 : 0;
+    const int tid = threadIdx.x - (group ? 512 : 128);
     int s = 0;
     uint32_t ph = 0;
+    uint32_t stage_it = 0;                              // stages seen by this warp, over all its tiles
     for (int t = tile_first; t < p.total_tiles; t += tile_step) {
       const TileCoord c = tile_coord(p, t, kTileM, rank);
-      for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
+      for (int k0 = c.kbeg; k0 < c.kend; k0 += BK, ++stage_it) {
+        if ((int)(stage_it % kSplitGroups) != group) {  // the other group's stage: just keep the ring position
+          if (++s == kStages) { s = 0; ph ^= 1; }
+          continue;
+        }
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + (size_t)s * kStageBytes;
         auto split_b = [&]() {
@@ -628,7 +639,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 16) {
     // ================================ promotion + epilogue ================================
     const int q = (warp - 8) & 3;                      // TMEM lane quarter == warp_id % 4
     const int half = (warp - 8) >> 2;                  // which BN/2 accumulator columns this warp owns
@@ -644,12 +655,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         mbar_wait(&tfull[buf], (chunk_it >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kAccCols + (uint32_t)(half * kCols);
-        if constexpr (kCols == 16) {
-          tmem_ld16_add(taddr, acc);
-        } else {
+        // 16 columns per tcgen05.ld: the 64 accumulators plus a 32-register landing zone would not fit the 96
+        // registers a 640-thread CTA leaves each thread
 #pragma unroll
-          for (int j = 0; j < kCols; j += 32) tmem_ld32_add(taddr + (uint32_t)j, acc + j);
-        }
+        for (int j = 0; j < kCols; j += 16) tmem_ld16_add(taddr + (uint32_t)j, acc + j);
         tc_fence_before();
         if (PAIR) {
           __syncwarp();

@@ -85,6 +85,20 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
   const int64_t ntiles = (rows + kEpiRows - 1) / kEpiRows;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * kEpiRows;
+    if constexpr (BWD) {
+      // The gradient and activation rows of this CTA's NEXT tile are pulled into L2 now, one 128-byte line per
+      // thread and matrix: when the tile is reached its 80 loads per thread hit L2 instead of stalling a whole
+      // DRAM round trip behind the FMA phase (no registers to spare for a software pipeline here).
+      const int64_t rn = (tile + gridDim.x) * kEpiRows;
+      const int lines = (cout + 31) >> 5;
+      for (int i = t; i < kEpiRows * lines; i += kEpiThreads) {
+        const int rr = i / lines, ch = i - rr * lines;
+        if (rn + rr < rows) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (rn + rr) * ldy + ch * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + (rn + rr) * ldgy + ch * 32));
+        }
+      }
+    }
     __syncthreads();                                 // previous tile done with s_a / s_red (and s_w loaded)
     for (int i = t; i < cin * kEpiRows; i += kEpiThreads) {
       int rr = i / cin, k = i - rr * cin;
