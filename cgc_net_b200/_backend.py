@@ -79,7 +79,7 @@ _SIGNATURES = {
     'cgc_bn_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64,
                    _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_softmax_fwd': [_c_vp, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp],
-    'cgc_softmax_bwd': [_c_vp, _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp],
+    'cgc_softmax_bwd': [_c_vp, _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp],
     'cgc_colmax_fwd': [_c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_vp],
     'cgc_colmax_bwd': [_c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp],
     'cgc_row_inv_clamped_sum': [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp],
@@ -494,9 +494,10 @@ class CudaBackend(object):
     def softmax_bwd(self, gs, s, gz):
         gp, ldg = _mat(gs)
         sp, lds = _mat(s)
-        if ldg != lds or not gz.is_contiguous():
-            raise CgcError('cgc_softmax_bwd: gs and s must share their leading dimension, gz contiguous')
-        self._check(self.lib.cgc_softmax_bwd(gp, sp, lds, s.shape[0], s.shape[1], _ptr(gz, torch.float32),
+        zp, ldz = _mat(gz)
+        if ldg != lds:
+            raise CgcError('cgc_softmax_bwd: gs and s must share their leading dimension')
+        self._check(self.lib.cgc_softmax_bwd(gp, sp, lds, s.shape[0], s.shape[1], zp, ldz,
                                              self._stream()), 'cgc_softmax_bwd')
 
     def colmax_fwd(self, x, b, n, out, arg):

@@ -426,7 +426,7 @@ k_softmax_fwd(const float* __restrict__ z, int64_t rows, int c, const int32_t* _
 template <int NREG>
 __global__ void __launch_bounds__(256)
 k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t lds, int64_t rows, int c,
-              float* __restrict__ gz) {
+              float* __restrict__ gz, int64_t ldgz) {
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
@@ -443,7 +443,7 @@ k_softmax_bwd(const float* __restrict__ gs, const float* __restrict__ s, int64_t
 #pragma unroll
   for (int j = 0; j < NREG; ++j) dot = fmaf(gv[j], pv[j], dot);
   dot = warp_sum(dot);
-  float* o = gz + r * (int64_t)c;
+  float* o = gz + r * ldgz;
 #pragma unroll
   for (int j = 0; j < NREG; ++j) {
     const int i = lane + 32 * j;
@@ -657,14 +657,14 @@ extern "C" int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const in
 }
 
 extern "C" int cgc_softmax_bwd(const float* gs, const float* s, int64_t lds, int64_t rows, int32_t c, float* gz,
-                               void* stream) {
-  CGC_REQUIRE(gs && s && gz && rows > 0 && c > 0 && lds >= c, CGC_ERR_ARG, "cgc_softmax_bwd: bad args");
+                               int64_t ldgz, void* stream) {
+  CGC_REQUIRE(gs && s && gz && rows > 0 && c > 0 && lds >= c && ldgz >= c, CGC_ERR_ARG, "cgc_softmax_bwd: bad args");
   CGC_REQUIRE(c <= 1280, CGC_ERR_UNSUPPORTED, "cgc_softmax_bwd: c=%d > 1280", c);
   const unsigned grid = (unsigned)ceil_div(rows, 8);
   cudaStream_t st = as_stream(stream);
-  if (c <= 128) k_softmax_bwd<4><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz);
-  else if (c <= 512) k_softmax_bwd<16><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz);
-  else k_softmax_bwd<40><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz);
+  if (c <= 128) k_softmax_bwd<4><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz, ldgz);
+  else if (c <= 512) k_softmax_bwd<16><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz, ldgz);
+  else k_softmax_bwd<40><<<grid, 256, 0, st>>>(gs, s, lds, rows, c, gz, ldgz);
   CGC_CHECK_LAUNCH("k_softmax_bwd");
   return 0;
 }

@@ -328,9 +328,10 @@ CGC_API int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ld
  * z and s_full are contiguous [rows, c]; s has leading dimension lds (>= c, padded for TMA). */
 CGC_API int cgc_softmax_fwd(const float* z, int64_t rows, int32_t c, const int32_t* num_nodes,
                     int32_t nmax, float* s, int64_t lds, float* s_full, int32_t* arg, void* stream);
-/* gz = s * (gs - sum_c gs * s);  gs and s share the leading dimension lds, gz is contiguous */
+/* gz = s * (gs - sum_c gs * s);  gs and s share the leading dimension lds; gz has its own (ldgz >= c: a leading
+ * dimension padded to 4 floats keeps the lin gradient contractions that consume gz on the tensor-core path) */
 CGC_API int cgc_softmax_bwd(const float* gs, const float* s, int64_t lds, int64_t rows, int32_t c,
-                    float* gz, void* stream);
+                    float* gz, int64_t ldgz, void* stream);
 
 /* torch.max(x, dim=1) over all nmax rows of each graph (network.py:264,275,284) */
 CGC_API int cgc_colmax_fwd(const float* x, int32_t num_graphs, int32_t nmax, int32_t c, float* out,
