@@ -62,6 +62,8 @@ _SIGNATURES = {
     'cgc_sage_layer_fwd_wide': [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp,
                                 _c_i64, _c_vp, _c_vp, _c_f32, _c_f32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_sage_dh': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
+    'cgc_sage_dh_bn': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int,
+                       _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_sage_layer_bwd_narrow': [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     'cgc_act_fwd': [_c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
     'cgc_act_bwd': [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32, _c_int, _c_vp, _c_i64, _c_vp],
@@ -384,6 +386,20 @@ class CudaBackend(object):
                                          _ptr(b, torch.float32), yp, ldy, nn, nmax, sa.shape[0],
                                          w.shape[0], w.shape[1], int(act), dp, ldd, self._stream()), 'cgc_sage_dh')
 
+    def sage_dh_bn(self, gx, sa, w, b, y, mean, invstd, gamma, d_gamma, d_beta, training, mask, dh, act=0):
+        """sage_dh with the BatchNorm backward folded in: ``gx`` is the gradient w.r.t. the BatchNorm output."""
+        gp, ldg = _mat(gx)
+        sp, lds = _mat(sa)
+        yp, ldy = _mat(y)
+        dp, ldd = _mat(dh)
+        nn, nmax = _mask(mask)
+        self._check(self.lib.cgc_sage_dh_bn(gp, ldg, sp, lds, _ptr(w.contiguous(), torch.float32),
+                                            _ptr(b, torch.float32), yp, ldy, _ptr(mean, torch.float32),
+                                            _ptr(invstd, torch.float32), _ptr(gamma, torch.float32),
+                                            _ptr(d_gamma, torch.float32), _ptr(d_beta, torch.float32), int(training),
+                                            nn, nmax, sa.shape[0], w.shape[0], w.shape[1], int(act), dp, ldd,
+                                            self._stream()), 'cgc_sage_dh_bn')
+
     def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b, act=0):
         gp, ldg = _mat(gy)
         sp, lds = _mat(sa)
@@ -472,7 +488,7 @@ class CudaBackend(object):
     def bn_bwd(self, gx, y, mean, invstd, gamma, mask, training, gy, d_gamma, d_beta):
         gp, ldg = _mat(gx)
         yp, ldy = _mat(y)
-        op, ldo = _mat(gy)
+        op, ldo = _mat(gy) if gy is not None else (None, 0)       # gy None: column sums only
         nn, nmax = _mask(mask)
         wp, wb = self._workspace(y.device)
         self._check(self.lib.cgc_bn_bwd(gp, ldg, yp, ldy, _ptr(mean, torch.float32),

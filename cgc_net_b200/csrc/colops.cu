@@ -541,7 +541,7 @@ extern "C" int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t
                           const float* invstd, const float* gamma, const int32_t* num_nodes, int32_t nmax,
                           int64_t rows, int32_t c, int training, float* gy, int64_t ldgy, float* d_gamma,
                           float* d_beta, void* work, int64_t work_bytes, void* stream) {
-  CGC_REQUIRE(gx && y && mean && invstd && gamma && gy && d_gamma && d_beta && work && rows > 0 && c > 0,
+  CGC_REQUIRE(gx && y && mean && invstd && gamma && d_gamma && d_beta && work && rows > 0 && c > 0,
               CGC_ERR_ARG, "cgc_bn_bwd: bad args");
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_bn_bwd: mask without nmax");
   int nrb;
@@ -566,6 +566,7 @@ extern "C" int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t
   }
   k_sum_finalize<<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nrb, c, d_beta, d_gamma);
   CGC_CHECK_LAUNCH("k_sum_finalize");
+  if (gy == nullptr) return 0;                       // sums only: the consumer folds the apply step (cgc_sage_dh_bn)
   const bool vec = c >= 64 && c % 4 == 0 && ldgx % 4 == 0 && ldy % 4 == 0 && ldgy % 4 == 0 && aligned16(gx) &&
                    aligned16(y) && aligned16(gy) && aligned16(mean) && aligned16(invstd) && aligned16(gamma) &&
                    aligned16(d_gamma) && aligned16(d_beta);

@@ -4,6 +4,8 @@
 //   cgc_scale_rows_bwd, cgc_row_inv_clamped_sum, cgc_add_rs_grad, cgc_dense_renorm_fwd/bwd
 // Reference: PyG 1.2.1 DenseSAGEConv.forward (called at model/network.py:114-116), nn.ReLU(inplace)
 // (network.py:87), _diff_pool (:194-208), _re_norm_adj (:183-191).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cgc {
@@ -57,12 +59,28 @@ k_epi_narrow(const float* __restrict__ sa, int64_t ldsa, const float* __restrict
 constexpr int kEpiThreads = 256;
 constexpr int kEpiRows = 8;
 
+// Backward with the BatchNorm backward folded in (bn.mean != null): `gy` is then the gradient w.r.t. the BatchNorm
+// OUTPUT and the kernel forms, per element, gy_bn = P gx - R y - Q with the per-column coefficients
+//   P = gamma invstd,  R = gamma invstd^2 d_gamma / rows,  Q = gamma invstd d_beta / rows - R mean     (training)
+//   P = gamma invstd,  R = Q = 0                                                                       (eval)
+// staged in shared memory once per CTA -- the separate pass that read gx and y and wrote gy (0.29 ms, 1.57 GB at the
+// BASELINE shape) disappears.
+struct EpiBn {
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* d_gamma;
+  const float* d_beta;
+  float inv_rows;
+  int training;
+};
+
 template <int NC, bool BWD>
 __global__ void __launch_bounds__(kEpiThreads, NC == 1 ? 4 : (NC == 2 ? 3 : 2))
 k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w, const float* __restrict__ bias,
            const int32_t* __restrict__ num_nodes, int nmax, int64_t rows, int cin, int cout,
            float* __restrict__ y, int64_t ldy, const float* __restrict__ gy, int64_t ldgy,
-           float* __restrict__ dh, int64_t lddh, int act, double* __restrict__ partial) {
+           float* __restrict__ dh, int64_t lddh, int act, double* __restrict__ partial, const EpiBn bn) {
   extern __shared__ float smem[];
   const ActGrad agrad(act);
   // forward with BatchNorm statistics (partial != null): every thread owns its columns in the CTA, so the column
@@ -74,7 +92,19 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
   float* s_a = s_w + cin * cout;                     // [cin][kEpiRows]  (transposed row tile)
   float* s_red = s_a + cin * kEpiRows;               // [8 warps][kEpiRows]
   int* s_valid = reinterpret_cast<int*>(s_red + (kEpiThreads / 32) * kEpiRows);   // [kEpiRows] row-mask flags of the tile
+  float* s_bn = reinterpret_cast<float*>(s_valid + kEpiRows);                     // [3][cout] P, R, Q (BWD with bn)
+  const bool with_bn = BWD && bn.mean != nullptr;
   for (int i = threadIdx.x; i < cin * cout; i += kEpiThreads) s_w[i] = w[i];
+  if (with_bn) {
+    for (int c = threadIdx.x; c < cout; c += kEpiThreads) {
+      const float is = bn.invstd[c], ga = bn.gamma[c];
+      const float pc = ga * is;
+      const float rc = bn.training ? pc * is * bn.d_gamma[c] * bn.inv_rows : 0.f;
+      s_bn[c] = pc;
+      s_bn[cout + c] = rc;
+      s_bn[2 * cout + c] = bn.training ? pc * bn.d_beta[c] * bn.inv_rows - rc * bn.mean[c] : 0.f;
+    }
+  }
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   float bj[NC];
 #pragma unroll
@@ -192,29 +222,40 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
         }
       }
     } else {
-      // gm = gy * [y > 0] * mask ; dot_r = sum_c gm * hn
+      // gm = gy * [y > 0] * mask ; dot_r = sum_c gm * hn      (gy: as given, or formed from the BatchNorm backward)
       float gm[kEpiRows][NC];
+      uint32_t vb = 0;
 #pragma unroll
       for (int rr = 0; rr < kEpiRows; ++rr) {
-        const int64_t r = r0 + rr;
         // (backward: per-thread mask evaluation as in round 1a -- routing it through the shared flags made this
         //  register-capped instantiation 1.4-2x slower)
-        const bool valid = (r < rows) && row_valid(num_nodes, nmax, r);
-        float s = 0.f;
+        const int64_t r = r0 + rr;
+        vb |= ((r < rows) && row_valid(num_nodes, nmax, r)) ? (1u << rr) : 0u;
+      }
+      float sdot[kEpiRows];
 #pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          int c = t + kEpiThreads * j;
+      for (int rr = 0; rr < kEpiRows; ++rr) sdot[rr] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int c = t + kEpiThreads * j;
+        float pc = 1.f, rc = 0.f, qc = 0.f;
+        if (with_bn && c < cout) { pc = s_bn[c]; rc = s_bn[cout + c]; qc = s_bn[2 * cout + c]; }
+#pragma unroll
+        for (int rr = 0; rr < kEpiRows; ++rr) {
+          const int64_t r = r0 + rr;
           float g = 0.f;
-          if (valid && c < cout) {                    // independent loads (no y -> gy dependency chain)
+          if (((vb >> rr) & 1u) && c < cout) {        // independent loads (no y -> gy dependency chain)
             const float yv = __ldg(y + r * ldy + c);
-            const float gv = gy[r * ldgy + c];
+            float gv = gy[r * ldgy + c];
+            if (with_bn) gv = fmaf(pc, gv, -fmaf(rc, yv, qc));
             g = gv * agrad(yv);
           }
           gm[rr][j] = g;
-          s = fmaf(g, acc[rr][j] * inv[rr], s);
+          sdot[rr] = fmaf(g, acc[rr][j] * inv[rr], sdot[rr]);
         }
-        part[rr] = warp_sum(s);
       }
+#pragma unroll
+      for (int rr = 0; rr < kEpiRows; ++rr) part[rr] = warp_sum(sdot[rr]);
       __syncthreads();                               // everyone has read s_red (norms)
       if (lane == 0) {
 #pragma unroll
@@ -256,9 +297,14 @@ template <bool BWD>
 static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const float* b,
                            const int32_t* num_nodes, int nmax, int64_t rows, int cin, int cout, float* y,
                            int64_t ldy, const float* gy, int64_t ldgy, float* dh, int64_t lddh, int act,
-                           cudaStream_t st, double* partial = nullptr, int64_t work_bytes = 0, int* blocks_out = nullptr) {
+                           cudaStream_t st, double* partial = nullptr, int64_t work_bytes = 0, int* blocks_out = nullptr,
+                           const EpiBn* bn_in = nullptr) {
+  EpiBn bn;
+  memset(&bn, 0, sizeof(bn));
+  if (bn_in != nullptr) bn = *bn_in;
   CGC_REQUIRE(act >= CGC_ACT_RELU && act <= CGC_ACT_LEAKY_RELU, CGC_ERR_ARG, "sage epilogue: unknown activation %d", act);
   if (cout <= 32) {
+    CGC_REQUIRE(bn_in == nullptr, CGC_ERR_UNSUPPORTED, "sage epilogue: BatchNorm folding needs cout > 32");
     CGC_REQUIRE(cin <= 64, CGC_ERR_UNSUPPORTED, "sage epilogue: cin=%d > 64", cin);
     size_t smem = sizeof(float) * (size_t)(cin * cout + cout);
     int64_t warps_needed = rows;
@@ -271,7 +317,9 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
   }
   const int nc = (int)ceil_div(cout, kEpiThreads);
   CGC_REQUIRE(nc <= 5, CGC_ERR_UNSUPPORTED, "sage epilogue: cout=%d > 1280", cout);
-  size_t smem = sizeof(float) * (size_t)(cin * cout + cin * kEpiRows + (kEpiThreads / 32) * kEpiRows + kEpiRows);
+  CGC_REQUIRE(bn_in == nullptr || BWD, CGC_ERR_ARG, "sage epilogue: BatchNorm folding is a backward option");
+  size_t smem = sizeof(float) * (size_t)(cin * cout + cin * kEpiRows + (kEpiThreads / 32) * kEpiRows + kEpiRows +
+                                         (bn_in != nullptr ? 3 * cout : 0));
   CGC_REQUIRE(smem <= 200 * 1024, CGC_ERR_UNSUPPORTED, "sage epilogue: W of %dx%d does not fit in shared memory",
               cin, cout);
   int64_t tiles = ceil_div(rows, kEpiRows);
@@ -288,7 +336,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     auto kern = k_epi_wide<N, BWD>;                                                                           \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     kern<<<(unsigned)blocks, kEpiThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, \
-                                                      gy, ldgy, dh, lddh, act, partial);                      \
+                                                      gy, ldgy, dh, lddh, act, partial, bn);                  \
   } break;
   switch (nc) {
     CGC_EPI_CASE(1)
@@ -624,6 +672,23 @@ extern "C" int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64
   CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_dh: mask without nmax");
   return launch_epilogue<true>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, const_cast<float*>(y), ldy, gy,
                                ldgy, dh, lddh, act, as_stream(stream));
+}
+
+extern "C" int cgc_sage_dh_bn(const float* gx, int64_t ldgx, const float* sa, int64_t ldsa, const float* w,
+                              const float* b, const float* y, int64_t ldy, const float* mean, const float* invstd,
+                              const float* gamma, const float* d_gamma, const float* d_beta, int training,
+                              const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin, int32_t cout, int act,
+                              float* dh, int64_t lddh, void* stream) {
+  CGC_REQUIRE(gx && sa && w && y && dh && mean && invstd && gamma && d_gamma && d_beta && rows > 0 && cin > 0 && cout > 0,
+              CGC_ERR_ARG, "cgc_sage_dh_bn: bad args");
+  CGC_REQUIRE(cout > 32 && cout <= 1280, CGC_ERR_UNSUPPORTED, "cgc_sage_dh_bn: needs 32 < cout <= 1280 (got %d)", cout);
+  CGC_REQUIRE(num_nodes == nullptr || nmax > 0, CGC_ERR_ARG, "cgc_sage_dh_bn: mask without nmax");
+  EpiBn bn;
+  bn.mean = mean; bn.invstd = invstd; bn.gamma = gamma; bn.d_gamma = d_gamma; bn.d_beta = d_beta;
+  bn.inv_rows = 1.0f / (float)rows;
+  bn.training = training;
+  return launch_epilogue<true>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, const_cast<float*>(y), ldy, gx, ldgx,
+                               dh, lddh, act, as_stream(stream), nullptr, 0, nullptr, &bn);
 }
 
 extern "C" int cgc_scale_rows_bwd(const float* dsa, const float* sa, const float* rs, int64_t rows, int32_t c,

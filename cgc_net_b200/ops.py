@@ -446,20 +446,27 @@ class GnnModuleFunction(Function):
             a, y, mean, invstd = saved[4 * k: 4 * k + 4]
             gx = g_cat[:, offs[k]: offs[k] + couts[k]]
             gy = _f32(m, couts[k], device=dev)
+            narrow = w.shape[1] <= 32 and w.shape[0] <= 64
+            fold_bn = cfg.has_bn and not narrow and 32 < w.shape[1] <= 1280 and w.shape[0] <= 64
             if cfg.has_bn:
                 d_gamma, d_beta = torch.empty_like(gamma), torch.empty_like(beta)
-                be.bn_bwd(gx, y, mean, invstd, gamma, cfg.mask, cfg.training, gy, d_gamma, d_beta)
+                # wide layer: only the column sums here, the apply step is folded into the epilogue backward below
+                be.bn_bwd(gx, y, mean, invstd, gamma, cfg.mask, cfg.training, None if fold_bn else gy, d_gamma, d_beta)
                 grads[4 * k + 2], grads[4 * k + 3] = d_gamma, d_beta
             else:
                 be.bn_apply(gx, None, None, None, None, cfg.mask, gy)     # gy = gx * mask
             d_w = torch.empty_like(w)
             d_b = torch.empty_like(b) if b is not None else None
             dsa = _f32(m, w.shape[0], device=dev)
-            if w.shape[1] <= 32 and w.shape[0] <= 64:
+            if narrow:
                 # narrow layer: dh, dW, db and dsa = dh W^T in ONE pass over the rows
                 be.sage_layer_bwd_narrow(gy, a, w, b, y, cfg.mask, dsa, d_w, d_b, cfg.act)
             else:
-                be.sage_dh(gy, a, w, b, y, cfg.mask, gy, cfg.act)   # gy <- dh = dL/d(sa W + b), in place
+                if fold_bn:
+                    be.sage_dh_bn(gx, a, w, b, y, mean, invstd, gamma, d_gamma, d_beta, cfg.training, cfg.mask, gy,
+                                  cfg.act)                      # gy <- dh, BatchNorm backward formed on the fly
+                else:
+                    be.sage_dh(gy, a, w, b, y, cfg.mask, gy, cfg.act)   # gy <- dh = dL/d(sa W + b), in place
                 be.gemm(a, gy, d_w, True, False)                # dW = sa^T dh   (K = M)
                 if d_b is not None:
                     be.colsum(gy, None, d_b)

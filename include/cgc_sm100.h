@@ -255,6 +255,16 @@ CGC_API int cgc_sage_dh(const float* gy, int64_t ldgy, const float* sa, int64_t 
                 int32_t nmax, int64_t rows, int32_t cin, int32_t cout, int act, float* dh,
                 int64_t lddh, void* stream);
 
+/* cgc_sage_dh with the BatchNorm backward of the layer folded in (wide layers, 32 < cout <= 1280): gx is the
+ * gradient w.r.t. the BatchNorm OUTPUT; d_gamma / d_beta are the column sums cgc_bn_bwd(..., gy = NULL, ...) has
+ * produced.  dh = d loss / d (sa W + b) as above, with gy = gamma invstd (gx mask - d_beta / rows - xhat d_gamma / rows)
+ * (training) or gamma invstd gx mask (eval) formed on the fly: the pass that wrote gy disappears. */
+CGC_API int cgc_sage_dh_bn(const float* gx, int64_t ldgx, const float* sa, int64_t ldsa, const float* w,
+                   const float* b, const float* y, int64_t ldy, const float* mean, const float* invstd,
+                   const float* gamma, const float* d_gamma, const float* d_beta, int training,
+                   const int32_t* num_nodes, int32_t nmax, int64_t rows, int32_t cin, int32_t cout, int act,
+                   float* dh, int64_t lddh, void* stream);
+
 /* Fused backward of a narrow layer epilogue (cout <= 32, cin <= 64) in one pass over the rows:
  * dsa = dh W^T [rows, cin], d_w = sa^T dh [cin, cout], d_b = sum_rows dh (nullable), with
  * dh = d loss / d (sa @ W + b) as in cgc_sage_dh (not materialised).  Deterministic (per-CTA partials in
@@ -317,6 +327,7 @@ CGC_API int cgc_bn_apply(const float* y, int64_t ldy, const float* mean, const f
                  int64_t rows, int32_t c, float* out, int64_t ldo, void* stream);
 /* d_gamma = sum g*xhat, d_beta = sum g (g = gx*mask);
  * gy = gamma*invstd*(g - d_beta/rows - xhat*d_gamma/rows)   (training)   or gamma*invstd*g */
+/* gy may be NULL: only d_gamma / d_beta (the column sums) are produced */
 CGC_API int cgc_bn_bwd(const float* gx, int64_t ldgx, const float* y, int64_t ldy, const float* mean,
                const float* invstd, const float* gamma, const int32_t* num_nodes, int32_t nmax,
                int64_t rows, int32_t c, int training, float* gy, int64_t ldgy, float* d_gamma,

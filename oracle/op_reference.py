@@ -367,6 +367,17 @@ class TorchBackend(object):
         # y = h / max(|h|, eps): d/dh = (g - hn (hn . g)) / |h|   when |h| >= eps, g / eps otherwise
         dh.copy_(torch.where(nrm >= L2_EPS, (gm - hn * dot) * inv, gm * inv))
 
+    def sage_dh_bn(self, gx, sa, w, b, y, mean, invstd, gamma, d_gamma, d_beta, training, mask, dh, act=0):
+        """cgc_sage_dh_bn: the BatchNorm backward apply step (from the given column sums), then sage_dh."""
+        m = y.shape[0]
+        valid = _valid_rows(mask, m, y.device)[:, None].float()
+        g = gx * valid
+        if training:
+            gy = gamma * invstd * (g - d_beta / m - (y - mean) * invstd * d_gamma / m)
+        else:
+            gy = gamma * invstd * g
+        self.sage_dh(gy, sa, w, b, y, mask, dh, act)
+
     def sage_layer_bwd_narrow(self, gy, sa, w, b, y, mask, dsa, d_w, d_b, act=0):
         dh = torch.empty_like(y)
         self.sage_dh(gy, sa, w, b, y, mask, dh, act)
@@ -493,6 +504,8 @@ class TorchBackend(object):
         dg, db = (g * xhat).sum(0), g.sum(0)
         d_gamma.copy_(dg)
         d_beta.copy_(db)
+        if gy is None:                  # column sums only (the consumer folds the apply step: sage_dh_bn)
+            return
         if training:
             gy.copy_(gamma * invstd * (g - db / m - xhat * dg / m))
         else:

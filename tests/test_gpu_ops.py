@@ -797,3 +797,33 @@ def test_sage_layer_fwd_wide(cuda_backend, cin, cout, act):
     mean, invstd = torch.zeros(cout), torch.zeros(cout)
     both(cuda_backend, 'sage_layer_fwd_wide', [sa, w, bias, mask, y, act, rmean, rvar, 0.1, 1e-5, mean, invstd],
          [4, 6, 7, 10, 11], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('cin,cout', [(20, 1140), (20, 114), (60, 300)])
+@pytest.mark.parametrize('training,act', [(True, 0), (False, 1)])
+def test_sage_dh_bn(cuda_backend, cin, cout, training, act):
+    """Epilogue backward with the BatchNorm backward folded in == bn_bwd (apply step) followed by sage_dh;
+    bn_bwd with gy = None produces the same column sums (ragged mask, strided gradient slice)."""
+    b, nmax = 5, 653
+    rows = b * nmax
+    g = torch.Generator().manual_seed(cin + cout)
+    sa = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax, seed=2)
+    y = torch.zeros(rows, cout)
+    REF.sage_epilogue_fwd(sa, w, bias, mask, y, act)
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    gamma = torch.rand(cout, generator=g) + 0.5
+    gxw = torch.randn(rows, cout + 40, generator=g)
+    gx = gxw[:, 40:40 + cout]
+    dg, db = torch.zeros(cout), torch.zeros(cout)
+    both(cuda_backend, 'bn_bwd', [gx, y, mean, invstd, gamma, mask, training, None, dg, db], [8, 9], rtol=1e-4, atol=1e-4)
+    dh = torch.zeros(rows, cout)
+    both(cuda_backend, 'sage_dh_bn', [gx, sa, w, bias, y, mean, invstd, gamma, dg, db, training, mask, dh, act], [12],
+         rtol=1e-4, atol=2e-6)
+    gy, dh2 = torch.zeros(rows, cout), torch.zeros(rows, cout)
+    REF.bn_bwd(gx, y, mean, invstd, gamma, mask, training, gy, torch.zeros(cout), torch.zeros(cout))
+    REF.sage_dh(gy, sa, w, bias, y, mask, dh2, act)
+    torch.testing.assert_close(dh, dh2, rtol=1e-5, atol=1e-7)

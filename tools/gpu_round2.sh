@@ -50,7 +50,9 @@ if has launches; then
 fi
 if has ncu_step; then
   timeout 1500 ncu --section SpeedOfLight --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
-    --clock-control none --profile-from-start off -f -o $OUT/step_r2 python tools/profile_step.py > $OUT/prof_step_full.log 2>&1; echo "ncu_step exit=$?"
+    --clock-control none --profile-from-start off -f -o /tmp/step_r2 python tools/profile_step.py > $OUT/prof_step_full.log 2>&1; echo "ncu_step exit=$?"
+  # the report is > 64 MB (gpurun_out is capped): summarise it here, bring back the table only
+  python tools/summarize_step_ncu.py /tmp/step_r2.ncu-rep > $OUT/step_r2_kernels.txt 2>&1; head -30 $OUT/step_r2_kernels.txt
 fi
 if has ncu_gather; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sage_gather_ell -s 2 -c 1 -f \
