@@ -102,10 +102,9 @@ class GNN_Module(nn.Module):
         else:
             self.lin = None
 
-    def forward(self, x, adj, mask=None, graph=None, num_graphs=None, nmax=None, scale=None, shared_adj_grad=None):
+    def forward(self, x, adj, mask=None, graph=None, num_graphs=None, nmax=None, scale=None):
         """``x [M, Cin]`` in the padded node layout.  Either ``graph`` (``ops.SparseGraph``,
-        stage 1) or a dense ``adj [B, N, N]`` with ``scale = ops.dense_row_scale(adj)``; ``shared_adj_grad`` =
-        the ``ops.SharedAdjGrad`` of that adjacency when several modules consume it."""
+        stage 1) or a dense ``adj [B, N, N]`` with ``scale = ops.dense_row_scale(adj)``."""
         if self.gin:
             return self._forward_gin(x, adj, mask, graph, num_graphs, nmax)
         params, buffers = [], []
@@ -129,8 +128,7 @@ class GNN_Module(nn.Module):
         rs, rsum = scale
         cfg = ops.GnnConfig(graph=None, num_graphs=num_graphs, nmax=nmax, mask=mask,
                             training=self.training, has_bn=self.has_bn,
-                            has_lin=self.lin is not None, bn_buffers=buffers, act=self.act,
-                            shared_adj_grad=shared_adj_grad)
+                            has_lin=self.lin is not None, bn_buffers=buffers, act=self.act)
         return ops.GnnModuleFunction.apply(cfg, x, adj, rs, rsum, *params)
 
     def _forward_gin(self, x, adj, mask, graph, num_graphs, nmax):
@@ -293,17 +291,9 @@ class SoftPoolingGcnEncoder(nn.Module):
                 adj = ops.DenseRenormFunction.apply(adj, ops.RENORM_P, mask)
             scale = ops.dense_row_scale(adj)
 
-        gin = self.GCN_embed_1.gin
         for stage in (1, 2, 3):
             embed = getattr(self, 'GCN_embed_%d' % stage)
-            # stage 2: embed, pool and the DiffPool step all consume the dense adjacency -> one shared gradient
-            # buffer instead of two 333 MB autograd additions (SAGE modules; the GIN variant chains small autograd
-            # nodes and keeps autograd's own accumulation)
-            shared = None
-            if graph is None and stage == 2 and adj.requires_grad and not gin and torch.is_grad_enabled():
-                shared = ops.SharedAdjGrad(3)
-            kw = dict(shared_adj_grad=shared) if not gin else {}
-            feat = embed(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale, **kw)
+            feat = embed(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
             if self.jk:
                 feat = getattr(self, 'jk%d' % stage)(feat, b, n)
             pooled, _ = ops.ColMaxFunction.apply(feat, b, n)
@@ -311,8 +301,8 @@ class SoftPoolingGcnEncoder(nn.Module):
             if stage == 3:
                 break
             pool = getattr(self, 'GCN_pool_%d' % stage)
-            assign = pool(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale, **kw)
-            cfg = ops.GnnConfig(graph=graph, num_graphs=b, nmax=n, mask=mask, shared_adj_grad=shared)
+            assign = pool(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
+            cfg = ops.GnnConfig(graph=graph, num_graphs=b, nmax=n, mask=mask)
             xp, ap, s_full, arg = ops.DiffPoolFunction.apply(cfg, assign, feat, adj, self.collect_assign)
             if self.collect_assign:
                 self.assign_matrix.append(s_full.view(b, n, -1))

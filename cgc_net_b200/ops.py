@@ -209,45 +209,17 @@ def build_sparse_graph(x, edge_index, batch, num_nodes_list=None, norm_adj=False
 
 
 # ----------------------------------------------------------------------------- GNN module
-class SharedAdjGrad(object):
-    """One gradient buffer for a dense adjacency that several autograd nodes consume (stage 2: GCN_embed_2,
-    GCN_pool_2 and the DiffPool step all read A').  Autograd would sum their three [B, C, C] gradients with two
-    element-wise kernels over 333 MB each; here every consumer ACCUMULATES into the same buffer (``beta = 1``
-    epilogues of the contractions that produce the gradient; the first one to run stores instead) and only the
-    consumer that runs last hands the buffer to autograd -- the others return None (= zero).  The result does not
-    depend on the order in which the engine schedules the consumers."""
-
-    def __init__(self, consumers):
-        self.consumers, self.done, self.buf = int(consumers), 0, None
-
-    def begin(self, like):
-        """-> (buffer, accumulate): accumulate is False for the first consumer of this backward pass."""
-        first = self.done == 0
-        if first:
-            self.buf = torch.empty_like(like)
-        return self.buf, not first
-
-    def end(self):
-        """-> the buffer if this was the last consumer (and reset for the next backward), else None."""
-        self.done += 1
-        if self.done < self.consumers:
-            return None
-        buf, self.done, self.buf = self.buf, 0, None
-        return buf
-
-
 class GnnConfig(object):
     """Static description of one ``GNN_Module`` call (not a tensor; passed through autograd)."""
 
     def __init__(self, graph=None, num_graphs=0, nmax=0, mask=None, training=True, has_bn=True,
-                 has_lin=False, bn_buffers=None, need_adj_grad=False, act=0, shared_adj_grad=None):
+                 has_lin=False, bn_buffers=None, need_adj_grad=False, act=0):
         self.graph = graph              # SparseGraph, or None when the adjacency is dense
         self.num_graphs, self.nmax = num_graphs, nmax
         self.mask = mask                # RowMask or None
         self.training, self.has_bn, self.has_lin = training, has_bn, has_lin
         self.bn_buffers = bn_buffers    # [(running_mean, running_var)] * 3 (updated in place)
         self.need_adj_grad = need_adj_grad
-        self.shared_adj_grad = shared_adj_grad      # SharedAdjGrad of the dense adjacency, or None
         self.act = act                  # ACTIVATIONS[name]: 0 relu, 1 elu, 2 leakyrelu (network.py:82-90)
 
 
@@ -421,12 +393,7 @@ class GnnModuleFunction(Function):
             g_cat = g_out.clone()                              # accumulated into below
         dense = cfg.graph is None
         want_adj = dense and ctx.needs_input_grad[2]
-        shared = cfg.shared_adj_grad if want_adj else None
-        acc_adj = False
-        if shared is not None:
-            d_adj, acc_adj = shared.begin(adj)
-        else:
-            d_adj = torch.empty_like(adj) if want_adj else None
+        d_adj = torch.empty_like(adj) if want_adj else None
         d_rs = torch.zeros_like(rs) if dense else None
         g_x0 = None
         offs = [0, couts[0], couts[0] + couts[1]]
@@ -491,11 +458,9 @@ class GnnModuleFunction(Function):
         if want_adj:
             b_, n_ = cfg.num_graphs, cfg.nmax
             be.gemm(ga_all.view(b_, n_, -1), xc_all.view(b_, n_, -1), d_adj, False, True,
-                    beta=1.0 if acc_adj else 0.0, precision=_prec(be, 'dense_dadj'))         # dA (+)= gA x^T
+                    precision=_prec(be, 'dense_dadj'))                                       # dA = gA x^T
             # rs_i = 1 / clamp(rsum_i, 1)  ->  dA_ij += -[rsum_i >= 1] d_rs_i / rsum_i^2   (all j)
             be.add_rs_grad(d_adj, rsum, d_rs)
-            if shared is not None:
-                d_adj = shared.end()
         return (None, g_x0, d_adj, None, None) + tuple(grads)
 
 
@@ -768,12 +733,12 @@ class DiffPoolFunction(Function):
         else:
             be.gemm(adj, _as3d(g_p, b, n), _as3d(g_s, b, n), True, False, beta=1.0)
             if ctx.want_adj:
-                shared = cfg.shared_adj_grad
-                g_adj, acc_adj = shared.begin(adj) if shared is not None else (torch.empty_like(adj), False)
-                be.gemm(_as3d(g_p, b, n), _as3d(s, b, n), g_adj, False, True, beta=1.0 if acc_adj else 0.0,
+                # (accumulating the three adjacency gradients of stage 2 into one buffer through beta = 1 epilogues was
+                #  measured: the tensor-core kernel's row-per-thread epilogue reads the old tile uncoalesced, 1000 us per
+                #  contraction instead of 209 us + 135 us for autograd's element-wise addition -- dropped)
+                g_adj = torch.empty_like(adj)
+                be.gemm(_as3d(g_p, b, n), _as3d(s, b, n), g_adj, False, True,
                         precision=_prec(be, 'pool_gadj'))                                # gP S^T
-                if shared is not None:
-                    g_adj = shared.end()
         g_x = _f32(m, x.shape[1], device=dev)
         be.gemm(_as3d(s, b, n), g_xp, g_x.view(b, n, -1), False, False, precision=_prec(be, 'pool_gx'))  # S gX'
         g_z = _mat(m, c, dev)                    # padded leading dimension: operand of the lin gradient contractions
