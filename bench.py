@@ -261,7 +261,8 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- gather roofline
-def gather_roofline(args, device, kind='gather', row_is_centre=True, norm_adj=False, pdl=True, check=True):
+def gather_roofline(args, device, kind='gather', row_is_centre=True, norm_adj=False, pdl=True, check=True,
+                    two_per_sm=False):
     """One kernel of the gather family alone at the BASELINE shape (B x nodes x F = 16): CUDA-graph replay over
     rotating input copies whose total footprint exceeds L2, timed with CUDA events on the launching stream.
 
@@ -297,7 +298,8 @@ def gather_roofline(args, device, kind='gather', row_is_centre=True, norm_adj=Fa
         def launch(i):
             # binary adjacency: no scale vector (mean derived from the row's slots), as ops._agg calls it
             be.sage_gather_ell(ells[i], vals[i], scs[i] if vals[i] is not None else None, perms[i], g.ell_width,
-                               g.rowptr, g.col, g.val, xs[i], b, n, outs[i], tables_ready=True, pdl=pdl)
+                               g.rowptr, g.col, g.val, xs[i], b, n, outs[i], tables_ready=True, pdl=pdl,
+                               two_per_sm=two_per_sm)
     elif kind == 'layer':
         torch.manual_seed(3)
         w = (torch.rand(FEAT, 20, device=device) - 0.5) * 0.5

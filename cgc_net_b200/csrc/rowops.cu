@@ -224,38 +224,29 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
     } else {
       // gm = gy * [y > 0] * mask ; dot_r = sum_c gm * hn      (gy: as given, or formed from the BatchNorm backward)
       float gm[kEpiRows][NC];
-      uint32_t vb = 0;
 #pragma unroll
       for (int rr = 0; rr < kEpiRows; ++rr) {
-        // (backward: per-thread mask evaluation as in round 1a -- routing it through the shared flags made this
-        //  register-capped instantiation 1.4-2x slower)
         const int64_t r = r0 + rr;
-        vb |= ((r < rows) && row_valid(num_nodes, nmax, r)) ? (1u << rr) : 0u;
-      }
-      float sdot[kEpiRows];
+        // (backward: per-thread mask evaluation as in round 1a -- routing it through the shared flags made this
+        //  register-capped instantiation 1.4-2x slower; the loop order rows-outer / columns-inner is the measured one
+        //  too: columns-outer with the BatchNorm coefficients in registers ran 1.7x slower)
+        const bool valid = (r < rows) && row_valid(num_nodes, nmax, r);
+        float s = 0.f;
 #pragma unroll
-      for (int rr = 0; rr < kEpiRows; ++rr) sdot[rr] = 0.f;
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int c = t + kEpiThreads * j;
-        float pc = 1.f, rc = 0.f, qc = 0.f;
-        if (with_bn && c < cout) { pc = s_bn[c]; rc = s_bn[cout + c]; qc = s_bn[2 * cout + c]; }
-#pragma unroll
-        for (int rr = 0; rr < kEpiRows; ++rr) {
-          const int64_t r = r0 + rr;
+        for (int j = 0; j < NC; ++j) {
+          int c = t + kEpiThreads * j;
           float g = 0.f;
-          if (((vb >> rr) & 1u) && c < cout) {        // independent loads (no y -> gy dependency chain)
+          if (valid && c < cout) {                    // independent loads (no y -> gy dependency chain)
             const float yv = __ldg(y + r * ldy + c);
             float gv = gy[r * ldgy + c];
-            if (with_bn) gv = fmaf(pc, gv, -fmaf(rc, yv, qc));
+            if (with_bn) gv = fmaf(s_bn[c], gv, -fmaf(s_bn[cout + c], yv, s_bn[2 * cout + c]));
             g = gv * agrad(yv);
           }
           gm[rr][j] = g;
-          sdot[rr] = fmaf(g, acc[rr][j] * inv[rr], sdot[rr]);
+          s = fmaf(g, acc[rr][j] * inv[rr], s);
         }
+        part[rr] = warp_sum(s);
       }
-#pragma unroll
-      for (int rr = 0; rr < kEpiRows; ++rr) part[rr] = warp_sum(sdot[rr]);
       __syncthreads();                               // everyone has read s_red (norms)
       if (lane == 0) {
 #pragma unroll

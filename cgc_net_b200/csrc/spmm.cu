@@ -334,11 +334,32 @@ struct EllGatherArgs {
   float* out;
   int64_t ldo;
   int nmax, feat, parts, rpp;
+  int n_hi, rpp_hi;      // balanced split: the first n_hi graphs get parts + 1 CTAs of rpp_hi rows each, so that the
+                         // grid covers every SM (64 graphs: 20 x 3 + 44 x 2 = 148 CTAs)
   int box_rows;          // STRIDED: rows per TMA box
   int early_tables;      // index tables may be read before pdl_wait()
   int lab_stage;         // CGC_LAB builds: 1 = exit at entry, 2 = exit after the tile copy (timeline measurements)
   uint32_t chunk;        // bytes per 1-D bulk copy
 };
+
+// CTA -> (graph, first table row, rows): graphs [0, n_hi) are cut into parts + 1 pieces of rpp_hi rows, the rest into
+// `parts` pieces of rpp rows
+__device__ __forceinline__ void ell_cta_rows(const EllGatherArgs& a, int nrow8, int& g, int& r0, int& nrows) {
+  const int hi_ctas = a.n_hi * (a.parts + 1);
+  int p, rpp;
+  if ((int)blockIdx.x < hi_ctas) {
+    g = blockIdx.x / (a.parts + 1);
+    p = blockIdx.x - g * (a.parts + 1);
+    rpp = a.rpp_hi;
+  } else {
+    const int b2 = blockIdx.x - hi_ctas;
+    g = a.n_hi + b2 / a.parts;
+    p = b2 - (b2 / a.parts) * a.parts;
+    rpp = a.rpp;
+  }
+  r0 = p * rpp;
+  nrows = min(rpp, nrow8 - r0);
+}
 
 // Unweighted tables may come without a scale vector (ell_scale == NULL): the row's scale is then the DenseSAGEConv
 // mean 1 / max(deg, 1) with deg counted from the row's own slots; the served row comes from the slot-0 tag.
@@ -353,9 +374,10 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
   constexpr int NW = W / 2;                            // 32-bit index words per row
   const int nmax = a.nmax, feat = a.feat, parts = a.parts;
   const int nrow8 = (nmax + 7) & ~7;
-  const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
-  const int r0 = p * a.rpp;
-  const int nrows = min(a.rpp, nrow8 - r0);
+  int g, r0, nrows;
+  ell_cta_rows(a, nrow8, g, r0, nrows);
+  const int p = r0 / max(nrows, 1);                    // (lab stage 3 only)
+  (void)p;
   pdl_launch_dependents();                             // the next PDL kernel may start its prologue
 #ifdef CGC_LAB
   if (a.lab_stage == 1) return;
@@ -503,6 +525,96 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
 }
 
 
+// ------------------------------------------------------------------ ELL16 gather, two CTAs per SM
+// The roofline configuration (pitch 8, unweighted, 16 features, contiguous operands) in a shape that lets TWO CTAs
+// share an SM: 512 threads x 8 rows, 64 registers (a row costs its 4 index registers and nothing else: served row from
+// the slot-0 tag, scale = 1 / max(deg, 1) counted from the slots), 2 x 113.6 KB of shared memory.  Under
+// programmatic dependent launch the NEXT launch's CTAs are then resident, with their index vectors loaded, while
+// this launch still gathers.  It only pays with the balanced 148-CTA grid: with 128 CTAs the block scheduler doubles
+// the next launch's CTAs up on the 20 idle SMs (measured 8.7 us).
+constexpr int kLeanThreads = 512;
+constexpr int kLeanRows = 8;
+
+__global__ void __launch_bounds__(kLeanThreads, 2)
+k_sage_gather_ell_lean(const EllGatherArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int W = 8, NW = 4, LPR = 4, G = kLeanThreads / LPR, RB = kLeanRows;
+  const int nmax = a.nmax, feat = a.feat;
+  const int nrow8 = (nmax + 7) & ~7;
+  int g, r0, nrows;
+  ell_cta_rows(a, nrow8, g, r0, nrows);
+  pdl_launch_dependents();
+  const int64_t grow0 = (int64_t)g * nmax;
+  const int64_t trow0 = (int64_t)g * nrow8 + r0;
+  const uint32_t row_bytes = (uint32_t)feat * 4u;
+  const uint32_t tile_bytes = (uint32_t)nmax * row_bytes;
+  float* s_x = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 2 * feat) s_x[(size_t)nmax * feat + threadIdx.x] = 0.f;
+  const int sl = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+  const uint32_t lane_base = smem_u32(smem_raw) + sl * 16u;
+  const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
+  const uint32_t ovf_mark = (uint32_t)nmax + 1u;
+  uint32_t idx[RB][NW];
+  auto load_all = [&]() {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int t = i * G + grp;
+      uint4 v = make_uint4(pad_word, pad_word, pad_word, pad_word);
+      if (t < nrows) v = ldg_u4(a.ell + (trow0 + t) * W);
+      idx[i][0] = v.x; idx[i][1] = v.y; idx[i][2] = v.z; idx[i][3] = v.w;
+    }
+  };
+  if (a.early_tables) load_all();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, tile_bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + grow0 * feat);
+    for (uint32_t off = 0; off < tile_bytes; off += a.chunk) bulk_g2s(smem_raw + off, src + off, min(a.chunk, tile_bytes - off), &bar);
+  }
+  if (!a.early_tables) load_all();
+  __syncthreads();
+  mbar_wait(&bar, 0);
+#pragma unroll
+  for (int i = 0; i < RB; ++i) {
+    const int t = i * G + grp;
+    if (t >= nrows) continue;
+    const int lrow = ((r0 + t) & ~7) + ell_served_row(idx[i][0]);
+    if (lrow >= nmax) continue;
+    const int64_t row = grow0 + lrow;
+    float4 o;
+    float s;
+    if ((idx[i][0] & kEllColMask) != ovf_mark) {
+      F32x4 acc;
+      acc.lo = 0ull; acc.hi = 0ull;
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        const uint32_t j = ell_slot(idx[i], u);
+        cnt += (j != (uint32_t)nmax) ? 1 : 0;
+        add_x4(acc, lds_x4(lane_base + j * row_bytes));
+      }
+      s = 1.0f / fmaxf((float)cnt, 1.0f);
+      o = unpack_x4(acc);
+    } else {
+      const int b = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
+      s = 1.0f / fmaxf((float)(e - b), 1.0f);
+      o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = b; k < e; ++k) {
+        const float4 v = lds_f4(lane_base + (uint32_t)(__ldg(a.col + k) - (int)grow0) * row_bytes);
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      }
+    }
+    o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+    *reinterpret_cast<float4*>(a.out + row * a.ldo + sl * 4) = o;
+  }
+}
+
+
 // ------------------------------------------------------------------ ELL16 gather, table slice staged in shared memory
 // Same result as k_sage_gather_ell for the table shapes whose rows do not fit one register batch per thread (pitch 16
 // and / or weighted): there a thread serves its rows in up to 7 batches, each of which started with global loads of
@@ -522,11 +634,10 @@ k_sage_gather_ell_staged(const __grid_constant__ CUtensorMap map_x, const EllSta
   const EllGatherArgs& a = sa.g;
   constexpr int G = THREADS / LPR;
   constexpr int NW = W / 2;
-  const int nmax = a.nmax, feat = a.feat, parts = a.parts;
+  const int nmax = a.nmax, feat = a.feat;
   const int nrow8 = (nmax + 7) & ~7;
-  const int g = blockIdx.x / parts, p = blockIdx.x - g * parts;
-  const int r0 = p * a.rpp;
-  const int nrows = min(a.rpp, nrow8 - r0);            // > 0 by construction of parts, multiple of 8
+  int g, r0, nrows;
+  ell_cta_rows(a, nrow8, g, r0, nrows);                // > 0 rows by construction, multiple of 8
   pdl_launch_dependents();
   const int64_t grow0 = (int64_t)g * nmax;
   const int64_t trow0 = (int64_t)g * nrow8 + r0;
@@ -914,6 +1025,8 @@ extern "C" int cgc_csr_to_ell16(const int32_t* rowptr, const int32_t* col, const
   return 0;
 }
 
+static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override);
+
 template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
 static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cudaStream_t st) {
   const int nmax = a.nmax, feat = a.feat;
@@ -935,22 +1048,64 @@ static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cu
   static const int parts_override = lab_env("CGC_GATHER_PARTS", 0);      // lab switches: CGC_LAB builds only
   static const int chunk_override = lab_env("CGC_GATHER_CHUNK", 0);
   static const int stage = lab_env("CGC_GATHER_STAGE", 0);
-  int parts = parts_override > 0 ? parts_override : kNumSMs / num_graphs;
-  if (parts < 1) parts = 1;
-  const int nrow8 = (nmax + 7) & ~7;
-  int rpp = (int)ceil_div(nrow8, parts);
-  rpp = (rpp + 7) & ~7;                                 // CTAs own whole 8-row blocks of the table
-  parts = (int)ceil_div(nrow8, rpp);
-  a.parts = parts;
-  a.rpp = rpp;
+  const int grid = ell_row_split(a, num_graphs, parts_override);
   a.lab_stage = stage;
   a.chunk = chunk_override > 0 ? (uint32_t)chunk_override : kBulkChunk;
   auto kern = k_sage_gather_ell<W, LPR, WEIGHTED, RB, THREADS, STRIDED, ACC>;
   static size_t smem_set[kMaxDevices] = {};             // per instantiation and device
   CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
-  PdlLaunch L(dim3((unsigned)(num_graphs * parts)), dim3(THREADS), smem, st, pdl);
+  PdlLaunch L(dim3((unsigned)grid), dim3(THREADS), smem, st, pdl);
   CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, a));
   CGC_CHECK_LAUNCH("k_sage_gather_ell");
+  return 0;
+}
+
+// Row split of the gather grids: `parts` CTAs per graph (rpp rows each) and, when the grid would leave SMs idle, one
+// extra CTA for the first n_hi graphs (rpp_hi rows each).  Returns the grid size.
+static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override) {
+  const int nrow8 = (a.nmax + 7) & ~7;
+  int parts = parts_override > 0 ? parts_override : kNumSMs / num_graphs;
+  if (parts < 1) parts = 1;
+  int rpp = (int)ceil_div(nrow8, parts);
+  rpp = (rpp + 7) & ~7;                                 // CTAs own whole 8-row blocks of the table
+  parts = (int)ceil_div(nrow8, rpp);
+  a.parts = parts;
+  a.rpp = rpp;
+  a.n_hi = 0;
+  a.rpp_hi = rpp;
+  const int spare = kNumSMs - parts * num_graphs;       // SMs a plain split leaves idle
+  if (parts_override <= 0 && spare > 0) {
+    int rpp_hi = (int)ceil_div(nrow8, parts + 1);
+    rpp_hi = (rpp_hi + 7) & ~7;
+    if ((int)ceil_div(nrow8, rpp_hi) == parts + 1) {
+      a.n_hi = spare < num_graphs ? spare : num_graphs;
+      a.rpp_hi = rpp_hi;
+    }
+  }
+  return a.n_hi * (parts + 1) + (num_graphs - a.n_hi) * parts;
+}
+
+// The two-CTAs-per-SM variant of the roofline configuration (see k_sage_gather_ell_lean)
+static int launch_ell_lean(EllGatherArgs a, int num_graphs, bool pdl, cudaStream_t st) {
+  const size_t smem = ((size_t)a.nmax + 2) * a.feat * 4;
+  const int grid = ell_row_split(a, num_graphs, 0);
+  a.lab_stage = 0;
+  a.chunk = kBulkChunk;
+  static size_t smem_set[kMaxDevices] = {};
+  {
+    CGC_CUDA(ensure_dynamic_smem(k_sage_gather_ell_lean, smem, smem_set));
+    static bool carve[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < kMaxDevices && !carve[dev]) {   // two CTAs per SM need the whole 228 KB as shared memory
+      CGC_CUDA(cudaFuncSetAttribute(k_sage_gather_ell_lean, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
+      carve[dev] = true;
+    }
+  }
+  PdlLaunch L(dim3((unsigned)grid), dim3(kLeanThreads), smem, st, pdl);
+  CGC_CUDA(cudaLaunchKernelEx(&L.cfg, k_sage_gather_ell_lean, a));
+  CGC_CHECK_LAUNCH("k_sage_gather_ell_lean");
   return 0;
 }
 
@@ -972,23 +1127,17 @@ static int launch_ell_staged(EllGatherArgs a, int num_graphs, int64_t ldx, bool 
   }
   EllStagedArgs sa;
   sa.tile_smem = (int)((tile + 127) & ~(size_t)127);
-  int parts = kNumSMs / num_graphs;
-  if (parts < 1) parts = 1;
-  const int nrow8 = (nmax + 7) & ~7;
-  int rpp = (int)ceil_div(nrow8, parts);
-  rpp = (rpp + 7) & ~7;
+  const int grid = ell_row_split(a, num_graphs, 0);
   const size_t per_row = (size_t)W * 2 + 4 + (WEIGHTED ? (size_t)W * 4 : 0);
-  const size_t smem = (size_t)sa.tile_smem + (size_t)rpp * per_row;
+  const size_t smem = (size_t)sa.tile_smem + (size_t)a.rpp * per_row;
   if (smem + 1024 > 227 * 1024) return 1;
-  a.parts = (int)ceil_div(nrow8, rpp);
-  a.rpp = rpp;
   a.lab_stage = 0;
   a.chunk = kBulkChunk;
   sa.g = a;
   auto kern = k_sage_gather_ell_staged<W, LPR, WEIGHTED, THREADS, STRIDED, ACC>;
   static size_t smem_set[kMaxDevices] = {};             // per instantiation and device
   CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
-  PdlLaunch L(dim3((unsigned)(num_graphs * a.parts)), dim3(THREADS), smem, st, pdl);
+  PdlLaunch L(dim3((unsigned)grid), dim3(THREADS), smem, st, pdl);
   CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, map, sa));
   CGC_CHECK_LAUNCH("k_sage_gather_ell_staged");
   return 0;
@@ -1010,6 +1159,9 @@ static int ell_gather_dispatch(const uint16_t* ell, const float* ell_val, const 
   const bool acc = (flags & CGC_GATHER_ACCUMULATE) != 0;
   const bool pdl = (flags & CGC_GATHER_NO_PDL) == 0;
   if (!pdl) a.early_tables = 0;
+  if ((flags & CGC_GATHER_TWO_PER_SM) && !wt && !strided && !acc && ell_scale == nullptr && width == 8 && feat == 16 &&
+      ldo == feat && 2 * (((size_t)nmax + 2) * feat * 4 + 1024 + 128) <= 228 * 1024)
+    return launch_ell_lean(a, num_graphs, pdl, st);
   // pitch 16 and / or weighted tables: the variant with the table slice staged in shared memory, when it fits
 #define CGC_ELL_STAGED(W_, LPR_, WT_)                                                                     \
   do {                                                                                                    \

@@ -186,6 +186,8 @@ CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, c
 #define CGC_GATHER_ACCUMULATE 1
 #define CGC_GATHER_TABLES_READY 2
 #define CGC_GATHER_NO_PDL 4      /* plain stream-ordered launch (A/B measurements of the programmatic launch) */
+#define CGC_GATHER_TWO_PER_SM 8  /* roofline configuration only (pitch 8, unweighted, no scale vector, 16 contiguous
+                                    features): the 512-thread / 64-register variant of which two CTAs share an SM */
 CGC_API int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
                         const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
                         const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,
