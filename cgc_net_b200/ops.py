@@ -29,6 +29,10 @@ from . import _backend
 
 RENORM_P = 0.4       # model/network.py:260,271,280
 BUILD_TRANSPOSED_ELL = False     # see build_sparse_graph
+FOLD_BN_BACKWARD = False         # cgc_sage_dh_bn (BatchNorm backward formed inside the wide epilogue backward): correct
+                                 # (tests/test_gpu_ops.py::test_sage_dh_bn) but measured SLOWER at the BASELINE shape:
+                                 # the register-capped kernel goes from 713 us to 1192 us, more than the 295 us apply
+                                 # pass it removes -> off
 BUILD_BACKWARD_ELL = False       # ELL16 table of A^T for the narrow CSC gathers of the backward: measured 26.6 us per
                                  # gather (pitch 16, weighted, 7 index batches per thread) + 65 us to build the table vs
                                  # 24.9 us for the generic CSC gather -> off
@@ -414,7 +418,8 @@ class GnnModuleFunction(Function):
             gx = g_cat[:, offs[k]: offs[k] + couts[k]]
             gy = _f32(m, couts[k], device=dev)
             narrow = w.shape[1] <= 32 and w.shape[0] <= 64
-            fold_bn = cfg.has_bn and not narrow and 32 < w.shape[1] <= 1280 and w.shape[0] <= 64
+            fold_bn = (FOLD_BN_BACKWARD and cfg.has_bn and not narrow and 32 < w.shape[1] <= 1280
+                       and w.shape[0] <= 64)
             if cfg.has_bn:
                 d_gamma, d_beta = torch.empty_like(gamma), torch.empty_like(beta)
                 # wide layer: only the column sums here, the apply step is folded into the epilogue backward below

@@ -827,3 +827,23 @@ def test_sage_dh_bn(cuda_backend, cin, cout, training, act):
     REF.bn_bwd(gx, y, mean, invstd, gamma, mask, training, gy, torch.zeros(cout), torch.zeros(cout))
     REF.sage_dh(gy, sa, w, bias, y, mask, dh2, act)
     torch.testing.assert_close(dh, dh2, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('b,nmax,maxdeg', [(3, 70, 8), (64, 1800, 8), (5, 333, 10), (150, 40, 8), (2, 1750, 8)])
+@pytest.mark.parametrize('ready', [True, False])
+def test_sage_gather_ell_two_per_sm(cuda_backend, b, nmax, maxdeg, ready):
+    """The two-CTAs-per-SM variant of the roofline configuration (pitch 8, unweighted, no scale vector, 16 contiguous
+    features) and the balanced row split (some graphs get one more CTA so that the grid covers every SM; 64 graphs:
+    20 x 3 + 44 x 2 = 148) == the generic CSR mean; rows above the pitch walk the CSR (maxdeg 10)."""
+    rows, feat = b * nmax, 16
+    rowptr, col = _random_csr(rows, maxdeg, seed=nmax, block=nmax) if rows < 5000 else _knn_csr(b, nmax)
+    ell, _, _, perm = _ell_tables(rowptr, col, None, None, b, nmax, 8, 1)
+    x = torch.randn(rows, feat, generator=torch.Generator().manual_seed(3))
+    deg = (rowptr[1:] - rowptr[:-1]).float().clamp(min=1)
+    want = torch.zeros(rows, feat)
+    REF.spmm(rowptr, col, None, x, None, 1.0 / deg, want, False)
+    for two in (True, False):
+        out = torch.zeros(rows, feat)
+        both(cuda_backend, 'sage_gather_ell', [ell, None, None, perm, 8, rowptr, col, None, x, b, nmax, out, False, ready,
+                                               True, two], [11], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
