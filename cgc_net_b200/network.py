@@ -102,9 +102,10 @@ class GNN_Module(nn.Module):
         else:
             self.lin = None
 
-    def forward(self, x, adj, mask=None, graph=None, num_graphs=None, nmax=None, scale=None):
+    def forward(self, x, adj, mask=None, graph=None, num_graphs=None, nmax=None, scale=None, agg_cache=None):
         """``x [M, Cin]`` in the padded node layout.  Either ``graph`` (``ops.SparseGraph``,
-        stage 1) or a dense ``adj [B, N, N]`` with ``scale = ops.dense_row_scale(adj)``."""
+        stage 1) or a dense ``adj [B, N, N]`` with ``scale = ops.dense_row_scale(adj)``; ``agg_cache`` = a dict shared
+        by the modules of one dense stage (the first layer's ``A x`` is computed once)."""
         if self.gin:
             return self._forward_gin(x, adj, mask, graph, num_graphs, nmax)
         params, buffers = [], []
@@ -128,7 +129,7 @@ class GNN_Module(nn.Module):
         rs, rsum = scale
         cfg = ops.GnnConfig(graph=None, num_graphs=num_graphs, nmax=nmax, mask=mask,
                             training=self.training, has_bn=self.has_bn,
-                            has_lin=self.lin is not None, bn_buffers=buffers, act=self.act)
+                            has_lin=self.lin is not None, bn_buffers=buffers, act=self.act, agg_cache=agg_cache)
         return ops.GnnModuleFunction.apply(cfg, x, adj, rs, rsum, *params)
 
     def _forward_gin(self, x, adj, mask, graph, num_graphs, nmax):
@@ -291,9 +292,11 @@ class SoftPoolingGcnEncoder(nn.Module):
                 adj = ops.DenseRenormFunction.apply(adj, ops.RENORM_P, mask)
             scale = ops.dense_row_scale(adj)
 
+        sage = not self.GCN_embed_1.gin
         for stage in (1, 2, 3):
             embed = getattr(self, 'GCN_embed_%d' % stage)
-            feat = embed(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
+            kw = dict(agg_cache={}) if (sage and graph is None) else {}      # dense stage: A x of layer 1 shared
+            feat = embed(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale, **kw)
             if self.jk:
                 feat = getattr(self, 'jk%d' % stage)(feat, b, n)
             pooled, _ = ops.ColMaxFunction.apply(feat, b, n)
@@ -301,7 +304,7 @@ class SoftPoolingGcnEncoder(nn.Module):
             if stage == 3:
                 break
             pool = getattr(self, 'GCN_pool_%d' % stage)
-            assign = pool(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale)
+            assign = pool(x, adj, mask, graph=graph, num_graphs=b, nmax=n, scale=scale, **kw)
             cfg = ops.GnnConfig(graph=graph, num_graphs=b, nmax=n, mask=mask)
             xp, ap, s_full, arg = ops.DiffPoolFunction.apply(cfg, assign, feat, adj, self.collect_assign)
             if self.collect_assign:

@@ -217,13 +217,17 @@ class GnnConfig(object):
     """Static description of one ``GNN_Module`` call (not a tensor; passed through autograd)."""
 
     def __init__(self, graph=None, num_graphs=0, nmax=0, mask=None, training=True, has_bn=True,
-                 has_lin=False, bn_buffers=None, need_adj_grad=False, act=0):
+                 has_lin=False, bn_buffers=None, need_adj_grad=False, act=0, agg_cache=None):
         self.graph = graph              # SparseGraph, or None when the adjacency is dense
         self.num_graphs, self.nmax = num_graphs, nmax
         self.mask = mask                # RowMask or None
         self.training, self.has_bn, self.has_lin = training, has_bn, has_lin
         self.bn_buffers = bn_buffers    # [(running_mean, running_var)] * 3 (updated in place)
         self.need_adj_grad = need_adj_grad
+        # dense stages: {(adjacency, layer-1 input) -> aggregated input}.  GCN_embed_k and GCN_pool_k aggregate the
+        # SAME x over the SAME adjacency in their first layer (network.py:270-276): the second module reuses the
+        # first one's A'x instead of reading the 333 MB adjacency again
+        self.agg_cache = agg_cache
         self.act = act                  # ACTIVATIONS[name]: 0 relu, 1 elu, 2 leakyrelu (network.py:82-90)
 
 
@@ -341,7 +345,13 @@ class GnnModuleFunction(Function):
                 saved += [a, y, mean, invstd]
                 x_prev, off = dst, off + couts[k]
                 continue
-            _agg(be, cfg, adj, rs, x_prev, a)
+            key = (adj.data_ptr(), x_prev.data_ptr(), tuple(x_prev.shape)) if (k == 0 and g is None) else None
+            if key is not None and cfg.agg_cache is not None and key in cfg.agg_cache:
+                a = cfg.agg_cache[key]
+            else:
+                _agg(be, cfg, adj, rs, x_prev, a)
+                if key is not None and cfg.agg_cache is not None:
+                    cfg.agg_cache[key] = a
             if cfg.has_bn and cfg.training and couts[k] <= 32 and w.shape[0] <= 64:
                 # narrow layer: epilogue and BatchNorm batch statistics in ONE pass over the rows
                 be.sage_layer_fwd_narrow(a, w, b, cfg.mask, y, cfg.act, rmean, rvar, BN_MOMENTUM, BN_EPS, mean, invstd)
