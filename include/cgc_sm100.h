@@ -140,12 +140,15 @@ CGC_API int cgc_sage_gather_mean_fwd(const int32_t* rowptr, const int32_t* col, 
                              const float* row_scale, const float* x, int32_t num_graphs,
                              int32_t nmax, int32_t feat, float* out, void* stream);
 
-/* Row-padded CSR ("ELL16") of the stage-1 adjacency, the index layout of cgc_sage_gather_ell_fwd.
+/* Row-padded CSR ("ELL16") of the stage-1 adjacency, the index layout of cgc_sage_gather_ell, cgc_sage_layer_ell_fwd
+ * and cgc_gather_wide_ell.
  * Graph g owns nrow8 = round_up(nmax, 8) table rows (cgc_ell16_rows() = num_graphs * nrow8 in total); table row
  * g*nrow8 + 8*blk + p holds the entries of local row 8*blk + ((perm[g*nrow8/8 + blk] >> 3p) & 7):
- *   ell[row * width + t] = LOCAL column id (column - g*nmax, uint16) of its t-th entry, `nmax` in unused slots
- *   (and everywhere for rows beyond nmax); a row with more than `width` entries gets slot 0 = nmax + 1 and the
- *   gather walks the CSR for it.  ell_val (nullable, with val) carries the entry weights, 0 in unused slots.
+ *   ell[row * width + t] = LOCAL column id (column - g*nmax, 12 bits of a uint16: nmax + 1 <= 4095) of its t-th
+ *   entry, `nmax` in unused slots (and everywhere for rows beyond nmax); a row with more than `width` entries gets
+ *   slot 0 = nmax + 1 and the gather walks the CSR for it.  Slot 0 additionally carries, in bits 12-14, the local row
+ *   (0..7 within its block) the table row serves -- the same information as `perm`, readable without a second load.
+ *   ell_val (nullable, with val) carries the entry weights, 0 in unused slots.
  * pair_rows != 0 chooses the slot order and the row-to-position map that minimise shared-memory bank conflicts
  * for 64-byte feature rows (slots go "even columns first" on even positions / "odd first" on odd ones; the
  * 8 rows of a block are paired smallest-with-largest even count); pair_rows == 0 keeps CSR order and the

@@ -79,6 +79,15 @@ if has gemmlab; then
   env TA=1 TB=0 M=1140 N=1180 K=115200 CGC_TC_BWARPS=1 timeout 120 python tools/profile_gemm.py >> $OUT/gemm_lab.log 2>&1
   cat $OUT/gemm_lab.log
 fi
+if has gatherstages; then
+  # timeline of the gather kernel: LAB build, kernel truncated at entry (1) / after the tile copy (2)
+  make -C cgc_net_b200/csrc clean > /dev/null; make -C cgc_net_b200/csrc LAB=1 -j > $OUT/build_lab.log 2>&1
+  : > $OUT/gather_stages.log
+  for st in 0 1 2; do
+    CGC_GATHER_STAGE=$st timeout 300 python tools/gather_lab.py --variants ell,ell-nopdl >> $OUT/gather_stages.log 2>&1
+  done
+  cat $OUT/gather_stages.log
+fi
 if has sanitizer; then
   for tool in memcheck racecheck synccheck; do
     timeout 900 compute-sanitizer --tool $tool --log-file $OUT/sanitizer_$tool.log \
