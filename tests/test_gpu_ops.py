@@ -324,7 +324,7 @@ def test_scale_rows_bwd(cuda_backend):
 
 
 # ------------------------------------------------------------------------------- batch norm
-@pytest.mark.parametrize('c', [20, 114, 1140])
+@pytest.mark.parametrize('c', [20, 114, 300, 1140])            # 300, 1140: the float4 column reductions
 @pytest.mark.parametrize('masked', [False, True])
 def test_batchnorm(cuda_backend, c, masked):
     b, nmax = 4, 701
