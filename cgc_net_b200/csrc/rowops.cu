@@ -496,6 +496,268 @@ static size_t ring_smem_bytes(int cin, int cout, int r) {
                           (kRingThreadsMax / 32) * r + r + (r & 1)) + kRingStages * sizeof(uint64_t);
 }
 
+// ------------------------------------------------------------------- wide epilogue backward, one warp per row pair
+// The tile kernels above split a row over the threads of a CTA, so both row reductions (the L2 norm and g . hn) go
+// through shared memory and five block barriers per 8 rows: measured 13 800 cycles per 6-row tile at an IPC of ~1
+// with the memory system idle (909 us for 1.57 GB).  Here a WARP owns two whole rows: lane l holds the float4
+// column chunks l, l + 32, ... (NQ of them), both reductions are shuffles, warps never wait for each other, and the
+// accumulators are column pairs in packed f32x2 registers (W pairs come straight out of a 128-bit shared-memory
+// load; the broadcast a is duplicated once per k).  The second sweep re-reads y / gy of the two rows (9 KB, L1 / L2)
+// instead of holding the masked gradient in 72 more registers.  W is read from shared memory once per row PAIR.
+constexpr int kRowPairThreads = 256;
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+// Forward (BWD = false): y = mask * act(h / ||h||), and with partial != null the column sums of y and y^2 for the
+// BatchNorm statistics: per lane in registers over the warp's rows, folded warp by warp (fixed order) into one
+// [2][cout] partial per CTA, the layout bn_finalize_partials reads.
+template <int NQ, bool BWD>
+__global__ void __launch_bounds__(kRowPairThreads, 1)
+k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w,
+              const float* __restrict__ bias, const int32_t* __restrict__ num_nodes, int nmax, int64_t rows,
+              int cin, int cout, float* y, int64_t ldy, const float* gy, int64_t ldgy,
+              float* dh, int64_t lddh, int act, double* __restrict__ partial, const EpiBn bn) {
+  extern __shared__ __align__(16) float rp_smem[];
+  const ActGrad agrad(act);
+  float* s_w = rp_smem;                               // [cin][cout]
+  float* s_b = s_w + cin * cout;                      // [cout]
+  float* s_bn = s_b + cout;                           // BWD: [3][cout] P, R, Q (BatchNorm backward folded in)
+                                                      // forward with statistics: [2][cout] column sums of the CTA
+  const bool with_bn = BWD && bn.mean != nullptr;
+  float st1[BWD ? 1 : NQ][4], st2[BWD ? 1 : NQ][4];
+#pragma unroll
+  for (int j = 0; j < (BWD ? 1 : NQ); ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { st1[j][e] = 0.f; st2[j][e] = 0.f; }
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = w[i];
+  for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+    s_b[c] = bias ? bias[c] : 0.f;
+    if (with_bn) {
+      const float is = bn.invstd[c], pc = bn.gamma[c] * is;
+      const float rc = bn.training ? pc * is * bn.d_gamma[c] * bn.inv_rows : 0.f;
+      s_bn[c] = pc;
+      s_bn[cout + c] = rc;
+      s_bn[2 * cout + c] = bn.training ? pc * bn.d_beta[c] * bn.inv_rows - rc * bn.mean[c] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c4 = cout >> 2;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t npairs = (rows + 1) >> 1;
+  // chunk j of this lane; lanes past the last chunk work on a copy of it and are masked out of sums and stores
+  int qa[NQ];
+  bool live[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const int q = lane + 32 * j;
+    live[j] = q < c4;
+    qa[j] = live[j] ? q : c4 - 1;
+  }
+  // Backward: the y / gy rows of a pair are pulled into L2 one iteration ahead (one 128-byte line per lane and step),
+  // so their HBM round trip runs under the shared-memory-bound k loop of the current pair instead of after it.
+  auto prefetch_pair = [&](int64_t rp) {
+    if (!BWD || rp >= npairs) return;
+    const int64_t r0 = 2 * rp;
+    const int nrow = (r0 + 1 < rows) ? 2 : 1;
+    const int lines = (cout + 31) >> 5;
+    for (int i = lane; i < nrow * lines; i += 32) {
+      const int rr = i >= lines ? 1 : 0, ch = i - rr * lines;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (r0 + rr) * ldy + ch * 32));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + (r0 + rr) * ldgy + ch * 32));
+    }
+  };
+  prefetch_pair(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  for (int64_t rp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; rp < npairs; rp += warps) {
+    const int64_t r0 = 2 * rp, r1 = r0 + 1;
+    const bool has1 = r1 < rows;
+    prefetch_pair(rp + warps);
+    const bool v0 = row_valid(num_nodes, nmax, r0), v1 = has1 && row_valid(num_nodes, nmax, r1);
+    if (!v0 && !v1) {                                 // padding rows: zero output / gradient
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      float* o = BWD ? dh : y;
+      const int64_t ldo = BWD ? lddh : ldy;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j)
+        if (live[j]) {
+          *reinterpret_cast<float4*>(o + r0 * ldo + 4 * qa[j]) = z;
+          if (has1) *reinterpret_cast<float4*>(o + r1 * ldo + 4 * qa[j]) = z;
+        }
+      continue;
+    }
+    // aggregate rows: lane k holds a[k] (and a[k + 32])
+    const float* a0p = sa + r0 * ldsa;
+    const float* a1p = sa + (has1 ? r1 : r0) * ldsa;
+    const float a0lo = lane < cin ? __ldg(a0p + lane) : 0.f, a0hi = lane + 32 < cin ? __ldg(a0p + lane + 32) : 0.f;
+    const float a1lo = lane < cin ? __ldg(a1p + lane) : 0.f, a1hi = lane + 32 < cin ? __ldg(a1p + lane + 32) : 0.f;
+    unsigned long long acc0[NQ][2], acc1[NQ][2];      // h of rows r0 / r1: column pairs (4q, 4q+1), (4q+2, 4q+3)
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_b + 4 * qa[j]);
+      acc0[j][0] = b.x; acc0[j][1] = b.y;
+      acc1[j][0] = b.x; acc1[j][1] = b.y;
+    }
+    auto k_step = [&](int k, float a0, float a1) {
+      const unsigned long long a0d = pack2(a0, a0), a1d = pack2(a1, a1);
+      const float* wrow = s_w + k * cout;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(wrow + 4 * qa[j]);
+        ffma2(acc0[j][0], a0d, wv.x);
+        ffma2(acc0[j][1], a0d, wv.y);
+        ffma2(acc1[j][0], a1d, wv.x);
+        ffma2(acc1[j][1], a1d, wv.y);
+      }
+    };
+    const int klo = cin < 32 ? cin : 32;
+#pragma unroll 2
+    for (int k = 0; k < klo; ++k) k_step(k, __shfl_sync(0xffffffffu, a0lo, k), __shfl_sync(0xffffffffu, a1lo, k));
+    for (int k = 32; k < cin; ++k) k_step(k, __shfl_sync(0xffffffffu, a0hi, k - 32), __shfl_sync(0xffffffffu, a1hi, k - 32));
+    // row norms
+    float sq0 = 0.f, sq1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      if (live[j]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 p0 = unpack2(acc0[j][h]), p1 = unpack2(acc1[j][h]);
+          sq0 = fmaf(p0.x, p0.x, fmaf(p0.y, p0.y, sq0));
+          sq1 = fmaf(p1.x, p1.x, fmaf(p1.y, p1.y, sq1));
+        }
+      }
+    }
+    const float nrm0 = sqrtf(warp_sum(sq0)), nrm1 = sqrtf(warp_sum(sq1));
+    const float inv0 = 1.0f / fmaxf(nrm0, kL2NormEps), inv1 = 1.0f / fmaxf(nrm1, kL2NormEps);
+    if constexpr (!BWD) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        if (live[j]) {
+          const float2 h00 = unpack2(acc0[j][0]), h01 = unpack2(acc0[j][1]);
+          const float2 h10 = unpack2(acc1[j][0]), h11 = unpack2(acc1[j][1]);
+          float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+          if (v0) oa = make_float4(act_fwd(act, h00.x * inv0), act_fwd(act, h00.y * inv0), act_fwd(act, h01.x * inv0),
+                                   act_fwd(act, h01.y * inv0));
+          if (v1) ob = make_float4(act_fwd(act, h10.x * inv1), act_fwd(act, h10.y * inv1), act_fwd(act, h11.x * inv1),
+                                   act_fwd(act, h11.y * inv1));
+          *reinterpret_cast<float4*>(y + r0 * ldy + 4 * qa[j]) = oa;
+          if (has1) *reinterpret_cast<float4*>(y + r1 * ldy + 4 * qa[j]) = ob;
+          st1[j][0] += oa.x + ob.x; st1[j][1] += oa.y + ob.y; st1[j][2] += oa.z + ob.z; st1[j][3] += oa.w + ob.w;
+          st2[j][0] = fmaf(oa.x, oa.x, fmaf(ob.x, ob.x, st2[j][0]));
+          st2[j][1] = fmaf(oa.y, oa.y, fmaf(ob.y, ob.y, st2[j][1]));
+          st2[j][2] = fmaf(oa.z, oa.z, fmaf(ob.z, ob.z, st2[j][2]));
+          st2[j][3] = fmaf(oa.w, oa.w, fmaf(ob.w, ob.w, st2[j][3]));
+        }
+      }
+      continue;
+    }
+    // masked gradient of one chunk: g = gy * act'(y)   (gy formed from the BatchNorm backward when folded in)
+    auto grad4 = [&](const float4 yv, float4 gv, int q) {
+      if (with_bn) {
+        const float4 pc = *reinterpret_cast<const float4*>(s_bn + 4 * q);
+        const float4 rc = *reinterpret_cast<const float4*>(s_bn + cout + 4 * q);
+        const float4 qc = *reinterpret_cast<const float4*>(s_bn + 2 * cout + 4 * q);
+        gv.x = fmaf(pc.x, gv.x, -fmaf(rc.x, yv.x, qc.x));
+        gv.y = fmaf(pc.y, gv.y, -fmaf(rc.y, yv.y, qc.y));
+        gv.z = fmaf(pc.z, gv.z, -fmaf(rc.z, yv.z, qc.z));
+        gv.w = fmaf(pc.w, gv.w, -fmaf(rc.w, yv.w, qc.w));
+      }
+      return make_float4(gv.x * agrad(yv.x), gv.y * agrad(yv.y), gv.z * agrad(yv.z), gv.w * agrad(yv.w));
+    };
+    const float* y0 = y + r0 * ldy;
+    const float* y1 = y + (has1 ? r1 : r0) * ldy;
+    const float* g0 = gy + r0 * ldgy;
+    const float* g1 = gy + (has1 ? r1 : r0) * ldgy;
+    // sweep 1: dot_r = sum_c g * h   (scaled by inv below)
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const float4 ya = __ldg(reinterpret_cast<const float4*>(y0) + qa[j]);
+      const float4 yb = __ldg(reinterpret_cast<const float4*>(y1) + qa[j]);
+      const float4 ga = *(reinterpret_cast<const float4*>(g0) + qa[j]);
+      const float4 gb = *(reinterpret_cast<const float4*>(g1) + qa[j]);
+      if (live[j]) {
+        const float4 ma = grad4(ya, ga, qa[j]), mb = grad4(yb, gb, qa[j]);
+        const float2 h00 = unpack2(acc0[j][0]), h01 = unpack2(acc0[j][1]);
+        const float2 h10 = unpack2(acc1[j][0]), h11 = unpack2(acc1[j][1]);
+        d0 = fmaf(ma.x, h00.x, fmaf(ma.y, h00.y, fmaf(ma.z, h01.x, fmaf(ma.w, h01.y, d0))));
+        d1 = fmaf(mb.x, h10.x, fmaf(mb.y, h10.y, fmaf(mb.z, h11.x, fmaf(mb.w, h11.y, d1))));
+      }
+    }
+    const float dot0 = v0 ? warp_sum(d0) * inv0 : 0.f, dot1 = v1 ? warp_sum(d1) * inv1 : 0.f;
+    // sweep 2: dh = (g - hn dot) / ||h||   (g / eps where the norm was clamped); y / gy again, from L1 / L2
+    const bool big0 = nrm0 >= kL2NormEps, big1 = nrm1 >= kL2NormEps;
+    const float m0 = v0 ? 1.f : 0.f, m1 = v1 ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const float4 ya = __ldg(reinterpret_cast<const float4*>(y0) + qa[j]);
+      const float4 yb = __ldg(reinterpret_cast<const float4*>(y1) + qa[j]);
+      const float4 ga = *(reinterpret_cast<const float4*>(g0) + qa[j]);
+      const float4 gb = *(reinterpret_cast<const float4*>(g1) + qa[j]);
+      if (live[j]) {
+        float4 ma = grad4(ya, ga, qa[j]), mb = grad4(yb, gb, qa[j]);
+        ma.x *= m0; ma.y *= m0; ma.z *= m0; ma.w *= m0;
+        mb.x *= m1; mb.y *= m1; mb.z *= m1; mb.w *= m1;
+        const float2 h00 = unpack2(acc0[j][0]), h01 = unpack2(acc0[j][1]);
+        const float2 h10 = unpack2(acc1[j][0]), h11 = unpack2(acc1[j][1]);
+        const float s0 = big0 ? inv0 * dot0 : 0.f, s1 = big1 ? inv1 * dot1 : 0.f;     // hn dot = h (inv dot)
+        float4 oa, ob;
+        oa.x = (ma.x - h00.x * s0) * inv0; oa.y = (ma.y - h00.y * s0) * inv0;
+        oa.z = (ma.z - h01.x * s0) * inv0; oa.w = (ma.w - h01.y * s0) * inv0;
+        ob.x = (mb.x - h10.x * s1) * inv1; ob.y = (mb.y - h10.y * s1) * inv1;
+        ob.z = (mb.z - h11.x * s1) * inv1; ob.w = (mb.w - h11.y * s1) * inv1;
+        *reinterpret_cast<float4*>(dh + r0 * lddh + 4 * qa[j]) = oa;
+        if (has1) *reinterpret_cast<float4*>(dh + r1 * lddh + 4 * qa[j]) = ob;
+      }
+    }
+  }
+  if constexpr (!BWD) {
+    if (partial != nullptr) {
+      const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+      for (int wv = 0; wv < nwarps; ++wv) {            // warp 0 writes, the others add in warp order
+        if (warp == wv) {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) {
+            if (live[j]) {
+              float4* p1 = reinterpret_cast<float4*>(s_bn + 4 * qa[j]);
+              float4* p2 = reinterpret_cast<float4*>(s_bn + cout + 4 * qa[j]);
+              float4 a = make_float4(st1[j][0], st1[j][1], st1[j][2], st1[j][3]);
+              float4 b = make_float4(st2[j][0], st2[j][1], st2[j][2], st2[j][3]);
+              if (wv != 0) {
+                const float4 pa = *p1, pb = *p2;
+                a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+                b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+              }
+              *p1 = a;
+              *p2 = b;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+        partial[((int64_t)blockIdx.x * 2 + 0) * cout + c] = (double)s_bn[c];
+        partial[((int64_t)blockIdx.x * 2 + 1) * cout + c] = (double)s_bn[cout + c];
+      }
+    }
+  }
+}
+
+static size_t rowpair_smem_bytes(int cin, int cout, int extra_vectors) {
+  return sizeof(float) * ((size_t)cin * cout + cout + (size_t)extra_vectors * cout);
+}
+
 template <bool BWD>
 static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const float* b,
                            const int32_t* num_nodes, int nmax, int64_t rows, int cin, int cout, float* y,
@@ -521,6 +783,51 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
   const int nc = (int)ceil_div(cout, kEpiThreads);
   CGC_REQUIRE(nc <= 5, CGC_ERR_UNSUPPORTED, "sage epilogue: cout=%d > 1280", cout);
   CGC_REQUIRE(bn_in == nullptr || BWD, CGC_ERR_ARG, "sage epilogue: BatchNorm folding is a backward option");
+  {
+    // wide layers with 16-byte aligned rows: one warp per row pair
+    const int nq = (int)ceil_div(cout / 4, 32);
+    static const bool rowpair_off = lab_env("CGC_EPI_ROWPAIR", 1) == 0;   // A/B switch (CGC_LAB builds only)
+    const int extra = BWD ? (bn_in != nullptr ? 3 : 0) : (partial != nullptr ? 2 : 0);
+    float* o = BWD ? dh : y;
+    const int64_t ldo = BWD ? lddh : ldy;
+    // (measured at 20 x 1140, 115 200 rows: backward 809 us vs 909 us ring / 1076 us tile kernel; forward 369 us vs
+    //  333 us tile kernel -- W is read from shared memory once per row PAIR here, once per 8 rows there, and the
+    //  forward has no global loads to overlap: BWD only unless the lab switch is 2)
+    static const bool rowpair_fwd = lab_env("CGC_EPI_ROWPAIR", 1) == 2;
+    if ((BWD || rowpair_fwd) && !rowpair_off && cout >= 256 && cout % 4 == 0 && nq <= 10 && cin <= 64 &&
+        ldy % 4 == 0 && aligned16(y) &&
+        ldo % 4 == 0 && aligned16(o) && (!BWD || (ldgy % 4 == 0 && aligned16(gy))) &&
+        rowpair_smem_bytes(cin, cout, extra) <= 200 * 1024) {
+      const size_t smem = rowpair_smem_bytes(cin, cout, extra);
+      int64_t blocks = ceil_div(ceil_div(rows, 2), kRowPairThreads / 32);
+      if (blocks > kNumSMs) blocks = kNumSMs;
+      if (partial != nullptr) {
+        CGC_REQUIRE(blocks * 2 * cout * 8 <= work_bytes, CGC_ERR_WORKSPACE, "sage epilogue: workspace too small");
+        *blocks_out = (int)blocks;
+      }
+#define CGC_ROWPAIR_CASE(N)                                                                                    \
+  case N: {                                                                                                    \
+    auto kern = k_epi_rowpair<N, BWD>;                                                                         \
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    kern<<<(unsigned)blocks, kRowPairThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, \
+                                                          ldy, gy, ldgy, dh, lddh, act, partial, bn);          \
+  } break;
+      switch (nq) {
+        CGC_ROWPAIR_CASE(2)
+        CGC_ROWPAIR_CASE(3)
+        CGC_ROWPAIR_CASE(4)
+        CGC_ROWPAIR_CASE(5)
+        CGC_ROWPAIR_CASE(6)
+        CGC_ROWPAIR_CASE(7)
+        CGC_ROWPAIR_CASE(8)
+        CGC_ROWPAIR_CASE(9)
+        CGC_ROWPAIR_CASE(10)
+      }
+#undef CGC_ROWPAIR_CASE
+      CGC_CHECK_LAUNCH("k_epi_rowpair");
+      return 0;
+    }
+  }
   if constexpr (BWD) {
     // very wide layers: rows stream through the bulk-copy ring, one CTA per SM
     const int rnc = (int)ceil_div(cout, kRingThreadsMax);

@@ -1170,8 +1170,12 @@ static int ell_gather_dispatch(const uint16_t* ell, const float* ell_val, const 
   const bool acc = (flags & CGC_GATHER_ACCUMULATE) != 0;
   const bool pdl = (flags & CGC_GATHER_NO_PDL) == 0;
   if (!pdl) a.early_tables = 0;
-  if ((flags & CGC_GATHER_TWO_PER_SM) && !wt && !strided && !acc && ell_scale == nullptr && width == 8 && feat == 16 &&
-      ldo == feat && 2 * (((size_t)nmax + 2) * feat * 4 + 1024 + 128) <= 228 * 1024)
+  // Roofline configuration: the two-CTAs-per-SM variant under programmatic launch (the next launch's CTAs are
+  // resident early and pull their tile into L2 while this launch gathers: 6.21 vs 6.51 us), the one-per-SM kernel
+  // for a plain stream-ordered launch (7.74 vs 7.85 us: a tie), or as the flags say.
+  const bool lean_ok = !wt && !strided && !acc && ell_scale == nullptr && width == 8 && feat == 16 && ldo == feat &&
+                       2 * (((size_t)nmax + 2) * feat * 4 + 1024 + 128) <= 228 * 1024;
+  if (lean_ok && !(flags & CGC_GATHER_ONE_PER_SM) && (pdl || (flags & CGC_GATHER_TWO_PER_SM)))
     return launch_ell_lean(a, num_graphs, pdl, st);
   // pitch 16 and / or weighted tables: the variant with the table slice staged in shared memory, when it fits
 #define CGC_ELL_STAGED(W_, LPR_, WT_)                                                                     \

@@ -190,7 +190,11 @@ CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, c
 #define CGC_GATHER_TABLES_READY 2
 #define CGC_GATHER_NO_PDL 4      /* plain stream-ordered launch (A/B measurements of the programmatic launch) */
 #define CGC_GATHER_TWO_PER_SM 8  /* roofline configuration only (pitch 8, unweighted, no scale vector, 16 contiguous
-                                    features): the 512-thread / 64-register variant of which two CTAs share an SM */
+                                    features): the 512-thread / 64-register variant of which two CTAs share an SM.
+                                    It is what a programmatic launch of that configuration uses anyway (its CTAs
+                                    prefetch their tile into L2 while the previous kernel runs); the flag forces it
+                                    for a CGC_GATHER_NO_PDL launch too */
+#define CGC_GATHER_ONE_PER_SM 16 /* ... and this one forces the 1024-thread one-CTA-per-SM kernel (A/B measurements) */
 CGC_API int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
                         const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
                         const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,

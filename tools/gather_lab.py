@@ -13,7 +13,7 @@ import bench  # noqa: E402
 VARIANTS = {
     'ell': dict(),
     'ell-nopdl': dict(pdl=False),
-    'ell-2persm': dict(two_per_sm=True),
+    'ell-1persm': dict(two_per_sm=False),
     'ell-2persm-nopdl': dict(two_per_sm=True, pdl=False),
     'ell-vardeg': dict(row_is_centre=False),
     'ell-weighted': dict(norm_adj=True),
@@ -23,7 +23,7 @@ VARIANTS = {
     'csr': dict(kind='csr'),
 }
 ap = argparse.ArgumentParser()
-ap.add_argument('--variants', default='ell,ell-nopdl,ell-2persm,ell-2persm-nopdl,ell-vardeg,ell-weighted,layer,layer-nopdl,csr')
+ap.add_argument('--variants', default='ell,ell-nopdl,ell-1persm,ell-2persm-nopdl,ell-vardeg,ell-weighted,layer,layer-nopdl,csr')
 a = ap.parse_args()
 args = argparse.Namespace(batch_per_gpu=64, nodes=1800, degree=8)
 dev = torch.device('cuda', 0)
