@@ -37,6 +37,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// The same copy delivered to the same shared-memory offset of every CTA of the cluster named in `mask` (one L2 read
+// for all of them); each destination's mbarrier at the offset of `bar` counts the bytes
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // 2-D tiled TMA load (box described by the tensor map) global -> shared
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -130,17 +149,29 @@ inline int pick_box_rows(int nmax, int row_bytes, int nbuf, int64_t budget, int6
 // Launch attribute list for a kernel that uses pdl_wait(): programmatic stream serialization.
 struct PdlLaunch {
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
-  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl) {
+  cudaLaunchAttribute attr[2];
+  // cluster > 1: thread-block clusters of that many consecutive CTAs
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, int cluster = 1) {
     cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    int n = 0;
+    if (pdl) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    if (cluster > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = (unsigned)cluster;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
   }
 };
 

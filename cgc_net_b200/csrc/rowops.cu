@@ -504,7 +504,8 @@ static size_t ring_smem_bytes(int cin, int cout, int r) {
 // accumulators are column pairs in packed f32x2 registers (W pairs come straight out of a 128-bit shared-memory
 // load; the broadcast a is duplicated once per k).  The second sweep re-reads y / gy of the two rows (9 KB, L1 / L2)
 // instead of holding the masked gradient in 72 more registers.  W is read from shared memory once per row PAIR.
-constexpr int kRowPairThreads = 256;
+constexpr int kRowPairThreads = 384;      // 12 warps at 168 registers (a few spilled words) beat 8 warps at 255: 655 vs 695 us
+constexpr int kRowPairThreadsAlt = 256;   // lab switch CGC_EPI_ROWPAIR_THREADS=256
 
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   unsigned long long v;
@@ -523,8 +524,8 @@ __device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long lon
 // Forward (BWD = false): y = mask * act(h / ||h||), and with partial != null the column sums of y and y^2 for the
 // BatchNorm statistics: per lane in registers over the warp's rows, folded warp by warp (fixed order) into one
 // [2][cout] partial per CTA, the layout bn_finalize_partials reads.
-template <int NQ, bool BWD>
-__global__ void __launch_bounds__(kRowPairThreads, 1)
+template <int NQ, bool BWD, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w,
               const float* __restrict__ bias, const int32_t* __restrict__ num_nodes, int nmax, int64_t rows,
               int cin, int cout, float* y, int64_t ldy, const float* gy, int64_t ldgy,
@@ -799,19 +800,25 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
         ldo % 4 == 0 && aligned16(o) && (!BWD || (ldgy % 4 == 0 && aligned16(gy))) &&
         rowpair_smem_bytes(cin, cout, extra) <= 200 * 1024) {
       const size_t smem = rowpair_smem_bytes(cin, cout, extra);
-      int64_t blocks = ceil_div(ceil_div(rows, 2), kRowPairThreads / 32);
+      static const int threads =
+          lab_env("CGC_EPI_ROWPAIR_THREADS", kRowPairThreads) == kRowPairThreadsAlt ? kRowPairThreadsAlt : kRowPairThreads;
+      int64_t blocks = ceil_div(ceil_div(rows, 2), threads / 32);
       if (blocks > kNumSMs) blocks = kNumSMs;
       if (partial != nullptr) {
         CGC_REQUIRE(blocks * 2 * cout * 8 <= work_bytes, CGC_ERR_WORKSPACE, "sage epilogue: workspace too small");
         *blocks_out = (int)blocks;
       }
-#define CGC_ROWPAIR_CASE(N)                                                                                    \
-  case N: {                                                                                                    \
-    auto kern = k_epi_rowpair<N, BWD>;                                                                         \
+#define CGC_ROWPAIR_LAUNCH(N, T)                                                                               \
+  {                                                                                                            \
+    auto kern = k_epi_rowpair<N, BWD, T>;                                                                      \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    kern<<<(unsigned)blocks, kRowPairThreads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, \
-                                                          ldy, gy, ldgy, dh, lddh, act, partial, bn);          \
-  } break;
+    kern<<<(unsigned)blocks, T, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, gy, ldgy, \
+                                            dh, lddh, act, partial, bn);                                       \
+  }
+#define CGC_ROWPAIR_CASE(N)                                                                                    \
+  case N:                                                                                                      \
+    if (threads == kRowPairThreads) CGC_ROWPAIR_LAUNCH(N, kRowPairThreads) else CGC_ROWPAIR_LAUNCH(N, kRowPairThreadsAlt) \
+    break;
       switch (nq) {
         CGC_ROWPAIR_CASE(2)
         CGC_ROWPAIR_CASE(3)
@@ -824,6 +831,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
         CGC_ROWPAIR_CASE(10)
       }
 #undef CGC_ROWPAIR_CASE
+#undef CGC_ROWPAIR_LAUNCH
       CGC_CHECK_LAUNCH("k_epi_rowpair");
       return 0;
     }

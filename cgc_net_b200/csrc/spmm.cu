@@ -334,8 +334,8 @@ struct EllGatherArgs {
   float* out;
   int64_t ldo;
   int nmax, feat, parts, rpp;
-  int n_hi, rpp_hi;      // balanced split: the first n_hi graphs get parts + 1 CTAs of rpp_hi rows each, so that the
-                         // grid covers every SM (64 graphs: 20 x 3 + 44 x 2 = 148 CTAs)
+  int n_hi, rpp_hi;      // balanced split: the first n_hi graphs get parts_hi CTAs of rpp_hi rows each, so that the
+  int parts_hi;          // grid covers every SM (64 graphs: 20 x 3 + 44 x 2 = 148 CTAs; clusters of 2: 10 x 4 + 54 x 2)
   int box_rows;          // STRIDED: rows per TMA box
   int early_tables;      // index tables may be read before pdl_wait()
   int lab_stage;         // CGC_LAB builds: 1 = exit at entry, 2 = exit after the tile copy (timeline measurements)
@@ -345,11 +345,11 @@ struct EllGatherArgs {
 // CTA -> (graph, first table row, rows): graphs [0, n_hi) are cut into parts + 1 pieces of rpp_hi rows, the rest into
 // `parts` pieces of rpp rows
 __device__ __forceinline__ void ell_cta_rows(const EllGatherArgs& a, int nrow8, int& g, int& r0, int& nrows) {
-  const int hi_ctas = a.n_hi * (a.parts + 1);
+  const int hi_ctas = a.n_hi * a.parts_hi;
   int p, rpp;
   if ((int)blockIdx.x < hi_ctas) {
-    g = blockIdx.x / (a.parts + 1);
-    p = blockIdx.x - g * (a.parts + 1);
+    g = blockIdx.x / a.parts_hi;
+    p = blockIdx.x - g * a.parts_hi;
     rpp = a.rpp_hi;
   } else {
     const int b2 = blockIdx.x - hi_ctas;
@@ -533,8 +533,13 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
 // this launch still gathers.  It only pays with the balanced 148-CTA grid: with 128 CTAs the block scheduler doubles
 // the next launch's CTAs up on the 20 idle SMs (measured 8.7 us).
 constexpr int kLeanThreads = 512;
+constexpr uint32_t kLeanChunk = 16384;   // bytes per bulk copy of the tile: 8 copies in flight for the 115 KB tile
+                                         // (4 copies of 32 KB: 6.20 us per launch, 8 of 16 KB: 5.94 us)
 constexpr int kLeanRows = 8;
 
+// CL > 1: the CL CTAs of a graph form a thread-block cluster and share ONE read of the tile: each issues every CL-th
+// chunk as a multicast bulk copy that lands in all of them (L2 -> SM traffic of a launch 17 MB -> 7.4 MB at B = 64).
+template <int CL>
 __global__ void __launch_bounds__(kLeanThreads, 2)
 k_sage_gather_ell_lean(const EllGatherArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -555,6 +560,11 @@ k_sage_gather_ell_lean(const EllGatherArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 2 * feat) s_x[(size_t)nmax * feat + threadIdx.x] = 0.f;
+  uint32_t crank = 0;
+  if (CL > 1) {
+    crank = cluster_rank();
+    cluster_barrier();                                   // every CTA's barrier exists before a peer's copy counts on it
+  }
   const int sl = threadIdx.x % LPR, grp = threadIdx.x / LPR;
   const uint32_t lane_base = smem_u32(smem_raw) + sl * 16u;
   const uint32_t pad_word = (uint32_t)nmax | ((uint32_t)nmax << 16);
@@ -576,16 +586,20 @@ k_sage_gather_ell_lean(const EllGatherArgs a) {
   // previous launch's gather phase, when the memory system is idle.  In the training step x is L2-resident already.
   if (threadIdx.x == 32) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + grow0 * feat);
-    for (uint32_t off = 0; off < tile_bytes; off += a.chunk) {
+    for (uint32_t off = crank * a.chunk; off < tile_bytes; off += CL * a.chunk) {
       const uint32_t n = min(a.chunk, tile_bytes - off);
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(n) : "memory");
     }
   }
   pdl_wait();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, tile_bytes);
+    mbar_expect_tx(&bar, tile_bytes);                    // the whole tile: this CTA's chunks and its peers'
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + grow0 * feat);
-    for (uint32_t off = 0; off < tile_bytes; off += a.chunk) bulk_g2s(smem_raw + off, src + off, min(a.chunk, tile_bytes - off), &bar);
+    for (uint32_t off = crank * a.chunk; off < tile_bytes; off += CL * a.chunk) {
+      const uint32_t n = min(a.chunk, tile_bytes - off);
+      if (CL > 1) bulk_g2s_multicast(smem_raw + off, src + off, n, &bar, (uint16_t)((1u << CL) - 1u));
+      else bulk_g2s(smem_raw + off, src + off, n, &bar);
+    }
   }
   if (!a.early_tables) load_all();
   __syncthreads();
@@ -623,6 +637,7 @@ k_sage_gather_ell_lean(const EllGatherArgs a) {
     o.x *= s; o.y *= s; o.z *= s; o.w *= s;
     *reinterpret_cast<float4*>(a.out + row * a.ldo + sl * 4) = o;
   }
+  if (CL > 1) cluster_barrier();                         // no CTA exits while a copy it issued may still be landing in a peer
 }
 
 
@@ -1073,7 +1088,9 @@ static int launch_ell(EllGatherArgs a, int num_graphs, int64_t ldx, bool pdl, cu
 
 // Row split of the gather grids: `parts` CTAs per graph (rpp rows each) and, when the grid would leave SMs idle, one
 // extra CTA for the first n_hi graphs (rpp_hi rows each).  Returns the grid size.
-static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override) {
+// cluster > 1: CTAs come in clusters of that many per graph (parts = cluster); the spare SMs then go to graphs that
+// get TWO clusters (2 x cluster CTAs).
+static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override, int cluster) {
   const int nrow8 = (a.nmax + 7) & ~7;
   int parts = parts_override > 0 ? parts_override : kNumSMs / num_graphs;
   if (parts < 1) parts = 1;
@@ -1084,8 +1101,17 @@ static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override) {
   a.rpp = rpp;
   a.n_hi = 0;
   a.rpp_hi = rpp;
+  a.parts_hi = parts + 1;
   const int spare = kNumSMs - parts * num_graphs;       // SMs a plain split leaves idle
-  if (parts_override <= 0 && spare > 0) {
+  if (cluster > 1) {
+    a.parts_hi = 2 * parts;
+    int rpp_hi = (int)ceil_div(nrow8, a.parts_hi);
+    rpp_hi = (rpp_hi + 7) & ~7;
+    if (parts == cluster && spare >= parts && (int)ceil_div(nrow8, rpp_hi) == a.parts_hi) {
+      a.n_hi = spare / parts < num_graphs ? spare / parts : num_graphs;
+      a.rpp_hi = rpp_hi;
+    }
+  } else if (parts_override <= 0 && spare > 0) {
     int rpp_hi = (int)ceil_div(nrow8, parts + 1);
     rpp_hi = (rpp_hi + 7) & ~7;
     if ((int)ceil_div(nrow8, rpp_hi) == parts + 1) {
@@ -1093,31 +1119,48 @@ static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override) {
       a.rpp_hi = rpp_hi;
     }
   }
-  return a.n_hi * (parts + 1) + (num_graphs - a.n_hi) * parts;
+  return a.n_hi * a.parts_hi + (num_graphs - a.n_hi) * parts;
+}
+static int ell_row_split(EllGatherArgs& a, int num_graphs, int parts_override) {
+  return ell_row_split(a, num_graphs, parts_override, 1);
 }
 
 // The two-CTAs-per-SM variant of the roofline configuration (see k_sage_gather_ell_lean)
-static int launch_ell_lean(EllGatherArgs a, int num_graphs, bool pdl, cudaStream_t st) {
-  const size_t smem = ((size_t)a.nmax + 2) * a.feat * 4;
-  const int grid = ell_row_split(a, num_graphs, 0);
-  a.lab_stage = 0;
-  a.chunk = kBulkChunk;
-  static size_t smem_set[kMaxDevices] = {};
-  {
-    CGC_CUDA(ensure_dynamic_smem(k_sage_gather_ell_lean, smem, smem_set));
-    static bool carve[kMaxDevices] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < kMaxDevices && !carve[dev]) {   // two CTAs per SM need the whole 228 KB as shared memory
-      CGC_CUDA(cudaFuncSetAttribute(k_sage_gather_ell_lean, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared));
-      carve[dev] = true;
-    }
+template <int CL>
+static int launch_ell_lean_cl(const EllGatherArgs& a, int grid, size_t smem, bool pdl, cudaStream_t st) {
+  auto kern = k_sage_gather_ell_lean<CL>;
+  static size_t smem_set[kMaxDevices] = {};             // per instantiation and device
+  CGC_CUDA(ensure_dynamic_smem(kern, smem, smem_set));
+  static bool carve[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < kMaxDevices && !carve[dev]) {   // two CTAs per SM need the whole 228 KB as shared memory
+    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    carve[dev] = true;
   }
-  PdlLaunch L(dim3((unsigned)grid), dim3(kLeanThreads), smem, st, pdl);
-  CGC_CUDA(cudaLaunchKernelEx(&L.cfg, k_sage_gather_ell_lean, a));
+  PdlLaunch L(dim3((unsigned)grid), dim3(kLeanThreads), smem, st, pdl, CL);
+  CGC_CUDA(cudaLaunchKernelEx(&L.cfg, kern, a));
   CGC_CHECK_LAUNCH("k_sage_gather_ell_lean");
   return 0;
+}
+
+static int launch_ell_lean(EllGatherArgs a, int num_graphs, bool pdl, bool multicast, cudaStream_t st) {
+  const size_t smem = ((size_t)a.nmax + 2) * a.feat * 4;
+  a.lab_stage = 0;
+  static const int chunk_override = lab_env("CGC_GATHER_CHUNK", 0);
+  a.chunk = chunk_override > 0 ? (uint32_t)chunk_override : kLeanChunk;
+  // CGC_GATHER_MULTICAST, 2 or 4 CTAs per graph: one cluster per graph, the tile is read from L2 once and multicast
+  EllGatherArgs c = a;
+  const int want = kNumSMs / num_graphs;
+  const int cl = want >= 4 ? 4 : want;
+  if (multicast && (cl == 2 || cl == 4)) {
+    const int grid = ell_row_split(c, num_graphs, cl, cl);
+    if (c.parts == cl && grid % cl == 0)
+      return cl == 2 ? launch_ell_lean_cl<2>(c, grid, smem, pdl, st) : launch_ell_lean_cl<4>(c, grid, smem, pdl, st);
+  }
+  const int grid = ell_row_split(a, num_graphs, 0);
+  return launch_ell_lean_cl<1>(a, grid, smem, pdl, st);
 }
 
 // Launch of the staged-table variant; returns 1 ("not taken") when the table slice does not fit behind the tile.
@@ -1176,7 +1219,7 @@ static int ell_gather_dispatch(const uint16_t* ell, const float* ell_val, const 
   const bool lean_ok = !wt && !strided && !acc && ell_scale == nullptr && width == 8 && feat == 16 && ldo == feat &&
                        2 * (((size_t)nmax + 2) * feat * 4 + 1024 + 128) <= 228 * 1024;
   if (lean_ok && !(flags & CGC_GATHER_ONE_PER_SM) && (pdl || (flags & CGC_GATHER_TWO_PER_SM)))
-    return launch_ell_lean(a, num_graphs, pdl, st);
+    return launch_ell_lean(a, num_graphs, pdl, (flags & CGC_GATHER_MULTICAST) != 0, st);
   // pitch 16 and / or weighted tables: the variant with the table slice staged in shared memory, when it fits
 #define CGC_ELL_STAGED(W_, LPR_, WT_)                                                                     \
   do {                                                                                                    \

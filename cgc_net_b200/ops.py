@@ -29,10 +29,11 @@ from . import _backend
 
 RENORM_P = 0.4       # model/network.py:260,271,280
 BUILD_TRANSPOSED_ELL = False     # see build_sparse_graph
-FOLD_BN_BACKWARD = False         # cgc_sage_dh_bn (BatchNorm backward formed inside the wide epilogue backward): correct
-                                 # (tests/test_gpu_ops.py::test_sage_dh_bn) but measured SLOWER at the BASELINE shape:
-                                 # the register-capped kernel goes from 713 us to 1192 us, more than the 295 us apply
-                                 # pass it removes -> off
+FOLD_BN_BACKWARD = True          # cgc_sage_dh_bn (BatchNorm backward formed inside the wide epilogue backward,
+                                 # tests/test_gpu_ops.py::test_sage_dh_bn).  At the BASELINE shape (tools/epi_lab.py):
+                                 # sums 186 us + folded epilogue 811 us = 997 us, against sums + apply 489 us +
+                                 # epilogue 695 us = 1184 us with the warp-per-row-pair kernel (the register-capped
+                                 # tile kernel of round 2a lost 479 us by folding and kept it off)
 BUILD_BACKWARD_ELL = False       # ELL16 table of A^T for the narrow CSC gathers of the backward: measured 26.6 us per
                                  # gather (pitch 16, weighted, 7 index batches per thread) + 65 us to build the table vs
                                  # 24.9 us for the generic CSC gather -> off

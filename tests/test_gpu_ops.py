@@ -833,7 +833,8 @@ def test_sage_dh_bn(cuda_backend, cin, cout, training, act):
 @pytest.mark.parametrize('ready', [True, False])
 def test_sage_gather_ell_two_per_sm(cuda_backend, b, nmax, maxdeg, ready):
     """The two-CTAs-per-SM variant of the roofline configuration (pitch 8, unweighted, no scale vector, 16 contiguous
-    features) and the balanced row split (some graphs get one more CTA so that the grid covers every SM; 64 graphs:
+    features; with 2 or 4 CTAs per graph they form a cluster and share one multicast copy of the tile: 64 x 1800 -> 2,
+    5 x 333 and 2 x 1750 -> 4) and the balanced row split (some graphs get one more CTA so that the grid covers every SM; 64 graphs:
     20 x 3 + 44 x 2 = 148) == the generic CSR mean; rows above the pitch walk the CSR (maxdeg 10)."""
     rows, feat = b * nmax, 16
     rowptr, col = _random_csr(rows, maxdeg, seed=nmax, block=nmax) if rows < 5000 else _knn_csr(b, nmax)
@@ -842,8 +843,11 @@ def test_sage_gather_ell_two_per_sm(cuda_backend, b, nmax, maxdeg, ready):
     deg = (rowptr[1:] - rowptr[:-1]).float().clamp(min=1)
     want = torch.zeros(rows, feat)
     REF.spmm(rowptr, col, None, x, None, 1.0 / deg, want, False)
-    for two in (True, False):
+    outs = []
+    for two, pdl, mc in ((True, True, False), (True, True, True), (True, False, True), (False, True, False)):
         out = torch.zeros(rows, feat)
-        both(cuda_backend, 'sage_gather_ell', [ell, None, None, perm, 8, rowptr, col, None, x, b, nmax, out, False, ready,
-                                               True, two], [11], rtol=1e-5, atol=1e-5)
+        gpu = both(cuda_backend, 'sage_gather_ell', [ell, None, None, perm, 8, rowptr, col, None, x, b, nmax, out, False,
+                                                     ready, pdl, two, mc], [11], rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+        outs.append(gpu[11].cpu())
+    assert all(torch.equal(outs[0], o) for o in outs[1:])        # same slot order in every kernel: bitwise equal

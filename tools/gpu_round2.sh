@@ -55,7 +55,7 @@ if has ncu_step; then
   python tools/summarize_step_ncu.py /tmp/step_r2.ncu-rep > $OUT/step_r2_kernels.txt 2>&1; head -30 $OUT/step_r2_kernels.txt
 fi
 if has ncu_epi; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_epi_wide -c 4 --profile-from-start off -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_epi_rowpair -c 2 --profile-from-start off -f \
     -o $OUT/prof_epi_r2 python tools/profile_step.py > $OUT/prof_epi.log 2>&1; echo "ncu_epi exit=$?"; ls -la $OUT/prof_epi_r2.ncu-rep
 fi
 if has ncu_gather; then

@@ -80,4 +80,34 @@ for norm_adj in (False, True):
     be.spmm(sg.rowptr, sg.col, sg.val, s, None, None, p2, False)
     torch.cuda.synchronize()
     check('wide gather na=%d' % norm_adj, p1, p2.cpu(), 1e-5)
+# round-2b kernels: two-per-SM gather (plain and cluster multicast), float4 column reductions, warp-per-row-pair
+# epilogue backward (plain and with the BatchNorm backward folded in)
+graphs = [graph.synthetic_cell_graph(333, 8, 16, seed=20 + i, row_is_centre=True) for i in range(5)]
+batch = graph.Batch.from_data_list(graphs).to(dev)
+xp, sg = ops.build_sparse_graph(batch.x, batch.edge_index, batch.batch, batch.num_nodes_list, False)
+ref = torch.empty_like(xp)
+be.spmm(sg.rowptr, sg.col, sg.val, xp, None, sg.rs, ref, False)
+for mc in (False, True):
+    out = torch.empty_like(xp)
+    be.sage_gather_ell(sg.ell, None, None, sg.ell_perm, sg.ell_width, sg.rowptr, sg.col, sg.val, xp, sg.num_graphs, sg.nmax,
+                       out, tables_ready=True, two_per_sm=True, multicast=mc)
+    torch.cuda.synchronize()
+    check('gather two-per-SM multicast=%d' % mc, out, ref.cpu(), 1e-5)
+rows, cin, cout = xp.shape[0], 20, 300
+sa = torch.randn(rows, cin, device=dev)
+w, bias = torch.randn(cin, cout, device=dev) / cin ** 0.5, torch.randn(cout, device=dev) * 0.1
+y, gx = torch.empty(rows, cout, device=dev), torch.randn(rows, cout, device=dev)
+rm, rv, mean, invstd = (torch.zeros(cout, device=dev) for _ in range(4))
+be.sage_layer_fwd_wide(sa, w, bias, sg.mask, y, 0, rm, rv, 0.1, 1e-5, mean, invstd)
+gamma, dg, db = torch.rand(cout, device=dev) + 0.5, torch.zeros(cout, device=dev), torch.zeros(cout, device=dev)
+gy, dh1, dh2 = (torch.empty(rows, cout, device=dev) for _ in range(3))
+be.bn_bwd(gx, y, mean, invstd, gamma, sg.mask, True, gy, dg, db)          # float4 sums + apply
+be.sage_dh(gy, sa, w, bias, y, sg.mask, dh1, 0)
+be.sage_dh_bn(gx, sa, w, bias, y, mean, invstd, gamma, dg, db, True, sg.mask, dh2, 0)
+colsum = torch.zeros(cout, device=dev)
+be.colsum(dh1, sg.mask, colsum)
+torch.cuda.synchronize()
+check('epilogue backward, BN folded', dh2, dh1.cpu(), 1e-4)
+valid = (torch.arange(rows, device=dev) % sg.nmax) < sg.mask.num_nodes.repeat_interleave(sg.nmax)
+check('float4 column sum', colsum, (dh1 * valid[:, None]).sum(0).cpu(), 1e-4)
 print('sanitizer workload ok')
