@@ -564,6 +564,8 @@ k_sage_gather_ell_lean(const EllGatherArgs a) {
   if (CL > 1) {
     crank = cluster_rank();
     cluster_barrier();                                   // every CTA's barrier exists before a peer's copy counts on it
+  } else {
+    __syncthreads();                                     // barrier and pad rows visible to the CTA (still in the prologue)
   }
   const int sl = threadIdx.x % LPR, grp = threadIdx.x / LPR;
   const uint32_t lane_base = smem_u32(smem_raw) + sl * 16u;
