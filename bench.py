@@ -262,7 +262,7 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------- gather roofline
 def gather_roofline(args, device, kind='gather', row_is_centre=True, norm_adj=False, pdl=True, check=True,
-                    two_per_sm=None, multicast=False):
+                    two_per_sm=None, multicast=True):
     """One kernel of the gather family alone at the BASELINE shape (B x nodes x F = 16): CUDA-graph replay over
     rotating input copies whose total footprint exceeds L2, timed with CUDA events on the launching stream.
 
@@ -406,8 +406,8 @@ def roofline_lines(args, device):
     for name, kw in (('unfused, plain stream-ordered launch (no PDL)', dict(pdl=False)),
                      ('unfused, one 1024-thread CTA per SM (k_sage_gather_ell; no early L2 prefetch of the tile)',
                       dict(two_per_sm=False)),
-                     ('unfused, two CTAs per SM, the CTAs of a graph as a cluster sharing one multicast copy of the tile',
-                      dict(multicast=True)),
+                     ('unfused, two CTAs per SM, every CTA copying its graph\'s whole tile itself (no cluster multicast)',
+                      dict(multicast=False)),
                      ('unfused, radius_graph-style adjacency (variable row degree, pitch-16 table)',
                       dict(row_is_centre=False)),
                      ('unfused, weighted table (norm_adj)', dict(norm_adj=True)),
@@ -420,8 +420,9 @@ def roofline_lines(args, device):
         except Exception as exc:                                         # a variant must not take the line down
             variants[name] = {'error': str(exc)[:200]}
     out['roofline'] = {
-        'kernel': 'k_sage_gather_ell_lean<1> (cgc_sage_gather_ell, F=16, unfused, fixed degree 8; two 512-thread CTAs '
-                  'per SM, the next launch pulls its tile into L2 while this one gathers)', 'bound': 'hbm',
+        'kernel': 'k_sage_gather_ell_lean<2> (cgc_sage_gather_ell, F=16, unfused, fixed degree 8; two 512-thread CTAs '
+                  'per SM, the two CTAs of a graph are a cluster sharing one multicast copy of the tile, the next '
+                  'launch pulls its tile into L2 while this one gathers)', 'bound': 'hbm',
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
         'traffic_source': tsrc, 'peak_source': which, 'algorithmic_bytes_per_launch': alg, 'us_per_launch': us,
         'timing': 'CUDA-graph replay of %d launches over %d rotating input copies (%.0f MB > L2), programmatic '

@@ -99,7 +99,7 @@ EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 
 GATHER_ACCUMULATE, GATHER_TABLES_READY, GATHER_NO_PDL, GATHER_TWO_PER_SM, GATHER_ONE_PER_SM = 1, 2, 4, 8, 16   # CGC_GATHER_*
-GATHER_MULTICAST = 32
+GATHER_NO_MULTICAST = 32
 
 
 class CgcError(RuntimeError):
@@ -294,7 +294,7 @@ class CudaBackend(object):
                     'cgc_sage_gather_ell_fwd')
 
     def sage_gather_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
-                        accumulate=False, tables_ready=False, pdl=True, two_per_sm=None, multicast=False):
+                        accumulate=False, tables_ready=False, pdl=True, two_per_sm=None, multicast=True):
         """General ELL16 gather: x / out may be column slices (leading dimensions); ``accumulate`` adds into out;
         ``tables_ready`` = the tables were not written by the kernel enqueued right before (PDL prologue);
         ``two_per_sm`` None = the library's choice, True / False force one kernel of the roofline configuration."""
@@ -303,7 +303,7 @@ class CudaBackend(object):
         flags = (GATHER_ACCUMULATE if accumulate else 0) | (GATHER_TABLES_READY if tables_ready else 0) | \
                 (0 if pdl else GATHER_NO_PDL) | \
                 (0 if two_per_sm is None else (GATHER_TWO_PER_SM if two_per_sm else GATHER_ONE_PER_SM)) | \
-                (GATHER_MULTICAST if multicast else 0)
+                (0 if multicast else GATHER_NO_MULTICAST)
         self._check(self.lib.cgc_sage_gather_ell(_ptr(ell, torch.int16), _ptr(ell_val, torch.float32),
                                                  _ptr(ell_scale, torch.float32), _ptr(perm, torch.int32), width,
                                                  _ptr(rowptr, torch.int32), _ptr(col, torch.int32),

@@ -524,7 +524,7 @@ __device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long lon
 // Forward (BWD = false): y = mask * act(h / ||h||), and with partial != null the column sums of y and y^2 for the
 // BatchNorm statistics: per lane in registers over the warp's rows, folded warp by warp (fixed order) into one
 // [2][cout] partial per CTA, the layout bn_finalize_partials reads.
-template <int NQ, bool BWD, int THREADS>
+template <int NQ, bool BWD, int THREADS, bool PADDED>
 __global__ void __launch_bounds__(THREADS, 1)
 k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w,
               const float* __restrict__ bias, const int32_t* __restrict__ num_nodes, int nmax, int64_t rows,
@@ -532,30 +532,38 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
               float* dh, int64_t lddh, int act, double* __restrict__ partial, const EpiBn bn) {
   extern __shared__ __align__(16) float rp_smem[];
   const ActGrad agrad(act);
-  float* s_w = rp_smem;                               // [cin][cout]
-  float* s_b = s_w + cin * cout;                      // [cout]
-  float* s_bn = s_b + cout;                           // BWD: [3][cout] P, R, Q (BatchNorm backward folded in)
-                                                      // forward with statistics: [2][cout] column sums of the CTA
+  // every per-column vector is padded to cw = cout rounded up to 4 (zero weights / bias / coefficients in the pad
+  // columns), so a lane's float4 chunk never straddles a row; pad columns are masked out of loads and stores below
+  const int cw = (cout + 3) & ~3;
+  const int tail = PADDED ? (cout & 3) : 0;           // valid elements of the last chunk (0 = all four)
+  float* s_w = rp_smem;                               // [cin][cw]
+  float* s_b = s_w + cin * cw;                        // [cw]
+  float* s_bn = s_b + cw;                             // BWD: [3][cw] P, R, Q (BatchNorm backward folded in)
+                                                      // forward with statistics: [2][cw] column sums of the CTA
   const bool with_bn = BWD && bn.mean != nullptr;
   float st1[BWD ? 1 : NQ][4], st2[BWD ? 1 : NQ][4];
 #pragma unroll
   for (int j = 0; j < (BWD ? 1 : NQ); ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { st1[j][e] = 0.f; st2[j][e] = 0.f; }
-  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = w[i];
-  for (int c = threadIdx.x; c < cout; c += blockDim.x) {
-    s_b[c] = bias ? bias[c] : 0.f;
+  for (int i = threadIdx.x; i < cin * cw; i += blockDim.x) {
+    const int k = i / cw, c = i - k * cw;
+    s_w[i] = c < cout ? w[k * cout + c] : 0.f;
+  }
+  for (int c = threadIdx.x; c < cw; c += blockDim.x) {
+    const bool in = c < cout;
+    s_b[c] = (bias && in) ? bias[c] : 0.f;
     if (with_bn) {
-      const float is = bn.invstd[c], pc = bn.gamma[c] * is;
-      const float rc = bn.training ? pc * is * bn.d_gamma[c] * bn.inv_rows : 0.f;
+      const float is = in ? bn.invstd[c] : 0.f, pc = in ? bn.gamma[c] * is : 0.f;
+      const float rc = (bn.training && in) ? pc * is * bn.d_gamma[c] * bn.inv_rows : 0.f;
       s_bn[c] = pc;
-      s_bn[cout + c] = rc;
-      s_bn[2 * cout + c] = bn.training ? pc * bn.d_beta[c] * bn.inv_rows - rc * bn.mean[c] : 0.f;
+      s_bn[cw + c] = rc;
+      s_bn[2 * cw + c] = (bn.training && in) ? pc * bn.d_beta[c] * bn.inv_rows - rc * bn.mean[c] : 0.f;
     }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int c4 = cout >> 2;
+  const int c4 = cw >> 2;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t npairs = (rows + 1) >> 1;
   // chunk j of this lane; lanes past the last chunk work on a copy of it and are masked out of sums and stores
@@ -581,6 +589,24 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
     }
   };
   prefetch_pair(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  // store / zero one chunk; the last chunk of a row keeps its hands off the columns past cout (they may belong to
+  // the next slice of a wider matrix)
+  auto store4 = [&](float* row, int q, const float4 v) {
+    if (!PADDED || tail == 0 || q != c4 - 1) {
+      *reinterpret_cast<float4*>(row + 4 * q) = v;
+    } else {
+      row[4 * q] = v.x;
+      if (tail > 1) row[4 * q + 1] = v.y;
+      if (tail > 2) row[4 * q + 2] = v.z;
+    }
+  };
+  auto mask4 = [&](float4& v, int q) {                // zero what was read past cout (garbage, possibly NaN)
+    if (PADDED && tail != 0 && q == c4 - 1) {
+      if (tail < 2) v.y = 0.f;
+      if (tail < 3) v.z = 0.f;
+      v.w = 0.f;
+    }
+  };
   for (int64_t rp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; rp < npairs; rp += warps) {
     const int64_t r0 = 2 * rp, r1 = r0 + 1;
     const bool has1 = r1 < rows;
@@ -593,8 +619,8 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
 #pragma unroll
       for (int j = 0; j < NQ; ++j)
         if (live[j]) {
-          *reinterpret_cast<float4*>(o + r0 * ldo + 4 * qa[j]) = z;
-          if (has1) *reinterpret_cast<float4*>(o + r1 * ldo + 4 * qa[j]) = z;
+          store4(o + r0 * ldo, qa[j], z);
+          if (has1) store4(o + r1 * ldo, qa[j], z);
         }
       continue;
     }
@@ -612,7 +638,7 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
     }
     auto k_step = [&](int k, float a0, float a1) {
       const unsigned long long a0d = pack2(a0, a0), a1d = pack2(a1, a1);
-      const float* wrow = s_w + k * cout;
+      const float* wrow = s_w + k * cw;
 #pragma unroll
       for (int j = 0; j < NQ; ++j) {
         const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(wrow + 4 * qa[j]);
@@ -652,8 +678,8 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
                                    act_fwd(act, h01.y * inv0));
           if (v1) ob = make_float4(act_fwd(act, h10.x * inv1), act_fwd(act, h10.y * inv1), act_fwd(act, h11.x * inv1),
                                    act_fwd(act, h11.y * inv1));
-          *reinterpret_cast<float4*>(y + r0 * ldy + 4 * qa[j]) = oa;
-          if (has1) *reinterpret_cast<float4*>(y + r1 * ldy + 4 * qa[j]) = ob;
+          store4(y + r0 * ldy, qa[j], oa);
+          if (has1) store4(y + r1 * ldy, qa[j], ob);
           st1[j][0] += oa.x + ob.x; st1[j][1] += oa.y + ob.y; st1[j][2] += oa.z + ob.z; st1[j][3] += oa.w + ob.w;
           st2[j][0] = fmaf(oa.x, oa.x, fmaf(ob.x, ob.x, st2[j][0]));
           st2[j][1] = fmaf(oa.y, oa.y, fmaf(ob.y, ob.y, st2[j][1]));
@@ -667,8 +693,8 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
     auto grad4 = [&](const float4 yv, float4 gv, int q) {
       if (with_bn) {
         const float4 pc = *reinterpret_cast<const float4*>(s_bn + 4 * q);
-        const float4 rc = *reinterpret_cast<const float4*>(s_bn + cout + 4 * q);
-        const float4 qc = *reinterpret_cast<const float4*>(s_bn + 2 * cout + 4 * q);
+        const float4 rc = *reinterpret_cast<const float4*>(s_bn + cw + 4 * q);
+        const float4 qc = *reinterpret_cast<const float4*>(s_bn + 2 * cw + 4 * q);
         gv.x = fmaf(pc.x, gv.x, -fmaf(rc.x, yv.x, qc.x));
         gv.y = fmaf(pc.y, gv.y, -fmaf(rc.y, yv.y, qc.y));
         gv.z = fmaf(pc.z, gv.z, -fmaf(rc.z, yv.z, qc.z));
@@ -689,7 +715,9 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
       const float4 ga = *(reinterpret_cast<const float4*>(g0) + qa[j]);
       const float4 gb = *(reinterpret_cast<const float4*>(g1) + qa[j]);
       if (live[j]) {
-        const float4 ma = grad4(ya, ga, qa[j]), mb = grad4(yb, gb, qa[j]);
+        float4 ma = grad4(ya, ga, qa[j]), mb = grad4(yb, gb, qa[j]);
+        mask4(ma, qa[j]);
+        mask4(mb, qa[j]);
         const float2 h00 = unpack2(acc0[j][0]), h01 = unpack2(acc0[j][1]);
         const float2 h10 = unpack2(acc1[j][0]), h11 = unpack2(acc1[j][1]);
         d0 = fmaf(ma.x, h00.x, fmaf(ma.y, h00.y, fmaf(ma.z, h01.x, fmaf(ma.w, h01.y, d0))));
@@ -708,6 +736,8 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
       const float4 gb = *(reinterpret_cast<const float4*>(g1) + qa[j]);
       if (live[j]) {
         float4 ma = grad4(ya, ga, qa[j]), mb = grad4(yb, gb, qa[j]);
+        mask4(ma, qa[j]);
+        mask4(mb, qa[j]);
         ma.x *= m0; ma.y *= m0; ma.z *= m0; ma.w *= m0;
         mb.x *= m1; mb.y *= m1; mb.z *= m1; mb.w *= m1;
         const float2 h00 = unpack2(acc0[j][0]), h01 = unpack2(acc0[j][1]);
@@ -718,8 +748,8 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
         oa.z = (ma.z - h01.x * s0) * inv0; oa.w = (ma.w - h01.y * s0) * inv0;
         ob.x = (mb.x - h10.x * s1) * inv1; ob.y = (mb.y - h10.y * s1) * inv1;
         ob.z = (mb.z - h11.x * s1) * inv1; ob.w = (mb.w - h11.y * s1) * inv1;
-        *reinterpret_cast<float4*>(dh + r0 * lddh + 4 * qa[j]) = oa;
-        if (has1) *reinterpret_cast<float4*>(dh + r1 * lddh + 4 * qa[j]) = ob;
+        store4(dh + r0 * lddh, qa[j], oa);
+        if (has1) store4(dh + r1 * lddh, qa[j], ob);
       }
     }
   }
@@ -732,7 +762,7 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
           for (int j = 0; j < NQ; ++j) {
             if (live[j]) {
               float4* p1 = reinterpret_cast<float4*>(s_bn + 4 * qa[j]);
-              float4* p2 = reinterpret_cast<float4*>(s_bn + cout + 4 * qa[j]);
+              float4* p2 = reinterpret_cast<float4*>(s_bn + cw + 4 * qa[j]);
               float4 a = make_float4(st1[j][0], st1[j][1], st1[j][2], st1[j][3]);
               float4 b = make_float4(st2[j][0], st2[j][1], st2[j][2], st2[j][3]);
               if (wv != 0) {
@@ -749,14 +779,15 @@ k_epi_rowpair(const float* __restrict__ sa, int64_t ldsa, const float* __restric
       }
       for (int c = threadIdx.x; c < cout; c += blockDim.x) {
         partial[((int64_t)blockIdx.x * 2 + 0) * cout + c] = (double)s_bn[c];
-        partial[((int64_t)blockIdx.x * 2 + 1) * cout + c] = (double)s_bn[cout + c];
+        partial[((int64_t)blockIdx.x * 2 + 1) * cout + c] = (double)s_bn[cw + c];
       }
     }
   }
 }
 
 static size_t rowpair_smem_bytes(int cin, int cout, int extra_vectors) {
-  return sizeof(float) * ((size_t)cin * cout + cout + (size_t)extra_vectors * cout);
+  const size_t cw = ((size_t)cout + 3) & ~(size_t)3;
+  return sizeof(float) * ((size_t)cin * cw + cw + (size_t)extra_vectors * cw);
 }
 
 template <bool BWD>
@@ -786,7 +817,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
   CGC_REQUIRE(bn_in == nullptr || BWD, CGC_ERR_ARG, "sage epilogue: BatchNorm folding is a backward option");
   {
     // wide layers with 16-byte aligned rows: one warp per row pair
-    const int nq = (int)ceil_div(cout / 4, 32);
+    const int nq = (int)ceil_div((cout + 3) / 4, 32);
     static const bool rowpair_off = lab_env("CGC_EPI_ROWPAIR", 1) == 0;   // A/B switch (CGC_LAB builds only)
     const int extra = BWD ? (bn_in != nullptr ? 3 : 0) : (partial != nullptr ? 2 : 0);
     float* o = BWD ? dh : y;
@@ -795,7 +826,9 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     //  333 us tile kernel -- W is read from shared memory once per row PAIR here, once per 8 rows there, and the
     //  forward has no global loads to overlap: BWD only unless the lab switch is 2)
     static const bool rowpair_fwd = lab_env("CGC_EPI_ROWPAIR", 1) == 2;
-    if ((BWD || rowpair_fwd) && !rowpair_off && cout >= 256 && cout % 4 == 0 && nq <= 10 && cin <= 64 &&
+    // any width from 64 columns up: vectors are padded to a multiple of 4 in shared memory, pad columns masked
+    // (cout = 114, stage 2: 155 us in the tile kernel, where 142 of 256 threads own no column)
+    if ((BWD || rowpair_fwd) && !rowpair_off && cout >= 64 && nq <= 10 && cin <= 64 &&
         ldy % 4 == 0 && aligned16(y) &&
         ldo % 4 == 0 && aligned16(o) && (!BWD || (ldgy % 4 == 0 && aligned16(gy))) &&
         rowpair_smem_bytes(cin, cout, extra) <= 200 * 1024) {
@@ -810,7 +843,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
       }
 #define CGC_ROWPAIR_LAUNCH(N, T)                                                                               \
   {                                                                                                            \
-    auto kern = k_epi_rowpair<N, BWD, T>;                                                                      \
+    auto kern = (cout & 3) ? k_epi_rowpair<N, BWD, T, true> : k_epi_rowpair<N, BWD, T, false>;                 \
     CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     kern<<<(unsigned)blocks, T, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, gy, ldgy, \
                                             dh, lddh, act, partial, bn);                                       \
@@ -820,6 +853,7 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     if (threads == kRowPairThreads) CGC_ROWPAIR_LAUNCH(N, kRowPairThreads) else CGC_ROWPAIR_LAUNCH(N, kRowPairThreadsAlt) \
     break;
       switch (nq) {
+        CGC_ROWPAIR_CASE(1)
         CGC_ROWPAIR_CASE(2)
         CGC_ROWPAIR_CASE(3)
         CGC_ROWPAIR_CASE(4)

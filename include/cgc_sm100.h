@@ -195,9 +195,9 @@ CGC_API int cgc_sage_gather_ell_fwd(const uint16_t* ell, const float* ell_val, c
                                     prefetch their tile into L2 while the previous kernel runs); the flag forces it
                                     for a CGC_GATHER_NO_PDL launch too */
 #define CGC_GATHER_ONE_PER_SM 16 /* ... and this one forces the 1024-thread one-CTA-per-SM kernel (A/B measurements) */
-#define CGC_GATHER_MULTICAST 32  /* two-per-SM kernel with 2 or 4 CTAs per graph: they form a thread-block cluster and
-                                    share ONE multicast read of the tile (measured 6.42 us against 5.94 us without:
-                                    the two cluster barriers cost more than the L2 -> SM traffic saved; kept for A/B) */
+#define CGC_GATHER_NO_MULTICAST 32 /* two-per-SM kernel with 2 or 4 CTAs per graph: by default they form a thread-block
+                                    cluster and share ONE multicast read of the tile (6.03 us per launch at the
+                                    BASELINE shape); with this flag every CTA copies the whole tile itself (6.24 us) */
 CGC_API int cgc_sage_gather_ell(const uint16_t* ell, const float* ell_val, const float* ell_scale,
                         const uint32_t* perm, int32_t width, const int32_t* rowptr, const int32_t* col,
                         const float* val, const float* x, int64_t ldx, int32_t num_graphs, int32_t nmax,

@@ -283,7 +283,7 @@ class TorchBackend(object):
             out[grow[over]] = full[grow[over]] * scale[over][:, None]
 
     def sage_gather_ell(self, ell, ell_val, ell_scale, perm, width, rowptr, col, val, x, num_graphs, nmax, out,
-                        accumulate=False, tables_ready=False, pdl=True, two_per_sm=None, multicast=False):
+                        accumulate=False, tables_ready=False, pdl=True, two_per_sm=None, multicast=True):
         """cgc_sage_gather_ell: strided x / out, optional +=."""
         res = torch.zeros(num_graphs * nmax, x.shape[1], dtype=x.dtype)
         self.sage_gather_ell_fwd(ell, ell_val, ell_scale, perm, width, rowptr, col, val, x.contiguous(), num_graphs,

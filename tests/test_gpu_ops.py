@@ -829,6 +829,44 @@ def test_sage_dh_bn(cuda_backend, cin, cout, training, act):
     torch.testing.assert_close(dh, dh2, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize('cin,cout', [(20, 114), (16, 1138), (33, 301), (20, 1140)])
+@pytest.mark.parametrize('fold', [False, True])
+def test_sage_dh_row_pair_kernel_padded_width(cuda_backend, cin, cout, fold):
+    """The warp-per-row-pair epilogue backward on column SLICES of wider 16-byte aligned buffers, widths that are not
+    multiples of 4 included (stage 2 of config #3: 114): the columns next to the slice hold NaN (y, gy) or a sentinel
+    (dh) -- nothing past the slice may be read into the result or written."""
+    b, nmax = 3, 211
+    rows = b * nmax
+    g = torch.Generator().manual_seed(cin * cout)
+    sa = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mask = _mask(b, nmax, seed=5)
+    wide = ((cout + 3) // 4) * 4 + 8
+    y_buf, g_buf, d_buf = (torch.full((rows, wide), float('nan')) for _ in range(3))
+    d_buf.fill_(777.0)
+    y, gy, dh = y_buf[:, 4:4 + cout], g_buf[:, 4:4 + cout], d_buf[:, 4:4 + cout]
+    y_dense = torch.zeros(rows, cout)
+    REF.sage_epilogue_fwd(sa, w, bias, mask, y_dense, 0)
+    y.copy_(y_dense)
+    gy.copy_(torch.randn(rows, cout, generator=g))
+    if fold:
+        mean, var = y_dense.mean(0), y_dense.var(0, unbiased=False)
+        invstd = 1.0 / torch.sqrt(var + 1e-5)
+        gamma = torch.rand(cout, generator=g) + 0.5
+        dg, db = torch.randn(cout, generator=g), torch.randn(cout, generator=g)
+        gpu = both(cuda_backend, 'sage_dh_bn', [gy, sa, w, bias, y, mean, invstd, gamma, dg, db, True, mask, dh, 0], [12],
+                   rtol=1e-4, atol=2e-6)
+        out = gpu[12]
+    else:
+        gpu = both(cuda_backend, 'sage_dh', [gy, sa, w, bias, y, mask, dh, 0], [6], rtol=1e-4, atol=2e-6)
+        out = gpu[6]
+    full = out._base if out._base is not None else out
+    full = full.cpu().view(rows, wide)
+    assert torch.isfinite(full[:, 4:4 + cout]).all()
+    assert (full[:, :4] == 777.0).all() and (full[:, 4 + cout:] == 777.0).all(), 'wrote outside the slice'
+
+
 @pytest.mark.parametrize('b,nmax,maxdeg', [(3, 70, 8), (64, 1800, 8), (5, 333, 10), (150, 40, 8), (2, 1750, 8)])
 @pytest.mark.parametrize('ready', [True, False])
 def test_sage_gather_ell_two_per_sm(cuda_backend, b, nmax, maxdeg, ready):
@@ -844,7 +882,7 @@ def test_sage_gather_ell_two_per_sm(cuda_backend, b, nmax, maxdeg, ready):
     want = torch.zeros(rows, feat)
     REF.spmm(rowptr, col, None, x, None, 1.0 / deg, want, False)
     outs = []
-    for two, pdl, mc in ((True, True, False), (True, True, True), (True, False, True), (False, True, False)):
+    for two, pdl, mc in ((True, True, True), (True, True, False), (True, False, True), (False, True, True)):
         out = torch.zeros(rows, feat)
         gpu = both(cuda_backend, 'sage_gather_ell', [ell, None, None, perm, 8, rowptr, col, None, x, b, nmax, out, False,
                                                      ready, pdl, two, mc], [11], rtol=1e-5, atol=1e-5)

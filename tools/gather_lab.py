@@ -14,7 +14,7 @@ VARIANTS = {
     'ell': dict(),
     'ell-nopdl': dict(pdl=False),
     'ell-1persm': dict(two_per_sm=False),
-    'ell-mc': dict(multicast=True),
+    'ell-nomc': dict(multicast=False),
     'ell-2persm-nopdl': dict(two_per_sm=True, pdl=False),
     'ell-vardeg': dict(row_is_centre=False),
     'ell-weighted': dict(norm_adj=True),
