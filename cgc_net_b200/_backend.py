@@ -172,11 +172,15 @@ class CudaBackend(object):
         return torch.cuda.current_stream().cuda_stream
 
     def _workspace(self, device):
-        w = self._work.get(device)
+        """One workspace per (device, stream): split-K partials, column-reduction partials and the completion
+        counters of two streams must not share scratch memory (kernels on one stream are ordered, across streams
+        they are not)."""
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        w = self._work.get(key)
         if w is None:
             w = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
             w[-256:].zero_()            # completion counters live in the tail (include/cgc_sm100.h, "workspace")
-            self._work[device] = w
+            self._work[key] = w
         return w.data_ptr(), self.work_bytes
 
     def _check(self, rc, name):
