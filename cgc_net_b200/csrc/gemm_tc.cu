@@ -37,18 +37,27 @@ namespace cgc {
 namespace tc {
 
 constexpr int BM = 128, BK = 32;                      // BN is a template parameter: 128, 64 or 32
-constexpr int kStages = 4;
+// Ring depth per instantiation.  The narrow-N kernels (BN <= 64, one CTA per tile) serve the dense-stage A'x / A'^T g
+// contractions, 333 MB streaming reads with 4 - 8 KB of B per stage: with 4 stages every stage spent ~3 700 cycles
+// between its TMA issue and its release (DRAM flight + split + MMA) and the ring, not DRAM or the split warps
+// (60 % busy) or the MMA warp (59 %), set the pace: 1 200 cycles per stage, 0.55 - 0.64 of the HBM peak
+// (profiles/gemm_dense_r2_ncu.txt).  Their accumulators need only 2 x BN <= 128 tensor-memory columns, which leaves
+// room for 6 staged A tiles (128 + 6 x 64 = 512) and 6 x 32 KB of shared memory.
+__host__ __device__ constexpr int stages_of(int bn, bool pair) { return (!pair && bn <= 64) ? 6 : 4; }
+__host__ __device__ constexpr int a_tmem_base_of(int bn, bool pair) { return (!pair && bn <= 64) ? 128 : 256; }
 constexpr int kOperandBytes = BM * BK * 4;            // A tile: 16 KB.  Stage = A (as landed) | B (as landed = B_hi) | B_lo
 constexpr int kThreads = 640;                          // warps 0-3 control, 4-7 split group 0, 8-15 promotion, 16-19 split group 1
 constexpr int kSplitThreads = 128;                    // threads of ONE split group (= rows of the A tile)
 constexpr int kSplitGroups = 2;                       // the groups take alternate stages of the ring
 constexpr int kEpiThreads = 256;
 constexpr int kDefaultChunkBlocks = 2;               // K-blocks accumulated in TMEM before promotion to fp32 registers
-constexpr int kATmemBase = 256;                       // accumulators: 2 buffers x BN columns in [0, 256); then the A operand
-                                                      // tiles: per stage hi[32] | lo[32]
+                                                      // tensor memory: accumulators (2 buffers x BN columns) in
+                                                      // [0, a_tmem_base); then the A operand tiles, per stage hi[32] | lo[32]
 constexpr int kATmemCols = 2 * BK;
 constexpr int kTmemCols = 512;                        // 2 * 128 accumulator + 4 * 64 operand columns
-constexpr size_t smem_bytes(int bn) { return (size_t)kStages * (kOperandBytes + 2 * bn * BK * 4) + 1024 /*align*/ + 256 /*barriers*/; }
+constexpr size_t smem_bytes(int bn, bool pair) {
+  return (size_t)stages_of(bn, pair) * (kOperandBytes + 2 * (pair ? bn / 2 : bn) * BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
+}
 
 struct Params {
   GemmParams g;
@@ -345,6 +354,8 @@ __device__ __forceinline__ void store_segment(const Params& p, const TileCoord& 
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  constexpr int kStages = stages_of(BN, PAIR);
+  constexpr int kATmemBase = a_tmem_base_of(BN, PAIR);
   constexpr int kBCols = PAIR ? BN / 2 : BN;          // B columns staged by this CTA
   constexpr int kBBytes = kBCols * BK * 4;
   constexpr int kTileM = PAIR ? 2 * BM : BM;
@@ -796,7 +807,7 @@ int gemm_tc(GemmParams p, int ta, int tb, int passes, void* work, int64_t work_b
   CGC_REQUIRE(ok, CGC_ERR_UNSUPPORTED, "cgc_gemm(tc): cuTensorMapEncodeTiled failed for B");
 
   int grid = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
-  const size_t smem = smem_bytes(bn);
+  const size_t smem = smem_bytes(bn, pair);
   if (pair) {
     // one cluster of 2 CTAs (same TPC) per 256-row tile; persistent over the tiles
     const int clusters = q.total_tiles < kNumSMs / 2 ? q.total_tiles : kNumSMs / 2;
