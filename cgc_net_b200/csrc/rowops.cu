@@ -7,7 +7,6 @@
 #include <string.h>
 
 #include "common.cuh"
-#include "ell_gather.cuh"
 
 namespace cgc {
 
@@ -285,219 +284,8 @@ k_epi_wide(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__
   }
 }
 
-// ------------------------------------------------------------------- wide epilogue backward, bulk-copy ring
-// The register-file version above keeps <= 10 loads per thread in flight (80 accumulators under a 128-register cap),
-// ~20 KB per SM: it streamed at 0.33 of the HBM peak.  Here the y / gy rows of a tile arrive through cp.async.bulk
-// into a two-stage shared-memory ring (73 KB in flight per SM while the other stage is consumed), ONE CTA of up to
-// 384 threads per SM owns the whole register file (no cap: the BatchNorm coefficients of the folded variant live in
-// registers), and the aggregate rows of the next tile are fetched a tile ahead.  Needs cout % 4 == 0 and 16-byte
-// aligned rows; the tile height R (8, 6 or 4 rows) is the largest whose ring fits next to W: cin * cout + 4 R cout
-// floats of shared memory (20 x 1140: R = 6, 55 KB in flight).
-constexpr int kRingThreadsMax = 384;
-constexpr int kRingStages = 2;
-
-template <int NC, int R>
-__global__ void __launch_bounds__(kRingThreadsMax, 1)
-k_epi_wide_bwd_ring(const float* __restrict__ sa, int64_t ldsa, const float* __restrict__ w,
-                    const float* __restrict__ bias, const int32_t* __restrict__ num_nodes, int nmax, int64_t rows,
-                    int cin, int cout, const float* __restrict__ y, int64_t ldy, const float* gy, int64_t ldgy,
-                    float* dh, int64_t lddh, int act, const EpiBn bn) {
-  extern __shared__ __align__(16) unsigned char ring_smem[];
-  const ActGrad agrad(act);
-  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = T >> 5;
-  float* s_w = reinterpret_cast<float*>(ring_smem);                 // [cin][cout]
-  float* s_ring = s_w + cin * cout;                                 // [stage][y | gy][R][cout]
-  float* s_a = s_ring + kRingStages * 2 * R * cout;          // [cin][R]  (transposed row tile)
-  float* s_red = s_a + cin * R;                              // [12 warps][R]
-  int* s_valid = reinterpret_cast<int*>(s_red + (kRingThreadsMax / 32) * R);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_valid + R);
-  const uint32_t row_bytes = (uint32_t)cout * 4u;
-  const int64_t ntiles = (rows + R - 1) / R;
-
-  // warp 0: lane l < 16 copies row l / 2 of y (even) or gy (odd) of the tile
-  auto issue = [&](int64_t tile, int s) {
-    const int64_t r0 = tile * R;
-    const int nr = (int)min((int64_t)R, rows - r0);
-    if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nr * 2u * row_bytes);
-    __syncwarp();
-    const int rr = lane >> 1, which = lane & 1;
-    if (lane < 2 * R && rr < nr) {
-      float* dst = s_ring + ((size_t)(s * 2 + which) * R + rr) * cout;
-      const float* src = which ? gy + (r0 + rr) * ldgy : y + (r0 + rr) * ldy;
-      bulk_g2s(dst, src, row_bytes, &full[s]);
-    }
-  };
-
-  if (t == 0) {
-    for (int s = 0; s < kRingStages; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 0) {
-    for (int s = 0; s < kRingStages; ++s) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < ntiles) issue(tile, s);
-    }
-  }
-  for (int i = t; i < cin * cout; i += T) s_w[i] = w[i];
-  const bool with_bn = bn.mean != nullptr;
-  float bj[NC], bp[NC], br[NC], bq[NC];
-#pragma unroll
-  for (int j = 0; j < NC; ++j) {
-    const int c = t + T * j;
-    bj[j] = (bias && c < cout) ? bias[c] : 0.f;
-    bp[j] = 1.f; br[j] = 0.f; bq[j] = 0.f;
-    if (with_bn && c < cout) {
-      const float is = bn.invstd[c], pc = bn.gamma[c] * is;
-      const float rc = bn.training ? pc * is * bn.d_gamma[c] * bn.inv_rows : 0.f;
-      bp[j] = pc;
-      br[j] = rc;
-      bq[j] = bn.training ? pc * bn.d_beta[c] * bn.inv_rows - rc * bn.mean[c] : 0.f;
-    }
-  }
-  // aggregate rows of a tile: element e = t + T * u  ->  row e / cin, channel e % cin  (cin * 8 <= 2 T)
-  auto load_a = [&](int64_t tile, float (&v)[2]) {
-    const int64_t r0 = tile * R;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = t + T * u, rr = e / cin, k = e - rr * cin;
-      v[u] = (tile < ntiles && rr < R && r0 + rr < rows) ? __ldg(sa + (r0 + rr) * ldsa + k) : 0.f;
-    }
-  };
-  float a_pre[2];
-  load_a(blockIdx.x, a_pre);
-
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int s = it & 1;
-    const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-    const int64_t r0 = tile * R;
-    __syncthreads();                                 // previous tile done with s_a / s_red / s_valid (and s_w loaded)
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = t + T * u, rr = e / cin, k = e - rr * cin;
-      if (rr < R) s_a[k * R + rr] = a_pre[u];
-    }
-    if (t < R) s_valid[t] = (r0 + t < rows && row_valid(num_nodes, nmax, r0 + t)) ? 1 : 0;
-    load_a(tile + gridDim.x, a_pre);                 // consumed one tile from now
-    __syncthreads();
-    uint32_t vmask = 0;
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) vmask |= (uint32_t)s_valid[rr] << rr;
-    // h = a W + b, two rows of the tile per packed f32x2 accumulator (see k_epi_wide)
-    unsigned long long acc2[R / 2][NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      unsigned long long bb;
-      asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(bj[j]));
-#pragma unroll
-      for (int q = 0; q < R / 2; ++q) acc2[q][j] = bb;
-    }
-#pragma unroll 4
-    for (int k = 0; k < cin; ++k) {
-      unsigned long long wv[NC];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int c = t + T * j;
-        const float w1 = (c < cout) ? s_w[k * cout + c] : 0.f;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(wv[j]) : "f"(w1));
-      }
-      const unsigned long long* ap = reinterpret_cast<const unsigned long long*>(s_a + k * R);   // row pairs (R even)
-      unsigned long long av[R / 2];
-#pragma unroll
-      for (int q = 0; q < R / 2; ++q) av[q] = ap[q];
-#pragma unroll
-      for (int q = 0; q < R / 2; ++q)
-#pragma unroll
-        for (int j = 0; j < NC; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[q][j]) : "l"(av[q]), "l"(wv[j]));
-    }
-    float acc[R][NC];
-#pragma unroll
-    for (int q = 0; q < R / 2; ++q)
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * q][j]), "=f"(acc[2 * q + 1][j]) : "l"(acc2[q][j]));
-    float part[R];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      float sq = 0.f;
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-        if (t + T * j < cout) sq = fmaf(acc[rr][j], acc[rr][j], sq);
-      part[rr] = warp_sum(sq);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int rr = 0; rr < R; ++rr) s_red[warp * R + rr] = part[rr];
-    }
-    __syncthreads();
-    float nrm[R], inv[R];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      float sq = 0.f;
-      for (int wv = 0; wv < nwarps; ++wv) sq += s_red[wv * R + rr];
-      nrm[rr] = sqrtf(sq);
-      inv[rr] = 1.0f / fmaxf(nrm[rr], kL2NormEps);
-    }
-    // gm = gy * act'(y) * mask ; dot_r = sum_c gm * hn     (rows of this tile are in the ring)
-    mbar_wait(&full[s], ph);
-    const float* ty = s_ring + (size_t)(s * 2 + 0) * R * cout;
-    const float* tg = s_ring + (size_t)(s * 2 + 1) * R * cout;
-    float gm[R][NC];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      const bool valid = (vmask >> rr) & 1u;
-      float dsum = 0.f;
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int c = t + T * j;
-        float g = 0.f;
-        if (valid && c < cout) {
-          const float yv = ty[rr * cout + c];
-          float gv = tg[rr * cout + c];
-          if (with_bn) gv = fmaf(bp[j], gv, -fmaf(br[j], yv, bq[j]));
-          g = gv * agrad(yv);
-        }
-        gm[rr][j] = g;
-        dsum = fmaf(g, acc[rr][j] * inv[rr], dsum);
-      }
-      part[rr] = warp_sum(dsum);
-    }
-    __syncthreads();                                 // norms read out of s_red; ring stage s consumed by everyone
-    if (warp == 0) {
-      const int64_t nxt = tile + (int64_t)kRingStages * gridDim.x;
-      if (nxt < ntiles) issue(nxt, s);               // refill the stage while the gradients are written
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int rr = 0; rr < R; ++rr) s_red[warp * R + rr] = part[rr];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      const int64_t r = r0 + rr;
-      if (r >= rows) break;
-      float dot = 0.f;
-      for (int wv = 0; wv < nwarps; ++wv) dot += s_red[wv * R + rr];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int c = t + T * j;
-        if (c < cout) {
-          const float hn = acc[rr][j] * inv[rr];
-          dh[r * lddh + c] = (nrm[rr] >= kL2NormEps) ? (gm[rr][j] - hn * dot) * inv[rr] : gm[rr][j] * inv[rr];
-        }
-      }
-    }
-  }
-}
-
-static size_t ring_smem_bytes(int cin, int cout, int r) {
-  return sizeof(float) * ((size_t)cin * cout + (size_t)kRingStages * 2 * r * cout + (size_t)cin * r +
-                          (kRingThreadsMax / 32) * r + r + (r & 1)) + kRingStages * sizeof(uint64_t);
-}
-
 // ------------------------------------------------------------------- wide epilogue backward, one warp per row pair
-// The tile kernels above split a row over the threads of a CTA, so both row reductions (the L2 norm and g . hn) go
+// The tile kernel above splits a row over the threads of a CTA, so both row reductions (the L2 norm and g . hn) go
 // through shared memory and five block barriers per 8 rows: measured 13 800 cycles per 6-row tile at an IPC of ~1
 // with the memory system idle (909 us for 1.57 GB).  Here a WARP owns two whole rows: lane l holds the float4
 // column chunks l, l + 32, ... (NQ of them), both reductions are shuffles, warps never wait for each other, and the
@@ -822,8 +610,8 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
     const int extra = BWD ? (bn_in != nullptr ? 3 : 0) : (partial != nullptr ? 2 : 0);
     float* o = BWD ? dh : y;
     const int64_t ldo = BWD ? lddh : ldy;
-    // (measured at 20 x 1140, 115 200 rows: backward 809 us vs 909 us ring / 1076 us tile kernel; forward 369 us vs
-    //  333 us tile kernel -- W is read from shared memory once per row PAIR here, once per 8 rows there, and the
+    // (measured at 20 x 1140, 115 200 rows: backward 653 us vs 1076 us for the tile kernel -- 909 us when that was fed
+    //  by a two-stage cp.async.bulk ring, a variant since removed; forward 369 us vs 333 us tile kernel -- W is read from shared memory once per row PAIR here, once per 8 rows there, and the
     //  forward has no global loads to overlap: BWD only unless the lab switch is 2)
     static const bool rowpair_fwd = lab_env("CGC_EPI_ROWPAIR", 1) == 2;
     // any width from 64 columns up: vectors are padded to a multiple of 4 in shared memory, pad columns masked
@@ -867,42 +655,6 @@ static int launch_epilogue(const float* sa, int64_t ldsa, const float* w, const 
 #undef CGC_ROWPAIR_CASE
 #undef CGC_ROWPAIR_LAUNCH
       CGC_CHECK_LAUNCH("k_epi_rowpair");
-      return 0;
-    }
-  }
-  if constexpr (BWD) {
-    // very wide layers: rows stream through the bulk-copy ring, one CTA per SM
-    const int rnc = (int)ceil_div(cout, kRingThreadsMax);
-    const int threads = (int)ceil_div(ceil_div(cout, rnc), 32) * 32;
-    static const bool ring_off = lab_env("CGC_EPI_RING", 1) == 0;          // A/B switch (CGC_LAB builds only)
-    int r = 0;
-    for (int cand = 8; cand >= 4 && r == 0; cand -= 2)
-      if (ring_smem_bytes(cin, cout, cand) <= 227 * 1024 && cin * cand <= 2 * threads) r = cand;
-    if (!ring_off && r != 0 && cout >= 512 && cout % 4 == 0 && ldy % 4 == 0 && ldgy % 4 == 0 && aligned16(y) &&
-        aligned16(gy) && rnc <= 4) {
-      const size_t smem = ring_smem_bytes(cin, cout, r);
-      int64_t blocks = ceil_div(rows, r);
-      if (blocks > kNumSMs) blocks = kNumSMs;
-#define CGC_RING_LAUNCH(N, RR)                                                                                 \
-  {                                                                                                            \
-    auto kern = k_epi_wide_bwd_ring<N, RR>;                                                                    \
-    CGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    kern<<<(unsigned)blocks, threads, smem, st>>>(sa, ldsa, w, b, num_nodes, nmax, rows, cin, cout, y, ldy, gy, \
-                                                  ldgy, dh, lddh, act, bn);                                    \
-  }
-#define CGC_RING_CASE(N)                                                                                       \
-  case N:                                                                                                      \
-    if (r == 8) CGC_RING_LAUNCH(N, 8) else if (r == 6) CGC_RING_LAUNCH(N, 6) else CGC_RING_LAUNCH(N, 4)        \
-    break;
-      switch (rnc) {
-        CGC_RING_CASE(1)
-        CGC_RING_CASE(2)
-        CGC_RING_CASE(3)
-        CGC_RING_CASE(4)
-      }
-#undef CGC_RING_CASE
-#undef CGC_RING_LAUNCH
-      CGC_CHECK_LAUNCH("k_epi_wide_bwd_ring");
       return 0;
     }
   }
