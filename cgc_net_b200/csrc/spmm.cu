@@ -363,9 +363,7 @@ __device__ __forceinline__ void ell_cta_rows(const EllGatherArgs& a, int nrow8, 
 
 // Unweighted tables may come without a scale vector (ell_scale == NULL): the row's scale is then the DenseSAGEConv
 // mean 1 / max(deg, 1) with deg counted from the row's own slots; the served row comes from the slot-0 tag.
-// (Measured and dropped: a 512-thread / 64-register variant that lets two CTAs share an SM, so that under
-// programmatic launch the next launch's CTAs are resident early -- the block scheduler then doubles CTAs up on the
-// 20 SMs the 128-CTA grid leaves idle and the launch waits for those: 8.7 us instead of 6.3 us.)
+// (The BASELINE configuration under a programmatic launch takes k_sage_gather_ell_lean below instead.)
 template <int W, int LPR, bool WEIGHTED, int RB, int THREADS, bool STRIDED, bool ACC>
 __global__ void __launch_bounds__(THREADS, 1)
 k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs a) {
@@ -530,11 +528,12 @@ k_sage_gather_ell(const __grid_constant__ CUtensorMap map_x, const EllGatherArgs
 // share an SM: 512 threads x 8 rows, 64 registers (a row costs its 4 index registers and nothing else: served row from
 // the slot-0 tag, scale = 1 / max(deg, 1) counted from the slots), 2 x 113.6 KB of shared memory.  Under
 // programmatic dependent launch the NEXT launch's CTAs are then resident, with their index vectors loaded, while
-// this launch still gathers.  It only pays with the balanced 148-CTA grid: with 128 CTAs the block scheduler doubles
-// the next launch's CTAs up on the 20 idle SMs (measured 8.7 us).
+// this launch still gathers, and pull their tile into L2 before griddepcontrol.wait.  It only pays on a grid that
+// covers every SM (ell_row_split): with 128 CTAs the block scheduler doubles the next launch's CTAs up on the 20 idle
+// SMs and the launch waits for those (measured 8.7 us against 6.0 - 6.2 us).
 constexpr int kLeanThreads = 512;
-constexpr uint32_t kLeanChunk = 16384;   // bytes per bulk copy of the tile: 8 copies in flight for the 115 KB tile
-                                         // (4 copies of 32 KB: 6.20 us per launch, 8 of 16 KB: 5.94 us)
+constexpr uint32_t kLeanChunk = 16384;   // bytes per bulk copy of the tile (8 KB and up measure the same, 4 KB and
+                                         // below are slower: profiles/gather_chunk_r2.txt)
 constexpr int kLeanRows = 8;
 
 // CL > 1: the CL CTAs of a graph form a thread-block cluster and share ONE read of the tile: each issues every CL-th
