@@ -347,3 +347,22 @@ def test_eighteen_feature_input(torch_backend):
     assert helpers.rel_err(lo, lr) < 1e-4
     losso.backward(), lossr.backward()
     _grad_check(ours, orc, batch)
+
+
+def test_folded_batchnorm_backward_is_a_pure_reformulation(torch_backend, monkeypatch):
+    """ops.FOLD_BN_BACKWARD routes the wide layers' backward through sage_dh_bn (BatchNorm backward formed inside the
+    epilogue backward) instead of bn_bwd(apply) + sage_dh: both wirings must give the same gradients."""
+    graphs = [graph.synthetic_cell_graph(n, 6, 16, seed=i) for i, n in enumerate([300, 400, 250])]
+    batch = graph.Batch.from_data_list(graphs)
+    grads = {}
+    for fold in (True, False):
+        monkeypatch.setattr(ops, 'FOLD_BN_BACKWARD', fold)
+        torch.manual_seed(0)
+        m = network.SoftPoolingGcnEncoder(400, 16, 20, 20, True, True, 20, 3, 0.1, [50], concat=True,
+                                          load_data_sparse=True).train()
+        _, loss = m(batch)
+        loss.backward()
+        grads[fold] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for k, g in grads[True].items():
+        scale = max(float(grads[False][k].abs().max()), 1e-6)
+        assert float((g - grads[False][k]).abs().max()) <= 1e-5 * scale + 1e-8, k
