@@ -64,6 +64,9 @@ def parse():
     ap.add_argument('--cpu-sample-graphs', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--overlap-allreduce', type=int, default=0, metavar='CHUNKS',
+                    help='N > 1 ranks: all-reduce the gradient bucket in CHUNKS pieces started from inside backward() '
+                         '(parallel.FlatGradBucket.enable_overlap; gloo-tested, off by default: not yet measured on NCCL)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.batch_per_gpu is None:
@@ -470,6 +473,7 @@ def run_ours(args):
                                           norm_adj=args.norm_adj).to(device).train()
     parallel.broadcast_parameters(model)
     bucket = parallel.FlatGradBucket(model.parameters())
+    overlapped = bool(args.overlap_allreduce > 0 and world > 1 and bucket.enable_overlap(args.overlap_allreduce))
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
 
     def step(batch):
@@ -543,7 +547,9 @@ def run_ours(args):
         'scaling': 'strong' if args.config == 4 else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'bench_config': args.config, 'graphs_rank0': b,
                    'global_graphs': total_graphs, 'global_nodes': total_nodes, 'clusters': [1140, 114],
-                   'parallelism': 'dp%d (batch-sharded, one flat-bucket all-reduce)' % world,
+                   'parallelism': 'dp%d (batch-sharded, %s)' % (
+                       world, 'flat-bucket all-reduce in %d chunks started inside backward' % args.overlap_allreduce
+                       if overlapped else 'one flat-bucket all-reduce'),
                    'gemm_pass_budget': budget or 'all 3xTF32',
                    'l2': 'working set >> L2: ~%d MB of [M,1140] fp32 activations per tensor, > 10 GB per step'
                          % (b * nmax * 1140 * 4 // 2 ** 20)},

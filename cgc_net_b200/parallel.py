@@ -27,16 +27,32 @@ class FlatGradBucket(object):
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        self.views = []
+        self.views, self.offsets = [], []
         off = 0
         for p in self.params:
             self.views.append(self.flat[off: off + p.numel()].view_as(p))
+            self.offsets.append(off)
             off += p.numel()
+        self._overlap = None
 
     def zero(self):
         """Use instead of ``optimizer.zero_grad()``."""
         for p in self.params:
             p.grad = None
+        if self._overlap is not None:
+            self._overlap.reset()
+
+    def enable_overlap(self, chunks=2, group=None):
+        """Start the all-reduce of a chunk of the bucket as soon as the backward pass has produced every gradient in
+        it, so the collective runs under the rest of the backward.  The parameter list is cut
+        into ``chunks`` contiguous ranges of roughly equal BYTES; autograd reaches parameters roughly in reverse
+        order, so the last range (read-out head, stage 3, stage 2) is reduced while stage 1 is still differentiating.
+        ``all_reduce_mean()`` then only launches what is left (parameters that received no gradient), waits for the
+        handles and applies 1/R.  Call once after construction; a no-op without an initialised process group."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return False
+        self._overlap = _EarlyReduce(self, max(1, int(chunks)), group)
+        return True
 
     def nbytes(self):
         return self.flat.numel() * self.flat.element_size()
@@ -63,9 +79,85 @@ class FlatGradBucket(object):
         world = dist.get_world_size(group)
         if world == 1:
             return
+        if self._overlap is not None:
+            self._overlap.finish()
+            self.flat.mul_(1.0 / world)
+            return
         self.pack()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.mul_(1.0 / world)
+
+
+class _EarlyReduce(object):
+    """Per-chunk asynchronous all-reduce driven by post-accumulate-grad hooks (see FlatGradBucket.enable_overlap)."""
+
+    def __init__(self, bucket, chunks, group):
+        self.bucket, self.group = bucket, group
+        n = len(bucket.params)
+        total = bucket.flat.numel()
+        # contiguous parameter ranges of ~equal bytes
+        bounds, acc, target = [0], 0, total / float(chunks)
+        for i, p in enumerate(bucket.params):
+            acc += p.numel()
+            if acc >= target * len(bounds) and len(bounds) < chunks and i + 1 < n:
+                bounds.append(i + 1)
+        bounds.append(n)
+        self.ranges = [(bounds[c], bounds[c + 1]) for c in range(len(bounds) - 1)]
+        self.chunk_of = {}
+        for c, (lo, hi) in enumerate(self.ranges):
+            for i in range(lo, hi):
+                self.chunk_of[i] = c
+        self.handles = []
+        for i, p in enumerate(bucket.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self.reset()
+
+    def reset(self):
+        self.pending = [hi - lo for lo, hi in self.ranges]
+        self.seen = [False] * len(self.bucket.params)
+        self.launched = [False] * len(self.ranges)
+        self.handles = []
+
+    def _span(self, c):
+        lo, hi = self.ranges[c]
+        b = self.bucket
+        end = b.offsets[hi] if hi < len(b.params) else b.flat.numel()
+        return b.flat[b.offsets[lo]: end]
+
+    def _launch(self, c):
+        self.launched[c] = True
+        self.handles.append(dist.all_reduce(self._span(c), op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _make_hook(self, i):
+        def hook(p):
+            b = self.bucket
+            v = b.views[i]
+            if p.grad is not None and (p.grad.data_ptr() != v.data_ptr() or p.grad.shape != v.shape):
+                v.copy_(p.grad)
+                p.grad = v
+            if not self.seen[i]:
+                self.seen[i] = True
+                c = self.chunk_of[i]
+                self.pending[c] -= 1
+                if self.pending[c] == 0 and not self.launched[c]:
+                    self._launch(c)
+        return hook
+
+    def finish(self):
+        b = self.bucket
+        for i, p in enumerate(b.params):                 # parameters autograd never reached: zero gradient
+            if not self.seen[i]:
+                if p.grad is None:
+                    b.views[i].zero_()
+                elif p.grad.data_ptr() != b.views[i].data_ptr():
+                    b.views[i].copy_(p.grad)
+                p.grad = b.views[i]
+        for c in range(len(self.ranges)):
+            if not self.launched[c]:
+                self._launch(c)
+        for h in self.handles:
+            h.wait()
+        self.reset()
 
 
 def broadcast_parameters(module, src=0, group=None):

@@ -33,7 +33,7 @@ def _graphs():
     return helpers.make_graphs([40, 55, 33, 61], [5, 6, 4, 8], seed=9)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=0):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     torch.set_num_threads(1)
@@ -45,22 +45,38 @@ def _worker(rank, world, port, out):
                 p.add_(1.0)
     parallel.broadcast_parameters(model, src=0)
     bucket = parallel.FlatGradBucket(model.parameters())
+    launched = []
+    if overlap:
+        assert bucket.enable_overlap(chunks=overlap)
+        orig = bucket._overlap._launch
+        bucket._overlap._launch = lambda c: (launched.append(c), orig(c))[1]
     shard = parallel.shard_for_rank(_graphs(), rank, world)
-    bucket.zero()
-    _, loss = model(graph.Batch.from_data_list(shard))
-    loss.backward()
-    bucket.all_reduce_mean()
+    for _ in range(2 if overlap else 1):              # overlapped mode: a second step checks the per-step reset
+        bucket.zero()
+        _, loss = model(graph.Batch.from_data_list(shard))
+        loss.backward()
+        early = list(launched)                         # chunks whose all-reduce started inside backward()
+        bucket.all_reduce_mean()
+        launched.clear()
     if rank == 0:
-        torch.save({'flat': bucket.flat.clone(), 'loss': loss.detach()}, out)
+        torch.save({'flat': bucket.flat.clone(), 'loss': loss.detach(), 'early': early,
+                    'grads_are_views': all(p.grad.data_ptr() == v.data_ptr()
+                                           for p, v in zip(bucket.params, bucket.views))}, out)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gradient_allreduce(tmp_path, torch_backend):
+@pytest.mark.parametrize('overlap', [0, 1, 3])
+def test_two_rank_gradient_allreduce(tmp_path, torch_backend, overlap):
+    """overlap = 0: one all-reduce after backward; 1 / 3: FlatGradBucket.enable_overlap with that many chunks (the
+    chunk all-reduces start from post-accumulate-grad hooks inside backward()) -- same reduced bucket."""
     out = str(tmp_path / 'rank0.pt')
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, overlap), nprocs=2, join=True)
     got = torch.load(out)
+    assert got['grads_are_views']
+    if overlap:
+        assert len(got['early']) >= 1, 'no chunk was reduced inside backward()'
     # single-process reference: mean over the two shards of each shard's own gradient
     graphs = _graphs()
     flats = []

@@ -33,24 +33,26 @@ def _graphs(world):
     return [graph.synthetic_cell_graph(600, 8, 16, seed=50 + i) for i in range(4 * world)]
 
 
-def _shard_grads(device, shard):
+def _shard_grads(device, shard, overlap=0):
     from cgc_net_b200 import graph, parallel
     model = _model(device)
     bucket = parallel.FlatGradBucket(model.parameters())
+    if overlap:
+        assert bucket.enable_overlap(chunks=overlap)          # chunk all-reduces start inside backward()
     bucket.zero()
     _, loss = model(graph.Batch.from_data_list(shard).to(device))
     loss.backward()
     return model, bucket
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=0):
     from cgc_net_b200 import parallel
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     device = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=device)
     graphs = _graphs(world)
-    model, bucket = _shard_grads(device, parallel.shard_for_rank(graphs, rank, world))
+    model, bucket = _shard_grads(device, parallel.shard_for_rank(graphs, rank, world), overlap)
     bucket.all_reduce_mean()
     torch.cuda.synchronize()
     flat = bucket.flat.clone()
@@ -70,16 +72,17 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('overlap', [0, 2])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_nccl_allreduce_matches_single_gpu(cuda_backend, tmp_path, world):
+def test_nccl_allreduce_matches_single_gpu(cuda_backend, tmp_path, world, overlap):
     if torch.cuda.device_count() < world:
         pytest.skip('needs %d GPUs' % world)
     out = str(tmp_path / 'rank0.pt')
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, overlap), nprocs=world, join=True)
     res = torch.load(out)
     got, want = res['got'], res['want']
     diff = float((got - want).abs().max())
-    print('world %d: bucket of %d gradients, max |allreduced - single-GPU mean| = %.3e (scale %.3e), bitwise %s'
-          % (world, got.numel(), diff, float(want.abs().max()), bool(torch.equal(got, want))))
+    print('world %d overlap %d: bucket of %d gradients, max |allreduced - single-GPU mean| = %.3e (scale %.3e), bitwise %s'
+          % (world, overlap, got.numel(), diff, float(want.abs().max()), bool(torch.equal(got, want))))
     assert res['same'], 'ranks disagree on the reduced bucket'
     assert diff <= 1e-6 * float(want.abs().max()) + 1e-9        # fp32 reduction order only
